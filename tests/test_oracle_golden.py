@@ -1,0 +1,192 @@
+"""Pin the CPU oracle (oracle/biear_oracle.py) to the reference's own outputs.
+
+The golden file was produced by tests/golden/make_golden.py from the unmodified reference
+(/root/reference/model_torch.py, utils.py).  No GPU needed.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import biear_oracle as orc
+from tests.common import (RTOL, assert_close, cfg_single, cfg_yaml, elem_rel_err, loss_a, rel_err, sub,
+                          upstream, wrap_err)
+
+
+def test_constants(golden):
+    cfg = cfg_yaml()
+    c = orc.constants(cfg)
+    for ours, key in ((c["fc"], "const.fc"), (c["Q0"], "const.Q0"), (c["f_fft"], "const.f_fft"),
+                      (c["deltaQ_vec"], "const.deltaQ_yaml"), (c["win_fn"], "const.win_fn")):
+        np.testing.assert_array_equal(ours.numpy(), golden[key])
+    # known answers from SURVEY.md section 4 item 6
+    assert cfg.win == 842 and cfg.hop == 842 and cfg.n_bins == 513
+    assert abs(c["fc"][0].item() - 50.0) < 1e-4 and abs(c["fc"][-1].item() - 7200.0) < 1e-2
+    assert abs(c["Q0"].min().item() - 1.6303) < 1e-3 and abs(c["Q0"].max().item() - 8.8117) < 1e-3
+    assert abs(c["deltaQ_vec"][0].item() - 0.3) < 1e-6 and abs(c["deltaQ_vec"][-1].item() - 5.0) < 1e-5
+    c64 = orc.constants(cfg_single(n_bands=64))
+    np.testing.assert_array_equal(c64["fc"].numpy(), golden["const.fc64"])
+    np.testing.assert_array_equal(c64["Q0"].numpy(), golden["const.Q064"])
+    np.testing.assert_array_equal(c64["deltaQ_vec"].numpy(), golden["const.deltaQ_single64"])
+
+
+def _run_dual(tag, golden, dtype, batch, seeds, cfg, out_std=0.02):
+    wl, wr = orc.synth_binaural(3, seed=1234)
+    wl, wr = torch.from_numpy(wl[:batch]).to(dtype), torch.from_numpy(wr[:batch]).to(dtype)
+    pl = orc.to_torch(orc.synth_controller(seeds[0], out_std=out_std), dtype, requires_grad=True)
+    pr = orc.to_torch(orc.synth_controller(seeds[1], out_std=out_std), dtype, requires_grad=True)
+    c = orc.constants(cfg, dtype)
+    up = {k: torch.from_numpy(v).to(dtype) for k, v in upstream(batch).items()}
+    tl, tr = [], []
+    yl, ql, xl = orc.adaptive_fb_forward(wl, pl, cfg, c, taps=tl)
+    yr, qr, xr = orc.adaptive_fb_forward(wr, pr, cfg, c, taps=tr)
+    ph_l = orc.subband_phase(xl, ql, c["f_fft"], c["fc"])
+    ph_r = orc.subband_phase(xr, qr, c["f_fft"], c["fc"])
+    return dict(wl=wl, wr=wr, pl=pl, pr=pr, c=c, up=up, tl=tl, tr=tr, yl=yl, yr=yr, ql=ql, qr=qr, xl=xl, xr=xr,
+                ph_l=ph_l, ph_r=ph_r)
+
+
+@pytest.mark.parametrize("tag,batch,seeds,cfgf,std", [
+    ("dual32", 3, (11, 12), cfg_yaml, 0.02),
+    ("clamp32", 2, (21, 22), cfg_yaml, 0.3),
+    ("abs32", 2, (11, 12), cfg_single, 0.02),
+])
+def test_adaptive_forward_fp32(golden, tag, batch, seeds, cfgf, std):
+    r = _run_dual(tag, golden, torch.float32, batch, seeds, cfgf(), std)
+    assert_close(r["yl"].detach(), golden[f"{tag}.YL"], RTOL, "YL")
+    assert_close(r["yr"].detach(), golden[f"{tag}.YR"], RTOL, "YR")
+    assert_close(r["ql"].detach(), golden[f"{tag}.QL"], RTOL, "QL")
+    assert_close(r["qr"].detach(), golden[f"{tag}.QR"], RTOL, "QR")
+    assert elem_rel_err(r["yl"].detach(), golden[f"{tag}.YL"]) <= RTOL
+    assert_close(torch.view_as_real(r["xl"][:, ::3]), golden[f"{tag}.XL"].view(np.float32).reshape(batch, 7, 513, 2),
+                 1e-5, "XL")
+    # Q[:,0,:] == Q0 always
+    np.testing.assert_array_equal(r["ql"][:, 0].detach().numpy(), np.broadcast_to(golden["const.Q0"], (batch, 100)))
+    if tag == "clamp32":
+        q = r["ql"].detach().numpy()
+        assert (q == orc.Q_MIN).mean() > 0.05, "strong-controller case must exercise the Q floor clamp"
+
+
+@pytest.mark.parametrize("tag,batch,seeds,std", [("dual", 3, (11, 12), 0.02), ("clamp", 2, (21, 22), 0.3)])
+def test_adaptive_backward_loss_a(golden, tag, batch, seeds, std):
+    """Gradients through Y and the Q path (well conditioned): fp32 oracle vs fp32 reference <= 1e-4."""
+    r = _run_dual(tag, golden, torch.float32, batch, seeds, cfg_yaml(), std)
+    loss_a(r["yl"], r["yr"], r["ql"], r["qr"], r["up"]).backward()
+    worst = 0.0
+    for side, p, taps in (("L", r["pl"], r["tl"]), ("R", r["pr"], r["tr"])):
+        for name, prm in p.items():
+            ref64 = golden[f"{tag}64.gradA.{side}.{name}"]
+            ref32 = golden[f"{tag}32.gradA.{side}.{name}"]
+            e = rel_err(sub(prm.grad.numpy()), ref32)
+            # the reference's own fp32-vs-fp64 error bounds what "matching" can mean
+            e_ref = rel_err(ref32, ref64)
+            worst = max(worst, e)
+            assert e <= max(RTOL, 3 * e_ref), f"{side}.{name}: {e:.2e} (reference self-error {e_ref:.2e})"
+        tap = torch.stack([t.grad if t.grad is not None else torch.zeros_like(t) for t in taps], 1)
+        e = rel_err(sub(tap.numpy()), golden[f"{tag}32.gradA.{side}.tap"])
+        assert e <= RTOL, f"{side}.tap {e:.2e}"
+    print(f"[{tag}] worst gradA error {worst:.2e}")
+
+
+def test_adaptive_fp64_truth(golden):
+    """fp64 oracle vs fp64 reference: establishes the oracle as an exact restatement (not just close)."""
+    r = _run_dual("dual", golden, torch.float64, 3, (11, 12), cfg_yaml())
+    assert rel_err(r["yl"].detach(), golden["dual64.YL"]) < 1e-12
+    assert rel_err(r["qr"].detach(), golden["dual64.QR"]) < 1e-12
+    assert wrap_err(r["ph_l"].detach(), golden["dual64.PL"]) < 1e-9
+    loss = (r["up"]["gPL"] * r["ph_l"]).sum() + (r["up"]["gPR"] * r["ph_r"]).sum()
+    loss.backward()
+    for side, p in (("L", r["pl"]), ("R", r["pr"])):
+        for name, prm in p.items():
+            assert rel_err(sub(prm.grad.numpy()), golden[f"dual64.gradB.{side}.{name}"]) < 1e-9, name
+
+
+def test_phase_fp32_conditioning(golden):
+    """Phase is ill-conditioned in fp32: the reference's own fp32 differs from its fp64 by ~1e-2.
+    The oracle must be no worse than 3x the reference's own error."""
+    r = _run_dual("dual", golden, torch.float32, 3, (11, 12), cfg_yaml())
+    e_ref = wrap_err(golden["dual32.PL"], golden["dual64.PL"])
+    e_orc = wrap_err(r["ph_l"].detach(), golden["dual64.PL"])
+    assert e_orc <= 3 * e_ref + 1e-6, (e_orc, e_ref)
+
+
+def test_fixed_and_ragged(golden):
+    cfg = orc.FrontEndConfig()
+    wl, wr = orc.synth_binaural(3, seed=1234)
+    tl = torch.from_numpy(wl)
+    y, q, x = orc.fixed_fb_forward(tl, cfg)
+    assert_close(y, golden["fixed.YL"], 1e-5, "fixed YL")
+    np.testing.assert_array_equal(q.numpy(), golden["fixed.QL"])
+    assert_close(orc.fixed_fb_forward(tl[:, :9000], cfg)[0], golden["fixed.YL_short9000"], 1e-5, "short clip")
+    ylong = orc.fixed_fb_forward(torch.cat([tl, tl], 1), cfg)[0]
+    assert_close(ylong, golden["fixed.YL_long32000"], 1e-5, "long clip")
+    # samples beyond the first second are ignored
+    np.testing.assert_array_equal(ylong.numpy(), y.numpy())
+    assert wrap_err(orc.subband_phase(x, q, orc.constants(cfg)["f_fft"], orc.constants(cfg)["fc"]),
+                    golden["fixed.PL"]) < 2e-2
+    assert_close(orc.auralnet_fb_forward(tl, cfg), golden["auralnet.YL"], 1e-5, "auralnet")
+    assert_close(orc.fixed_fb_forward(tl, orc.FrontEndConfig(n_bands=64))[0], golden["fixed64.YL"], 1e-5, "64 bands")
+    with pytest.raises(ValueError):
+        orc.fixed_fb_forward(tl[0], cfg)
+
+
+def test_adaptive_at_init_equals_fixed():
+    """Zero-initialised last controller layer => Q == Q0 for all frames, Y identical to the fixed FB
+    (SURVEY.md section 4 item 1)."""
+    cfg = cfg_yaml()
+    wl, _ = orc.synth_binaural(2, seed=5)
+    p = orc.synth_controller(3)
+    p["q_out.8.weight"][:] = 0
+    p["q_out.8.bias"][:] = 0
+    ya, qa, _ = orc.adaptive_fb_forward(torch.from_numpy(wl), orc.to_torch(p), cfg)
+    yf, qf, _ = orc.fixed_fb_forward(torch.from_numpy(wl), cfg)
+    np.testing.assert_array_equal(ya.numpy(), yf.numpy())
+    np.testing.assert_array_equal(qa.numpy(), qf.numpy())
+
+
+def test_single_controller(golden):
+    cfg = cfg_single()
+    wl, wr = orc.synth_binaural(3, seed=1234)
+    tl, tr = torch.from_numpy(wl[:2]), torch.from_numpy(wr[:2])
+    p = orc.to_torch(orc.synth_controller(31, in_mult=4), requires_grad=True)
+    yl, yr, q, _, _, _ = orc.single_controller_forward(tl, tr, p, cfg)
+    assert_close(yl.detach(), golden["single.YL"], RTOL, "single YL")
+    assert_close(yr.detach(), golden["single.YR"], RTOL, "single YR")
+    assert_close(q.detach(), golden["single.Q"], RTOL, "single Q")
+    up = {k: torch.from_numpy(v) for k, v in upstream(2).items()}
+    ((up["gYL"] * torch.log(yl + 1e-8)).sum() + (up["gYR"] * torch.log(yr + 1e-8)).sum() + (up["gQL"] * q).sum()).backward()
+    for name, prm in p.items():
+        assert rel_err(sub(prm.grad.numpy()), golden[f"single.gradA.{name}"]) <= 2 * RTOL, name
+
+
+def test_cc_feature(golden):
+    cl, cr = orc.synth_binaural(6, seed=77)
+    ours = orc.cc_feature_batch(cl, cr)
+    assert np.max(np.abs(ours - golden["cc.default"])) <= 1e-6
+    assert np.max(np.abs(orc.cc_feature_batch(cl[:2], cr[:2], 16000, 64, 1.0) - golden["cc.lags64_1ms"])) <= 1e-6
+    assert np.max(np.abs(orc.cc_feature_batch(cl[:2], cr[:2], 16000, 128, 5.0) - golden["cc.lags128_5ms"])) <= 1e-6
+    q16 = lambda x: (np.round(x * 32767) / 32768).astype(np.float32)
+    assert np.max(np.abs(orc.cc_feature_batch(q16(cl[:2]), q16(cr[:2])) - golden["cc.int16"])) <= 1e-6
+    z = np.zeros(16000, np.float32)
+    np.testing.assert_array_equal(orc.cc_feature(z, z), golden["cc.silence"])
+    dc = np.full(16000, 0.25, np.float32)
+    assert np.max(np.abs(orc.cc_feature(dc + cl[0] * 0.1, cr[0]) - golden["cc.dc_vs_noise"])) <= 1e-6
+
+
+def test_dq_closed_form_matches_autograd():
+    """kappa (a2 - Y m2) etc. equals autograd of the materialised-W formulation (fp64)."""
+    cfg = cfg_yaml()
+    c = orc.constants(cfg, torch.float64)
+    wl, _ = orc.synth_binaural(2, seed=9)
+    x = orc.stft_frames(torch.from_numpy(wl).double(), cfg, c["win_fn"])[:, 4]
+    rs = np.random.RandomState(0)
+    q = (c["Q0"] * torch.from_numpy(np.exp(0.7 * rs.standard_normal((2, 100))))).clamp(orc.Q_MIN, orc.Q_MAX)
+    q.requires_grad_(True)
+    gy = torch.from_numpy(rs.standard_normal((2, 100)))
+    gp = torch.from_numpy(rs.standard_normal((2, 100)))
+    w = orc.band_weights(q, c["fc"], c["f_fft"], sanitize=False)
+    y = orc.band_energy(x.abs(), w)
+    ph = orc.subband_phase(x.unsqueeze(1), q.unsqueeze(1), c["f_fft"], c["fc"])[:, 0]
+    ((gy * y).sum() + (gp * ph).sum()).backward()
+    m = orc.band_moments(x, q.detach(), c["fc"], c["f_fft"])
+    dq = orc.dq_closed_form(m, q.detach(), c["fc"], gy, gp)
+    assert rel_err(dq, q.grad) < 1e-10
