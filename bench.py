@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""bench.py -- binaural audio-seconds/second of the BiEAR active-mode front-end, forward + backward.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+
+Workload (BASELINE.json configs[1]): batch 256 synthetic binaural clips (1 s, 2 ears, 16 kHz, fp32) per GPU,
+adaptive Q (dual controllers, conf/config.yaml settings), CC on, train mode.  One step = STFT of all frames,
+the 19-frame Q recurrence (band energies + sub-band phase + controller), the CC feature, a loss over
+log-energies / phase / Q regularisers and the backward pass into the controller weights (dQ closed form);
+with N > 1 ranks the batch is sharded (weak scaling, 256 clips per rank) and the controller gradients are
+all-reduced over NCCL every step.
+
+Prints ONE JSON line (rank 0).  `value` is measured with the inputs resident in HBM, `e2e` through the
+same public call with pinned HOST buffers (H2D of both waveforms and D2H of the loss inside the timed region).
+`--impl reference` times the CPU restatement of the reference (oracle/) on the host cores instead.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FS, T, NBANDS, NBINS = 16000, 19, 100, 513
+CONFIG_YAML = dict(deltaQ_base=1.0, deltaQ_low_factor=0.3, deltaQ_high_factor=5.0, deltaQ_mode="relative")
+REG_Q_W = REG_SMOOTH_W = 1e-3                      # conf/config.yaml
+# algorithmic bytes per audio-second, module-boundary form (X materialised), fwd+bwd
+A_FULL = 128000 + 15200 + 15200 + 155952 + 15200 + 15200
+METRIC = "binaural audio-sec/sec front-end fwd+bwd"
+UNIT = "audio-s/s"
+N_ROTATE = 8                                       # resident input batches cycled through (> L2 in total)
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def synth_binaural(batch, seed, n=FS):
+    """AR(1)-tilted noise, per-clip integer ITD in [-12,12] and ILD gain in [0.5,1], joint peak-normalised
+    (SURVEY.md 8(d)); numpy RandomState so every rank/run sees the same clips for a given seed."""
+    rs = np.random.RandomState(seed)
+    src = rs.standard_normal((batch, n + 64)).astype(np.float32)
+    s = np.empty_like(src)
+    acc = np.zeros(batch, np.float32)
+    for i in range(src.shape[1]):
+        acc = 0.9 * acc + src[:, i]
+        s[:, i] = acc
+    itd = rs.randint(-12, 13, size=batch)
+    ild = rs.uniform(0.5, 1.0, size=batch).astype(np.float32)
+    idx = (32 - itd)[:, None] + np.arange(n)[None, :]
+    wl = s[:, 32:32 + n]
+    wr = ild[:, None] * np.take_along_axis(s, idx, axis=1) + 0.01 * rs.standard_normal((batch, n)).astype(np.float32)
+    peak = np.maximum(np.abs(wl).max(1), np.abs(wr).max(1))[:, None]
+    return np.ascontiguousarray(wl / peak, np.float32), np.ascontiguousarray(wr / peak, np.float32)
+
+
+class ClockSampler:
+    """nvidia-smi poller for the timed region (B200_PROFILING.md clocks line)."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                smax.append(float(r[1]))
+                power.append(float(r[2]))
+                for name, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def build_frontend(device):
+    import biear_b200
+    torch.manual_seed(0)
+    m = biear_b200.BinauralAdaptiveGammatoneFB(alpha=0.0, fixed_frontend_q=False, **CONFIG_YAML)
+    with torch.no_grad():
+        for fb in (m.fb_L, m.fb_R):   # default zero-init pins Q == Q0; make the controller actually act
+            torch.nn.init.normal_(fb.q_out[-1].weight, std=0.02)
+    return m.to(device).train()
+
+
+def make_step(model, up):
+    """The public-API call a user makes: waveforms in, loss out, gradients left on the parameters."""
+    from biear_b200 import ops
+    params = [p for p in model.parameters() if p.requires_grad]
+    log_q0 = torch.log(model.Q0 + 1e-8).view(1, 1, -1)
+
+    def step(wl, wr):
+        for p in params:
+            p.grad = None
+        o = model.forward_features(wl, wr, want_phase=True)
+        cc = ops.cc_feature(wl, wr, FS, NBANDS, 3.0)
+        x1 = torch.clamp(torch.log(o["YL"] + 1e-8), -12.0, 12.0)          # model_torch.py:1080-1083
+        x2 = torch.clamp(torch.log(o["YR"] + 1e-8), -12.0, 12.0)
+        lq = torch.log(0.5 * (o["QL"] + o["QR"]) + 1e-8)                   # train_biear.py:476-490
+        loss = (up["gYL"] * x1).mean() + (up["gYR"] * x2).mean() \
+            + (up["gPL"] * o["phaseL"]).mean() + (up["gPR"] * o["phaseR"]).mean() + (up["gC"] * cc).mean() \
+            + REG_Q_W * ((lq - log_q0) ** 2).mean() + REG_SMOOTH_W * ((lq[..., 1:] - lq[..., :-1]) ** 2).mean()
+        loss.backward()
+        return loss
+
+    return step, params
+
+
+def run_ours(args):
+    from biear_b200 import _lib, ops
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    B = args.batch
+    model = build_frontend(dev)
+    rs = np.random.RandomState(3)
+    up = {k: torch.from_numpy(rs.standard_normal((B, T, NBANDS)).astype(np.float32)).to(dev)
+          for k in ("gYL", "gYR", "gPL", "gPR")}
+    up["gC"] = torch.from_numpy(rs.standard_normal((B, NBANDS)).astype(np.float32)).to(dev)
+    step, params = make_step(model, up)
+    flat_numel = sum(p.numel() for p in params)
+
+    def allreduce_grads():
+        if dist is None:
+            return
+        flat = torch.cat([p.grad.reshape(-1) for p in params])
+        dist.all_reduce(flat)
+        flat.mul_(1.0 / world)
+        off = 0
+        for p in params:
+            n = p.numel()
+            p.grad.copy_(flat[off:off + n].view_as(p))
+            off += n
+
+    # resident inputs: N_ROTATE distinct batches, cycled, so a step never finds its inputs in L2
+    host = [synth_binaural(B, seed=1234 + 17 * rank + i) for i in range(2)]
+    dev_in = []
+    for i in range(N_ROTATE):
+        wl, wr = host[i % 2]
+        sh = (i // 2) * 7
+        dev_in.append((torch.from_numpy(np.roll(wl, sh, axis=1)).to(dev), torch.from_numpy(np.roll(wr, sh, axis=1)).to(dev)))
+    pinned = [(torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()) for a, b in host]
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- resident-input timing ----------------------------------------------------------------
+    for i in range(args.warmup):
+        step(*dev_in[i % N_ROTATE])
+        allreduce_grads()
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _lib.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(*dev_in[i % N_ROTATE])
+        allreduce_grads()
+    e1.record()
+    sync_all()
+    launches = _lib.launch_count()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end: pinned host waveforms in, loss out ------------------------------------------
+    def e2e_step(i):
+        a, b = pinned[i % 2]
+        wl = a.to(dev, non_blocking=True)
+        wr = b.to(dev, non_blocking=True)
+        loss = step(wl, wr)
+        allreduce_grads()
+        return float(loss.item())            # D2H read of the step's result
+
+    for i in range(max(1, args.warmup // 2)):
+        e2e_step(i)
+    sync_all()
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    e1.record()
+    sync_all()
+    ms_e2e = max(e0.elapsed_time(e1), 0.0)
+    wall_e2e = (time.perf_counter() - t0) * 1e3
+
+    # ---- dominant kernel alone (band stage, one frame, both ears), for the roofline line ----------
+    roof = kernel_roofline(model, dev_in, dev, B)
+
+    times = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(times[0]), float(times[1])
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    clips = B * world * args.steps
+    value = clips / (ms * 1e-3)
+    peak, peak_src = measured_peaks()
+    step_frac = value / world * A_FULL / 1e9 / peak
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"BiEAR active front-end fwd+bwd, adaptive Q (dual) + phase + CC, batch {B} x 1 s "
+                               f"binaural clips @16 kHz per GPU, conf/config.yaml settings, train mode",
+                   "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                   "l2": f"inputs rotate over {N_ROTATE} resident batches "
+                         f"({N_ROTATE * B * 2 * FS * 4 / 1e6:.0f} MB > 126 MB L2)",
+                   "allreduce_floats": flat_numel if world > 1 else 0},
+        "e2e": {"value": clips / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * B * FS * 4,
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "wall_ms_per_step": wall_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roof,
+        "roofline_step": {"bound": "hbm", "achieved": value / world * A_FULL / 1e9, "peak": peak, "unit": "GB/s",
+                          "frac": step_frac, "bytes_per_audio_s": A_FULL, "peak_source": peak_src,
+                          "note": "whole step per GPU; the adaptive path is bound by the 19-step dependency chain "
+                                  "and fp32/MUFU work, not HBM (SURVEY.md 8(d))"},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(sample_batch=16, budget_s=20.0)
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def kernel_roofline(model, dev_in, dev, B):
+    """Time the band-stage kernel alone: one frame, both ears (2B items), rotating over frames and input
+    batches so the spectra come from HBM; CUDA events on the launching (current) stream."""
+    from biear_b200 import ops
+    fb = model.fb_L
+    with torch.no_grad():
+        xs = [torch.view_as_real(fb._spectra([a, b])) for a, b in dev_in]
+        q = (fb.Q0.view(1, -1) * torch.exp(0.3 * torch.randn(2 * B, NBANDS, device=dev))).clamp(0.05, 30.0).contiguous()
+        n_launch = 0
+        for w in range(2):
+            if w == 1:
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            for rep in range(3):
+                for i, xr in enumerate(xs):
+                    for t in range(T):
+                        ops.band_forward(xr, t, q, fb.fc, fb.df, fb.cutoff, True, True)
+                        n_launch += (w == 1)
+        e1.record()
+        torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / n_launch
+    items = 2 * B
+    alg = items * (NBINS * 8 + NBANDS * 4 * 5)     # X_t in; Q in; Y, phase, dY/dQ, dphase/dQ out
+    peak, peak_src = measured_peaks()
+    ach = alg / (us * 1e-6) / 1e9
+    return {"kernel": "band_kernel<fwd> (one frame, both ears)", "bound": "hbm", "achieved": ach, "peak": peak,
+            "unit": "GB/s", "frac": ach / peak, "traffic": None, "us_per_launch": us,
+            "algorithmic_bytes_per_launch": alg, "peak_source": peak_src}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle's restatement of the reference, timed on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_step_factory(sample_batch):
+    from oracle import biear_oracle as orc          # checker / CPU baseline only
+    cfg = orc.FrontEndConfig(deltaq_base=1.0, deltaq_low=0.3, deltaq_high=5.0, deltaq_mode="relative")
+    c = orc.constants(cfg)
+    wl, wr = orc.synth_binaural(sample_batch, seed=1234)
+    tl, tr = torch.from_numpy(wl), torch.from_numpy(wr)
+    pl = orc.to_torch(orc.synth_controller(11), requires_grad=True)
+    pr = orc.to_torch(orc.synth_controller(12), requires_grad=True)
+    rs = np.random.RandomState(3)
+    up = {k: torch.from_numpy(rs.standard_normal((sample_batch, T, NBANDS)).astype(np.float32))
+          for k in ("gYL", "gYR", "gPL", "gPR")}
+    gc = torch.from_numpy(rs.standard_normal((sample_batch, NBANDS)).astype(np.float32))
+    log_q0 = torch.log(c["Q0"] + 1e-8).view(1, 1, -1)
+
+    def step():
+        for p in list(pl.values()) + list(pr.values()):
+            p.grad = None
+        yl, yr, ql, qr, xl, xr = orc.binaural_forward(tl, tr, pl, pr, cfg, c=c)
+        phl = orc.subband_phase(xl, ql, c["f_fft"], c["fc"])
+        phr = orc.subband_phase(xr, qr, c["f_fft"], c["fc"])
+        cc = torch.from_numpy(orc.cc_feature_batch(wl, wr))
+        lq = torch.log(0.5 * (ql + qr) + 1e-8)
+        loss = (up["gYL"] * orc.log_energy(yl)).mean() + (up["gYR"] * orc.log_energy(yr)).mean() \
+            + (up["gPL"] * phl).mean() + (up["gPR"] * phr).mean() + (gc * cc).mean() \
+            + REG_Q_W * ((lq - log_q0) ** 2).mean() + REG_SMOOTH_W * ((lq[..., 1:] - lq[..., :-1]) ** 2).mean()
+        loss.backward()
+        return float(loss)
+
+    return step
+
+
+def cpu_baseline(sample_batch=16, budget_s=20.0, steps=None, warmup=1):
+    step = cpu_step_factory(sample_batch)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        step()
+        n += 1
+        el = time.perf_counter() - t0
+        if (steps is not None and n >= steps) or (steps is None and (el >= budget_s or n >= 50)):
+            break
+    return {"value": sample_batch * n / el, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} steps of batch {sample_batch} (same clips/weights recipe), oracle/biear_oracle.py "
+                      f"(torch CPU fp32 restatement of model_torch.py + utils.py CC), {el:.1f} s, "
+                      f"os.cpu_count()={os.cpu_count()}",
+            "ms_per_step": el / n * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 16
+    warm = min(args.warmup, 2)
+    steps = max(1, min(args.steps, 20))
+    cb = cpu_baseline(sample_batch=sample, steps=steps, warmup=warm)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    out = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": world, "steps": steps,
+        "warmup": warm, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"BiEAR active front-end fwd+bwd, adaptive Q (dual) + phase + CC, batch {args.batch} x 1 s "
+                               f"binaural clips @16 kHz per GPU, conf/config.yaml settings, train mode",
+                   "note": f"CPU arm: each step is a bounded sample of {sample} clips of that workload, eval-mode dropout"},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="clips per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,85 @@
+"""ctypes binding of ``biear_b200/lib/libbiear_b200.so`` (the C ABI declared in ``include/biear_b200.h``).
+
+The library is the product's only compute path: there is no CPU or PyTorch fallback behind these
+calls.  If the shared object is missing (not built) or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libbiear_b200.so")
+ABI_VERSION = 2
+
+_p = c_void_p
+_i = c_int
+_l = c_int64
+_f = c_float
+
+# name -> (restype, argtypes); mirrors include/biear_b200.h one to one
+SIGNATURES = {
+    "biear_abi_version": (_i, []),
+    "biear_last_error": (c_char_p, []),
+    "biear_launch_count": (_l, []),
+    "biear_reset_launch_count": (None, []),
+    "biear_init": (_i, []),
+    "biear_stft_fwd": (_i, [_p, _l, _l, _l, _p, _i, _i, _i, _i, _i, _p, _p]),
+    "biear_band_fwd": (_i, [_p, _l, _p, _l, _p, _l, _i, _i, _f, _f, _p, _l, _p, _l, _p, _p, _l, _p]),
+    "biear_band_bwd": (_i, [_p, _l, _p, _l, _p, _l, _i, _i, _f, _f, _p, _l, _p, _l, _p, _l, _i, _p]),
+    "biear_cc_fwd": (_i, [_p, _p, _l, _l, _l, _i, _i, _p, _p, _i, _p, _p]),
+}
+
+_lib = None
+_inited_devices = set()
+
+
+class BiearLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once) and type its entry points.  Raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BiearLibraryError(
+            f"{LIB_PATH} not found: build it with `make -C biear_b200/csrc` (or "
+            f"`python -c 'import __graft_entry__ as g; g.build()'`).  There is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:   # stale build
+            raise BiearLibraryError(f"{LIB_PATH} does not export {name}; rebuild it") from e
+        fn.restype = res
+        fn.argtypes = args
+    got = lib.biear_abi_version()
+    if got != ABI_VERSION:
+        raise BiearLibraryError(f"{LIB_PATH} has ABI version {got}, host code expects {ABI_VERSION}; rebuild it")
+    _lib = lib
+    return lib
+
+
+def check(code: int, what: str):
+    if code != 0:
+        msg = load().biear_last_error().decode("utf-8", "replace")
+        raise BiearLibraryError(f"{what} failed with code {code}: {msg}")
+
+
+def ensure_init(device_index: int):
+    """Per-device one-time setup; must run outside CUDA-graph capture (it uploads a table)."""
+    if device_index in _inited_devices:
+        return
+    check(load().biear_init(), "biear_init")
+    _inited_devices.add(device_index)
+
+
+def launch_count() -> int:
+    return int(load().biear_launch_count())
+
+
+def reset_launch_count():
+    load().biear_reset_launch_count()

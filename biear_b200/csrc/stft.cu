@@ -1,0 +1,137 @@
+// Framing + window + zero-padded 1024-point real FFT of every (row, frame): one launch for the
+// whole batch, both ears, all frames (the spectrum does not depend on Q, so it is hoisted out of the
+// reference's per-frame loop).
+//
+// Replaces model_torch.py:289-312 (_frame_1s) and :334-335 (frame * win_fn, torch.fft.rfft(n=n_fft))
+// of the reference.
+//
+// Mapping: 64 threads cooperate on one frame (packed 512-point complex radix-8 Stockham FFT, three
+// passes, one padded 4.6 KB shared buffer per frame; the first pass reads straight from HBM), four
+// frames per CTA, CTAs stride over the frame list.  HBM traffic = the waveform once in, X once out.
+#include "common.cuh"
+#include "fft_dev.cuh"
+
+namespace biear {
+
+constexpr int kFramesPerCta = 4;
+constexpr int kStftThreads = kFramesPerCta * kFftThreads;
+
+struct StftArgs {
+    const float* wav;
+    long long rows, nsamp, row_stride;
+    const float* win_fn;
+    const float2* tw;
+    int limit;        // padded clip length: max(fs, win)
+    int n_avail;      // frames the reference's unfold() yields
+    int T, win, hop;
+    float2* X;        // (rows, T, 513)
+    long long n_frames;
+};
+
+__global__ void __launch_bounds__(kStftThreads) stft_fwd_kernel(const StftArgs a) {
+    __shared__ float2 s_tw[kNfft];
+    __shared__ float2 s_buf[kFramesPerCta][kFftSlots];
+
+    for (int i = threadIdx.x; i < kNfft; i += kStftThreads) s_tw[i] = a.tw[i];
+
+    const int g = threadIdx.x / kFftThreads;
+    const int j = threadIdx.x % kFftThreads;
+    float2* buf = s_buf[g];
+    const int valid_len = min(min(a.win, kNfft), a.limit);
+
+    for (long long base = (long long)blockIdx.x * kFramesPerCta; base < a.n_frames;
+         base += (long long)gridDim.x * kFramesPerCta) {
+        const long long fi = base + g;
+        const bool live = fi < a.n_frames;
+        const long long row = live ? fi / a.T : 0;
+        const int t = live ? (int)(fi % a.T) : 0;
+        const bool frame_valid = live && t < a.n_avail;
+        const long long start = (long long)t * a.hop;
+        const float* wrow = a.wav + row * a.row_stride;
+
+        // pass 1 (Ns = 1): packed, windowed samples straight from global memory
+        float2 v[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int i0 = 2 * (j + r * 64);
+            float x0 = 0.f, x1 = 0.f;
+            if (frame_valid) {
+                const long long s0 = start + i0;
+                if (i0 < valid_len && s0 < a.limit && s0 < a.nsamp) x0 = __ldg(wrow + s0) * __ldg(a.win_fn + i0);
+                if (i0 + 1 < valid_len && s0 + 1 < a.limit && s0 + 1 < a.nsamp)
+                    x1 = __ldg(wrow + s0 + 1) * __ldg(a.win_fn + i0 + 1);
+            }
+            v[r] = make_float2(x0, x1);
+        }
+        __syncthreads();   // twiddles loaded (first trip) / previous trip's unpack reads done
+        fft512_butterfly(v, j, 1, s_tw);
+        fft512_scatter<true>(v, buf, j, 1);
+        __syncthreads();
+        fft512_gather<true>(v, buf, j);
+        fft512_butterfly(v, j, 8, s_tw);
+        __syncthreads();
+        fft512_scatter<true>(v, buf, j, 8);
+        __syncthreads();
+        fft512_gather<true>(v, buf, j);
+        fft512_butterfly(v, j, 64, s_tw);
+        __syncthreads();
+        fft512_scatter<true>(v, buf, j, 64);
+        __syncthreads();
+
+        if (live) {
+            float2* out = a.X + fi * kBins;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int k = j + r * 64;          // 0..255
+                float2 xk, xm;
+                rfft_unpack<true>(buf, k, s_tw, xk, xm);
+                out[k] = xk;
+                out[kNhalf - k] = xm;
+            }
+            if (j == 0) {
+                float2 xk, xm;
+                rfft_unpack<true>(buf, 256, s_tw, xk, xm);
+                out[256] = xk;
+            }
+        }
+    }
+}
+
+}  // namespace biear
+
+extern "C" int biear_stft_fwd(const float* wav, int64_t rows, int64_t nsamp, int64_t wav_row_stride,
+                              const float* win_fn, int fs, int T, int win, int hop, int n_fft, float* X,
+                              void* stream) {
+    using namespace biear;
+    BIEAR_REQUIRE(n_fft == kNfft, "biear_stft_fwd: n_fft=%d unsupported (only 1024)", n_fft);
+    BIEAR_REQUIRE(rows >= 0 && nsamp >= 0 && fs >= 1 && T >= 1 && win >= 1 && hop >= 1,
+                  "biear_stft_fwd: bad shape rows=%lld nsamp=%lld fs=%d T=%d win=%d hop=%d", (long long)rows,
+                  (long long)nsamp, fs, T, win, hop);
+    BIEAR_REQUIRE(wav_row_stride >= nsamp, "biear_stft_fwd: row stride %lld < nsamp %lld",
+                  (long long)wav_row_stride, (long long)nsamp);
+    if (rows == 0) return 0;
+    BIEAR_REQUIRE(wav && win_fn && X, "biear_stft_fwd: null pointer");
+    int err = 0;
+    cudaStream_t st = as_stream(stream);
+    StftArgs a;
+    a.tw = twiddle_table(st, &err);
+    if (err) return err;
+    a.wav = wav;
+    a.rows = rows;
+    a.nsamp = nsamp;
+    a.row_stride = wav_row_stride;
+    a.win_fn = win_fn;
+    a.limit = fs > win ? fs : win;
+    a.n_avail = (a.limit - win) / hop + 1;   // torch.Tensor.unfold(size=win, step=hop) frame count
+    a.T = T;
+    a.win = win;
+    a.hop = hop;
+    a.X = reinterpret_cast<float2*>(X);
+    a.n_frames = rows * T;
+    const long long ctas_needed = (a.n_frames + kFramesPerCta - 1) / kFramesPerCta;
+    const long long cap = (long long)kSmCountB200 * 8;
+    const int grid = (int)(ctas_needed < cap ? ctas_needed : cap);
+    stft_fwd_kernel<<<grid, kStftThreads, 0, st>>>(a);
+    BIEAR_LAUNCH_CHECK("stft_fwd_kernel");
+    return 0;
+}

@@ -1,0 +1,402 @@
+"""Host-side mirror of the reference's binaural front-end modules (model_torch.py:70-776), running on the
+sm_100a kernels of this package.
+
+Same class names, constructor keywords, forward signatures, buffers and state-dict keys as the reference,
+so `DeepEarActiveWaveform(bifb_class=...)`, `train_biear.py`'s parameter groups / freeze helpers and
+checkpoints written by either implementation work unchanged.  What differs is the execution plan:
+
+  * the spectra X do not depend on Q, so framing + Hann + rFFT for every (ear, clip, frame) is ONE
+    launch up front instead of 19 x 2 cuFFT calls inside the frame loop;
+  * one band kernel per frame serves both ears, never materialises the (B,100,513) weight tensor and
+    emits band energy, sub-band phase and the exact dY/dQ, dphase/dQ Jacobians in the same pass, so the
+    reference's second W rebuild (_subband_phase_from_X) and autograd's W-sized backward disappear;
+  * the two per-ear Q controllers run as one batched (ear-stacked) chain;
+  * the batch-global `isfinite(Q).all()` guard (model_torch.py:378-380) is evaluated on the device, so
+    the frame loop has no host synchronisation.
+
+All compute requires CUDA tensors; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+Q_MIN, Q_MAX = 0.05, 30.0
+
+
+# ------------------------------------------------------------------------------------------------
+# ERB constants (model_torch.py:19-51), float64 numpy on the host exactly as the reference computes them
+# ------------------------------------------------------------------------------------------------
+def erb_hz(f_hz):
+    return 24.7 * (4.37 * f_hz / 1000.0 + 1.0)
+
+
+def erb_rate(f_hz):
+    return 21.4 * np.log10(4.37 * f_hz / 1000.0 + 1.0)
+
+
+def inv_erb_rate(e):
+    return (10 ** (e / 21.4) - 1.0) * 1000.0 / 4.37
+
+
+def erb_spaced_fc_and_q(N=100, fmin=50.0, fmax=7200.0, erb_factor=1.019):
+    e = np.linspace(erb_rate(fmin), erb_rate(fmax), N)
+    fc = inv_erb_rate(e)
+    return fc, fc / (erb_factor * erb_hz(fc))
+
+
+def make_deltaQ_profile(fc_hz: torch.Tensor, deltaQ_base: float = 2.0, low_factor: float = 0.5,
+                        high_factor: float = 1.0) -> torch.Tensor:
+    e = erb_rate(fc_hz.detach().cpu().numpy())
+    e = (e - e.min()) / (e.max() - e.min() + 1e-12)
+    mult = torch.tensor(low_factor + (high_factor - low_factor) * e, dtype=torch.float32, device=fc_hz.device)
+    return torch.clamp(deltaQ_base * mult, min=1e-3)
+
+
+# ------------------------------------------------------------------------------------------------
+# shared geometry / buffers
+# ------------------------------------------------------------------------------------------------
+class _FilterbankBase(nn.Module):
+    """Frame geometry and the fc / Q0 / f_fft buffers every filterbank variant registers."""
+
+    def _init_geometry(self, fs, timesteps, n_fft, Nbands, fmin, fmax, hop_ratio, window_buffer=True):
+        self.fs = fs
+        self.timesteps = timesteps
+        self.n_fft = n_fft
+        self.Nbands = Nbands
+        self.win = int(round(fs / timesteps))
+        self.hop = max(1, int(round(self.win * hop_ratio)))
+        if window_buffer:
+            self.register_buffer("win_fn", torch.hann_window(self.win), persistent=False)
+        self.register_buffer("f_fft", torch.linspace(0, fs / 2, n_fft // 2 + 1))
+        if fmax is None:
+            fmax = fs / 2 * 0.9
+        fc_np, q0_np = erb_spaced_fc_and_q(Nbands, fmin, fmax, erb_factor=1.019)
+        self.register_buffer("fc", torch.tensor(fc_np, dtype=torch.float32))
+        self.register_buffer("Q0", torch.tensor(q0_np, dtype=torch.float32))
+
+    @property
+    def df(self) -> float:
+        return (self.fs / 2) / (self.n_fft // 2)
+
+    def _spectra(self, wavs: List[torch.Tensor]) -> torch.Tensor:
+        """[(B,Nsamp)] * E -> X (E*B, T, F) complex64, one launch for all ears."""
+        for w in wavs:
+            if w.dim() != 2:
+                raise ValueError(f"Expected wav_1s (B,N), got {w.shape}")
+        wav = wavs[0] if len(wavs) == 1 else torch.cat(wavs, dim=0)
+        if wav.requires_grad:
+            raise RuntimeError("biear_b200: gradients with respect to the waveform are not implemented")
+        wav = wav.float().contiguous()
+        return ops.stft(wav, self.win_fn, self.fs, self.timesteps, self.win, self.hop, self.n_fft)
+
+
+def _make_controller(in_features: int, Nbands: int):
+    """Same modules, same construction order (=> same default init under a given seed) as
+    model_torch.py:256-267, 283-287."""
+    q_rnn = nn.GRU(input_size=in_features, hidden_size=128, batch_first=True)
+    q_out = nn.Sequential(
+        nn.Linear(128, 128), nn.LayerNorm(128), nn.SiLU(), nn.Dropout(p=0.1),
+        nn.Linear(128, 128), nn.LayerNorm(128), nn.SiLU(), nn.Dropout(p=0.1),
+        nn.Linear(128, Nbands),
+    )
+    nn.init.zeros_(q_out[-1].weight)
+    nn.init.zeros_(q_out[-1].bias)
+    return q_rnn, q_out
+
+
+class _ControllerStack:
+    """Weights of G structurally identical controllers stacked along a leading group axis, so that the
+    per-ear chains of the dual front-end run as one batched chain (autograd un-stacks the gradients)."""
+
+    def __init__(self, mods):
+        st = lambda f: torch.stack([f(m) for m in mods])
+        self.w_ih = st(lambda m: m.q_rnn.weight_ih_l0).transpose(1, 2)   # (G, in, 384)
+        self.w_hh = st(lambda m: m.q_rnn.weight_hh_l0).transpose(1, 2)   # (G, 128, 384)
+        self.b_ih = st(lambda m: m.q_rnn.bias_ih_l0).unsqueeze(1)        # (G, 1, 384)
+        self.b_hh = st(lambda m: m.q_rnn.bias_hh_l0).unsqueeze(1)
+        self.lin = []
+        for i in (0, 4, 8):
+            self.lin.append((st(lambda m: m.q_out[i].weight).transpose(1, 2),
+                             st(lambda m: m.q_out[i].bias).unsqueeze(1)))
+        self.ln = []
+        for i in (1, 5):
+            self.ln.append((st(lambda m: m.q_out[i].weight).unsqueeze(1), st(lambda m: m.q_out[i].bias).unsqueeze(1),
+                            mods[0].q_out[i].eps))
+        self.p_drop = mods[0].q_out[3].p
+        self.hid = mods[0].q_rnn.hidden_size
+
+    def step(self, feat: torch.Tensor, h: Optional[torch.Tensor], training: bool):
+        """feat (G,B,in), h (G,B,128) or None -> (pre-tanh output (G,B,N), new h).  torch.nn.GRU gate
+        order (r, z, n) and n = tanh(i_n + r * (W_hn h + b_hn)); q_out as model_torch.py:257-267."""
+        gi = torch.baddbmm(self.b_ih, feat, self.w_ih)
+        if h is None:
+            gh = self.b_hh.expand(-1, feat.shape[1], -1)
+        else:
+            gh = torch.baddbmm(self.b_hh, h, self.w_hh)
+        i_r, i_z, i_n = gi.split(self.hid, dim=-1)
+        h_r, h_z, h_n = gh.split(self.hid, dim=-1)
+        r = torch.sigmoid(i_r + h_r)
+        z = torch.sigmoid(i_z + h_z)
+        n = torch.tanh(i_n + r * h_n)
+        h_new = (1.0 - z) * n if h is None else (1.0 - z) * n + z * h
+        a = h_new
+        for k in range(2):
+            w, b = self.lin[k]
+            g, beta, eps = self.ln[k]
+            a = torch.baddbmm(b, a, w)
+            a = F.layer_norm(a, (a.shape[-1],), None, None, eps) * g + beta
+            a = F.silu(a)
+            a = F.dropout(a, self.p_drop, training)
+        w, b = self.lin[2]
+        return torch.baddbmm(b, a, w), h_new
+
+
+def _next_q(delta, q0, dq, mode):
+    if mode == "relative":
+        q = q0 * (1.0 + dq * delta)
+    else:
+        q = q0 + dq * delta
+    return torch.clamp(q, Q_MIN, Q_MAX)
+
+
+def _adaptive_chain(x: torch.Tensor, ears: int, ctrl_mods, fc, q0, dq_vec, dq_mode, df, training,
+                    shared: bool, want_phase: bool, band_mode: str, cutoff: float):
+    """The 19-step Q recurrence for `ears` ears of B clips.
+
+    x: (ears*B, T, F) complex64, ear-major.  ctrl_mods: G controller-owning modules.
+      dual  : ears == G (each ear has its own controller and its own Q)       model_torch.py:314-386
+      single: ears == 2, G == 1, shared=True (one Q for both ears, carried Y memory)  model_torch.py:695-776
+    Returns Y (ears*B,T,N), Q (G*B,T,N), phase (ears*B,T,N) or None.
+    """
+    rows, T, Fbins = x.shape
+    B = rows // ears
+    G = len(ctrl_mods)
+    N = fc.numel()
+    xr = torch.view_as_real(x)
+    stack = _ControllerStack(ctrl_mods)
+    q0g = q0.view(1, 1, N)
+    dqg = dq_vec.view(1, 1, N)
+    q = q0.view(1, 1, N).expand(G, B, N)
+    h = None
+    mem = None
+    ys, qs, phs = [], [], []
+    for t in range(T):
+        q_rows = (q.expand(ears, B, N) if shared else q).reshape(rows, N)
+        y, ph = ops.BandFrame.apply(q_rows, xr, t, fc, df, cutoff, want_phase, band_mode)
+        ys.append(y)
+        qs.append(q.reshape(G * B, N))
+        if want_phase:
+            phs.append(ph)
+        if t == T - 1:
+            # The reference runs the controller once more and discards the result (model_torch.py:361-380);
+            # that step only consumes dropout RNG and receives zero gradient, so it is skipped.
+            break
+        yc = torch.log1p(torch.clamp(y, min=0.0)).view(ears, B, N)
+        ycd = yc.detach()
+        if shared:
+            if mem is None:
+                mem = torch.zeros_like(ycd)
+            feat = torch.cat([yc[0], mem[0], yc[1], mem[1]], dim=-1).unsqueeze(0)      # (1,B,4N)
+        else:
+            feat = torch.cat([yc, 0.2 * ycd], dim=-1)                                  # (G,B,2N)
+        pre, h = stack.step(feat, h, training)
+        q_new = _next_q(torch.tanh(pre), q0g, dqg, dq_mode)
+        # batch-global non-finite fallback of the reference, decided per controller, on the device
+        ok = torch.isfinite(q_new).flatten(1).all(dim=1).view(G, 1, 1)
+        q = torch.where(ok, q_new, q0g.expand_as(q_new))
+        h = h * ok
+        if shared:
+            mem = 0.8 * mem + 0.2 * ycd
+    y_all = torch.stack(ys, dim=1)
+    q_all = torch.stack(qs, dim=1)
+    ph_all = torch.stack(phs, dim=1) if want_phase else None
+    return y_all, q_all, ph_all
+
+
+def _fixed_bands(x: torch.Tensor, fc, q_fixed, df, want_phase, cutoff):
+    """Fixed-Q path: every (row, frame) item in one launch with a broadcast Q vector."""
+    y, ph, _, _ = ops.band_forward(torch.view_as_real(x), None, q_fixed.contiguous(), fc, df, cutoff,
+                                   want_phase, False)
+    return y, ph
+
+
+# ------------------------------------------------------------------------------------------------
+# monaural filterbanks
+# ------------------------------------------------------------------------------------------------
+class FramewiseAdaptiveGammatoneFB(_FilterbankBase):
+    """model_torch.py:200-386.  forward(wav_1s (B,Nsamp)) -> Y (B,T,N), Q (B,T,N), X (B,T,F) complex."""
+
+    def __init__(self, fs, timesteps=19, n_fft=1024, Nbands=100, Q0=8.0, fmin=50.0, fmax=None, hop_ratio=1.0,
+                 alpha=0.2, deltaQ_base: float = 2.0, deltaQ_low_factor: float = 0.5,
+                 deltaQ_high_factor: float = 1.0, deltaQ_mode: str = "absolute"):
+        super().__init__()
+        self.alpha = alpha
+        self._init_geometry(fs, timesteps, n_fft, Nbands, fmin, fmax, hop_ratio)
+        self.register_buffer("deltaQ_vec", make_deltaQ_profile(self.fc, deltaQ_base, deltaQ_low_factor,
+                                                               deltaQ_high_factor))
+        self.deltaQ_mode = deltaQ_mode.lower()
+        self.q_rnn, self.q_out = _make_controller(2 * Nbands, Nbands)
+        self.Q_min, self.Q_max = Q_MIN, Q_MAX
+        self.freeze_Q = False
+        self.band_mode = "jacobian"
+        self.cutoff = ops.DEFAULT_CUTOFF
+
+    def forward(self, wav_1s: torch.Tensor):
+        x = self._spectra([wav_1s])
+        if self.freeze_Q:
+            y, _ = _fixed_bands(x, self.fc, self.Q0, self.df, False, self.cutoff)
+            return y, self.Q0.view(1, 1, -1).expand(x.shape[0], self.timesteps, -1), x
+        y, q, _ = _adaptive_chain(x, 1, [self], self.fc, self.Q0, self.deltaQ_vec, self.deltaQ_mode, self.df,
+                                  self.training, False, False, self.band_mode, self.cutoff)
+        return y, q, x
+
+
+class FramewiseFixedGammatoneFB(_FilterbankBase):
+    """model_torch.py:391-487: Q == clamp(Q0) for every frame, no controller, no parameters."""
+
+    def __init__(self, fs, timesteps=19, n_fft=1024, Nbands=100, fmin=50.0, fmax=None, hop_ratio=1.0):
+        super().__init__()
+        self._init_geometry(fs, timesteps, n_fft, Nbands, fmin, fmax, hop_ratio)
+        self.Q_min, self.Q_max = Q_MIN, Q_MAX
+        self.cutoff = ops.DEFAULT_CUTOFF
+
+    def forward(self, wav_1s: torch.Tensor):
+        x = self._spectra([wav_1s])
+        qf = torch.clamp(self.Q0, self.Q_min, self.Q_max)
+        y, _ = _fixed_bands(x, self.fc, qf, self.df, False, self.cutoff)
+        return y, qf.view(1, 1, -1).expand(x.shape[0], self.timesteps, -1), x
+
+
+class AuralNetGammatoneFB(_FilterbankBase):
+    """model_torch.py:70-195: fixed-Q filterbank in batched form; forward(wav) -> Y (B,T,N) only."""
+
+    def __init__(self, fs=16000, timesteps=19, n_fft=1024, Nbands=100, fmin=50.0, fmax=None, hop_ratio=1.0):
+        super().__init__()
+        self._init_geometry(fs, timesteps, n_fft, Nbands, fmin, fmax, hop_ratio)
+        self.Q_min, self.Q_max = Q_MIN, Q_MAX
+        self.cutoff = ops.DEFAULT_CUTOFF
+
+    def forward(self, wav_1s: torch.Tensor):
+        x = self._spectra([wav_1s])
+        y, _ = _fixed_bands(x, self.fc, torch.clamp(self.Q0, self.Q_min, self.Q_max), self.df, False, self.cutoff)
+        return y
+
+
+# ------------------------------------------------------------------------------------------------
+# binaural filterbanks
+# ------------------------------------------------------------------------------------------------
+class BinauralAdaptiveGammatoneFB(nn.Module):
+    """model_torch.py:492-573 (dual: two independent monaural filterbanks).
+
+    forward(wavL_1s, wavR_1s) -> (YL, YR, QL, QR, XL, XR), as the reference.
+    forward_features(...) additionally returns the sub-band phases computed in the same band pass
+    (what DeepEarActiveWaveform._subband_phase_from_X, model_torch.py:1039-1063, recomputes from X and Q).
+    """
+
+    def __init__(self, fs=16000, timesteps=19, n_fft=1024, Nbands=100, fmin=50.0, fmax=None, hop_ratio=1.0,
+                 alpha: float = 0.2, fixed_frontend_q: bool = False, deltaQ_base: float = 2.0,
+                 deltaQ_low_factor: float = 0.5, deltaQ_high_factor: float = 1.0, deltaQ_mode: str = "absolute"):
+        super().__init__()
+        self.controller_mode = "dual"
+        self.fs = fs
+        self.timesteps = timesteps
+        self.n_fft = n_fft
+        self.Nbands = Nbands
+        self.alpha = float(alpha)
+        fc_np, q0_np = erb_spaced_fc_and_q(Nbands, fmin, (fs / 2 * 0.9) if fmax is None else fmax, erb_factor=1.019)
+        self.register_buffer("fc", torch.tensor(fc_np, dtype=torch.float32))
+        self.register_buffer("Q0", torch.tensor(q0_np, dtype=torch.float32))
+        self.register_buffer("f_fft", torch.linspace(0, fs / 2, n_fft // 2 + 1))
+        self.fixed_frontend_q = bool(fixed_frontend_q)
+        if self.fixed_frontend_q:
+            mk = lambda: FramewiseFixedGammatoneFB(fs=fs, timesteps=timesteps, n_fft=n_fft, Nbands=Nbands, fmin=fmin,
+                                                   fmax=fmax, hop_ratio=hop_ratio)
+        else:
+            mk = lambda: FramewiseAdaptiveGammatoneFB(
+                fs=fs, timesteps=timesteps, n_fft=n_fft, Nbands=Nbands, Q0=8.0, fmin=fmin, fmax=fmax,
+                hop_ratio=hop_ratio, alpha=alpha, deltaQ_base=deltaQ_base, deltaQ_low_factor=deltaQ_low_factor,
+                deltaQ_high_factor=deltaQ_high_factor, deltaQ_mode=deltaQ_mode)
+        self.fb_L = mk()
+        self.fb_R = mk()
+        self.freeze_Q = False   # kept for compatibility; like the reference it is not propagated to fb_L/fb_R
+
+    def forward_features(self, wavL_1s: torch.Tensor, wavR_1s: torch.Tensor, want_phase: bool = True):
+        fb = self.fb_L
+        if wavL_1s.shape != wavR_1s.shape:
+            raise ValueError(f"wavL {tuple(wavL_1s.shape)} and wavR {tuple(wavR_1s.shape)} differ")
+        x = fb._spectra([wavL_1s, wavR_1s])
+        B = wavL_1s.shape[0]
+        frozen = (not self.fixed_frontend_q) and self.fb_L.freeze_Q and self.fb_R.freeze_Q
+        if self.fixed_frontend_q or frozen:
+            qf = fb.Q0 if frozen else torch.clamp(fb.Q0, Q_MIN, Q_MAX)
+            y, ph = _fixed_bands(x, fb.fc, qf, fb.df, want_phase, fb.cutoff)
+            q = qf.view(1, 1, -1).expand(2 * B, fb.timesteps, -1)
+        else:
+            if self.fb_L.freeze_Q != self.fb_R.freeze_Q:
+                raise NotImplementedError("freeze_Q on one ear only")
+            y, q, ph = _adaptive_chain(x, 2, [self.fb_L, self.fb_R], fb.fc, fb.Q0, fb.deltaQ_vec, fb.deltaQ_mode,
+                                       fb.df, self.training, False, want_phase, fb.band_mode, fb.cutoff)
+        out = {"YL": y[:B], "YR": y[B:], "QL": q[:B], "QR": q[B:], "XL": x[:B], "XR": x[B:]}
+        if want_phase:
+            out["phaseL"], out["phaseR"] = ph[:B], ph[B:]
+        return out
+
+    def forward(self, wavL_1s: torch.Tensor, wavR_1s: torch.Tensor):
+        o = self.forward_features(wavL_1s, wavR_1s, want_phase=False)
+        return o["YL"], o["YR"], o["QL"], o["QR"], o["XL"], o["XR"]
+
+
+class BinauralAdaptiveGammatoneFB_SingleController(_FilterbankBase):
+    """model_torch.py:579-776: one controller (GRU(4N->128) + MLP) sets a single Q for both ears; the
+    controller sees [YLc, YLmem, YRc, YRmem] with a carried memory (beta = 0.8)."""
+
+    def __init__(self, fs=16000, timesteps=19, n_fft=1024, Nbands=100, fmin=50.0, fmax=None, hop_ratio=1.0,
+                 alpha: float = 0.2, fixed_frontend_q: bool = False, deltaQ_base: float = 2.0,
+                 deltaQ_low_factor: float = 0.5, deltaQ_high_factor: float = 1.0, deltaQ_mode: str = "absolute"):
+        super().__init__()
+        self.controller_mode = "single"
+        self.alpha = float(alpha)
+        self.fixed_frontend_q = bool(fixed_frontend_q)
+        self._init_geometry(fs, timesteps, n_fft, Nbands, fmin, fmax, hop_ratio)
+        self.register_buffer("deltaQ_vec", make_deltaQ_profile(self.fc, deltaQ_base, deltaQ_low_factor,
+                                                               deltaQ_high_factor))
+        self.deltaQ_mode = deltaQ_mode.lower()
+        self.Q_min, self.Q_max = Q_MIN, Q_MAX
+        self.freeze_Q = False
+        self.band_mode = "jacobian"
+        self.cutoff = ops.DEFAULT_CUTOFF
+        if not self.fixed_frontend_q:
+            self.q_rnn, self.q_out = _make_controller(4 * Nbands, Nbands)
+            self.fb_L = self.fb_R = None
+        else:   # no controller parameters exist; the reference delegates to two fixed filterbanks
+            self.q_rnn = self.q_out = None
+            mk = lambda: FramewiseFixedGammatoneFB(fs=fs, timesteps=timesteps, n_fft=n_fft, Nbands=Nbands, fmin=fmin,
+                                                   fmax=fmax, hop_ratio=hop_ratio)
+            self.fb_L = mk()
+            self.fb_R = mk()
+
+    def forward_features(self, wavL_1s, wavR_1s, want_phase: bool = True):
+        x = self._spectra([wavL_1s, wavR_1s])
+        B = wavL_1s.shape[0]
+        if self.fixed_frontend_q or self.freeze_Q:
+            qf = torch.clamp(self.Q0, Q_MIN, Q_MAX) if self.fixed_frontend_q else self.Q0
+            y, ph = _fixed_bands(x, self.fc, qf, self.df, want_phase, self.cutoff)
+            q = qf.view(1, 1, -1).expand(B, self.timesteps, -1)
+        else:
+            y, q, ph = _adaptive_chain(x, 2, [self], self.fc, self.Q0, self.deltaQ_vec, self.deltaQ_mode, self.df,
+                                       self.training, True, want_phase, self.band_mode, self.cutoff)
+        out = {"YL": y[:B], "YR": y[B:], "QL": q, "QR": q, "XL": x[:B], "XR": x[B:]}
+        if want_phase:
+            out["phaseL"], out["phaseR"] = ph[:B], ph[B:]
+        return out
+
+    def forward(self, wavL_1s, wavR_1s):
+        o = self.forward_features(wavL_1s, wavR_1s, want_phase=False)
+        return o["YL"], o["YR"], o["QL"], o["QR"], o["XL"], o["XR"]

@@ -1,0 +1,237 @@
+"""Torch-facing wrappers of the C ABI (device pointers + the current CUDA stream go straight through).
+
+PyTorch is used here for device memory, streams and autograd bookkeeping only; every numeric result
+comes from the sm_100a kernels in ``biear_b200/csrc``.  All functions raise on CPU tensors: there is
+no fallback path.
+"""
+from __future__ import annotations
+
+from ctypes import c_void_p
+from functools import lru_cache
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+DEFAULT_CUTOFF = 6.0   # Gaussian support half-width in units of bw (1.5e-8 on Y, 4e-7 on dY/dQ)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
+
+
+def _stream(device) -> c_void_p:
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _need_cuda(t: torch.Tensor, name: str, dtype=torch.float32):
+    if not t.is_cuda:
+        raise RuntimeError(f"biear_b200: {name} must be a CUDA tensor (got {t.device}); there is no CPU path")
+    if t.dtype != dtype:
+        raise TypeError(f"biear_b200: {name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"biear_b200: {name} must be contiguous")
+
+
+def _prepare(device):
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    _lib.ensure_init(idx)
+    return _lib.load()
+
+
+# ------------------------------------------------------------------------------------------------
+# STFT
+# ------------------------------------------------------------------------------------------------
+def stft(wav: torch.Tensor, win_fn: torch.Tensor, fs: int, timesteps: int, win: int, hop: int,
+         n_fft: int) -> torch.Tensor:
+    """(rows, nsamp) fp32 -> X (rows, T, n_fft//2+1) complex64.  model_torch.py:289-312, 334-335."""
+    if wav.dim() != 2:
+        raise ValueError(f"Expected wav_1s (B,N), got {tuple(wav.shape)}")
+    _need_cuda(wav, "wav")
+    _need_cuda(win_fn, "win_fn")
+    with torch.cuda.device(wav.device):
+        lib = _prepare(wav.device)
+        rows, nsamp = wav.shape
+        nbins = n_fft // 2 + 1
+        xr = torch.empty((rows, timesteps, nbins, 2), dtype=torch.float32, device=wav.device)
+        _lib.check(lib.biear_stft_fwd(_ptr(wav), rows, nsamp, nsamp, _ptr(win_fn), fs, timesteps, win, hop,
+                                      n_fft, _ptr(xr), _stream(wav.device)), "biear_stft_fwd")
+    return torch.view_as_complex(xr)
+
+
+# ------------------------------------------------------------------------------------------------
+# band stage
+# ------------------------------------------------------------------------------------------------
+def band_forward(xr: torch.Tensor, t: Optional[int], q: torch.Tensor, fc: torch.Tensor, df: float,
+                 cutoff: float = DEFAULT_CUTOFF, want_phase: bool = True, want_jac: bool = True):
+    """Band energies (+ phase, + exact Jacobians wrt Q).
+
+    xr: (rows, T, F, 2) fp32 view of the spectra.
+    t is an int:  one frame; q is (rows, N); outputs are (rows, N).
+    t is None:    all frames; q is (N,) [broadcast, fixed-Q path] or (rows, T, N); outputs (rows, T, N).
+    Returns (Y, phase|None, dYdQ|None, dPdQ|None).
+    """
+    _need_cuda(xr, "X")
+    _need_cuda(q, "Q")
+    _need_cuda(fc, "fc")
+    rows, T, F, two = xr.shape
+    assert two == 2
+    N = fc.numel()
+    dev = xr.device
+    with torch.cuda.device(dev):
+        lib = _prepare(dev)
+        if t is not None:
+            if q.shape != (rows, N):
+                raise ValueError(f"Q must be ({rows},{N}), got {tuple(q.shape)}")
+            items, x_off, x_stride, q_stride = rows, t * F * 2, T * F * 2, N
+            out_shape = (rows, N)
+        else:
+            items, x_off, x_stride = rows * T, 0, F * 2
+            if q.dim() == 1:
+                q_stride = 0
+            elif q.shape == (rows, T, N):
+                q_stride = N
+            else:
+                raise ValueError(f"Q must be ({N},) or ({rows},{T},{N}), got {tuple(q.shape)}")
+            out_shape = (rows, T, N)
+        y = torch.empty(out_shape, dtype=torch.float32, device=dev)
+        ph = torch.empty(out_shape, dtype=torch.float32, device=dev) if want_phase else None
+        dy = torch.empty(out_shape, dtype=torch.float32, device=dev) if want_jac else None
+        dp = torch.empty(out_shape, dtype=torch.float32, device=dev) if (want_jac and want_phase) else None
+        x_ptr = c_void_p(xr.data_ptr() + 4 * x_off)
+        _lib.check(lib.biear_band_fwd(x_ptr, x_stride, _ptr(q), q_stride, _ptr(fc), items, N, F, float(df),
+                                      float(cutoff), _ptr(y), N, _ptr(ph), N, _ptr(dy), _ptr(dp), N,
+                                      _stream(dev)), "biear_band_fwd")
+    return y, ph, dy, dp
+
+
+def band_backward(xr: torch.Tensor, t: Optional[int], q: torch.Tensor, fc: torch.Tensor, df: float,
+                  g_y: Optional[torch.Tensor], g_phase: Optional[torch.Tensor],
+                  cutoff: float = DEFAULT_CUTOFF) -> torch.Tensor:
+    """dL/dQ by recomputation (nothing saved by the forward).  Shapes as in band_forward; q must be
+    per-item here (the broadcast fixed-Q path has no gradient)."""
+    _need_cuda(xr, "X")
+    _need_cuda(q, "Q")
+    rows, T, F, _ = xr.shape
+    N = fc.numel()
+    dev = xr.device
+    for name, g in (("gY", g_y), ("gphase", g_phase)):
+        if g is not None:
+            _need_cuda(g, name)
+    with torch.cuda.device(dev):
+        lib = _prepare(dev)
+        if t is not None:
+            items, x_off, x_stride = rows, t * F * 2, T * F * 2
+        else:
+            items, x_off, x_stride = rows * T, 0, F * 2
+        dq = torch.empty_like(q)
+        x_ptr = c_void_p(xr.data_ptr() + 4 * x_off)
+        _lib.check(lib.biear_band_bwd(x_ptr, x_stride, _ptr(q), N, _ptr(fc), items, N, F, float(df), float(cutoff),
+                                      _ptr(g_y), N, _ptr(g_phase), N, _ptr(dq), N, 0, _stream(dev)),
+                   "biear_band_bwd")
+    return dq
+
+
+class BandFrame(torch.autograd.Function):
+    """One frame of the adaptive band stage as an autograd node: (Q_t) -> (Y_t, phase_t).
+
+    mode "jacobian": the forward also emits dY/dQ and dphase/dQ (2 floats per band) and the backward
+    is one fused multiply-add; mode "recompute": nothing is saved and the backward re-runs the band
+    kernel in its dL/dQ form.  Both give the closed-form gradient of SURVEY.md A.3.
+    """
+
+    @staticmethod
+    def forward(ctx, q, xr, t, fc, df, cutoff, want_phase, mode):
+        ctx.set_materialize_grads(False)
+        q = q.contiguous()
+        need_grad = q.requires_grad
+        jac = need_grad and mode == "jacobian"
+        y, ph, dy, dp = band_forward(xr, t, q, fc, df, cutoff, want_phase, jac)
+        ctx.mode = mode
+        ctx.meta = (t, df, cutoff)
+        if need_grad:
+            if jac:
+                ctx.save_for_backward(dy, dp) if dp is not None else ctx.save_for_backward(dy)
+            else:
+                ctx.save_for_backward(xr, q, fc)
+        if ph is None:
+            ph = y.new_empty(0)
+            ctx.mark_non_differentiable(ph)
+        return y, ph
+
+    @staticmethod
+    def backward(ctx, g_y, g_ph):
+        if g_y is None and g_ph is None:
+            return (None,) * 8
+        if ctx.mode == "jacobian":
+            saved = ctx.saved_tensors
+            dq = None
+            if g_y is not None:
+                dq = g_y * saved[0]
+            if g_ph is not None and len(saved) > 1:
+                dq = g_ph * saved[1] if dq is None else torch.addcmul(dq, g_ph, saved[1])
+        else:
+            xr, q, fc = ctx.saved_tensors
+            t, df, cutoff = ctx.meta
+            dq = band_backward(xr, t, q, fc, df,
+                               g_y.contiguous() if g_y is not None else None,
+                               g_ph.contiguous() if g_ph is not None else None, cutoff)
+        return (dq,) + (None,) * 7
+
+
+# ------------------------------------------------------------------------------------------------
+# cross-correlation feature
+# ------------------------------------------------------------------------------------------------
+@lru_cache(maxsize=32)
+def _cc_tables(nsamp: int, fs: float, num_lags: int, max_lag_ms: float):
+    """Integer lag range the reference keeps and np.interp's (left index, weight) for every output point,
+    computed with the same float64 expressions as utils.py:408-418."""
+    max_lag_sec = max_lag_ms * 1e-3
+    reach = int(np.ceil(abs(max_lag_sec) * fs)) + 2
+    lo, hi = max(-(nsamp - 1), -reach), min(nsamp - 1, reach)
+    lag_idx = np.arange(lo, hi + 1)
+    lag_sec = lag_idx / fs
+    keep = np.logical_and(lag_sec >= -max_lag_sec, lag_sec <= max_lag_sec)
+    ks = lag_idx[keep]
+    if ks.size == 0:
+        raise ValueError("cross-correlation: empty lag range")
+    xp = lag_sec[keep]
+    target = np.linspace(-max_lag_sec, max_lag_sec, num_lags)
+    j = np.searchsorted(xp, target, side="right") - 1
+    idx = np.clip(j, 0, max(len(xp) - 2, 0))
+    if len(xp) > 1:
+        frac = (target - xp[idx]) / (xp[idx + 1] - xp[idx])
+    else:
+        frac = np.zeros_like(target)
+    left = target <= xp[0]
+    right = target >= xp[-1]
+    idx = np.where(left, 0, np.where(right, len(xp) - 1, idx))
+    frac = np.where(left | right, 0.0, frac)
+    return int(ks[0]), int(ks[-1]), idx.astype(np.int32), frac.astype(np.float32)
+
+
+_cc_dev_cache = {}
+
+
+def cc_feature(wav_l: torch.Tensor, wav_r: torch.Tensor, fs: float = 16000, num_lags: int = 100,
+               max_lag_ms: float = 3.0) -> torch.Tensor:
+    """(B, nsamp) x2 fp32 -> (B, num_lags) fp32.  utils.py:390-420 (compute_cross_correlation_feature)."""
+    if wav_l.dim() != 2 or wav_l.shape != wav_r.shape:
+        raise ValueError(f"expected two (B,N) waveforms, got {tuple(wav_l.shape)} and {tuple(wav_r.shape)}")
+    _need_cuda(wav_l, "wavL")
+    _need_cuda(wav_r, "wavR")
+    dev = wav_l.device
+    B, nsamp = wav_l.shape
+    key = (nsamp, float(fs), int(num_lags), float(max_lag_ms), dev.index)
+    if key not in _cc_dev_cache:
+        k_min, k_max, idx, frac = _cc_tables(nsamp, float(fs), int(num_lags), float(max_lag_ms))
+        _cc_dev_cache[key] = (k_min, k_max, torch.from_numpy(idx).to(dev), torch.from_numpy(frac).to(dev))
+    k_min, k_max, idx_d, frac_d = _cc_dev_cache[key]
+    with torch.cuda.device(dev):
+        lib = _prepare(dev)
+        out = torch.empty((B, num_lags), dtype=torch.float32, device=dev)
+        _lib.check(lib.biear_cc_fwd(_ptr(wav_l), _ptr(wav_r), B, nsamp, nsamp, k_min, k_max, _ptr(idx_d),
+                                    _ptr(frac_d), num_lags, _ptr(out), _stream(dev)), "biear_cc_fwd")
+    return out

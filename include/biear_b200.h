@@ -1,0 +1,107 @@
+/*
+ * biear_b200.h -- C ABI of libbiear_b200.so: the B200 (sm_100a) implementation of BiEAR's
+ * active-mode binaural front-end hot path.
+ *
+ * The reference (anonymous-speech-researcher/BiEAR) is pure Python/PyTorch and has no FFI of its
+ * own; the "binding" a maintainer adds is a ctypes stub inside model_torch.py.
+ * Each entry point below names the reference code it replaces (paths relative to the reference
+ * root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; the caller allocates and
+ *     owns all buffers; contiguous row-major fp32 unless a stride argument says otherwise;
+ *     complex values are interleaved (re, im) float pairs.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Functions only
+ *     enqueue work; they never synchronise (the *_host variants do, once, at the end).
+ *   - return value: 0 on success, otherwise a cudaError_t (> 0) or BIEAR_EINVAL (-1);
+ *     biear_last_error() returns a thread-local description of the last failure.
+ *   - there is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef BIEAR_B200_H
+#define BIEAR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BIEAR_ABI_VERSION 2
+#define BIEAR_EINVAL (-1)
+
+/* ABI version (== BIEAR_ABI_VERSION of the library that was built). */
+int biear_abi_version(void);
+
+/* Description of the last error raised on the calling thread ("" if none). */
+const char* biear_last_error(void);
+
+/* Number of kernels this library has launched since load / since the last reset (all threads). */
+int64_t biear_launch_count(void);
+void biear_reset_launch_count(void);
+
+/* One-time per-device setup (uploads the FFT twiddle table).  Synchronous; call it once per device
+ * before the first biear_stft_fwd and outside any CUDA-graph capture.  Idempotent. */
+int biear_init(void);
+
+/*
+ * Framing + Hann window + zero-padded real FFT for every (row, frame).
+ * Replaces model_torch.py:289-312 (_frame_1s) and :334-335 (frame * win_fn; torch.fft.rfft(n=n_fft)).
+ *   wav     (rows, nsamp) with row stride wav_row_stride floats; only the first `fs` samples of a
+ *           row are used, shorter rows are zero padded (reference: pad/truncate to fs).
+ *   win_fn  (win) window samples (the module's hann_window buffer).
+ *   X       (rows, T, n_fft/2+1, 2) out.
+ * Supported: n_fft == 1024; any fs, T >= 1, win >= 1, hop >= 1.
+ */
+int biear_stft_fwd(const float* wav, int64_t rows, int64_t nsamp, int64_t wav_row_stride,
+                   const float* win_fn, int fs, int T, int win, int hop, int n_fft,
+                   float* X, void* stream);
+
+/*
+ * Gaussian band weighting + contraction for `items` independent (spectrum, Q-vector) pairs.
+ * Replaces model_torch.py:340-346 (bw, W = exp(-0.5 u^2), row-normalise, nan_to_num,
+ * einsum("bf,bnf->bn")) and, when phase != NULL, :1050-1060 (_subband_phase_from_X) in the same
+ * pass; the (B,N,F) weight tensor is never materialised.  Item i reads spectrum X + i*x_stride
+ * (F interleaved complex values; strides are in floats) and Q + i*q_stride (N values); a stride of 0
+ * broadcasts (fixed-Q path).
+ *   Y      (items, N)  band energies  nan_to_num(sum_f |X| W)              (required)
+ *   phase  (items, N)  atan2(Im Z, Re Z), Z = sum_f W X                    (nullable)
+ *   dYdQ   (items, N)  exact dY/dQ     = k (a2 - Y m2)                      (nullable)
+ *   dPdQ   (items, N)  exact dphase/dQ = k (Re Z Im z2 - Im Z Re z2)/|Z|^2  (nullable)
+ *          with m2 = sum W u^2, a2 = sum |X| W u^2, z2 = sum X W u^2, k = -fc/((Q+1e-8)^2 bw):
+ *          what autograd derives in the reference, in closed form.
+ *   cutoff: Gaussian support half-width in units of bw (|u| <= cutoff); <= 0 selects dense.
+ */
+int biear_band_fwd(const float* X, int64_t x_stride, const float* Q, int64_t q_stride,
+                   const float* fc, int64_t items, int N, int F, float df, float cutoff,
+                   float* Y, int64_t y_stride, float* phase, int64_t phase_stride,
+                   float* dYdQ, float* dPdQ, int64_t jac_stride, void* stream);
+
+/*
+ * Backward of biear_band_fwd into Q by recomputation (nothing saved by the forward):
+ *   dQ = gY * dY/dQ + gphase * dphase/dQ      per (item, band), written by one lane, no atomics.
+ * This is the memory-lean form of what autograd derives from model_torch.py:340-346 / :1050-1060.
+ *   gY, gphase (items, N) with item strides (either may be NULL, not both); dQ (items, N);
+ *   accumulate != 0 adds into dQ instead of overwriting.
+ */
+int biear_band_bwd(const float* X, int64_t x_stride, const float* Q, int64_t q_stride,
+                   const float* fc, int64_t items, int N, int F, float df, float cutoff,
+                   const float* gY, int64_t gy_stride, const float* gphase, int64_t gphase_stride,
+                   float* dQ, int64_t dq_stride, int accumulate, void* stream);
+
+/*
+ * Broadband interaural cross-correlation feature.  Replaces utils.py:390-420
+ * (compute_cross_correlation_feature; byte-identical copy in create_h5_data/utils_save.py).
+ *   wavL, wavR (B, nsamp) with row stride; lags k_min..k_max (inclusive) are the integer lags the
+ *   reference keeps (|k|/fs <= max_lag); interp_idx/interp_frac (num_lags) give, for every output
+ *   point, the left neighbour inside the cropped lag axis and the linear weight of its right
+ *   neighbour (np.interp semantics, computed by the host in float64).
+ *   cc (B, num_lags) out.
+ */
+int biear_cc_fwd(const float* wavL, const float* wavR, int64_t B, int64_t nsamp, int64_t row_stride,
+                 int k_min, int k_max, const int32_t* interp_idx, const float* interp_frac,
+                 int num_lags, float* cc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BIEAR_B200_H */

@@ -1,0 +1,387 @@
+"""GPU parity tests: the sm_100a kernels (through the C ABI / the module mirror) against the committed golden
+vectors of the unmodified reference and against the CPU oracle on the same seeded inputs.
+
+Tolerance contract (BASELINE.json north_star): max relative error <= 1e-4 in fp32 on filterbank outputs, CC
+features and dQ; phase and gradients through phase are ill-conditioned in fp32 in the reference itself
+(its fp32 differs from its own fp64 by ~7e-3), so they are held to a small multiple of the reference's own
+fp32-vs-fp64 error against the fp64 record.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import biear_oracle as orc
+from tests.common import (CONFIG_SINGLE, CONFIG_YAML, RTOL, assert_close, cfg_single, cfg_yaml, elem_rel_err,
+                          rel_err, sub, upstream, wrap_err)
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def bb():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import biear_b200
+    from biear_b200 import _lib
+    _lib.load()   # must exist on a GPU box: no fallback
+    return biear_b200
+
+
+def _kw(d):
+    return dict(deltaQ_base=d["deltaq_base"], deltaQ_low_factor=d["deltaq_low"], deltaQ_high_factor=d["deltaq_high"],
+                deltaQ_mode=d["deltaq_mode"])
+
+
+def _load_ctrl(mod, weights):
+    sd = {k: torch.from_numpy(v) for k, v in weights.items()}
+    res = mod.load_state_dict(sd, strict=False)
+    assert not res.unexpected_keys, res
+
+
+def _dual(bb, batch, seeds, kw, std=0.02, band_mode="jacobian"):
+    torch.manual_seed(0)
+    m = bb.BinauralAdaptiveGammatoneFB(alpha=0.0, fixed_frontend_q=False, **_kw(kw))
+    _load_ctrl(m.fb_L, orc.synth_controller(seeds[0], out_std=std))
+    _load_ctrl(m.fb_R, orc.synth_controller(seeds[1], out_std=std))
+    m = m.to(DEV).eval()
+    m.fb_L.band_mode = band_mode
+    wl, wr = orc.synth_binaural(3, seed=1234)
+    tl = torch.from_numpy(wl[:batch]).to(DEV)
+    tr = torch.from_numpy(wr[:batch]).to(DEV)
+    return m, tl, tr
+
+
+def _np(t):
+    return t.detach().float().cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------------
+# kernels one by one
+# ------------------------------------------------------------------------------------------------
+def test_stft_against_golden_and_oracle(bb, golden):
+    from biear_b200 import ops
+    cfg = cfg_yaml()
+    c = orc.constants(cfg)
+    wl, wr = orc.synth_binaural(3, seed=1234)
+    x = ops.stft(torch.from_numpy(wl).to(DEV), c["win_fn"].to(DEV), cfg.fs, cfg.timesteps, cfg.win, cfg.hop, cfg.n_fft)
+    assert x.shape == (3, 19, 513) and x.dtype == torch.complex64
+    ours = _np(torch.view_as_real(x))
+    assert_close(ours[:, ::3], golden["dual32.XL"].view(np.float32).reshape(3, 7, 513, 2), 1e-5, "X vs reference")
+    ref64 = torch.view_as_real(orc.stft_frames(torch.from_numpy(wl).double(), cfg, c["win_fn"].double())).numpy()
+    assert rel_err(ours, ref64) <= 2e-6
+    # the imaginary parts of DC and Nyquist are exactly zero in the reference's rfft
+    assert np.all(ours[..., 0, 1] == 0) and np.all(ours[..., 512, 1] == 0)
+
+
+@pytest.mark.parametrize("nsamp", [1, 841, 842, 843, 9000, 15998, 16001, 32000])
+def test_stft_ragged_lengths(bb, nsamp):
+    """pad / truncate to fs samples, frames past the clip are zero (model_torch.py:289-312)."""
+    from biear_b200 import ops
+    cfg = cfg_yaml()
+    c = orc.constants(cfg)
+    rs = np.random.RandomState(nsamp)
+    w = torch.from_numpy(rs.uniform(-1, 1, (2, nsamp)).astype(np.float32))
+    x = ops.stft(w.to(DEV), c["win_fn"].to(DEV), cfg.fs, cfg.timesteps, cfg.win, cfg.hop, cfg.n_fft)
+    ref = orc.stft_frames(w.double(), cfg, c["win_fn"].double())
+    assert rel_err(_np(torch.view_as_real(x)), torch.view_as_real(ref).numpy()) <= 2e-6
+
+
+@pytest.mark.parametrize("fs,T,hop_ratio", [(16000, 19, 0.5), (8000, 10, 1.0), (16000, 32, 1.0), (16000, 12, 1.0),
+                                            (900, 1, 1.0)])
+def test_stft_other_geometries(bb, fs, T, hop_ratio):
+    """hop != win, win > n_fft (truncating rfft), fewer available frames than T, fs < win."""
+    from biear_b200 import ops
+    cfg = orc.FrontEndConfig(fs=fs, timesteps=T, hop_ratio=hop_ratio)
+    win_fn = torch.hann_window(cfg.win)
+    rs = np.random.RandomState(T)
+    w = torch.from_numpy(rs.uniform(-1, 1, (3, fs + 17)).astype(np.float32))
+    x = ops.stft(w.to(DEV), win_fn.to(DEV), cfg.fs, cfg.timesteps, cfg.win, cfg.hop, cfg.n_fft)
+    ref = orc.stft_frames(w.double(), cfg, win_fn.double())
+    assert x.shape == ref.shape
+    assert rel_err(_np(torch.view_as_real(x)), torch.view_as_real(ref).numpy()) <= 2e-6
+
+
+def test_band_kernel_against_fp64_oracle(bb):
+    """Y, phase and both Jacobians of one frame for log-normally perturbed Q (incl. clamp bounds),
+    against the float64 closed form / autograd of the oracle."""
+    from biear_b200 import ops
+    cfg = cfg_yaml()
+    c64 = orc.constants(cfg, torch.float64)
+    wl, _ = orc.synth_binaural(4, seed=9)
+    x64 = orc.stft_frames(torch.from_numpy(wl).double(), cfg, c64["win_fn"])
+    rs = np.random.RandomState(0)
+    q = (c64["Q0"] * torch.from_numpy(np.exp(0.7 * rs.standard_normal((4, 100))))).clamp(orc.Q_MIN, orc.Q_MAX)
+    q[0, :10] = orc.Q_MIN
+    q[1, -10:] = orc.Q_MAX
+    q[2, 50:60] = orc.Q_MIN
+    t = 4
+    m = orc.band_moments(x64[:, t], q, c64["fc"], c64["f_fft"])
+    one = torch.ones_like(q)
+    dy_ref = orc.dq_closed_form(m, q, c64["fc"], g_y=one)
+    dp_ref = orc.dq_closed_form(m, q, c64["fc"], g_phase=one)
+    ph_ref = torch.atan2(m["Z"].imag, m["Z"].real)
+
+    xr = torch.view_as_real(x64.to(torch.complex64)).contiguous().to(DEV)
+    q32 = q.float().to(DEV)
+    fc32 = c64["fc"].float().to(DEV)
+    for cutoff in (6.0, 0.0):
+        y, ph, dy, dp = ops.band_forward(xr, t, q32, fc32, 15.625, cutoff, True, True)
+        assert_close(_np(y), m["Y"].numpy(), 1e-5, f"Y cutoff={cutoff}")
+        assert elem_rel_err(_np(y), m["Y"].numpy()) <= RTOL
+        assert_close(_np(dy), dy_ref.numpy(), RTOL, f"dY/dQ cutoff={cutoff}")
+        # phase / its Jacobian: weight by |Z| (the ill-conditioned entries are those with |Z| -> 0)
+        wgt = (m["Z"].abs() / m["Z"].abs().max()).numpy()
+        d = np.abs(_np(ph) - ph_ref.numpy()) % (2 * np.pi)
+        assert np.max(np.minimum(d, 2 * np.pi - d) * wgt) <= 1e-4
+        assert np.max(np.abs(_np(dp) - dp_ref.numpy()) * wgt ** 2) / np.max(np.abs(dp_ref.numpy()) * wgt ** 2) <= 1e-3
+        # recompute-form backward == Jacobian form
+        gy = torch.from_numpy(rs.standard_normal((4, 100)).astype(np.float32)).to(DEV)
+        gp = torch.from_numpy(rs.standard_normal((4, 100)).astype(np.float32)).to(DEV)
+        dq = ops.band_backward(xr, t, q32, fc32, 15.625, gy, gp, cutoff)
+        torch.testing.assert_close(dq, gy * dy + gp * dp, rtol=1e-5, atol=1e-6 * float((gy * dy).abs().max()))
+        dq_y = ops.band_backward(xr, t, q32, fc32, 15.625, gy, None, cutoff)
+        torch.testing.assert_close(dq_y, gy * dy, rtol=1e-5, atol=1e-6 * float((gy * dy).abs().max()))
+
+
+def test_band_nonfinite_q(bb):
+    """nan_to_num semantics: NaN / Inf Q rows give Y = 0 exactly as the reference (model_torch.py:343-346)."""
+    from biear_b200 import ops
+    cfg = cfg_yaml()
+    c = orc.constants(cfg)
+    wl, _ = orc.synth_binaural(2, seed=9)
+    x = orc.stft_frames(torch.from_numpy(wl), cfg, c["win_fn"])
+    q = c["Q0"].repeat(2, 1).clone()
+    q[0, 3] = float("nan")
+    q[0, 7] = float("inf")
+    q[1, 11] = -1e-8          # bw -> +inf
+    ref = orc.band_energy(x[:, 2].abs(), orc.band_weights(q, c["fc"], c["f_fft"]))
+    y, _, _, _ = ops.band_forward(torch.view_as_real(x).contiguous().to(DEV), 2, q.to(DEV), c["fc"].to(DEV), 15.625,
+                                  6.0, False, False)
+    y = _np(y)
+    assert y[0, 3] == 0 and y[0, 7] == 0
+    assert np.isfinite(y).all()
+    mask = np.ones_like(y, bool)
+    mask[1, 11] = False
+    assert rel_err(y[mask], ref.numpy()[mask]) <= 1e-5
+
+
+def test_cc_against_golden(bb, golden):
+    from biear_b200 import ops
+    cl, cr = orc.synth_binaural(6, seed=77)
+    tl, tr = torch.from_numpy(cl).to(DEV), torch.from_numpy(cr).to(DEV)
+    tol = 1e-4   # max-abs(ref) <= 1 by construction
+    assert np.max(np.abs(_np(ops.cc_feature(tl, tr)) - golden["cc.default"])) <= tol
+    assert np.max(np.abs(_np(ops.cc_feature(tl[:2], tr[:2], 16000, 64, 1.0)) - golden["cc.lags64_1ms"])) <= tol
+    assert np.max(np.abs(_np(ops.cc_feature(tl[:2], tr[:2], 16000, 128, 5.0)) - golden["cc.lags128_5ms"])) <= tol
+    q16 = lambda x: (np.round(x * 32767) / 32768).astype(np.float32)
+    a, b = torch.from_numpy(q16(cl[:2])).to(DEV), torch.from_numpy(q16(cr[:2])).to(DEV)
+    assert np.max(np.abs(_np(ops.cc_feature(a, b)) - golden["cc.int16"])) <= tol
+    z = torch.zeros(1, 16000, device=DEV)
+    np.testing.assert_array_equal(_np(ops.cc_feature(z, z))[0], golden["cc.silence"])
+    dc = torch.from_numpy((np.full(16000, 0.25, np.float32) + cl[0] * 0.1)[None]).to(DEV)
+    assert np.max(np.abs(_np(ops.cc_feature(dc, tr[:1]))[0] - golden["cc.dc_vs_noise"])) <= tol
+    # tighter: the fp32 kernel is within 2e-6 of the float64 reference on these inputs
+    assert np.max(np.abs(_np(ops.cc_feature(tl, tr)) - golden["cc.default"])) <= 2e-6
+
+
+@pytest.mark.parametrize("nsamp,num_lags,ms", [(16000, 100, 3.0), (4000, 32, 1.0), (700, 100, 3.0), (16000, 128, 5.0),
+                                               (48, 10, 3.0)])
+def test_cc_against_oracle_shapes(bb, nsamp, num_lags, ms):
+    from biear_b200 import ops
+    rs = np.random.RandomState(nsamp + num_lags)
+    a = rs.uniform(-1, 1, (3, nsamp)).astype(np.float32)
+    b = (0.5 * np.roll(a, 3, axis=1) + 0.1 * rs.standard_normal((3, nsamp))).astype(np.float32)
+    ref = orc.cc_feature_batch(a, b, 16000, num_lags, ms)
+    ours = _np(ops.cc_feature(torch.from_numpy(a).to(DEV), torch.from_numpy(b).to(DEV), 16000, num_lags, ms))
+    assert np.max(np.abs(ours - ref)) <= 1e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# module mirror against the reference's golden outputs
+# ------------------------------------------------------------------------------------------------
+def test_fixed_frontend_and_ragged(bb, golden):
+    wl, wr = orc.synth_binaural(3, seed=1234)
+    tl, tr = torch.from_numpy(wl).to(DEV), torch.from_numpy(wr).to(DEV)
+    fixed = bb.BinauralAdaptiveGammatoneFB(fixed_frontend_q=True).to(DEV).eval()
+    assert len(list(fixed.parameters())) == 0          # train_biear.py:410-412 checks exactly this
+    with torch.no_grad():
+        yl, yr, ql, qr, xl, xr = fixed(tl, tr)
+        assert_close(_np(yl), golden["fixed.YL"], RTOL, "fixed YL")
+        assert_close(_np(yr), golden["fixed.YR"], RTOL, "fixed YR")
+        assert elem_rel_err(_np(yl), golden["fixed.YL"]) <= RTOL
+        np.testing.assert_array_equal(_np(ql), golden["fixed.QL"])
+        assert xl.dtype == torch.complex64 and xl.shape == (3, 19, 513)
+        ys = fixed(tl[:, :9000].contiguous(), tr[:, :9000].contiguous())[0]
+        assert_close(_np(ys), golden["fixed.YL_short9000"], RTOL, "short clip")
+        y2 = fixed(torch.cat([tl, tl], 1), torch.cat([tr, tr], 1))[0]
+        assert_close(_np(y2), golden["fixed.YL_long32000"], RTOL, "long clip")
+        # samples beyond the first second are ignored: bit-identical
+        assert torch.equal(y2, yl)
+        o = fixed.forward_features(tl, tr)
+        assert wrap_err(_np(o["phaseL"]), golden["fixed.PL"]) < 2e-2
+        aur = bb.AuralNetGammatoneFB().to(DEV).eval()
+        assert_close(_np(aur(tl)), golden["auralnet.YL"], RTOL, "auralnet")
+        f64 = bb.BinauralAdaptiveGammatoneFB(Nbands=64, fixed_frontend_q=True).to(DEV).eval()
+        assert_close(_np(f64(tl, tr)[0]), golden["fixed64.YL"], RTOL, "64 bands")
+        with pytest.raises(ValueError):
+            fixed(tl[0], tr[0])
+
+
+@pytest.mark.parametrize("tag,batch,seeds,kw,std", [
+    ("dual32", 3, (11, 12), CONFIG_YAML, 0.02),
+    ("clamp32", 2, (21, 22), CONFIG_YAML, 0.3),
+    ("abs32", 2, (11, 12), CONFIG_SINGLE, 0.02),
+])
+def test_dual_adaptive_forward(bb, golden, tag, batch, seeds, kw, std):
+    m, tl, tr = _dual(bb, batch, seeds, kw, std)
+    with torch.no_grad():
+        o = m.forward_features(tl, tr)
+    for k in ("YL", "YR", "QL", "QR"):
+        assert_close(_np(o[k]), golden[f"{tag}.{k}"], RTOL, f"{tag}.{k}")
+    assert elem_rel_err(_np(o["YL"]), golden[f"{tag}.YL"]) <= RTOL
+    assert elem_rel_err(_np(o["QR"]), golden[f"{tag}.QR"]) <= RTOL
+    np.testing.assert_array_equal(_np(o["QL"])[:, 0], np.broadcast_to(golden["const.Q0"], (batch, 100)))
+    if tag == "clamp32":
+        assert (_np(o["QL"]) == orc.Q_MIN).mean() > 0.05
+    # phase: against the reference's fp64 record, relative to the reference's own fp32 error
+    t64 = tag.replace("32", "64")
+    if f"{t64}.PL" in golden.files:
+        for side in ("L", "R"):
+            e_ref = wrap_err(golden[f"{tag}.P{side}"], golden[f"{t64}.P{side}"])
+            e_our = wrap_err(_np(o[f"phase{side}"]), golden[f"{t64}.P{side}"])
+            assert e_our <= 3 * e_ref + 1e-5, (tag, side, e_our, e_ref)
+    # drop-in signature: forward returns the reference's 6-tuple
+    with torch.no_grad():
+        out = m(tl, tr)
+    assert len(out) == 6 and out[4].dtype == torch.complex64
+    assert torch.equal(out[0], o["YL"]) and torch.equal(out[3], o["QR"])
+
+
+def _grads(m):
+    g = {}
+    for side, fb in (("L", m.fb_L), ("R", m.fb_R)):
+        for name, prm in fb.named_parameters():
+            g[f"{side}.{name}"] = _np(prm.grad)
+    return g
+
+
+@pytest.mark.parametrize("band_mode", ["jacobian", "recompute"])
+@pytest.mark.parametrize("tag,batch,seeds,std", [("dual", 3, (11, 12), 0.02), ("clamp", 2, (21, 22), 0.3)])
+def test_dual_adaptive_backward_through_y(bb, golden, tag, batch, seeds, std, band_mode):
+    """dL/d(controller weights) for a loss through Y and Q (loss A of make_golden.py) -- this is dQ pushed
+    through the reference's own controller backward, so it checks the dQ kernel on every frame."""
+    m, tl, tr = _dual(bb, batch, seeds, CONFIG_YAML, std, band_mode)
+    up = {k: torch.from_numpy(v).to(DEV) for k, v in upstream(batch).items()}
+    yl, yr, ql, qr, _, _ = m(tl, tr)
+    loss = (up["gYL"] * torch.log(yl + 1e-8)).sum() + (up["gYR"] * torch.log(yr + 1e-8)).sum() \
+        + (up["gQL"] * ql).sum() + (up["gQR"] * qr).sum()
+    loss.backward()
+    worst = 0.0
+    for key, g in _grads(m).items():
+        ref32 = golden[f"{tag}32.gradA.{key}"]
+        ref64 = golden[f"{tag}64.gradA.{key}"]
+        e = rel_err(sub(g), ref32)
+        e_ref = rel_err(ref32, ref64)
+        worst = max(worst, e)
+        assert e <= max(RTOL, 3 * e_ref), f"{key}: {e:.2e} (reference self-error {e_ref:.2e})"
+    print(f"[{tag}/{band_mode}] worst gradA error {worst:.2e}")
+
+
+def test_dual_adaptive_backward_through_phase(bb, golden):
+    """Loss B (through phase only): ill-conditioned in fp32; compare with the fp64 record and require
+    our error to stay within 3x the reference's own fp32 error."""
+    m, tl, tr = _dual(bb, 3, (11, 12), CONFIG_YAML)
+    up = {k: torch.from_numpy(v).to(DEV) for k, v in upstream(3).items()}
+    o = m.forward_features(tl, tr)
+    ((up["gPL"] * o["phaseL"]).sum() + (up["gPR"] * o["phaseR"]).sum()).backward()
+    for key, g in _grads(m).items():
+        ref32 = golden[f"dual32.gradB.{key}"]
+        ref64 = golden[f"dual64.gradB.{key}"]
+        e = rel_err(sub(g), ref64)
+        e_ref = rel_err(ref32, ref64)
+        assert e <= 3 * e_ref + 1e-6, f"{key}: {e:.2e} vs reference self-error {e_ref:.2e}"
+
+
+def test_single_controller(bb, golden):
+    torch.manual_seed(0)
+    m = bb.BinauralAdaptiveGammatoneFB_SingleController(**_kw(CONFIG_SINGLE))
+    _load_ctrl(m, orc.synth_controller(31, in_mult=4))
+    m = m.to(DEV).eval()
+    wl, wr = orc.synth_binaural(3, seed=1234)
+    tl, tr = torch.from_numpy(wl[:2]).to(DEV), torch.from_numpy(wr[:2]).to(DEV)
+    yl, yr, q, q2, xl, xr = m(tl, tr)
+    assert q2 is q or torch.equal(q, q2)
+    assert_close(_np(yl), golden["single.YL"], RTOL, "single YL")
+    assert_close(_np(yr), golden["single.YR"], RTOL, "single YR")
+    assert_close(_np(q), golden["single.Q"], RTOL, "single Q")
+    up = {k: torch.from_numpy(v).to(DEV) for k, v in upstream(2).items()}
+    ((up["gYL"] * torch.log(yl + 1e-8)).sum() + (up["gYR"] * torch.log(yr + 1e-8)).sum() + (up["gQL"] * q).sum()).backward()
+    for name, prm in m.named_parameters():
+        assert rel_err(sub(_np(prm.grad)), golden[f"single.gradA.{name}"]) <= 2 * RTOL, name
+
+
+# ------------------------------------------------------------------------------------------------
+# size-independent properties at the benchmark size (B = 256)
+# ------------------------------------------------------------------------------------------------
+def test_properties_full_size(bb):
+    B = 256
+    wl, wr = orc.synth_binaural(B, seed=4321)
+    tl, tr = torch.from_numpy(wl).to(DEV), torch.from_numpy(wr).to(DEV)
+    torch.manual_seed(0)
+    adaptive = bb.BinauralAdaptiveGammatoneFB(**_kw(CONFIG_YAML)).to(DEV).eval()   # zero-init last layer: Q == Q0
+    fixed = bb.BinauralAdaptiveGammatoneFB(fixed_frontend_q=True).to(DEV).eval()
+    with torch.no_grad():
+        ya, _, qa, _, xa, _ = adaptive(tl, tr)
+        yf, yfr, qf, _, xf, _ = fixed(tl, tr)
+        # (1) adaptive at initialisation == fixed, bit for bit
+        assert torch.equal(qa, qf.expand_as(qa)) and torch.equal(ya, yf) and torch.equal(xa, xf)
+        # (2) a 10 s input gives the result of its first second (section 4 item 5)
+        y10 = fixed(torch.cat([tl, tl.flip(1)], 1), torch.cat([tr, tr], 1))[0]
+        assert torch.equal(y10, yf)
+        # (3) homogeneity of the fixed filterbank: scaling by a power of two scales Y exactly
+        y2 = fixed(tl * 0.5, tr * 0.5)[0]
+        assert torch.equal(y2 * 2.0, yf)
+        # (4) swapping the ears swaps the outputs
+        ys = fixed(tr, tl)
+        assert torch.equal(ys[0], yfr) and torch.equal(ys[1], yf)
+        # (5) batch independence: any sub-batch reproduces its rows
+        ysub = fixed(tl[37:59].contiguous(), tr[37:59].contiguous())[0]
+        assert torch.equal(ysub, yf[37:59])
+        # (6) W rows are normalised: Y lies within [min |X|, max |X|] of its frame
+        mag = xf.abs()
+        assert bool((yf <= mag.amax(-1, keepdim=True) * (1 + 1e-5)).all())
+        assert bool((yf >= mag.amin(-1, keepdim=True) * (1 - 1e-5)).all())
+        # (7) Parseval for the STFT kernel: sum |X|^2 (two-sided) == n_fft * sum (frame * win)^2
+        c = orc.constants(cfg_yaml())
+        frames = orc.frame_clip(torch.from_numpy(wl[:8]), cfg_yaml()) * c["win_fn"]
+        e_time = (frames.double() ** 2).sum(-1) * 1024
+        p = (xf[:8].abs().double().cpu()) ** 2
+        e_freq = p[..., 0] + p[..., 512] + 2 * p[..., 1:512].sum(-1)
+        assert rel_err(e_freq.numpy(), e_time.numpy()) <= 1e-5
+    # (8) CC: symmetric under exchanging ears + reversing the lag axis; peak at the imposed ITD
+    from biear_b200 import ops
+    cc = ops.cc_feature(tl, tr)
+    cc_sw = ops.cc_feature(tr, tl)
+    assert float((cc - cc_sw.flip(1)).abs().max()) <= 1e-5
+    assert float(cc.abs().max()) <= 1.0 + 1e-6
+
+
+def test_randomised_controller_full_size_against_oracle_rows(bb):
+    """B = 256 adaptive run; a handful of rows re-run through the fp32 CPU oracle (rows are independent)."""
+    B = 256
+    m, _, _ = _dual(bb, 1, (11, 12), CONFIG_YAML)
+    wl, wr = orc.synth_binaural(B, seed=99)
+    with torch.no_grad():
+        o = m.forward_features(torch.from_numpy(wl).to(DEV), torch.from_numpy(wr).to(DEV))
+    rows = [0, 100, 255]
+    cfg = cfg_yaml()
+    pl = orc.to_torch(orc.synth_controller(11))
+    pr = orc.to_torch(orc.synth_controller(12))
+    yl, ql, _ = orc.adaptive_fb_forward(torch.from_numpy(wl[rows]), pl, cfg)
+    yr, qr, _ = orc.adaptive_fb_forward(torch.from_numpy(wr[rows]), pr, cfg)
+    assert_close(_np(o["YL"])[rows], yl.numpy(), RTOL, "YL rows")
+    assert_close(_np(o["YR"])[rows], yr.numpy(), RTOL, "YR rows")
+    assert_close(_np(o["QL"])[rows], ql.numpy(), RTOL, "QL rows")
+    assert_close(_np(o["QR"])[rows], qr.numpy(), RTOL, "QR rows")
