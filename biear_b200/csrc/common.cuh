@@ -52,9 +52,13 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 __device__ __forceinline__ float ex2_approx(float x) {
+#ifdef BIEAR_EXACT_EXP   // diagnostic builds only
+    return exp2f(x);
+#else
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+#endif
 }
 
 __device__ __forceinline__ float sanitize(float v) {   // torch.nan_to_num(v, 0, 0, 0)

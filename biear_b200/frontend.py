@@ -167,7 +167,7 @@ def _next_q(delta, q0, dq, mode):
 
 
 def _adaptive_chain(x: torch.Tensor, ears: int, ctrl_mods, fc, q0, dq_vec, dq_mode, df, training,
-                    shared: bool, want_phase: bool, band_mode: str, cutoff: float):
+                    shared: bool, want_phase: bool, band_mode: str, cutoff: float, engine: str = "chain"):
     """The 19-step Q recurrence for `ears` ears of B clips.
 
     x: (ears*B, T, F) complex64, ear-major.  ctrl_mods: G controller-owning modules.
@@ -180,6 +180,20 @@ def _adaptive_chain(x: torch.Tensor, ears: int, ctrl_mods, fc, q0, dq_vec, dq_mo
     G = len(ctrl_mods)
     N = fc.numel()
     xr = torch.view_as_real(x)
+    if engine == "fused":
+        if shared or G != ears or N > 128:
+            raise NotImplementedError("the fused recurrence covers the dual front-end with at most 128 bands")
+        st = lambda f: torch.stack([f(m) for m in ctrl_mods])
+        w = {"w_ih": st(lambda m: m.q_rnn.weight_ih_l0), "w_hh": st(lambda m: m.q_rnn.weight_hh_l0),
+             "b_ih": st(lambda m: m.q_rnn.bias_ih_l0), "b_hh": st(lambda m: m.q_rnn.bias_hh_l0),
+             "w1": st(lambda m: m.q_out[0].weight), "b1": st(lambda m: m.q_out[0].bias),
+             "ln1_g": st(lambda m: m.q_out[1].weight), "ln1_b": st(lambda m: m.q_out[1].bias),
+             "w2": st(lambda m: m.q_out[4].weight), "b2": st(lambda m: m.q_out[4].bias),
+             "ln2_g": st(lambda m: m.q_out[5].weight), "ln2_b": st(lambda m: m.q_out[5].bias),
+             "w3": st(lambda m: m.q_out[8].weight), "b3": st(lambda m: m.q_out[8].bias)}
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if training else 0   # CPU generator: no device sync
+        return ops.adaptive_sequence(xr, fc, q0, dq_vec, w, dq_mode == "relative", training, want_phase, cutoff,
+                                     df, seed)
     stack = _ControllerStack(ctrl_mods)
     q0g = q0.view(1, 1, N)
     dqg = dq_vec.view(1, 1, N)
@@ -246,6 +260,7 @@ class FramewiseAdaptiveGammatoneFB(_FilterbankBase):
         self.Q_min, self.Q_max = Q_MIN, Q_MAX
         self.freeze_Q = False
         self.band_mode = "jacobian"
+        self.engine = "fused"
         self.cutoff = ops.DEFAULT_CUTOFF
 
     def forward(self, wav_1s: torch.Tensor):
@@ -254,7 +269,8 @@ class FramewiseAdaptiveGammatoneFB(_FilterbankBase):
             y, _ = _fixed_bands(x, self.fc, self.Q0, self.df, False, self.cutoff)
             return y, self.Q0.view(1, 1, -1).expand(x.shape[0], self.timesteps, -1), x
         y, q, _ = _adaptive_chain(x, 1, [self], self.fc, self.Q0, self.deltaQ_vec, self.deltaQ_mode, self.df,
-                                  self.training, False, False, self.band_mode, self.cutoff)
+                                  self.training, False, False, self.band_mode, self.cutoff,
+                                  self.engine if self.Nbands <= 128 else "chain")
         return y, q, x
 
 
@@ -326,6 +342,9 @@ class BinauralAdaptiveGammatoneFB(nn.Module):
         self.fb_L = mk()
         self.fb_R = mk()
         self.freeze_Q = False   # kept for compatibility; like the reference it is not propagated to fb_L/fb_R
+        # "fused": one C call runs the whole recurrence on the cluster kernels of csrc/ctrl.cu;
+        # "chain": per-frame band kernel + batched torch controller (kept as a cross-check)
+        self.engine = "fused"
 
     def forward_features(self, wavL_1s: torch.Tensor, wavR_1s: torch.Tensor, want_phase: bool = True):
         fb = self.fb_L
@@ -341,8 +360,9 @@ class BinauralAdaptiveGammatoneFB(nn.Module):
         else:
             if self.fb_L.freeze_Q != self.fb_R.freeze_Q:
                 raise NotImplementedError("freeze_Q on one ear only")
+            engine = self.engine if fb.Nbands <= 128 else "chain"
             y, q, ph = _adaptive_chain(x, 2, [self.fb_L, self.fb_R], fb.fc, fb.Q0, fb.deltaQ_vec, fb.deltaQ_mode,
-                                       fb.df, self.training, False, want_phase, fb.band_mode, fb.cutoff)
+                                       fb.df, self.training, False, want_phase, fb.band_mode, fb.cutoff, engine)
         out = {"YL": y[:B], "YR": y[B:], "QL": q[:B], "QR": q[B:], "XL": x[:B], "XR": x[B:]}
         if want_phase:
             out["phaseL"], out["phaseR"] = ph[:B], ph[B:]

@@ -235,3 +235,133 @@ def cc_feature(wav_l: torch.Tensor, wav_r: torch.Tensor, fs: float = 16000, num_
         _lib.check(lib.biear_cc_fwd(_ptr(wav_l), _ptr(wav_r), B, nsamp, nsamp, k_min, k_max, _ptr(idx_d),
                                     _ptr(frac_d), num_lags, _ptr(out), _stream(dev)), "biear_cc_fwd")
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# fused adaptive recurrence (dual front-end)
+# ------------------------------------------------------------------------------------------------
+WEIGHT_NAMES = ("w_ih", "w_hh", "b_ih", "b_hh", "w1", "b1", "ln1_g", "ln1_b", "w2", "b2", "ln2_g", "ln2_b", "w3", "b3")
+HID = 128
+
+
+def _fill(params, **tensors):
+    for k, v in tensors.items():
+        setattr(params, k, v.data_ptr() if v is not None else None)
+
+
+class AdaptiveSequence(torch.autograd.Function):
+    """The whole 19-frame Q recurrence of the dual front-end as one autograd node.
+
+    forward : T band-stage launches + (T-1) fused controller steps, issued from C (biear_adaptive_fwd);
+    backward: (T-1) fused controller-step backward launches (biear_adaptive_bwd) that carry
+              dL/dQ_{t+1} -> dL/dY_t, dL/dh_{t-1} down the chain and leave per-sample pre-activation
+              gradients, from which the weight gradients are formed with batched GEMMs off the chain.
+    Inputs : xr (E*B,T,F,2), fc/q0/dq (N), 14 weight tensors stacked over the G = E controllers.
+    Outputs: Y (E*B,T,N), Q (G*B,T,N), phase (E*B,T,N) [empty when want_phase is False].
+    """
+
+    @staticmethod
+    def forward(ctx, xr, fc, q0, dq, relative, training, want_phase, cutoff, df, seed, *weights):
+        ctx.set_materialize_grads(False)
+        _need_cuda(xr, "X")
+        dev = xr.device
+        rows, T, F, _ = xr.shape
+        N = fc.numel()
+        G = weights[0].shape[0]
+        B = rows // G
+        weights = tuple(w.detach().contiguous() for w in weights)
+        for name, w in zip(WEIGHT_NAMES, weights):
+            _need_cuda(w, name)
+        Kin = weights[0].shape[2]
+        need_grad = any(ctx.needs_input_grad[10:])
+        f32 = dict(dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            lib = _prepare(dev)
+            Y = torch.empty((rows, T, N), **f32)
+            Q = torch.empty((rows, T, N), **f32)
+            P = torch.empty((rows, T, N), **f32) if want_phase else None
+            dY = torch.empty((rows, T, N), **f32)
+            dP = torch.empty((rows, T, N), **f32) if want_phase else None
+            S = max(T - 1, 1)
+            sv = {k: torch.empty((G, S, B, d), **f32) for k, d in
+                  (("H", HID), ("gates", 4 * HID), ("xh1", HID), ("d1", HID), ("xh2", HID), ("d2", HID), ("rstd", 2),
+                   ("delta", N))}
+            flags = torch.zeros((S, G), dtype=torch.int32, device=dev)
+            prm = _lib.SeqParams()
+            prm.G, prm.E, prm.B, prm.T, prm.N, prm.F, prm.Kin = G, G, B, T, N, F, Kin
+            prm.relative, prm.training, prm.seed = int(relative), int(training), int(seed)
+            prm.df, prm.cutoff, prm.q_min, prm.q_max = float(df), float(cutoff), 0.05, 30.0
+            _fill(prm, fc=fc, q0=q0, dq=dq, X=xr, Y=Y, phase=P, dYdQ=dY, dPdQ=dP, Q=Q, flags=flags, **sv,
+                  **dict(zip(WEIGHT_NAMES, weights)))
+            from ctypes import byref
+            _lib.check(lib.biear_adaptive_fwd(byref(prm), _stream(dev)), "biear_adaptive_fwd")
+        ctx.prm = prm
+        ctx.keep = (xr, fc, q0, dq, weights, Y, Q, P, dY, dP, sv, flags)   # owners of every pointer in prm
+        ctx.dims = (G, B, T, N, Kin)
+        if P is None:
+            P = Y.new_empty(0)
+            ctx.mark_non_differentiable(P)
+        if not need_grad:
+            ctx.mark_non_differentiable(Y, Q)
+        return Y, Q, P
+
+    @staticmethod
+    def backward(ctx, gY, gQ, gP):
+        from ctypes import byref
+        xr, fc, q0, dq, weights, Y, Q, P, dY, dP, sv, flags = ctx.keep
+        G, B, T, N, Kin = ctx.dims
+        none10 = (None,) * 10
+        if T < 2 or (gY is None and gQ is None and gP is None):
+            return none10 + (None,) * len(WEIGHT_NAMES)
+        dev = Y.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        S = T - 1
+        gY = gY.contiguous() if gY is not None else None
+        gQ = gQ.contiguous() if gQ is not None else None
+        gP = gP.contiguous() if (gP is not None and P is not None) else None
+        with torch.cuda.device(dev):
+            lib = _prepare(dev)
+            wk = {"dYc": torch.empty((G * B, T, N), **f32), "dH": torch.empty((G * B, HID), **f32),
+                  "GG": torch.empty((G, S, B, 4 * HID), **f32), "G_a1": torch.empty((G, S, B, HID), **f32),
+                  "G_v1": torch.empty((G, S, B, HID), **f32), "G_a2": torch.empty((G, S, B, HID), **f32),
+                  "G_v2": torch.empty((G, S, B, HID), **f32), "G_pre": torch.empty((G, S, B, N), **f32)}
+            prm = ctx.prm
+            _fill(prm, gY=gY, gQ=gQ, gP=gP, **wk)
+            _lib.check(lib.biear_adaptive_bwd(byref(prm), _stream(dev)), "biear_adaptive_bwd")
+            _fill(prm, gY=None, gQ=None, gP=None)
+
+            # ---- weight gradients: a few large batched GEMMs over all (step, clip) samples, off the chain ----
+            M = S * B
+            GG = wk["GG"].view(G, M, 4 * HID)
+            yc = torch.log1p(torch.clamp(Y.view(G, B, T, N)[:, :, :S], min=0.0)).transpose(1, 2).reshape(G, M, N)
+            keep = (flags == 0).to(torch.float32).t().reshape(G, S, 1, 1)             # h_t survives into step t+1
+            H = sv["H"]
+            hprev = torch.cat([torch.zeros((G, 1, B, HID), **f32), H[:, :-1] * keep[:, :-1]], dim=1).view(G, M, HID)
+            g_i = GG[:, :, :3 * HID]
+            a = torch.bmm(g_i.transpose(1, 2), yc)                                       # (G,384,N)
+            d_w_ih = torch.cat([a, 0.2 * a], dim=2) if Kin == 2 * N else None
+            g_rz, g_hn = GG[:, :, :2 * HID], GG[:, :, 3 * HID:]
+            d_w_hh = torch.cat([torch.bmm(g_rz.transpose(1, 2), hprev), torch.bmm(g_hn.transpose(1, 2), hprev)], dim=1)
+            d_b_ih = g_i.sum(1)
+            d_b_hh = torch.cat([g_rz.sum(1), g_hn.sum(1)], dim=1)
+
+            def lin(gout, xin):
+                go = gout.view(G, M, -1)
+                return torch.bmm(go.transpose(1, 2), xin.view(G, M, -1)), go.sum(1)
+
+            d_w1, d_b1 = lin(wk["G_a1"], H)
+            d_w2, d_b2 = lin(wk["G_a2"], sv["d1"])
+            d_w3, d_b3 = lin(wk["G_pre"], sv["d2"])
+            gv1, gv2 = wk["G_v1"].view(G, M, HID), wk["G_v2"].view(G, M, HID)
+            d_g1, d_be1 = (gv1 * sv["xh1"].view(G, M, HID)).sum(1), gv1.sum(1)
+            d_g2, d_be2 = (gv2 * sv["xh2"].view(G, M, HID)).sum(1), gv2.sum(1)
+        grads = (d_w_ih, d_w_hh, d_b_ih, d_b_hh, d_w1, d_b1, d_g1, d_be1, d_w2, d_b2, d_g2, d_be2, d_w3, d_b3)
+        return none10 + grads
+
+
+def adaptive_sequence(xr, fc, q0, dq, weights, relative: bool, training: bool, want_phase: bool,
+                      cutoff: float, df: float, seed: int = 0):
+    """weights: dict name -> (G, ...) tensor (WEIGHT_NAMES).  Returns Y, Q, phase|None."""
+    y, q, ph = AdaptiveSequence.apply(xr, fc, q0, dq, relative, training, want_phase, cutoff, df, seed,
+                                      *[weights[k] for k in WEIGHT_NAMES])
+    return y, q, (ph if want_phase else None)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BIEAR_ABI_VERSION 2
+#define BIEAR_ABI_VERSION 3
 #define BIEAR_EINVAL (-1)
 
 /* ABI version (== BIEAR_ABI_VERSION of the library that was built). */
@@ -87,6 +87,56 @@ int biear_band_bwd(const float* X, int64_t x_stride, const float* Q, int64_t q_s
                    const float* fc, int64_t items, int N, int F, float df, float cutoff,
                    const float* gY, int64_t gy_stride, const float* gphase, int64_t gphase_stride,
                    float* dQ, int64_t dq_stride, int accumulate, void* stream);
+
+/*
+ * Parameter block of the fused adaptive recurrence (dual front-end: one Q controller per ear).
+ * Replaces the frame loop of FramewiseAdaptiveGammatoneFB.forward (model_torch.py:333-380) for both ears
+ * and DeepEarActiveWaveform._subband_phase_from_X (:1039-1063), and their autograd backward.
+ * Row order everywhere: ear-major, row = ear * B + clip.  "saved" tensors are laid out (G, T-1, B, D):
+ * index ((g * (T-1) + t) * B + b) * D, so that one controller's samples of all steps are contiguous.
+ */
+typedef struct BiearSeqParams {
+    /* geometry */
+    int32_t G, E, B, T, N, F, Kin;   /* controllers, ears, clips, frames, bands, bins, controller input width */
+    int32_t relative;                /* deltaQ_mode: 1 = Q0 (1 + dQ delta), 0 = Q0 + dQ delta */
+    int32_t training;                /* dropout on (p = 0.1, Philox keyed by seed) */
+    int32_t reserved;
+    uint64_t seed;
+    float df, cutoff, q_min, q_max;
+    /* constants (N) */
+    const float *fc, *q0, *dq;
+    /* controller weights, stacked over the G controllers, torch layouts (out, in) */
+    const float *w_ih, *w_hh, *b_ih, *b_hh;          /* (G,384,Kin) (G,384,128) (G,384) (G,384) */
+    const float *w1, *b1, *ln1_g, *ln1_b;            /* (G,128,128) (G,128) x3 */
+    const float *w2, *b2, *ln2_g, *ln2_b;
+    const float *w3, *b3;                            /* (G,N,128) (G,N) */
+    /* spectra (E*B, T, F, 2) */
+    const float* X;
+    /* forward outputs (E*B, T, N); phase / dPdQ nullable together */
+    float *Y, *phase, *dYdQ, *dPdQ;
+    float* Q;                                        /* (G*B, T, N) */
+    /* saved by the forward for the backward */
+    float *H, *gates, *xh1, *d1, *xh2, *d2, *rstd, *delta;   /* D = 128, 512 (r,z,n,hn), 128 x4, 2, N */
+    int32_t* flags;                                  /* (T-1, G), zero-initialised: non-finite-Q fallback taken */
+    /* backward inputs (nullable): dL/dY, dL/dphase (E*B,T,N), dL/dQ (G*B,T,N) */
+    const float *gY, *gP, *gQ;
+    /* backward work space / outputs */
+    float* dYc;                                      /* (E*B, T, N) dL/dY through the controllers */
+    float* dH;                                       /* (G*B, 128) */
+    float* GG;                                       /* (G,T-1,B,512) dL/d[r_pre, z_pre, n_in_pre, hn] */
+    float *G_a1, *G_v1, *G_a2, *G_v2;                /* (G,T-1,B,128) dL/d pre-LN and dL/d LN-output, layers 1, 2 */
+    float* G_pre;                                    /* (G,T-1,B,N) dL/d(pre-tanh output) */
+} BiearSeqParams;
+
+/* Whole forward recurrence: for t in [0,T): band stage of frame t (both ears), then the controller step
+ * producing Q_{t+1}.  2T-1 launches on `stream`, no host synchronisation. */
+int biear_adaptive_fwd(const BiearSeqParams* p, void* stream);
+/* Whole backward recurrence (t = T-2 .. 0): per-sample gradients into GG / G_* (the caller forms the weight
+ * gradients from them with GEMMs) and the chain dL/dQ_{t+1} -> dL/dY_t, dL/dh_{t-1}. */
+int biear_adaptive_bwd(const BiearSeqParams* p, void* stream);
+/* Single controller steps (testing / profiling). */
+int biear_ctrl_step_fwd(const BiearSeqParams* p, int t, void* stream);
+int biear_ctrl_step_bwd(const BiearSeqParams* p, int t, void* stream);
 
 /*
  * Broadband interaural cross-correlation feature.  Replaces utils.py:390-420
