@@ -18,7 +18,6 @@ import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
 import threading
 import time
@@ -68,53 +67,114 @@ def synth_binaural(batch, seed, n=FS):
 
 
 class ClockSampler:
-    """nvidia-smi poller for the timed region (B200_PROFILING.md clocks line)."""
+    """In-process NVML poller for the timed region (the fields of B200_PROFILING.md's clocks line).  NVML is
+    initialised BEFORE the timed region: spawning nvidia-smi next to a running launch loop was measured to stall
+    kernel launches for ~1 s while it initialises (round-1 log: 51 ms/step vs 8 ms/step for the same code)."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+               ("sw_power_cap", 0x4))
+
+    def __init__(self, gpu_index, period_s=0.02):
+        self.period = period_s
+        self.rows = []
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.handle = None
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].isdigit() else gpu_index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self._sample()                      # first call pays NVML's lazy setup, outside the timed region
+            self.rows.clear()
+        except Exception as e:  # noqa: BLE001
+            self.handle = None
+            self.err = repr(e)
+
+    def _sample(self):
+        nv = self.nv
+        sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+        try:
+            power = nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+        except Exception:  # noqa: BLE001
+            power = None
+        try:
+            mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+        except Exception:  # noqa: BLE001
+            mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+        self.rows.append((sm, power, mask))
+
+    def _loop(self):
+        while not self.stop_flag.is_set():
+            try:
+                self._sample()
+            except Exception:  # noqa: BLE001
+                pass
+            self.stop_flag.wait(self.period)
+
+    def start(self):
+        if self.handle is None:
+            return
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.handle is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"NVML unavailable: {self.err}"]}
+        self.stop_flag.set()
+        self.thread.join(timeout=2)
+        sm = [r[0] for r in self.rows]
+        power = [r[1] for r in self.rows if r[1] is not None]
+        reasons = sorted({name for _, _, m in self.rows for name, bit in self.REASONS if m & bit})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.sm_max,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": reasons}
+
+
+class SmiSampler:
+    """Fallback when NVML cannot be loaded in-process: an nvidia-smi poller, started (and given 2 s to finish
+    its own initialisation) BEFORE the timed region so that it cannot stall the launch loop."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.gpu = gpu_index
-        self.rows = []
-        self.proc = None
-
-    def start(self):
+        import subprocess
+        self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                ["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
                  "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
+            threading.Thread(target=lambda: [self.rows.append([c.strip() for c in ln.split(",")])
+                                             for ln in self.proc.stdout], daemon=True).start()
+            time.sleep(2.0)
+        except Exception:  # noqa: BLE001
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def start(self):
+        self.first = len(self.rows)
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons, power = [], [], set(), []
+        sm, smax, power, reasons = [], [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for r in self.rows:
+        for r in self.rows[self.first:]:
             try:
-                sm.append(float(r[0]))
-                smax.append(float(r[1]))
-                power.append(float(r[2]))
-                for name, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
+                sm.append(float(r[0])), smax.append(float(r[1])), power.append(float(r[2]))
+                reasons.update(n for n, v in zip(names, r[3:7]) if v.lower().startswith("active"))
+            except Exception:  # noqa: BLE001
                 continue
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_sampler(gpu_index):
+    s = ClockSampler(gpu_index)
+    return s if s.handle is not None else SmiSampler(gpu_index)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -175,17 +235,12 @@ def run_ours(args):
     step, params = make_step(model, up)
     flat_numel = sum(p.numel() for p in params)
 
+    from biear_b200.dist import FlatGradAllReducer
+    reducer = FlatGradAllReducer(params) if dist is not None else None
+
     def allreduce_grads():
-        if dist is None:
-            return
-        flat = torch.cat([p.grad.reshape(-1) for p in params])
-        dist.all_reduce(flat)
-        flat.mul_(1.0 / world)
-        off = 0
-        for p in params:
-            n = p.numel()
-            p.grad.copy_(flat[off:off + n].view_as(p))
-            off += n
+        if reducer is not None:
+            reducer()                     # one flat-bucket NCCL all-reduce (sum, x 1/world)
 
     # resident inputs: N_ROTATE distinct batches, cycled, so a step never finds its inputs in L2
     host = [synth_binaural(B, seed=1234 + 17 * rank + i) for i in range(2)]
@@ -207,7 +262,8 @@ def run_ours(args):
         step(*dev_in[i % N_ROTATE])
         allreduce_grads()
     sync_all()
-    sampler = ClockSampler(local)
+    sampler = make_sampler(local) if rank == 0 else None
+    sync_all()
     if rank == 0:
         sampler.start()
     _lib.reset_launch_count()

@@ -1,0 +1,219 @@
+"""Drop-in namespace for the reference's ``model_torch`` module.
+
+``train_biear.py`` / ``evaluate_biear.py`` do ``from model_torch import build_model, build_model_active,
+N_SECTORS, N_DIST_CLASS`` (train_biear.py:12, evaluate_biear.py:11).  Putting this package directory first on
+``sys.path`` (route (i)) resolves that import here, and the scripts run unchanged with the
+front-end executing on the sm_100a kernels of this package.
+
+What is native and what is plain PyTorch:
+  * the binaural front-end (``bifb``) -- STFT, Gaussian band stage, Q controllers, sub-band phase, and their
+    backward -- is this package's CUDA path (frontend.py / ops.py / csrc);
+  * the back-end (ILD/IPD GRU encoders, body MLP, 8 sub-heads; model_torch.py:828-960, 1088-1110) is generic
+    cuDNN/cuBLAS work and is kept as ordinary ``torch.nn`` modules with the reference's module tree, so that
+    state-dict keys, default initialisation order (same parameters under the same seed) and the optimiser's
+    parameter groups are identical.
+
+The one structural change in ``DeepEarActiveWaveform.forward``: the sub-band phase comes out of the same band
+pass that produces Y (``bifb.forward_features``) instead of a second W(Q) rebuild from (X, Q)
+(model_torch.py:1039-1063, 1085-1086), and the four ``isfinite(...).all()`` host synchronisations
+(:1071-1074) collapse into one device-side reduction that is only read back when it fails.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .frontend import (AuralNetGammatoneFB, BinauralAdaptiveGammatoneFB,  # noqa: F401  (re-exported)
+                       BinauralAdaptiveGammatoneFB_SingleController, FramewiseAdaptiveGammatoneFB,
+                       FramewiseFixedGammatoneFB, erb_hz, erb_rate, erb_spaced_fc_and_q, inv_erb_rate,
+                       make_deltaQ_profile)
+
+N_SECTORS = 8
+N_DIST_CLASS = 5
+DATA_DIM = 100
+LATENT_DIM = 100
+
+
+def _zero_nonfinite(x):
+    return torch.nan_to_num(x, nan=0.0, posinf=0.0, neginf=0.0)
+
+
+class _PairEncoder(nn.Module):
+    """LayerNorm -> GRU(in->hidden) -> GRU(hidden->latent) -> mean over frames (model_torch.py:828-867).
+    Sub-classes define the interaural feature built from the left/right inputs."""
+
+    def __init__(self, input_dim=DATA_DIM, hidden_dim=200, latent_dim=LATENT_DIM):
+        super().__init__()
+        self.in_norm = nn.LayerNorm(input_dim)
+        self.gru1 = nn.GRU(input_dim, hidden_dim, batch_first=True)
+        self.gru2 = nn.GRU(hidden_dim, latent_dim, batch_first=True)
+
+    def interaural(self, xL, xR):
+        raise NotImplementedError
+
+    def forward(self, xL, xR):
+        seq, _ = self.gru1(self.in_norm(self.interaural(xL, xR)))
+        seq, _ = self.gru2(seq)
+        return _zero_nonfinite(seq.mean(dim=1))
+
+
+class ILDEncoder(_PairEncoder):
+    """Level difference of the log band energies, clamped to +-10 (model_torch.py:828-846)."""
+
+    def interaural(self, xL, xR):
+        return torch.clamp(_zero_nonfinite(xL - xR), -10.0, 10.0)
+
+
+class IPDEncoder(_PairEncoder):
+    """Wrapped phase difference (model_torch.py:848-867)."""
+
+    def interaural(self, xL, xR):
+        d = xL - xR
+        return _zero_nonfinite(torch.atan2(torch.sin(d), torch.cos(d)))
+
+
+def _mlp_head(out_dim):
+    return nn.Sequential(nn.Linear(100, 50), nn.ReLU(), nn.Linear(50, 10), nn.ReLU(), nn.Linear(10, out_dim))
+
+
+class SubHead(nn.Module):
+    """Per-sector head: presence logit, normalised angle in (0,1), distance-class logits (model_torch.py:869-906)."""
+
+    def __init__(self, body_dim=200, n_dist_class=N_DIST_CLASS):
+        super().__init__()
+        self.shared = nn.Sequential(nn.Linear(body_dim, 100), nn.ReLU(), nn.Dropout(0.2))
+        self.sound = _mlp_head(1)
+        self.aoa = _mlp_head(1)
+        self.dist = _mlp_head(n_dist_class)
+
+    def forward(self, body_feat):
+        h = self.shared(body_feat)
+        return self.sound(h), torch.sigmoid(self.aoa(h)), self.dist(h)
+
+
+def _body(feat_dim):
+    return nn.Sequential(nn.Linear(feat_dim, 512), nn.ReLU(), nn.Dropout(0.2),
+                         nn.Linear(512, 400), nn.ReLU(), nn.Dropout(0.2),
+                         nn.Linear(400, 200), nn.ReLU(), nn.Dropout(0.2))
+
+
+class _BackEnd(nn.Module):
+    """Encoders + CC projection + body + sector heads shared by the passive and the active model.
+    Attribute names and creation order follow model_torch.py:908-960 / 1006-1026."""
+
+    def _init_backend(self, use_cc, data_dim, latent_dim, n_sectors, n_dist_class):
+        self.use_cc = use_cc
+        self.encoder_ild = ILDEncoder(input_dim=data_dim, hidden_dim=200, latent_dim=latent_dim)
+        self.encoder_ipd = IPDEncoder(input_dim=data_dim, hidden_dim=200, latent_dim=latent_dim)
+        if use_cc:
+            self.cc_proj = nn.Linear(data_dim, latent_dim)
+        self.body = _body(2 * latent_dim + (latent_dim if use_cc else 0))
+        self.subheads = nn.ModuleList([SubHead(200, n_dist_class=n_dist_class) for _ in range(n_sectors)])
+
+    def _backend(self, x1, x2, x3, ph_l, ph_r):
+        feats = [self.encoder_ild(x1, x2), self.encoder_ipd(ph_l, ph_r)]
+        if self.use_cc:
+            feats.append(self.cc_proj(x3))
+        body = self.body(torch.cat(feats, dim=-1))
+        outs = [head(body) for head in self.subheads]
+        sound = torch.cat([o[0] for o in outs], dim=1)
+        aoa = torch.cat([o[1] for o in outs], dim=1)
+        dist = torch.stack([o[2] for o in outs], dim=1)
+        return sound, aoa, dist
+
+
+class DeepEarTorchILD(_BackEnd):
+    """Passive model on precomputed features: forward(x1, x2, x3, x4, x5) (model_torch.py:908-960)."""
+
+    def __init__(self, use_cc: bool = True, data_dim: int = DATA_DIM, latent_dim: int = LATENT_DIM,
+                 n_sectors: int = N_SECTORS, n_dist_class: int = N_DIST_CLASS):
+        super().__init__()
+        self._init_backend(use_cc, data_dim, latent_dim, n_sectors, n_dist_class)
+
+    def forward(self, x1, x2, x3, x4, x5):
+        return self._backend(x1, x2, x3, x4, x5)
+
+
+class DeepEarActiveWaveform(_BackEnd):
+    """Active model: raw binaural waveforms -> front-end -> back-end (model_torch.py:965-1112).
+
+    forward(wavL_1s, wavR_1s, x3=None) -> (sound_logits (B,S), aoa_pred (B,S), dist_logits (B,S,C)).
+    """
+
+    def __init__(self, fs=16000, timesteps=19, n_fft=1024, n_bands=DATA_DIM, use_cc=True, latent_dim=LATENT_DIM,
+                 n_sectors=N_SECTORS, n_dist_class=N_DIST_CLASS, fb_alpha: float = 0.2,
+                 fixed_frontend_q: bool = False, deltaQ_base: float = 2.0, deltaQ_low_factor: float = 0.5,
+                 deltaQ_high_factor: float = 1.0, deltaQ_mode: str = "absolute", bifb_class=None):
+        super().__init__()
+        self.fb_alpha = fb_alpha
+        cls = bifb_class if bifb_class is not None else BinauralAdaptiveGammatoneFB
+        self.bifb = cls(fs=fs, timesteps=timesteps, n_fft=n_fft, Nbands=n_bands, alpha=fb_alpha,
+                        fixed_frontend_q=bool(fixed_frontend_q), deltaQ_base=deltaQ_base,
+                        deltaQ_low_factor=deltaQ_low_factor, deltaQ_high_factor=deltaQ_high_factor,
+                        deltaQ_mode=deltaQ_mode)
+        self._init_backend(use_cc, n_bands, latent_dim, n_sectors, n_dist_class)
+        self.last_QL = self.last_QR = self.last_Q = None
+
+    def _assert_finite(self, tensors):
+        """model_torch.py:1032-1037, 1071-1074 with one device-side reduction instead of four host syncs."""
+        bad = torch.stack([(~torch.isfinite(t)).sum() for _, t in tensors])
+        if bool(bad.any()):            # the only host read on the forward path
+            for (name, t), n in zip(tensors, bad.tolist()):
+                if n:
+                    raise RuntimeError(f"[NaN/Inf] {name} has {n} non-finite values. "
+                                       f"min={t.min().item()} max={t.max().item()}")
+
+    def forward(self, wavL_1s, wavR_1s, x3=None):
+        wavL_1s = wavL_1s.float()
+        wavR_1s = wavR_1s.float()
+        if hasattr(self.bifb, "forward_features"):
+            o = self.bifb.forward_features(wavL_1s, wavR_1s, want_phase=True)
+            YL, YR, QL, QR, ph_l, ph_r = o["YL"], o["YR"], o["QL"], o["QR"], o["phaseL"], o["phaseR"]
+        else:   # a foreign bifb_class that only implements the reference's 6-tuple protocol
+            raise TypeError("bifb_class must provide forward_features(wavL, wavR, want_phase) "
+                            "(biear_b200 front-ends do); the reference's own classes run on its own model")
+        self._assert_finite((("YL", YL), ("YR", YR), ("QL", QL), ("QR", QR)))
+        self.last_QL, self.last_QR, self.last_Q = QL, QR, 0.5 * (QL + QR)
+        x1 = torch.clamp(torch.log(YL + 1e-8), -12.0, 12.0)
+        x2 = torch.clamp(torch.log(YR + 1e-8), -12.0, 12.0)
+        if self.use_cc:
+            if x3 is None:
+                x3 = torch.zeros(wavL_1s.size(0), DATA_DIM, device=wavL_1s.device)
+            x3 = x3.float()
+        return self._backend(x1, x2, x3, ph_l, ph_r)
+
+
+def build_model(use_cc: bool = True, data_dim: int = DATA_DIM, latent_dim: int = LATENT_DIM,
+                n_sectors: int = N_SECTORS, n_dist_class: int = N_DIST_CLASS) -> nn.Module:
+    """model_torch.py:1252-1265."""
+    return DeepEarTorchILD(use_cc=use_cc, data_dim=data_dim, latent_dim=latent_dim, n_sectors=n_sectors,
+                           n_dist_class=n_dist_class)
+
+
+def _build_active(bifb_class, use_cc, fs, timesteps, n_fft, data_dim, latent_dim, n_sectors, n_dist_class, fb_alpha,
+                  fixed_frontend_q, deltaQ_base, deltaQ_low_factor, deltaQ_high_factor, deltaQ_mode):
+    return DeepEarActiveWaveform(fs=fs, timesteps=timesteps, n_fft=n_fft, n_bands=data_dim, use_cc=use_cc,
+                                 latent_dim=latent_dim, n_sectors=n_sectors, n_dist_class=n_dist_class,
+                                 fb_alpha=fb_alpha, fixed_frontend_q=bool(fixed_frontend_q), deltaQ_base=deltaQ_base,
+                                 deltaQ_low_factor=deltaQ_low_factor, deltaQ_high_factor=deltaQ_high_factor,
+                                 deltaQ_mode=deltaQ_mode, bifb_class=bifb_class)
+
+
+def build_model_active(use_cc=True, fs=16000, timesteps=19, n_fft=1024, data_dim=DATA_DIM, latent_dim=LATENT_DIM,
+                       n_sectors=N_SECTORS, n_dist_class=N_DIST_CLASS, fb_alpha: float = 0.2,
+                       fixed_frontend_q: bool = False, deltaQ_base: float = 2.0, deltaQ_low_factor: float = 0.5,
+                       deltaQ_high_factor: float = 1.0, deltaQ_mode: str = "absolute") -> nn.Module:
+    """model_torch.py:1303-1334 (dual controllers)."""
+    return _build_active(None, use_cc, fs, timesteps, n_fft, data_dim, latent_dim, n_sectors, n_dist_class, fb_alpha,
+                         fixed_frontend_q, deltaQ_base, deltaQ_low_factor, deltaQ_high_factor, deltaQ_mode)
+
+
+def build_model_active_single_controller(use_cc=True, fs=16000, timesteps=19, n_fft=1024, data_dim=DATA_DIM,
+                                         latent_dim=LATENT_DIM, n_sectors=N_SECTORS, n_dist_class=N_DIST_CLASS,
+                                         fb_alpha: float = 0.2, fixed_frontend_q: bool = False,
+                                         deltaQ_base: float = 2.0, deltaQ_low_factor: float = 0.5,
+                                         deltaQ_high_factor: float = 1.0, deltaQ_mode: str = "absolute") -> nn.Module:
+    """model_torch.py:1267-1300 (one shared controller for both ears)."""
+    return _build_active(BinauralAdaptiveGammatoneFB_SingleController, use_cc, fs, timesteps, n_fft, data_dim,
+                         latent_dim, n_sectors, n_dist_class, fb_alpha, fixed_frontend_q, deltaQ_base,
+                         deltaQ_low_factor, deltaQ_high_factor, deltaQ_mode)
