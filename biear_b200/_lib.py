@@ -11,7 +11,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BIEAR_B200_LIB") or os.path.join(_HERE, "lib", "libbiear_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _p = c_void_p
 _i = c_int
@@ -23,16 +23,16 @@ _f = c_float
 class SeqParams(Structure):
     """struct BiearSeqParams of include/biear_b200.h (field for field)."""
     _fields_ = (
-        [(n, c_int32) for n in ("G", "E", "B", "T", "N", "F", "Kin", "relative", "training", "reserved")]
+        [(n, c_int32) for n in ("G", "E", "B", "T", "N", "F", "Kin", "relative", "training", "force_strict")]
         + [("seed", c_uint64)]
         + [(n, c_float) for n in ("df", "cutoff", "q_min", "q_max")]
         + [(n, c_void_p) for n in (
             "fc", "q0", "dq",
             "w_ih", "w_hh", "b_ih", "b_hh", "w1", "b1", "ln1_g", "ln1_b", "w2", "b2", "ln2_g", "ln2_b", "w3", "b3",
-            "X", "Y", "phase", "dYdQ", "dPdQ", "Q",
-            "H", "gates", "xh1", "d1", "xh2", "d2", "rstd", "delta", "flags",
+            "X", "Y", "phase", "dYdQ", "dPdQ", "Q", "delta",
+            "gates", "xh1", "d1", "xh2", "d2", "rstd", "yc", "H", "flags",
             "gY", "gP", "gQ",
-            "dYc", "dH", "GG", "G_a1", "G_v1", "G_a2", "G_v2", "G_pre")]
+            "GG", "G_a1", "G_v1", "G_a2", "G_v2", "G_pre", "workspace")]
     )
 
 
@@ -49,8 +49,9 @@ SIGNATURES = {
     "biear_cc_fwd": (_i, [_p, _p, _l, _l, _l, _i, _i, _p, _p, _i, _p, _p]),
     "biear_adaptive_fwd": (_i, [POINTER(SeqParams), _p]),
     "biear_adaptive_bwd": (_i, [POINTER(SeqParams), _p]),
-    "biear_ctrl_step_fwd": (_i, [POINTER(SeqParams), _i, _p]),
-    "biear_ctrl_step_bwd": (_i, [POINTER(SeqParams), _i, _p]),
+    "biear_adaptive_workspace_floats": (_l, [_i, _i]),
+    "biear_wgrad_scratch_floats": (_l, [_i, _i, _i, _l]),
+    "biear_ctrl_wgrad": (_i, [_p, _l, _l, _i, _p, _l, _l, _i, _i, _l, _p, _p, _p, _p]),
 }
 
 _lib = None

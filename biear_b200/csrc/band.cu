@@ -34,10 +34,6 @@ struct BandArgs {
     const float* gP; long long gp_stride;
     float* dQ; long long dq_stride;
     int accumulate;
-    // Q fallback of the adaptive recurrence (model_torch.py:378-380): when the group's flag is set (or
-    // force_q0), Q0 is used instead of Q and written back into Q_out.
-    const int* q_flags; long long rows_per_group; int force_q0;
-    const float* q0; float* q_out;
 };
 
 enum { kBandForward = 0, kBandBackward = 1 };
@@ -64,7 +60,6 @@ __global__ void __launch_bounds__(kBandThreads) band_kernel(const BandArgs a) {
         __syncthreads();
 
         const float* q_row = a.Q + item * a.q_stride;
-        const bool use_q0 = a.force_q0 || (a.q_flags && a.q_flags[item / a.rows_per_group] != 0);
         // quads are ordered by frequency = by cost; deal them to the warps in snake order
         for (int round = 0, q0 = 0; q0 < quads; ++round, q0 += kBandWarps) {
             const int slot = (round & 1) ? (kBandWarps - 1 - warp) : warp;
@@ -73,15 +68,7 @@ __global__ void __launch_bounds__(kBandThreads) band_kernel(const BandArgs a) {
             const int n = (quad << 2) + (lane >> 3);
             const bool active = n < a.N;
             const float fc = active ? __ldg(a.fc + n) : 1.0f;
-            float q = 1.0f;
-            if (active) {
-                if (use_q0) {
-                    q = __ldg(a.q0 + n);
-                    if ((lane & 7) == 0) a.q_out[item * a.q_stride + n] = q;
-                } else {
-                    q = q_row[n];
-                }
-            }
+            const float q = active ? q_row[n] : 1.0f;
             const BandParams p = band_params(fc, q, a.df, a.cutoff, a.F, active);
             const BandSums s = band_accumulate(s_spec, a.F, p, lane);
             const BandResult r = band_finish(s);
@@ -120,25 +107,6 @@ static int launch_band(const BandArgs& a, int mode, cudaStream_t st) {
         band_kernel<kBandBackward><<<grid, kBandThreads, smem, st>>>(a);
     BIEAR_LAUNCH_CHECK(mode == kBandForward ? "band_fwd_kernel" : "band_bwd_kernel");
     return 0;
-}
-
-// One frame of the adaptive recurrence: all E*B rows, outputs written in place into the (rows, T, N) buffers.
-int launch_band_frame(const BiearSeqParams& p, int t, cudaStream_t st) {
-    BandArgs a = {};
-    const long long rows = (long long)p.E * p.B;
-    a.X = p.X + (long long)t * p.F * 2; a.x_stride = (long long)p.T * p.F * 2;
-    a.Q = p.Q + (long long)t * p.N; a.q_stride = (long long)p.T * p.N;
-    a.fc = p.fc; a.items = rows; a.N = p.N; a.F = p.F; a.df = p.df; a.cutoff = p.cutoff;
-    a.Y = p.Y + (long long)t * p.N; a.y_stride = a.q_stride;
-    a.phase = p.phase ? p.phase + (long long)t * p.N : nullptr; a.phase_stride = a.q_stride;
-    a.dYdQ = p.dYdQ ? p.dYdQ + (long long)t * p.N : nullptr;
-    a.dPdQ = (p.dPdQ && p.phase) ? p.dPdQ + (long long)t * p.N : nullptr;
-    a.jac_stride = a.q_stride;
-    a.q0 = p.q0; a.q_out = p.Q + (long long)t * p.N;
-    a.rows_per_group = p.B;
-    a.force_q0 = (t == 0);                       // Q_0 = Q0 (model_torch.py:322)
-    a.q_flags = t > 0 ? p.flags + (long long)(t - 1) * p.G : nullptr;
-    return launch_band(a, kBandForward, st);
 }
 
 }  // namespace biear

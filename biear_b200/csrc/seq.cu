@@ -1,0 +1,802 @@
+// Persistent adaptive-recurrence kernels: the whole 19-frame Q recurrence of the dual front-end, forward and
+// backward, each as ONE cluster kernel.
+//
+// Replaces, for both ears at once, the frame loop of the reference
+//   model_torch.py:333-380   per frame: W(Q_t) build + contraction -> Y_t;  Y_ctrl = log1p(clamp(Y,0));
+//                            feat = [Y_ctrl, 0.2*Y_ctrl.detach()]; GRU(200->128) one step;
+//                            q_out = Linear-LayerNorm-SiLU-Dropout x2 + Linear(128->N); delta = tanh;
+//                            Q_{t+1} = clamp(Q0 (1 + dQ delta)) or clamp(Q0 + dQ delta); non-finite fallback
+//   model_torch.py:1039-1063 the second W(Q_t) build for the sub-band phase
+// (~60 library launches + 2 host syncs per frame there) and everything autograd derives from them.
+//
+// Forward:  cluster = 8 CTAs = one tile of 32 rows of one controller, resident for all T frames.  Per frame:
+//   band stage (CTA c: rows 4c..4c+3; Y/phase/Jacobians -> HBM, log1p(Y) -> every CTA's shared memory)
+//   -> GRU cell -> 2 x (Linear, LayerNorm, SiLU, Dropout) -> Linear -> tanh -> Q_{t+1} (-> HBM and -> the shared
+//   memory of the CTA that runs the band stage of that row).  Five cluster barriers per frame, no HBM round trip.
+// Backward: same cluster/tile ownership, t = T-2 .. 0: closed-form dL/dQ_{t+1} -> tanh/clamp ->
+//   transposed Linear / LayerNorm / SiLU / Dropout chain -> GRU cell backward -> dL/dh_{t-1} (registers) and
+//   dL/dY_t through the controller (shared memory of the owning CTA).  Weight gradients are NOT formed on the
+//   serial chain: the per-sample pre-activation gradients are stored (tile layout) and biear_ctrl_wgrad turns
+//   them into dW with split-K GEMMs afterwards.
+//
+// See seq_dev.cuh for the cluster/thread layout and the weight images.
+#include "band_dev.cuh"
+#include "seq_dev.cuh"
+
+namespace biear {
+
+// ==================================================================================================
+// weight images
+// ==================================================================================================
+__global__ void __launch_bounds__(256) pack_fwd_images_kernel(const BiearSeqParams p, float* __restrict__ img) {
+    const int g = blockIdx.x / kCS, c = blockIdx.x % kCS;
+    const int N = p.N, NU = bands_per_cta(N);
+    float* out = img + (long long)blockIdx.x * fwd_img_floats(N);
+    const float* w_ih = p.w_ih + (long long)g * 3 * kHid * p.Kin;
+    const float* w_hh = p.w_hh + (long long)g * 3 * kHid * kHid;
+    const float* w1 = p.w1 + (long long)g * kHid * kHid;
+    const float* w2 = p.w2 + (long long)g * kHid * kHid;
+    const float* w3 = p.w3 + (long long)g * N * kHid;
+    // gate images: consecutive threads walk k (the contiguous axis of the torch layout) for coalesced reads
+    for (int idx = threadIdx.x; idx < kU * 3 * N; idx += blockDim.x) {
+        const int k = idx % N, gu = idx / N, gate = gu % 3, u = gu / 3;
+        const long long o = gate * kHid + c * kU + u;
+        out[fwd_img_wih(N) + (k * kU + u) * 4 + gate] = fmaf(0.2f, w_ih[o * p.Kin + N + k], w_ih[o * p.Kin + k]);
+    }
+    for (int idx = threadIdx.x; idx < kU * N; idx += blockDim.x) out[fwd_img_wih(N) + idx * 4 + 3] = 0.f;
+    for (int idx = threadIdx.x; idx < kU * 3 * kHid; idx += blockDim.x) {
+        const int k = idx % kHid, gu = idx / kHid, gate = gu % 3, u = gu / 3;
+        const int o = gate * kHid + c * kU + u;
+        out[fwd_img_whh(N) + (k * kU + u) * 4 + gate] = w_hh[o * kHid + k];
+    }
+    for (int idx = threadIdx.x; idx < kU * kHid; idx += blockDim.x) out[fwd_img_whh(N) + idx * 4 + 3] = 0.f;
+    for (int idx = threadIdx.x; idx < kU * kHid; idx += blockDim.x) {
+        const int k = idx % kHid, u = idx / kHid;
+        out[fwd_img_w1(N) + k * kU + u] = w1[(c * kU + u) * kHid + k];
+        out[fwd_img_w2(N) + k * kU + u] = w2[(c * kU + u) * kHid + k];
+        const int n = c * NU + u;
+        out[fwd_img_w3(N) + k * kU + u] = (u < NU && n < N) ? w3[n * kHid + k] : 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(256) pack_bwd_images_kernel(const BiearSeqParams p, float* __restrict__ img) {
+    const int g = blockIdx.x / kCS, c = blockIdx.x % kCS;
+    const int N = p.N, NU = bands_per_cta(N);
+    float* out = img + (long long)blockIdx.x * bwd_img_floats(N);
+    const float* w_ih = p.w_ih + (long long)g * 3 * kHid * p.Kin;
+    const float* w_hh = p.w_hh + (long long)g * 3 * kHid * kHid;
+    const float* w1 = p.w1 + (long long)g * kHid * kHid;
+    const float* w2 = p.w2 + (long long)g * kHid * kHid;
+    const float* w3 = p.w3 + (long long)g * N * kHid;
+    for (int idx = threadIdx.x; idx < N * kU; idx += blockDim.x)
+        out[bwd_img_w3c(N) + idx] = w3[(idx / kU) * kHid + c * kU + (idx % kU)];
+    for (int idx = threadIdx.x; idx < kHid * kU; idx += blockDim.x) {
+        const int o = idx / kU, u = idx % kU;
+        out[bwd_img_w2c(N) + idx] = w2[o * kHid + c * kU + u];
+        out[bwd_img_w1c(N) + idx] = w1[o * kHid + c * kU + u];
+    }
+    for (int idx = threadIdx.x; idx < 3 * kHid * kU; idx += blockDim.x) {
+        const int o = idx / kU, u = idx % kU;
+        out[bwd_img_whhc(N) + idx] = w_hh[o * kHid + c * kU + u];
+        const int n = c * NU + u;
+        out[bwd_img_wihc(N) + idx] = (u < NU && n < N) ? w_ih[(long long)o * p.Kin + n] : 0.f;
+    }
+}
+
+// ==================================================================================================
+// forward
+// ==================================================================================================
+struct FwdSmem {   // offsets in floats
+    int N, tile;
+    __host__ __device__ FwdSmem(int N_, int F) : N(N_), tile(spec_tile_len(F)) {}
+    __host__ __device__ int img() const { return 0; }
+    __host__ __device__ int vec() const { return fwd_img_floats(N); }           // per-CTA constants, see V_*
+    __host__ __device__ int yc() const { return vec() + 1024; }                 // [128][32]; aliased by a2
+    __host__ __device__ int h0() const { return yc() + kHid * kR; }             // [128][32] x 2 (ping-pong)
+    __host__ __device__ int a1() const { return h0() + 2 * kHid * kR; }
+    __host__ __device__ int red() const { return a1() + kHid * kR; }            // 16 x 128
+    __host__ __device__ int stat() const { return red() + 16 * 128; }           // 2 x 256
+    __host__ __device__ int q() const { return stat() + 2 * kSeqThreads; }      // [128][4]: Q_t of this CTA's 4 rows
+    __host__ __device__ int ystage() const { return q() + kHid * kRT; }         // [4][128]
+    __host__ __device__ int spec() const { return ystage() + kRT * kHid; }      // [4][tile] float4
+    __host__ __device__ int misc() const { return spec() + kRT * tile * 4; }
+    __host__ __device__ int total() const { return misc() + 16; }
+};
+// vec area
+constexpr int V_BR = 0, V_BZ = 16, V_BIN = 32, V_BHN = 48, V_B1 = 64, V_B2 = 80, V_B3 = 96, V_Q0S = 112, V_DQS = 128;
+constexpr int V_LN1G = 256, V_LN1B = 384, V_LN2G = 512, V_LN2B = 640, V_FC = 768, V_Q0 = 896;
+
+__device__ __forceinline__ long long tile_base(const BiearSeqParams& p, int g, int t, int tiles, int tile) {
+    return ((long long)(g * (p.T - 1) + t)) * tiles + tile;
+}
+// H is (G, T, tiles, 128, 32): index 0 is the all-zero initial state, h_t sits at step index t + 1.
+__device__ __forceinline__ float* h_tile(const BiearSeqParams& p, int g, int t, int tiles, int tile) {
+    return p.H + (((long long)g * p.T + (t + 1)) * tiles + tile) * (kHid * kR);
+}
+
+// LayerNorm + SiLU + Dropout over the full rows held in buf_s ([feature][32], overwritten in place with the layer
+// output).  Every CTA of the cluster does this redundantly (the next layer needs all 128 features everywhere);
+// only the warp whose 16 features are the CTA's own slice saves them.
+__device__ __forceinline__ void ln_silu_drop_fwd(const BiearSeqParams& p, float* buf_s, float* stat_s,
+                                                 const float* __restrict__ gamma_s, const float* __restrict__ beta_s,
+                                                 int layer, int t, long long grow0, int rank, float* xh_tile,
+                                                 float* d_tile, float* rstd_tile) {
+    constexpr int PARTS = kSeqThreads / kR, FPP = kHid / PARTS;     // 8 parts of 16 features
+    const int row = threadIdx.x % kR, part = threadIdx.x / kR;
+    const int f0 = part * FPP;
+    float v[FPP];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < FPP; ++i) {
+        v[i] = buf_s[(f0 + i) * kR + row];
+        s += v[i];
+    }
+    stat_s[part * kR + row] = s;
+    __syncthreads();
+    float mean = 0.f;
+#pragma unroll
+    for (int q = 0; q < PARTS; ++q) mean += stat_s[q * kR + row];
+    mean *= (1.0f / kHid);
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < FPP; ++i) {
+        v[i] -= mean;
+        ss = fmaf(v[i], v[i], ss);
+    }
+    stat_s[kSeqThreads + part * kR + row] = ss;
+    __syncthreads();
+    float var = 0.f;
+#pragma unroll
+    for (int q = 0; q < PARTS; ++q) var += stat_s[kSeqThreads + q * kR + row];
+    const float rstd = rsqrtf(var * (1.0f / kHid) + kLnEps);
+    const bool mine = part == rank;
+    if (rank == 0 && part == 0) rstd_tile[layer * kR + row] = rstd;
+#pragma unroll
+    for (int i4 = 0; i4 < FPP / 4; ++i4) {
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (p.training) sc = dropout_scale4(p.seed, t, layer, grow0 + row, (f0 >> 2) + i4);
+        const float scv[4] = {sc.x, sc.y, sc.z, sc.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = i4 * 4 + j, f = f0 + i;
+            const float xh = v[i] * rstd;
+            const float y = fmaf(xh, gamma_s[f], beta_s[f]);
+            const float o = (y / (1.0f + expf(-y))) * scv[j];
+            buf_s[f * kR + row] = o;
+            if (mine) {
+                xh_tile[f * kR + row] = xh;
+                d_tile[f * kR + row] = o;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// Spectra of this CTA's 4 rows for frame t -> shared {abs, re, im, 0} tiles (zeros for padding rows / bins).
+__device__ __forceinline__ void load_spectra(const BiearSeqParams& p, float4* spec_s, int tile, long long grow0,
+                                             int b0, int t) {
+    for (int idx = threadIdx.x; idx < kRT * tile; idx += kSeqThreads) {
+        const int i = idx / tile, k = idx - i * tile;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < p.F && b0 + i < p.B) {
+            const float2 c = __ldg(reinterpret_cast<const float2*>(p.X) + ((grow0 + i) * p.T + t) * p.F + k);
+            v = make_float4(sqrtf(fmaf(c.x, c.x, c.y * c.y)), c.x, c.y, 0.f);
+        }
+        spec_s[idx] = v;
+    }
+}
+
+// STRICT == false: one cluster per tile, state carried in shared memory (the fast path).
+// STRICT == true : ONE cluster walks all tiles frame by frame with the state going through global memory, which
+//                  makes the reference's batch-global non-finite fallback exact; it exits at once unless the fast
+//                  path recorded a non-finite Q (or p.force_strict).
+template <bool STRICT>
+__global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqParams p, const float* __restrict__ img) {
+    extern __shared__ __align__(16) float smem[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int N = p.N, T = p.T, S = p.T - 1;
+    const int tiles = (p.B + kR - 1) / kR;
+    const int n_tiles = p.G * tiles;
+    const int NU = bands_per_cta(N);
+    const FwdSmem L(N, p.F);
+    float* img_s = smem + L.img();
+    float* vec_s = smem + L.vec();
+    float* yc_s = smem + L.yc();
+    float* a2_s = yc_s;
+    float* hbuf_s = smem + L.h0();
+    float* a1_s = smem + L.a1();
+    float* red_s = smem + L.red();
+    float* stat_s = smem + L.stat();
+    float* q_s = smem + L.q();
+    float* ystage_s = smem + L.ystage();
+    float4* spec_s = reinterpret_cast<float4*>(smem + L.spec());
+    int* ctr_s = reinterpret_cast<int*>(smem + L.misc());
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int ks = tid >> 7, slot = tid & 127, rg = slot / kU, u = slot % kU;
+    const int ug = rank * kU + u;
+    const int nu_c = max(0, min(NU, N - rank * NU));
+    const int quads = (N + 3) >> 2;
+    int* any_flag = p.flags + S * p.G;
+
+    if (STRICT) {
+        if (!p.force_strict && *reinterpret_cast<volatile int*>(any_flag) == 0) return;   // uniform over the grid
+        cluster.sync();                                       // everyone has read the old any-flag
+        for (int i = rank * kSeqThreads + tid; i < S * p.G; i += kCS * kSeqThreads) p.flags[i] = 0;
+        __threadfence();
+        cluster.sync();
+    }
+    const int tl_begin = STRICT ? 0 : (int)(blockIdx.x / kCS);
+    const int tl_end = STRICT ? n_tiles : tl_begin + 1;
+    int cur_g = -1, spec_t = -1, hsel = 0;
+
+    for (int t = 0; t < T; ++t) {
+        for (int tl = tl_begin; tl < tl_end; ++tl) {
+            const int g = tl / tiles, tile = tl % tiles;
+            const int b0 = tile * kR;
+            const long long grow0 = (long long)g * p.B + b0 + rank * kRT;   // global row of this CTA's first band-stage row
+            const int bb0 = b0 + rank * kRT;                                // its clip index
+            if (g != cur_g) {   // (re)load this CTA's weight image and constants
+                __syncthreads();
+                copy_f4(reinterpret_cast<float4*>(img_s),
+                        reinterpret_cast<const float4*>(img + (long long)(g * kCS + rank) * fwd_img_floats(N)),
+                        fwd_img_floats(N) / 4);
+                for (int i = tid; i < kHid; i += kSeqThreads) {
+                    vec_s[V_LN1G + i] = p.ln1_g[g * kHid + i];
+                    vec_s[V_LN1B + i] = p.ln1_b[g * kHid + i];
+                    vec_s[V_LN2G + i] = p.ln2_g[g * kHid + i];
+                    vec_s[V_LN2B + i] = p.ln2_b[g * kHid + i];
+                    vec_s[V_FC + i] = i < N ? p.fc[i] : 1.0f;
+                    vec_s[V_Q0 + i] = i < N ? p.q0[i] : 1.0f;
+                }
+                if (tid < kU) {
+                    const float* b_ih = p.b_ih + g * 3 * kHid;
+                    const float* b_hh = p.b_hh + g * 3 * kHid;
+                    const int o = rank * kU + tid;
+                    vec_s[V_BR + tid] = b_ih[o] + b_hh[o];
+                    vec_s[V_BZ + tid] = b_ih[kHid + o] + b_hh[kHid + o];
+                    vec_s[V_BIN + tid] = b_ih[2 * kHid + o];
+                    vec_s[V_BHN + tid] = b_hh[2 * kHid + o];
+                    vec_s[V_B1 + tid] = p.b1[g * kHid + o];
+                    vec_s[V_B2 + tid] = p.b2[g * kHid + o];
+                    const int n = rank * NU + tid;
+                    const bool own = tid < NU && n < N;
+                    vec_s[V_B3 + tid] = own ? p.b3[g * N + n] : 0.f;
+                    vec_s[V_Q0S + tid] = own ? p.q0[n] : 1.f;
+                    vec_s[V_DQS + tid] = own ? p.dq[n] : 0.f;
+                }
+                cur_g = g;
+                __syncthreads();
+            }
+            // ---- state of this (tile, frame) ---------------------------------------------------------------
+            bool fallback_prev = false;                       // Q_t was replaced by Q0 and h_{t-1} dropped
+            if (STRICT && t > 0) fallback_prev = __ldcg(p.flags + (t - 1) * p.G + g) != 0;
+            const bool use_q0 = (t == 0) || fallback_prev;
+            const bool h_zero = use_q0;
+            float* hcur_s = hbuf_s + hsel * kHid * kR;
+            float* hnext_s = hbuf_s + (hsel ^ 1) * kHid * kR;
+            if (use_q0) {
+                for (int idx = tid; idx < kRT * N; idx += kSeqThreads) {
+                    const int i = idx / N, n = idx - i * N;
+                    q_s[n * kRT + i] = vec_s[V_Q0 + n];
+                    if (bb0 + i < p.B) p.Q[((grow0 + i) * T + t) * N + n] = vec_s[V_Q0 + n];
+                }
+            } else if (STRICT) {
+                for (int idx = tid; idx < kRT * N; idx += kSeqThreads) {
+                    const int i = idx / N, n = idx - i * N;
+                    q_s[n * kRT + i] = (bb0 + i < p.B) ? __ldcg(p.Q + ((grow0 + i) * T + t) * N + n) : vec_s[V_Q0 + n];
+                }
+                const float4* hsrc = reinterpret_cast<const float4*>(h_tile(p, g, t - 1, tiles, tile));
+                for (int i = tid; i < kHid * kR / 4; i += kSeqThreads) reinterpret_cast<float4*>(hcur_s)[i] = __ldcg(hsrc + i);
+            }
+            if (STRICT && fallback_prev && rank == 0) {   // h_{t-1} was dropped: it must not feed dW_hh either
+                float4* hdst = reinterpret_cast<float4*>(h_tile(p, g, t - 1, tiles, tile));
+                for (int i = tid; i < kHid * kR / 4; i += kSeqThreads) hdst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (STRICT || spec_t != t) load_spectra(p, spec_s, L.tile, grow0, bb0, t);
+            if (tid == 0) *ctr_s = 0;
+            __syncthreads();
+
+            // ---- band stage of frame t for this CTA's 4 rows (model_torch.py:340-346, 1050-1060) ---------------
+            for (;;) {
+                int item = 0;
+                if (lane == 0) item = atomicAdd(ctr_s, 1);
+                item = __shfl_sync(0xffffffffu, item, 0);
+                if (item >= kRT * quads) break;
+                const int i = item & 3;
+                const int quad = quads - 1 - (item >> 2);      // widest (highest) bands first
+                const int n = (quad << 2) + (lane >> 3);
+                const bool active = n < N;
+                const float fc = active ? vec_s[V_FC + n] : 1.0f;
+                const float q = active ? q_s[n * kRT + i] : 1.0f;
+                const BandParams bp = band_params(fc, q, p.df, p.cutoff, p.F, active);
+                const BandSums sums = band_accumulate(spec_s + i * L.tile, p.F, bp, lane);
+                const BandResult r = band_finish(sums);
+                if (!active || (lane & 7) != 0) continue;
+                ystage_s[i * kHid + n] = log1pf(fmaxf(r.Y, 0.0f));
+                if (bb0 + i >= p.B) continue;
+                const long long e = ((grow0 + i) * T + t) * N + n;
+                p.Y[e] = r.Y;
+                const float qe = q + 1e-8f;
+                const float kappa = -fc / (qe * qe * bp.bw);
+                p.dYdQ[e] = kappa * (r.a2 - r.Yraw * r.m2);
+                if (p.phase) {
+                    p.phase[e] = atan2f(r.Zi, r.Zr);
+                    const float mag2 = r.Zr * r.Zr + r.Zi * r.Zi;
+                    p.dPdQ[e] = mag2 > 0.0f ? kappa * (r.Zr * r.z2i - r.Zi * r.z2r) / mag2 : 0.0f;
+                }
+            }
+            if (t == T - 1) {
+                // The reference runs the controller once more and discards the result (model_torch.py:361-380).
+                if (STRICT) __syncthreads();
+                continue;
+            }
+            __syncthreads();
+            const long long tb = tile_base(p, g, t, tiles, tile);
+            if (tid < N) {   // features of my 4 rows -> every CTA of the cluster (+ saved for dW_ih)
+                const float4 v = make_float4(ystage_s[tid], ystage_s[kHid + tid], ystage_s[2 * kHid + tid],
+                                             ystage_s[3 * kHid + tid]);
+#pragma unroll
+                for (int dst = 0; dst < kCS; ++dst)
+                    *reinterpret_cast<float4*>(cluster.map_shared_rank(yc_s, dst) + tid * kR + rank * kRT) = v;
+                *reinterpret_cast<float4*>(p.yc + tb * N * kR + tid * kR + rank * kRT) = v;
+            }
+            cluster.sync();   // #1: yc complete everywhere
+
+            // ---- GRU cell (torch gate order r, z, n; n = tanh(i_n + r * (W_hn h + b_hn))) ----------------------
+            {
+                float ar[kRT] = {0.f, 0.f, 0.f, 0.f}, az[kRT] = {0.f, 0.f, 0.f, 0.f};
+                float ain[kRT] = {0.f, 0.f, 0.f, 0.f}, ahn[kRT] = {0.f, 0.f, 0.f, 0.f};
+                const int kh = (N + 1) >> 1;
+                dot_rows3(ar, az, ain, yc_s + rg * kRT, reinterpret_cast<const float4*>(img_s + fwd_img_wih(N)) + u,
+                          ks ? kh : 0, ks ? N : kh);
+                if (!h_zero)
+                    dot_rows3(ar, az, ahn, hcur_s + rg * kRT, reinterpret_cast<const float4*>(img_s + fwd_img_whh(N)) + u,
+                              ks ? 64 : 0, ks ? 128 : 64);
+                float acc[16];
+#pragma unroll
+                for (int i = 0; i < kRT; ++i) {
+                    acc[i] = ar[i];
+                    acc[4 + i] = az[i];
+                    acc[8 + i] = ain[i];
+                    acc[12 + i] = ahn[i];
+                }
+                reduce_halves<16>(acc, red_s, ks, slot);
+                if (ks == 0) {
+                    const float br = vec_s[V_BR + u], bz = vec_s[V_BZ + u], bin = vec_s[V_BIN + u], bhn = vec_s[V_BHN + u];
+                    float hv[kRT], vr[kRT], vz[kRT], vn[kRT], vh[kRT];
+#pragma unroll
+                    for (int i = 0; i < kRT; ++i) {
+                        vr[i] = 1.0f / (1.0f + expf(-(acc[i] + br)));
+                        vz[i] = 1.0f / (1.0f + expf(-(acc[4 + i] + bz)));
+                        vh[i] = acc[12 + i] + bhn;
+                        vn[i] = tanhf(acc[8 + i] + bin + vr[i] * vh[i]);
+                        const float hp = h_zero ? 0.0f : hcur_s[ug * kR + rg * kRT + i];
+                        hv[i] = (1.0f - vz[i]) * vn[i] + vz[i] * hp;
+                    }
+                    store4(h_tile(p, g, t, tiles, tile) + ug * kR + rg * kRT, hv);
+                    float* gt = p.gates + tb * 4 * kHid * kR + ug * kR + rg * kRT;
+                    store4(gt, vr);
+                    store4(gt + kHid * kR, vz);
+                    store4(gt + 2 * kHid * kR, vn);
+                    store4(gt + 3 * kHid * kR, vh);
+                    broadcast_rows(cluster, hnext_s, ug, rg * kRT, hv);
+                }
+            }
+            cluster.sync();   // #2: h_t complete everywhere
+
+            // ---- Linear 1 -> LayerNorm -> SiLU -> Dropout ------------------------------------------------------
+            {
+                float acc[kRT] = {0.f, 0.f, 0.f, 0.f};
+                dot_rows(acc, hnext_s + rg * kRT, img_s + fwd_img_w1(N) + u, ks ? 64 : 0, ks ? 128 : 64);
+                reduce_halves<kRT>(acc, red_s, ks, slot);
+                if (ks == 0) {
+                    const float bb = vec_s[V_B1 + u];
+#pragma unroll
+                    for (int i = 0; i < kRT; ++i) acc[i] += bb;
+                    broadcast_rows(cluster, a1_s, ug, rg * kRT, acc);
+                }
+            }
+            cluster.sync();   // #3
+            ln_silu_drop_fwd(p, a1_s, stat_s, vec_s + V_LN1G, vec_s + V_LN1B, 0, t, (long long)g * p.B + b0, rank,
+                             p.xh1 + tb * kHid * kR, p.d1 + tb * kHid * kR, p.rstd + tb * 2 * kR);
+
+            // ---- Linear 2 -> LayerNorm -> SiLU -> Dropout ------------------------------------------------------
+            {
+                float acc[kRT] = {0.f, 0.f, 0.f, 0.f};
+                dot_rows(acc, a1_s + rg * kRT, img_s + fwd_img_w2(N) + u, ks ? 64 : 0, ks ? 128 : 64);
+                reduce_halves<kRT>(acc, red_s, ks, slot);
+                if (ks == 0) {
+                    const float bb = vec_s[V_B2 + u];
+#pragma unroll
+                    for (int i = 0; i < kRT; ++i) acc[i] += bb;
+                    broadcast_rows(cluster, a2_s, ug, rg * kRT, acc);   // a2 aliases yc: all yc reads ended before #2
+                }
+            }
+            cluster.sync();   // #4
+            ln_silu_drop_fwd(p, a2_s, stat_s, vec_s + V_LN2G, vec_s + V_LN2B, 1, t, (long long)g * p.B + b0, rank,
+                             p.xh2 + tb * kHid * kR, p.d2 + tb * kHid * kR, p.rstd + tb * 2 * kR);
+
+            // ---- Linear 3 -> tanh -> Q_{t+1} (model_torch.py:367-380) -------------------------------------------
+            {
+                float acc[kRT] = {0.f, 0.f, 0.f, 0.f};
+                const bool mine = u < nu_c;
+                if (mine) dot_rows(acc, a2_s + rg * kRT, img_s + fwd_img_w3(N) + u, ks ? 64 : 0, ks ? 128 : 64);
+                reduce_halves<kRT>(acc, red_s, ks, slot);
+                if (ks == 0 && mine) {
+                    const int n = rank * NU + u;
+                    const float bb = vec_s[V_B3 + u], q0 = vec_s[V_Q0S + u], dq = vec_s[V_DQS + u];
+                    float qv[kRT];
+                    bool bad = false;
+#pragma unroll
+                    for (int i = 0; i < kRT; ++i) {
+                        const int b = b0 + rg * kRT + i;
+                        const float delta = tanhf(acc[i] + bb);
+                        const float qu = p.relative ? q0 * (1.0f + dq * delta) : fmaf(dq, delta, q0);
+                        qv[i] = fminf(fmaxf(qu, p.q_min), p.q_max);
+                        if (b < p.B) {
+                            bad = bad || !finite_f(qu);
+                            const long long e = (((long long)g * p.B + b) * T + (t + 1)) * N + n;
+                            p.Q[e] = qv[i];
+                            p.delta[e] = delta;
+                        }
+                    }
+                    if (bad) {   // NaN / Inf: the reference falls back for the whole batch of this ear
+                        atomicOr(p.flags + t * p.G + g, 1);
+                        atomicOr(any_flag, 1);
+                    }
+                    // Q_{t+1} of rows 4rg..4rg+3 goes to the CTA that runs their band stage
+                    store4(cluster.map_shared_rank(q_s, rg) + n * kRT, qv);
+                }
+            }
+            if (!STRICT && t + 1 < T) {   // overlap the next frame's spectra with the barrier
+                load_spectra(p, spec_s, L.tile, grow0, bb0, t + 1);
+                spec_t = t + 1;
+            }
+            if (STRICT) __threadfence();   // H / Q / flags of this step visible to the whole cluster
+            cluster.sync();   // #5: Q_{t+1} delivered; a2 / yc free for the next frame
+            if (!STRICT) hsel ^= 1;   // strict: h_{t-1} is reloaded from global memory, the buffers keep their roles
+        }
+    }
+}
+
+// ==================================================================================================
+// backward
+// ==================================================================================================
+struct BwdSmem {   // offsets in floats
+    int N;
+    __host__ __device__ BwdSmem(int N_) : N(N_) {}
+    __host__ __device__ int img() const { return 0; }
+    __host__ __device__ int vec() const { return bwd_img_floats(N); }              // LN params, q0, dq
+    __host__ __device__ int bufa() const { return vec() + 1024; }                  // [128][32]; first quarter of gate
+    __host__ __device__ int gate() const { return bufa(); }                        // [4*128][32]: drp, dzp, dnp, dhn
+    __host__ __device__ int dpre() const { return gate() + 4 * kHid * kR; }        // [128][32]; aliased by bufb
+    __host__ __device__ int red() const { return dpre() + kHid * kR; }             // 8 x 128
+    __host__ __device__ int stat() const { return red() + 8 * 128; }               // 2 x 256
+    __host__ __device__ int stage() const { return stat() + 2 * kSeqThreads; }     // [4][128]
+    __host__ __device__ int dyc() const { return stage() + kRT * kHid; }           // [128][4]
+    __host__ __device__ int total() const { return dyc() + kHid * kRT; }
+};
+constexpr int VB_LN1G = 0, VB_LN1B = 128, VB_LN2G = 256, VB_LN2B = 384, VB_Q0 = 512, VB_DQ = 640;
+
+// Backward of Dropout -> SiLU -> LayerNorm on the full rows in buf_s (dL/d(layer output) on entry, dL/d(pre-LayerNorm
+// activation) on exit).  Redundant in every CTA; the warp owning the CTA's feature slice writes the saved gradients.
+__device__ __forceinline__ void ln_silu_drop_bwd(const BiearSeqParams& p, float* buf_s, float* stat_s,
+                                                 const float* __restrict__ gamma_s, const float* __restrict__ beta_s,
+                                                 int layer, int t, long long grow0, int rank,
+                                                 const float* __restrict__ xh_tile, const float* __restrict__ rstd_tile,
+                                                 float* gv_tile, float* ga_tile) {
+    constexpr int PARTS = kSeqThreads / kR, FPP = kHid / PARTS;
+    const int row = threadIdx.x % kR, part = threadIdx.x / kR;
+    const int f0 = part * FPP;
+    const bool mine = part == rank;
+    float xh[FPP], dxh[FPP];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < FPP; ++i) xh[i] = __ldg(xh_tile + (f0 + i) * kR + row);
+#pragma unroll
+    for (int i4 = 0; i4 < FPP / 4; ++i4) {
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (p.training) sc = dropout_scale4(p.seed, t, layer, grow0 + row, (f0 >> 2) + i4);
+        const float scv[4] = {sc.x, sc.y, sc.z, sc.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = i4 * 4 + j, f = f0 + i;
+            const float gm = gamma_s[f];
+            const float y = fmaf(xh[i], gm, beta_s[f]);
+            const float sg = 1.0f / (1.0f + expf(-y));
+            const float d = buf_s[f * kR + row] * scv[j];
+            const float dv = d * sg * (1.0f + y * (1.0f - sg));
+            if (mine) gv_tile[f * kR + row] = dv;
+            dxh[i] = dv * gm;
+            s1 += dxh[i];
+            s2 = fmaf(dxh[i], xh[i], s2);
+        }
+    }
+    stat_s[part * kR + row] = s1;
+    stat_s[kSeqThreads + part * kR + row] = s2;
+    __syncthreads();
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int q = 0; q < PARTS; ++q) {
+        m1 += stat_s[q * kR + row];
+        m2 += stat_s[kSeqThreads + q * kR + row];
+    }
+    m1 *= (1.0f / kHid);
+    m2 *= (1.0f / kHid);
+    const float rstd = __ldg(rstd_tile + layer * kR + row);
+#pragma unroll
+    for (int i = 0; i < FPP; ++i) {
+        const int f = f0 + i;
+        const float da = rstd * (dxh[i] - m1 - xh[i] * m2);
+        buf_s[f * kR + row] = da;
+        if (mine) ga_tile[f * kR + row] = da;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqParams p, const float* __restrict__ img) {
+    extern __shared__ __align__(16) float smem[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int N = p.N, T = p.T, S = p.T - 1;
+    const int tiles = (p.B + kR - 1) / kR;
+    const int NU = bands_per_cta(N);
+    const BwdSmem L(N);
+    float* img_s = smem + L.img();
+    float* vec_s = smem + L.vec();
+    float* bufa_s = smem + L.bufa();
+    float* gate_s = smem + L.gate();
+    float* dpre_s = smem + L.dpre();
+    float* bufb_s = dpre_s;
+    float* red_s = smem + L.red();
+    float* stat_s = smem + L.stat();
+    float* stage_s = smem + L.stage();
+    float* dyc_s = smem + L.dyc();
+    const int tid = threadIdx.x;
+    const int ks = tid >> 7, slot = tid & 127, rg = slot / kU, u = slot % kU;
+    const int ug = rank * kU + u;
+    const int nu_c = max(0, min(NU, N - rank * NU));
+    const int tl = blockIdx.x / kCS;
+    const int g = tl / tiles, tile = tl % tiles;
+    const int b0 = tile * kR;
+    const long long grow0 = (long long)g * p.B + b0 + rank * kRT;
+    const int bb0 = b0 + rank * kRT;
+
+    copy_f4(reinterpret_cast<float4*>(img_s),
+            reinterpret_cast<const float4*>(img + (long long)(g * kCS + rank) * bwd_img_floats(N)), bwd_img_floats(N) / 4);
+    for (int i = tid; i < kHid; i += kSeqThreads) {
+        vec_s[VB_LN1G + i] = p.ln1_g[g * kHid + i];
+        vec_s[VB_LN1B + i] = p.ln1_b[g * kHid + i];
+        vec_s[VB_LN2G + i] = p.ln2_g[g * kHid + i];
+        vec_s[VB_LN2B + i] = p.ln2_b[g * kHid + i];
+        vec_s[VB_Q0 + i] = i < N ? p.q0[i] : 1.0f;
+        vec_s[VB_DQ + i] = i < N ? p.dq[i] : 0.0f;
+    }
+    for (int i = tid; i < kHid * kRT; i += kSeqThreads) dyc_s[i] = 0.f;
+    float dh_carry[kRT] = {0.f, 0.f, 0.f, 0.f};     // dL/dh_t arriving from step t+1 (owned by the ks == 0 threads)
+    cluster.sync();
+
+    for (int t = S - 1; t >= 0; --t) {
+        const bool flagged = p.flags[t * p.G + g] != 0;                    // Q_{t+1} was replaced by Q0, h_t dropped
+        const bool h_reset = (t == 0) || (p.flags[(t - 1) * p.G + g] != 0);
+        const bool has_ctrl_next = (t + 1) < S;                              // a controller step consumed Y_{t+1}
+        const long long tb = tile_base(p, g, t, tiles, tile);
+
+        // ---- dL/dQ_{t+1} (external + band-stage Jacobians) -> dL/dpre, this CTA's 4 rows ---------
+        for (int idx = tid; idx < kRT * N; idx += kSeqThreads) {
+            const int i = idx / N, n = idx - i * N;
+            float dpre = 0.f;
+            if (bb0 + i < p.B && !flagged) {
+                const long long e = ((grow0 + i) * T + (t + 1)) * N + n;
+                float gy = p.gY ? __ldg(p.gY + e) : 0.f;
+                if (has_ctrl_next) gy += dyc_s[n * kRT + i];
+                float d = gy * __ldg(p.dYdQ + e);
+                if (p.gP) d = fmaf(__ldg(p.gP + e), __ldg(p.dPdQ + e), d);
+                if (p.gQ) d += __ldg(p.gQ + e);
+                const float delta = __ldg(p.delta + e);
+                const float q0 = vec_s[VB_Q0 + n], dq = vec_s[VB_DQ + n];
+                const float qu = p.relative ? q0 * (1.0f + dq * delta) : fmaf(dq, delta, q0);
+                const float scale = p.relative ? q0 * dq : dq;
+                if (qu >= p.q_min && qu <= p.q_max) dpre = d * scale * (1.0f - delta * delta);
+            }
+            stage_s[i * kHid + n] = dpre;
+        }
+        __syncthreads();
+        if (tid < N) {
+            const float4 v = make_float4(stage_s[tid], stage_s[kHid + tid], stage_s[2 * kHid + tid], stage_s[3 * kHid + tid]);
+#pragma unroll
+            for (int dst = 0; dst < kCS; ++dst)
+                *reinterpret_cast<float4*>(cluster.map_shared_rank(dpre_s, dst) + tid * kR + rank * kRT) = v;
+            *reinterpret_cast<float4*>(p.G_pre + tb * N * kR + tid * kR + rank * kRT) = v;
+        }
+        cluster.sync();   // #1
+
+        // ---- Linear 3 ^T --------------------------------------------------------------------------------------
+        {
+            float acc[kRT] = {0.f, 0.f, 0.f, 0.f};
+            const int nh = (N + 1) >> 1;
+            dot_rows(acc, dpre_s + rg * kRT, img_s + bwd_img_w3c(N) + u, ks ? nh : 0, ks ? N : nh);
+            reduce_halves<kRT>(acc, red_s, ks, slot);
+            if (ks == 0) broadcast_rows(cluster, bufa_s, ug, rg * kRT, acc);
+        }
+        cluster.sync();   // #2
+        ln_silu_drop_bwd(p, bufa_s, stat_s, vec_s + VB_LN2G, vec_s + VB_LN2B, 1, t, (long long)g * p.B + b0, rank,
+                         p.xh2 + tb * kHid * kR, p.rstd + tb * 2 * kR, p.G_v2 + tb * kHid * kR, p.G_a2 + tb * kHid * kR);
+        // ---- Linear 2 ^T --------------------------------------------------------------------------------------
+        {
+            float acc[kRT] = {0.f, 0.f, 0.f, 0.f};
+            dot_rows(acc, bufa_s + rg * kRT, img_s + bwd_img_w2c(N) + u, ks ? 64 : 0, ks ? 128 : 64);
+            reduce_halves<kRT>(acc, red_s, ks, slot);
+            if (ks == 0) broadcast_rows(cluster, bufb_s, ug, rg * kRT, acc);   // bufb aliases dpre: its reads ended before #2
+        }
+        cluster.sync();   // #3
+        ln_silu_drop_bwd(p, bufb_s, stat_s, vec_s + VB_LN1G, vec_s + VB_LN1B, 0, t, (long long)g * p.B + b0, rank,
+                         p.xh1 + tb * kHid * kR, p.rstd + tb * 2 * kR, p.G_v1 + tb * kHid * kR, p.G_a1 + tb * kHid * kR);
+        // ---- Linear 1 ^T, GRU cell backward ------------------------------------------------------------------------
+        float dh_direct[kRT] = {0.f, 0.f, 0.f, 0.f};
+        {
+            float acc[kRT] = {0.f, 0.f, 0.f, 0.f};
+            dot_rows(acc, bufb_s + rg * kRT, img_s + bwd_img_w1c(N) + u, ks ? 64 : 0, ks ? 128 : 64);
+            reduce_halves<kRT>(acc, red_s, ks, slot);
+            if (ks == 0) {
+                const float* gt = p.gates + tb * 4 * kHid * kR + ug * kR + rg * kRT;
+                const float4 r4 = __ldg(reinterpret_cast<const float4*>(gt));
+                const float4 z4 = __ldg(reinterpret_cast<const float4*>(gt + kHid * kR));
+                const float4 n4 = __ldg(reinterpret_cast<const float4*>(gt + 2 * kHid * kR));
+                const float4 h4 = __ldg(reinterpret_cast<const float4*>(gt + 3 * kHid * kR));
+                float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (!h_reset)
+                    p4 = __ldg(reinterpret_cast<const float4*>(h_tile(p, g, t - 1, tiles, tile) + ug * kR + rg * kRT));
+                const float rr[4] = {r4.x, r4.y, r4.z, r4.w}, zz[4] = {z4.x, z4.y, z4.z, z4.w};
+                const float nn[4] = {n4.x, n4.y, n4.z, n4.w}, hn[4] = {h4.x, h4.y, h4.z, h4.w};
+                const float hp[4] = {p4.x, p4.y, p4.z, p4.w};
+                float v0[kRT], v1[kRT], v2[kRT], v3[kRT];
+#pragma unroll
+                for (int i = 0; i < kRT; ++i) {
+                    float dh = acc[i];
+                    if (t < S - 1 && !flagged) dh += dh_carry[i];
+                    const float dn = dh * (1.0f - zz[i]);
+                    const float dz = dh * (hp[i] - nn[i]);
+                    dh_direct[i] = dh * zz[i];
+                    const float dnp = dn * (1.0f - nn[i] * nn[i]);
+                    v0[i] = dnp * hn[i] * rr[i] * (1.0f - rr[i]);      // dL/d r_pre
+                    v1[i] = dz * zz[i] * (1.0f - zz[i]);                // dL/d z_pre
+                    v2[i] = dnp;                                         // dL/d (i_n pre-activation)
+                    v3[i] = dnp * rr[i];                                 // dL/d (W_hn h + b_hn)
+                }
+                float* gg = p.GG + tb * 4 * kHid * kR + ug * kR + rg * kRT;
+                store4(gg, v0);
+                store4(gg + kHid * kR, v1);
+                store4(gg + 2 * kHid * kR, v2);
+                store4(gg + 3 * kHid * kR, v3);
+                broadcast_rows(cluster, gate_s, 0 * kHid + ug, rg * kRT, v0);   // gate_s[0:128] aliases bufa: free since #3
+                broadcast_rows(cluster, gate_s, 1 * kHid + ug, rg * kRT, v1);
+                broadcast_rows(cluster, gate_s, 2 * kHid + ug, rg * kRT, v2);
+                broadcast_rows(cluster, gate_s, 3 * kHid + ug, rg * kRT, v3);
+            }
+        }
+        cluster.sync();   // #4
+        // ---- dL/dh_{t-1} = z * dh + W_hh^T [drp, dzp, dhn];  dL/dY_t = W_ih[:, :N]^T [drp, dzp, dnp] * d log1p --------
+        {
+            float acc[2 * kRT] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            const float* x = gate_s + rg * kRT;
+            const float* whhc = img_s + bwd_img_whhc(N) + u;
+            const float* wihc = img_s + bwd_img_wihc(N) + u;
+            // rows o of W_hh: [0,128) r gate, [128,256) z gate, [256,384) n gate (pairs with dhn = gate block 3)
+            if (ks == 0) {
+                dot_rows(acc, x, whhc, 0, 192);
+            } else {
+                dot_rows(acc, x, whhc, 192, 256);
+                dot_rows(acc, x + kHid * kR, whhc, 256, 384);
+            }
+            const bool mine = u < nu_c;
+            if (mine) dot_rows(acc + kRT, x, wihc, ks ? 192 : 0, ks ? 384 : 192);
+            reduce_halves<2 * kRT>(acc, red_s, ks, slot);
+            if (ks == 0) {
+#pragma unroll
+                for (int i = 0; i < kRT; ++i) dh_carry[i] = acc[i] + dh_direct[i];
+                if (mine) {
+                    const int n = rank * NU + u;
+                    float dy[kRT];
+#pragma unroll
+                    for (int i = 0; i < kRT; ++i) {
+                        const int b = b0 + rg * kRT + i;
+                        float y = 0.f;
+                        if (b < p.B) y = __ldg(p.Y + (((long long)g * p.B + b) * T + t) * N + n);
+                        dy[i] = y >= 0.0f ? acc[kRT + i] / (1.0f + y) : 0.0f;
+                    }
+                    store4(cluster.map_shared_rank(dyc_s, rg) + n * kRT, dy);
+                }
+            }
+        }
+        cluster.sync();   // #5: dL/dY_t delivered; gate / dpre buffers free for the next step
+    }
+}
+
+// ==================================================================================================
+// host side
+// ==================================================================================================
+static int validate_seq(const BiearSeqParams* p, const char* who, bool backward) {
+    BIEAR_REQUIRE(p != nullptr, "%s: null parameter block", who);
+    BIEAR_REQUIRE(p->G >= 1 && p->B >= 1 && p->T >= 1 && p->N >= 1 && p->N <= kHid && p->F >= 2,
+                  "%s: bad geometry G=%d B=%d T=%d N=%d F=%d", who, p->G, p->B, p->T, p->N, p->F);
+    BIEAR_REQUIRE(p->E == p->G && p->Kin == 2 * p->N,
+                  "%s: only the dual front-end (one controller per ear, Kin = 2N) is fused; got E=%d G=%d Kin=%d",
+                  who, p->E, p->G, p->Kin);
+    BIEAR_REQUIRE(p->fc && p->q0 && p->dq && p->w_ih && p->w_hh && p->b_ih && p->b_hh && p->w1 && p->b1 && p->ln1_g &&
+                      p->ln1_b && p->w2 && p->b2 && p->ln2_g && p->ln2_b && p->w3 && p->b3,
+                  "%s: null constant / weight pointer", who);
+    BIEAR_REQUIRE(p->Y && p->Q && p->delta && p->dYdQ && p->flags && p->workspace, "%s: null output pointer", who);
+    BIEAR_REQUIRE(!p->phase == !p->dPdQ, "%s: phase and dPdQ must be given together", who);
+    if (p->T > 1)
+        BIEAR_REQUIRE(p->H && p->gates && p->xh1 && p->d1 && p->xh2 && p->d2 && p->rstd && p->yc,
+                      "%s: null saved-state pointer", who);
+    if (backward) {
+        BIEAR_REQUIRE(p->GG && p->G_a1 && p->G_v1 && p->G_a2 && p->G_v2 && p->G_pre, "%s: null backward buffer", who);
+        BIEAR_REQUIRE(!p->gP || p->dPdQ, "%s: gphase given but the forward saved no dphase/dQ", who);
+    } else {
+        BIEAR_REQUIRE(p->X, "%s: null spectra", who);
+    }
+    return 0;
+}
+
+template <typename Kern>
+static int launch_cluster(Kern kern, const char* name, int clusters, size_t smem, cudaStream_t st,
+                          const BiearSeqParams& p, const float* img) {
+    int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name);
+    if (e) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(clusters * kCS));
+    cfg.blockDim = dim3(kSeqThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = check_cuda(cudaLaunchKernelEx(&cfg, kern, p, img), name);
+    if (e) return e;
+    count_launch();
+    return 0;
+}
+
+}  // namespace biear
+
+extern "C" int64_t biear_adaptive_workspace_floats(int G, int N) {
+    using namespace biear;
+    if (G < 1 || N < 1 || N > kHid) return 0;
+    const int per_cta = fwd_img_floats(N) > bwd_img_floats(N) ? fwd_img_floats(N) : bwd_img_floats(N);
+    return (int64_t)G * kCS * per_cta;
+}
+
+extern "C" int biear_adaptive_fwd(const BiearSeqParams* p, void* stream) {
+    using namespace biear;
+    if (int e = validate_seq(p, "biear_adaptive_fwd", false)) return e;
+    cudaStream_t st = as_stream(stream);
+    const size_t smem = sizeof(float) * (size_t)FwdSmem(p->N, p->F).total();
+    BIEAR_REQUIRE(smem <= 227 * 1024, "biear_adaptive_fwd: N=%d F=%d needs %zu B of shared memory", p->N, p->F, smem);
+    const int tiles = (p->B + kR - 1) / kR;
+    pack_fwd_images_kernel<<<p->G * kCS, 256, 0, st>>>(*p, p->workspace);
+    BIEAR_LAUNCH_CHECK("pack_fwd_images_kernel");
+    if (!p->force_strict)
+        if (int e = launch_cluster(seq_fwd_kernel<false>, "seq_fwd_kernel", p->G * tiles, smem, st, *p, p->workspace)) return e;
+    // replay with batch-global fallback semantics; returns immediately unless a non-finite Q was recorded
+    return launch_cluster(seq_fwd_kernel<true>, "seq_fwd_kernel<strict>", 1, smem, st, *p, p->workspace);
+}
+
+extern "C" int biear_adaptive_bwd(const BiearSeqParams* p, void* stream) {
+    using namespace biear;
+    if (int e = validate_seq(p, "biear_adaptive_bwd", true)) return e;
+    if (p->T < 2) return 0;
+    cudaStream_t st = as_stream(stream);
+    const size_t smem = sizeof(float) * (size_t)BwdSmem(p->N).total();
+    BIEAR_REQUIRE(smem <= 227 * 1024, "biear_adaptive_bwd: N=%d needs %zu B of shared memory", p->N, smem);
+    const int tiles = (p->B + kR - 1) / kR;
+    pack_bwd_images_kernel<<<p->G * kCS, 256, 0, st>>>(*p, p->workspace);
+    BIEAR_LAUNCH_CHECK("pack_bwd_images_kernel");
+    return launch_cluster(seq_bwd_kernel, "seq_bwd_kernel", p->G * tiles, smem, st, *p, p->workspace);
+}

@@ -1,0 +1,161 @@
+// Building blocks of the persistent adaptive-recurrence kernels (seq.cu).
+//
+// One thread-block CLUSTER of 8 CTAs owns a TILE of 32 rows (clips of one ear = one controller) for the WHOLE
+// 19-frame recurrence: band stage of frame t -> log1p features -> GRU cell -> Linear/LayerNorm/SiLU/Dropout x2
+// -> Linear -> tanh -> Q_{t+1} -> band stage of frame t+1 ...  Nothing on the serial chain goes through HBM:
+//   * the controller's 173 k weights are SLICED across the cluster -- CTA c owns hidden units [16c, 16c+16) of
+//     every 128-wide layer and a 1/8 slice of the bands of the last layer -- and stay resident in shared memory
+//     for all steps (an 83 KB "image" per CTA, laid out by a pack kernel so that it is copied with 128-bit loads);
+//   * the (32 x 128) activations are exchanged between the CTAs through distributed shared memory;
+//   * CTA c runs the band stage for rows 4c .. 4c+3 of the tile and broadcasts log1p(Y) to its peers; the Q of
+//     those rows comes back from the CTAs that own the corresponding bands of the last layer.
+//
+// Thread layout of the GEMM phases (256 threads): tid = ks*128 + rg*16 + u
+//   u  in [0,16)  output unit inside the CTA's slice
+//   rg in [0,8)   row group: rows 4rg .. 4rg+3 of the tile (the rows whose band stage CTA rg runs)
+//   ks in {0,1}   half of the contraction range; the halves are summed through shared memory
+// Activations live feature-major, [feature][32 rows], in shared memory AND in the tensors saved for the backward
+// pass ("tile layout": (G, T-1, tiles, D, 32)), so a thread moves its 4 rows of one feature with one 128-bit access.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace biear {
+namespace cg = cooperative_groups;
+
+constexpr int kHid = 128;           // GRU / MLP width (model_torch.py:256-267)
+constexpr int kSeqThreads = 256;
+constexpr int kCS = 8;              // CTAs per cluster
+constexpr int kU = kHid / kCS;      // hidden units per CTA (16)
+constexpr int kR = 32;              // rows per tile
+constexpr int kRT = 4;              // rows per thread = rows per CTA in the band stage
+constexpr float kDropP = 0.1f;      // model_torch.py:261, 265
+constexpr float kLnEps = 1e-5f;
+static_assert(2 * (kR / kRT) * kU == kSeqThreads, "thread layout");
+static_assert(kR / kRT == kCS, "row groups == CTAs of the cluster");
+
+__host__ __device__ constexpr int bands_per_cta(int N) { return (N + kCS - 1) / kCS; }
+
+// ---- shared-memory weight images (offsets in floats) ------------------------------------------------------
+// forward image of CTA (g, c):
+//   wih4 [k<N][u][4]   {Weff[r,u][k], Weff[z,u][k], Weff[n,u][k], 0},  Weff = W_ih[:, :N] + 0.2 W_ih[:, N:]
+//                      (feat = [yc, 0.2*yc.detach()]  =>  W_ih feat = Weff yc)
+//   whh4 [k<128][u][4] {W_hh[r,u][k], W_hh[z,u][k], W_hh[n,u][k], 0}
+//   w1 [k<128][u], w2 [k<128][u], w3 [k<128][u] (band c*NU+u; zero beyond the CTA's slice)
+__host__ __device__ constexpr int fwd_img_wih(int) { return 0; }
+__host__ __device__ constexpr int fwd_img_whh(int N) { return N * kU * 4; }
+__host__ __device__ constexpr int fwd_img_w1(int N) { return fwd_img_whh(N) + kHid * kU * 4; }
+__host__ __device__ constexpr int fwd_img_w2(int N) { return fwd_img_w1(N) + kHid * kU; }
+__host__ __device__ constexpr int fwd_img_w3(int N) { return fwd_img_w2(N) + kHid * kU; }
+__host__ __device__ constexpr int fwd_img_floats(int N) { return fwd_img_w3(N) + kHid * kU; }
+// backward image of CTA (g, c): column slices for the transposed products
+//   w3c [n<N][u] = W3[n][16c+u];  w2c, w1c [o<128][u] = W[o][16c+u];  whhc [o<384][u] = W_hh[o][16c+u];
+//   wihc [o<384][u] = W_ih[o][c*NU+u] (first N columns only: the detached half of feat carries no gradient)
+__host__ __device__ constexpr int bwd_img_w3c(int) { return 0; }
+__host__ __device__ constexpr int bwd_img_w2c(int N) { return N * kU; }
+__host__ __device__ constexpr int bwd_img_w1c(int N) { return bwd_img_w2c(N) + kHid * kU; }
+__host__ __device__ constexpr int bwd_img_whhc(int N) { return bwd_img_w1c(N) + kHid * kU; }
+__host__ __device__ constexpr int bwd_img_wihc(int N) { return bwd_img_whhc(N) + 3 * kHid * kU; }
+__host__ __device__ constexpr int bwd_img_floats(int N) { return bwd_img_wihc(N) + 3 * kHid * kU; }
+
+// ---- Philox4x32-10 (counter-based RNG for the dropout masks; regenerated in the backward, not stored) ------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+    const unsigned int M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const unsigned int hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        const unsigned int hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0;
+        key.y += W1;
+    }
+    return ctr;
+}
+
+__device__ __forceinline__ float keep_scale(unsigned int v) {
+    const float uni = (float)(v >> 8) * (1.0f / 16777216.0f);    // [0,1)
+    return uni >= kDropP ? 1.0f / (1.0f - kDropP) : 0.0f;
+}
+
+// keep-mask scales (0 or 1/(1-p)) of features 4*fq .. 4*fq+3 of (step, layer, global row)
+__device__ __forceinline__ float4 dropout_scale4(unsigned long long seed, int step, int layer, long long row, int fq) {
+    const uint4 r = philox4x32_10(make_uint4((unsigned)row, (unsigned)(row >> 32), (unsigned)(step * 2 + layer), (unsigned)fq),
+                                  make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+    return make_float4(keep_scale(r.x), keep_scale(r.y), keep_scale(r.z), keep_scale(r.w));
+}
+
+// 128-bit global -> shared copy of `n4` float4 by the whole CTA, loads batched 8 deep
+__device__ __forceinline__ void copy_f4(float4* __restrict__ dst, const float4* __restrict__ src, int n4) {
+    int i = threadIdx.x;
+    for (; i + 7 * kSeqThreads < n4; i += 8 * kSeqThreads) {
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __ldg(src + i + j * kSeqThreads);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[i + j * kSeqThreads] = v[j];
+    }
+    for (; i < n4; i += kSeqThreads) dst[i] = __ldg(src + i);
+}
+
+// acc[i] += sum_{k in [k0,k1)} x_s[k*32 + i] * w_s[k*16]     (x_s / w_s already offset to the thread's rows / unit)
+__device__ __forceinline__ void dot_rows(float acc[kRT], const float* __restrict__ x_s, const float* __restrict__ w_s,
+                                         int k0, int k1) {
+#pragma unroll 8
+    for (int k = k0; k < k1; ++k) {
+        const float4 x = *reinterpret_cast<const float4*>(x_s + k * kR);
+        const float wk = w_s[k * kU];
+        acc[0] = fmaf(wk, x.x, acc[0]);
+        acc[1] = fmaf(wk, x.y, acc[1]);
+        acc[2] = fmaf(wk, x.z, acc[2]);
+        acc[3] = fmaf(wk, x.w, acc[3]);
+    }
+}
+
+// Three gate rows at once: the weights of one k are a float4 {r, z, n, -}.
+__device__ __forceinline__ void dot_rows3(float a0[kRT], float a1[kRT], float a2[kRT], const float* __restrict__ x_s,
+                                          const float4* __restrict__ w4_s, int k0, int k1) {
+#pragma unroll 4
+    for (int k = k0; k < k1; ++k) {
+        const float4 x = *reinterpret_cast<const float4*>(x_s + k * kR);
+        const float4 w = w4_s[k * kU];
+        a0[0] = fmaf(w.x, x.x, a0[0]); a0[1] = fmaf(w.x, x.y, a0[1]); a0[2] = fmaf(w.x, x.z, a0[2]); a0[3] = fmaf(w.x, x.w, a0[3]);
+        a1[0] = fmaf(w.y, x.x, a1[0]); a1[1] = fmaf(w.y, x.y, a1[1]); a1[2] = fmaf(w.y, x.z, a1[2]); a1[3] = fmaf(w.y, x.w, a1[3]);
+        a2[0] = fmaf(w.z, x.x, a2[0]); a2[1] = fmaf(w.z, x.y, a2[1]); a2[2] = fmaf(w.z, x.z, a2[2]); a2[3] = fmaf(w.z, x.w, a2[3]);
+    }
+}
+
+// Sum the two k-halves: the ks == 1 threads park their accumulators, the ks == 0 threads add them.
+// red_s holds NACC floats for each of the 128 (rg,u) slots.  Contains two block barriers.
+template <int NACC>
+__device__ __forceinline__ void reduce_halves(float* acc, float* red_s, int ks, int slot) {
+    __syncthreads();
+    if (ks == 1) {
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) red_s[i * 128 + slot] = acc[i];
+    }
+    __syncthreads();
+    if (ks == 0) {
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) acc[i] += red_s[i * 128 + slot];
+    }
+}
+
+// Write 4 row values of one feature into the [feature][32] buffer of every CTA of the cluster.
+__device__ __forceinline__ void broadcast_rows(cg::cluster_group& cluster, float* buf_s, int feature, int row0,
+                                               const float v[kRT]) {
+    const float4 val = make_float4(v[0], v[1], v[2], v[3]);
+#pragma unroll
+    for (int dst = 0; dst < kCS; ++dst) {
+        float* remote = cluster.map_shared_rank(buf_s, dst);
+        *reinterpret_cast<float4*>(remote + feature * kR + row0) = val;
+    }
+}
+
+__device__ __forceinline__ void store4(float* p, const float v[kRT]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+__device__ __forceinline__ bool finite_f(float v) { return fabsf(v) <= 3.402823466e+38f; }
+
+}  // namespace biear

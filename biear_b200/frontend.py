@@ -180,7 +180,7 @@ def _adaptive_chain(x: torch.Tensor, ears: int, ctrl_mods, fc, q0, dq_vec, dq_mo
     G = len(ctrl_mods)
     N = fc.numel()
     xr = torch.view_as_real(x)
-    if engine == "fused":
+    if engine in ("fused", "fused-strict"):
         if shared or G != ears or N > 128:
             raise NotImplementedError("the fused recurrence covers the dual front-end with at most 128 bands")
         st = lambda f: torch.stack([f(m) for m in ctrl_mods])
@@ -193,7 +193,7 @@ def _adaptive_chain(x: torch.Tensor, ears: int, ctrl_mods, fc, q0, dq_vec, dq_mo
              "w3": st(lambda m: m.q_out[8].weight), "b3": st(lambda m: m.q_out[8].bias)}
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if training else 0   # CPU generator: no device sync
         return ops.adaptive_sequence(xr, fc, q0, dq_vec, w, dq_mode == "relative", training, want_phase, cutoff,
-                                     df, seed)
+                                     df, seed, strict=(engine == "fused-strict"))
     stack = _ControllerStack(ctrl_mods)
     q0g = q0.view(1, 1, N)
     dqg = dq_vec.view(1, 1, N)
@@ -342,7 +342,8 @@ class BinauralAdaptiveGammatoneFB(nn.Module):
         self.fb_L = mk()
         self.fb_R = mk()
         self.freeze_Q = False   # kept for compatibility; like the reference it is not propagated to fb_L/fb_R
-        # "fused": one C call runs the whole recurrence on the cluster kernels of csrc/ctrl.cu;
+        # "fused": the whole recurrence in one persistent cluster kernel per direction (csrc/seq.cu);
+        # "fused-strict": only its batch-global-fallback replay pass (testing);
         # "chain": per-frame band kernel + batched torch controller (kept as a cross-check)
         self.engine = "fused"
 

@@ -249,19 +249,35 @@ def _fill(params, **tensors):
         setattr(params, k, v.data_ptr() if v is not None else None)
 
 
+TILE = 32   # rows per tile of the "tile layout" tensors (G, T-1, tiles, D, 32), see include/biear_b200.h
+
+
+def ctrl_wgrad(a: torch.Tensor, do: int, bm: torch.Tensor, di: int, chunks: int, want_bias: bool = True):
+    """dW (G, do, di) [, db (G, do)] from tile-layout operands a (G, chunks', Da, 32) and bm (G, chunks', Db, 32):
+    the first `do` / `di` features of each and the first `chunks` chunks are used (biear_ctrl_wgrad)."""
+    G = a.shape[0]
+    dev = a.device
+    lib = _prepare(dev)
+    dw = torch.empty((G, do, di), dtype=torch.float32, device=dev)
+    db = torch.empty((G, do), dtype=torch.float32, device=dev) if want_bias else None
+    scratch = torch.empty(int(lib.biear_wgrad_scratch_floats(G, do, di, chunks)), dtype=torch.float32, device=dev)
+    _lib.check(lib.biear_ctrl_wgrad(_ptr(a), a.stride(0), a.stride(1), do, _ptr(bm), bm.stride(0), bm.stride(1), di, G,
+                                    chunks, _ptr(dw), _ptr(db), _ptr(scratch), _stream(dev)), "biear_ctrl_wgrad")
+    return dw, db
+
+
 class AdaptiveSequence(torch.autograd.Function):
     """The whole 19-frame Q recurrence of the dual front-end as one autograd node.
 
-    forward : T band-stage launches + (T-1) fused controller steps, issued from C (biear_adaptive_fwd);
-    backward: (T-1) fused controller-step backward launches (biear_adaptive_bwd) that carry
-              dL/dQ_{t+1} -> dL/dY_t, dL/dh_{t-1} down the chain and leave per-sample pre-activation
-              gradients, from which the weight gradients are formed with batched GEMMs off the chain.
+    forward : ONE persistent cluster kernel (biear_adaptive_fwd) carries every 32-row tile through all frames;
+    backward: ONE persistent cluster kernel (biear_adaptive_bwd) runs the chain t = T-2 .. 0 and leaves the
+              per-sample pre-activation gradients, from which biear_ctrl_wgrad forms the weight gradients.
     Inputs : xr (E*B,T,F,2), fc/q0/dq (N), 14 weight tensors stacked over the G = E controllers.
     Outputs: Y (E*B,T,N), Q (G*B,T,N), phase (E*B,T,N) [empty when want_phase is False].
     """
 
     @staticmethod
-    def forward(ctx, xr, fc, q0, dq, relative, training, want_phase, cutoff, df, seed, *weights):
+    def forward(ctx, xr, fc, q0, dq, relative, training, want_phase, cutoff, df, seed, strict, *weights):
         ctx.set_materialize_grads(False)
         _need_cuda(xr, "X")
         dev = xr.device
@@ -273,31 +289,36 @@ class AdaptiveSequence(torch.autograd.Function):
         for name, w in zip(WEIGHT_NAMES, weights):
             _need_cuda(w, name)
         Kin = weights[0].shape[2]
-        need_grad = any(ctx.needs_input_grad[10:])
+        need_grad = any(ctx.needs_input_grad[11:])
         f32 = dict(dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             lib = _prepare(dev)
             Y = torch.empty((rows, T, N), **f32)
             Q = torch.empty((rows, T, N), **f32)
+            D = torch.empty((rows, T, N), **f32)
             P = torch.empty((rows, T, N), **f32) if want_phase else None
             dY = torch.empty((rows, T, N), **f32)
             dP = torch.empty((rows, T, N), **f32) if want_phase else None
             S = max(T - 1, 1)
-            sv = {k: torch.empty((G, S, B, d), **f32) for k, d in
-                  (("H", HID), ("gates", 4 * HID), ("xh1", HID), ("d1", HID), ("xh2", HID), ("d2", HID), ("rstd", 2),
-                   ("delta", N))}
-            flags = torch.zeros((S, G), dtype=torch.int32, device=dev)
+            tiles = (B + TILE - 1) // TILE
+            # h_t lives at step index t+1 of H; H[:, 0] = 0 is "h_{-1}", so H[:, :S] are the GRU's previous states
+            H = torch.empty((G, S + 1, tiles, HID, TILE), **f32)
+            H[:, 0].zero_()
+            sv = {k: torch.empty((G, S, tiles, d, TILE), **f32) for k, d in
+                  (("gates", 4 * HID), ("xh1", HID), ("d1", HID), ("xh2", HID), ("d2", HID), ("rstd", 2), ("yc", N))}
+            flags = torch.zeros((S * G + 1,), dtype=torch.int32, device=dev)
+            work = torch.empty(int(lib.biear_adaptive_workspace_floats(G, N)), **f32)
             prm = _lib.SeqParams()
             prm.G, prm.E, prm.B, prm.T, prm.N, prm.F, prm.Kin = G, G, B, T, N, F, Kin
-            prm.relative, prm.training, prm.seed = int(relative), int(training), int(seed)
+            prm.relative, prm.training, prm.seed, prm.force_strict = int(relative), int(training), int(seed), int(strict)
             prm.df, prm.cutoff, prm.q_min, prm.q_max = float(df), float(cutoff), 0.05, 30.0
-            _fill(prm, fc=fc, q0=q0, dq=dq, X=xr, Y=Y, phase=P, dYdQ=dY, dPdQ=dP, Q=Q, flags=flags, **sv,
-                  **dict(zip(WEIGHT_NAMES, weights)))
+            _fill(prm, fc=fc, q0=q0, dq=dq, X=xr, Y=Y, phase=P, dYdQ=dY, dPdQ=dP, Q=Q, delta=D, flags=flags,
+                  workspace=work, H=H, **sv, **dict(zip(WEIGHT_NAMES, weights)))
             from ctypes import byref
             _lib.check(lib.biear_adaptive_fwd(byref(prm), _stream(dev)), "biear_adaptive_fwd")
         ctx.prm = prm
-        ctx.keep = (xr, fc, q0, dq, weights, Y, Q, P, dY, dP, sv, flags)   # owners of every pointer in prm
-        ctx.dims = (G, B, T, N, Kin)
+        ctx.keep = (xr, fc, q0, dq, weights, Y, Q, D, P, dY, dP, sv, flags, work, H)   # owners of every pointer
+        ctx.dims = (G, B, T, N, Kin, tiles)
         if P is None:
             P = Y.new_empty(0)
             ctx.mark_non_differentiable(P)
@@ -308,11 +329,11 @@ class AdaptiveSequence(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gY, gQ, gP):
         from ctypes import byref
-        xr, fc, q0, dq, weights, Y, Q, P, dY, dP, sv, flags = ctx.keep
-        G, B, T, N, Kin = ctx.dims
-        none10 = (None,) * 10
+        xr, fc, q0, dq, weights, Y, Q, D, P, dY, dP, sv, flags, work, H = ctx.keep
+        G, B, T, N, Kin, tiles = ctx.dims
+        none11 = (None,) * 11
         if T < 2 or (gY is None and gQ is None and gP is None):
-            return none10 + (None,) * len(WEIGHT_NAMES)
+            return none11 + (None,) * len(WEIGHT_NAMES)
         dev = Y.device
         f32 = dict(dtype=torch.float32, device=dev)
         S = T - 1
@@ -321,47 +342,40 @@ class AdaptiveSequence(torch.autograd.Function):
         gP = gP.contiguous() if (gP is not None and P is not None) else None
         with torch.cuda.device(dev):
             lib = _prepare(dev)
-            wk = {"dYc": torch.empty((G * B, T, N), **f32), "dH": torch.empty((G * B, HID), **f32),
-                  "GG": torch.empty((G, S, B, 4 * HID), **f32), "G_a1": torch.empty((G, S, B, HID), **f32),
-                  "G_v1": torch.empty((G, S, B, HID), **f32), "G_a2": torch.empty((G, S, B, HID), **f32),
-                  "G_v2": torch.empty((G, S, B, HID), **f32), "G_pre": torch.empty((G, S, B, N), **f32)}
+            wk = {k: torch.empty((G, S, tiles, d, TILE), **f32) for k, d in
+                  (("GG", 4 * HID), ("G_a1", HID), ("G_v1", HID), ("G_a2", HID), ("G_v2", HID), ("G_pre", N))}
             prm = ctx.prm
             _fill(prm, gY=gY, gQ=gQ, gP=gP, **wk)
             _lib.check(lib.biear_adaptive_bwd(byref(prm), _stream(dev)), "biear_adaptive_bwd")
             _fill(prm, gY=None, gQ=None, gP=None)
 
-            # ---- weight gradients: a few large batched GEMMs over all (step, clip) samples, off the chain ----
-            M = S * B
-            GG = wk["GG"].view(G, M, 4 * HID)
-            yc = torch.log1p(torch.clamp(Y.view(G, B, T, N)[:, :, :S], min=0.0)).transpose(1, 2).reshape(G, M, N)
-            keep = (flags == 0).to(torch.float32).t().reshape(G, S, 1, 1)             # h_t survives into step t+1
-            H = sv["H"]
-            hprev = torch.cat([torch.zeros((G, 1, B, HID), **f32), H[:, :-1] * keep[:, :-1]], dim=1).view(G, M, HID)
-            g_i = GG[:, :, :3 * HID]
-            a = torch.bmm(g_i.transpose(1, 2), yc)                                       # (G,384,N)
-            d_w_ih = torch.cat([a, 0.2 * a], dim=2) if Kin == 2 * N else None
-            g_rz, g_hn = GG[:, :, :2 * HID], GG[:, :, 3 * HID:]
-            d_w_hh = torch.cat([torch.bmm(g_rz.transpose(1, 2), hprev), torch.bmm(g_hn.transpose(1, 2), hprev)], dim=1)
-            d_b_ih = g_i.sum(1)
-            d_b_hh = torch.cat([g_rz.sum(1), g_hn.sum(1)], dim=1)
-
-            def lin(gout, xin):
-                go = gout.view(G, M, -1)
-                return torch.bmm(go.transpose(1, 2), xin.view(G, M, -1)), go.sum(1)
-
-            d_w1, d_b1 = lin(wk["G_a1"], H)
-            d_w2, d_b2 = lin(wk["G_a2"], sv["d1"])
-            d_w3, d_b3 = lin(wk["G_pre"], sv["d2"])
-            gv1, gv2 = wk["G_v1"].view(G, M, HID), wk["G_v2"].view(G, M, HID)
-            d_g1, d_be1 = (gv1 * sv["xh1"].view(G, M, HID)).sum(1), gv1.sum(1)
-            d_g2, d_be2 = (gv2 * sv["xh2"].view(G, M, HID)).sum(1), gv2.sum(1)
+            # ---- weight gradients: split-K GEMMs over all (step, tile) chunks, off the serial chain ----
+            K = S * tiles
+            fl = lambda t: t.view(G, K, t.shape[3], TILE)
+            GG = fl(wk["GG"])
+            Hk = H.view(G, (S + 1) * tiles, HID, TILE)      # chunk = (step, tile); group stride covers S+1 steps
+            h_prev, h_cur = Hk[:, :K], Hk[:, tiles:]
+            a, d_b_ih = ctrl_wgrad(GG, 3 * HID, fl(sv["yc"]), N, K)                      # dL/dW_ih[:, :N]
+            d_w_ih = torch.cat([a, 0.2 * a], dim=2) if Kin == 2 * N else None            # feat = [yc, 0.2 yc.detach()]
+            d_rz, _ = ctrl_wgrad(GG, 2 * HID, h_prev, HID, K, want_bias=False)           # r, z rows of W_hh
+            GGn = GG[:, :, 3 * HID:]                                                     # dL/d(W_hn h + b_hn)
+            d_n, d_b_hn = ctrl_wgrad(GGn, HID, h_prev, HID, K)
+            d_w_hh = torch.cat([d_rz, d_n], dim=1)
+            d_b_hh = torch.cat([d_b_ih[:, :2 * HID], d_b_hn], dim=1)
+            d_w1, d_b1 = ctrl_wgrad(fl(wk["G_a1"]), HID, h_cur, HID, K)
+            d_w2, d_b2 = ctrl_wgrad(fl(wk["G_a2"]), HID, fl(sv["d1"]), HID, K)
+            d_w3, d_b3 = ctrl_wgrad(fl(wk["G_pre"]), N, fl(sv["d2"]), HID, K)
+            gv1, gv2 = fl(wk["G_v1"]), fl(wk["G_v2"])
+            d_g1, d_be1 = (gv1 * fl(sv["xh1"])).sum((1, 3)), gv1.sum((1, 3))
+            d_g2, d_be2 = (gv2 * fl(sv["xh2"])).sum((1, 3)), gv2.sum((1, 3))
         grads = (d_w_ih, d_w_hh, d_b_ih, d_b_hh, d_w1, d_b1, d_g1, d_be1, d_w2, d_b2, d_g2, d_be2, d_w3, d_b3)
-        return none10 + grads
+        return none11 + grads
 
 
 def adaptive_sequence(xr, fc, q0, dq, weights, relative: bool, training: bool, want_phase: bool,
-                      cutoff: float, df: float, seed: int = 0):
-    """weights: dict name -> (G, ...) tensor (WEIGHT_NAMES).  Returns Y, Q, phase|None."""
-    y, q, ph = AdaptiveSequence.apply(xr, fc, q0, dq, relative, training, want_phase, cutoff, df, seed,
+                      cutoff: float, df: float, seed: int = 0, strict: bool = False):
+    """weights: dict name -> (G, ...) tensor (WEIGHT_NAMES).  Returns Y, Q, phase|None.
+    strict=True skips the fast pass and runs the batch-global-fallback replay pass only (testing)."""
+    y, q, ph = AdaptiveSequence.apply(xr, fc, q0, dq, relative, training, want_phase, cutoff, df, seed, strict,
                                       *[weights[k] for k in WEIGHT_NAMES])
     return y, q, (ph if want_phase else None)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BIEAR_ABI_VERSION 3
+#define BIEAR_ABI_VERSION 4
 #define BIEAR_EINVAL (-1)
 
 /* ABI version (== BIEAR_ABI_VERSION of the library that was built). */
@@ -92,15 +92,18 @@ int biear_band_bwd(const float* X, int64_t x_stride, const float* Q, int64_t q_s
  * Parameter block of the fused adaptive recurrence (dual front-end: one Q controller per ear).
  * Replaces the frame loop of FramewiseAdaptiveGammatoneFB.forward (model_torch.py:333-380) for both ears
  * and DeepEarActiveWaveform._subband_phase_from_X (:1039-1063), and their autograd backward.
- * Row order everywhere: ear-major, row = ear * B + clip.  "saved" tensors are laid out (G, T-1, B, D):
- * index ((g * (T-1) + t) * B + b) * D, so that one controller's samples of all steps are contiguous.
+ * Row order of the row-major tensors: ear-major, row = ear * B + clip.
+ * "Tile layout" tensors are (G, T-1, tiles, D, 32) with tiles = ceil(B / 32): 32 consecutive clips of one
+ * controller form a tile, stored feature-major ([D][32]); rows of the last tile beyond B are padding (their
+ * gradient entries are exactly zero).  The forward writes them, the backward reads them and writes the
+ * per-sample pre-activation gradients in the same layout; biear_ctrl_wgrad turns those into weight gradients.
  */
 typedef struct BiearSeqParams {
     /* geometry */
-    int32_t G, E, B, T, N, F, Kin;   /* controllers, ears, clips, frames, bands, bins, controller input width */
+    int32_t G, E, B, T, N, F, Kin;   /* controllers, ears, clips, frames, bands (<= 128), bins, controller input width */
     int32_t relative;                /* deltaQ_mode: 1 = Q0 (1 + dQ delta), 0 = Q0 + dQ delta */
     int32_t training;                /* dropout on (p = 0.1, Philox keyed by seed) */
-    int32_t reserved;
+    int32_t force_strict;            /* testing: skip the optimistic pass, run the batch-global (strict) pass only */
     uint64_t seed;
     float df, cutoff, q_min, q_max;
     /* constants (N) */
@@ -112,31 +115,54 @@ typedef struct BiearSeqParams {
     const float *w3, *b3;                            /* (G,N,128) (G,N) */
     /* spectra (E*B, T, F, 2) */
     const float* X;
-    /* forward outputs (E*B, T, N); phase / dPdQ nullable together */
+    /* forward outputs, row-major (E*B, T, N); phase / dPdQ nullable together */
     float *Y, *phase, *dYdQ, *dPdQ;
-    float* Q;                                        /* (G*B, T, N) */
-    /* saved by the forward for the backward */
-    float *H, *gates, *xh1, *d1, *xh2, *d2, *rstd, *delta;   /* D = 128, 512 (r,z,n,hn), 128 x4, 2, N */
-    int32_t* flags;                                  /* (T-1, G), zero-initialised: non-finite-Q fallback taken */
+    float *Q, *delta;                                /* (G*B, T, N): Q used for frame t; tanh output that produced it */
+    /* saved by the forward for the backward, tile layout, D = 512 (r,z,n,hn), 128 x4, 2, N */
+    float *gates, *xh1, *d1, *xh2, *d2, *rstd, *yc;
+    /* GRU states (G, T, tiles, 128, 32): step index 0 is h_{-1} = 0 and must be zeroed by the caller, h_t is written
+       at step index t+1 -- so H[:, :T-1] are the "previous states" and H[:, 1:] the "new states" of the T-1 steps */
+    float* H;
+    int32_t* flags;                                  /* ((T-1)*G + 1), zero-initialised by the caller: flags[t*G+g] != 0
+                                                        <=> the non-finite-Q fallback (model_torch.py:378-380) was
+                                                        taken after step t for controller g; last entry: any */
     /* backward inputs (nullable): dL/dY, dL/dphase (E*B,T,N), dL/dQ (G*B,T,N) */
     const float *gY, *gP, *gQ;
-    /* backward work space / outputs */
-    float* dYc;                                      /* (E*B, T, N) dL/dY through the controllers */
-    float* dH;                                       /* (G*B, 128) */
-    float* GG;                                       /* (G,T-1,B,512) dL/d[r_pre, z_pre, n_in_pre, hn] */
-    float *G_a1, *G_v1, *G_a2, *G_v2;                /* (G,T-1,B,128) dL/d pre-LN and dL/d LN-output, layers 1, 2 */
-    float* G_pre;                                    /* (G,T-1,B,N) dL/d(pre-tanh output) */
+    /* backward outputs, tile layout: dL/d[r_pre, z_pre, n_in_pre, hn] (D = 512); dL/d pre-LN and dL/d LN-output of
+       layers 1, 2 (D = 128 each); dL/d(pre-tanh output) (D = N) */
+    float *GG, *G_a1, *G_v1, *G_a2, *G_v2, *G_pre;
+    /* scratch: biear_adaptive_workspace_floats(G, N) floats (packed per-CTA weight images) */
+    float* workspace;
 } BiearSeqParams;
 
-/* Whole forward recurrence: for t in [0,T): band stage of frame t (both ears), then the controller step
- * producing Q_{t+1}.  2T-1 launches on `stream`, no host synchronisation. */
+/* Floats of scratch the two calls below need in BiearSeqParams.workspace. */
+int64_t biear_adaptive_workspace_floats(int G, int N);
+
+/* Whole forward recurrence in ONE persistent cluster kernel (plus a weight-packing launch and a conditional
+ * replay launch that exits immediately unless a non-finite Q was produced): each cluster of 8 CTAs carries 32 rows
+ * through all T frames with the controller weights and the recurrent state resident in (distributed) shared
+ * memory.  No host synchronisation.
+ * Non-finite fallback: the reference resets Q to Q0 and the GRU state for the WHOLE batch of an ear when any
+ * Q_{t+1} is non-finite (model_torch.py:378-380).  The persistent pass records such events in `flags`; if any
+ * occurred, the replay launch recomputes the recurrence with exactly those batch-global semantics. */
 int biear_adaptive_fwd(const BiearSeqParams* p, void* stream);
-/* Whole backward recurrence (t = T-2 .. 0): per-sample gradients into GG / G_* (the caller forms the weight
- * gradients from them with GEMMs) and the chain dL/dQ_{t+1} -> dL/dY_t, dL/dh_{t-1}. */
+/* Whole backward recurrence (t = T-2 .. 0) in one persistent cluster kernel: applies the band stage's closed-form
+ * dQ, carries dL/dQ_{t+1} -> dL/dY_t, dL/dh_{t-1} down the chain in shared memory / registers and
+ * writes the per-sample pre-activation gradients GG / G_* (tile layout). */
 int biear_adaptive_bwd(const BiearSeqParams* p, void* stream);
-/* Single controller steps (testing / profiling). */
-int biear_ctrl_step_fwd(const BiearSeqParams* p, int t, void* stream);
-int biear_ctrl_step_bwd(const BiearSeqParams* p, int t, void* stream);
+
+/*
+ * Weight gradient of one Linear layer from tile-layout operands:
+ *   dW[g][o][i] = sum_{k < chunks, r < 32} A[g][k][o][r] * Bm[g][k][i][r]      (o < Do, i < Di)
+ *   db[g][o]    = sum_{k, r} A[g][k][o][r]                                      (db nullable)
+ * A is (G, chunks, Do, 32) with chunk stride a_chunk_stride floats and group stride a_group_stride, likewise Bm;
+ * `scratch` holds biear_wgrad_scratch_floats(G, Do, Di, chunks) floats of split-K partials (deterministic
+ * two-pass reduction, no atomics).  Replaces the weight-gradient GEMMs autograd runs for model_torch.py:256-267.
+ */
+int64_t biear_wgrad_scratch_floats(int G, int Do, int Di, int64_t chunks);
+int biear_ctrl_wgrad(const float* A, int64_t a_group_stride, int64_t a_chunk_stride, int Do,
+                     const float* Bm, int64_t b_group_stride, int64_t b_chunk_stride, int Di,
+                     int G, int64_t chunks, float* dW, float* db, float* scratch, void* stream);
 
 /*
  * Broadband interaural cross-correlation feature.  Replaces utils.py:390-420

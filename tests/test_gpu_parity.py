@@ -254,7 +254,7 @@ def test_fixed_frontend_and_ragged(bb, golden):
             fixed(tl[0], tr[0])
 
 
-@pytest.mark.parametrize("engine", ["fused", "chain"])
+@pytest.mark.parametrize("engine", ["fused", "fused-strict", "chain"])
 @pytest.mark.parametrize("tag,batch,seeds,kw,std", [
     ("dual32", 3, (11, 12), CONFIG_YAML, 0.02),
     ("clamp32", 2, (21, 22), CONFIG_YAML, 0.3),
@@ -298,7 +298,8 @@ def _grads(m):
     return g
 
 
-@pytest.mark.parametrize("engine,band_mode", [("fused", "jacobian"), ("chain", "jacobian"), ("chain", "recompute")])
+@pytest.mark.parametrize("engine,band_mode", [("fused", "jacobian"), ("fused-strict", "jacobian"), ("chain", "jacobian"),
+                                              ("chain", "recompute")])
 @pytest.mark.parametrize("tag,batch,seeds,std", [("dual", 3, (11, 12), 0.02), ("clamp", 2, (21, 22), 0.3)])
 def test_dual_adaptive_backward_through_y(bb, golden, tag, batch, seeds, std, engine, band_mode):
     """dL/d(controller weights) for a loss through Y and Q (loss A of make_golden.py) -- this is dQ pushed
@@ -377,6 +378,75 @@ def test_fused_train_mode_gradient_is_consistent(bb):
     # the masks are really applied: about 10 % of the saved post-dropout activations are exactly zero
     o = m.forward_features(tl, tr)
     assert torch.isfinite(o["YL"]).all() and torch.isfinite(o["QL"]).all()
+
+
+def test_fused_multi_tile_batches_match_chain_engine(bb):
+    """Batches that span several 32-row tiles / end in a partial tile: the persistent kernels (fast and strict
+    pass) against the per-frame band kernel + torch controller, forward and weight gradients."""
+    for batch in (33, 70):
+        wl, wr = orc.synth_binaural(batch, seed=77)
+        tl, tr = torch.from_numpy(wl).to(DEV), torch.from_numpy(wr).to(DEV)
+        rs = np.random.RandomState(5)
+        up = {k: torch.from_numpy(rs.standard_normal((batch, 19, 100)).astype(np.float32)).to(DEV)
+              for k in ("gYL", "gYR", "gPL", "gQL", "gQR")}
+        res = {}
+        for engine in ("chain", "fused", "fused-strict"):
+            m, _, _ = _dual(bb, 1, (11, 12), CONFIG_YAML, 0.05, engine)
+            o = m.forward_features(tl, tr)
+            ((up["gYL"] * torch.log(o["YL"] + 1e-8)).sum() + (up["gYR"] * torch.log(o["YR"] + 1e-8)).sum()
+             + (up["gQL"] * o["QL"]).sum() + (up["gQR"] * o["QR"]).sum() + 1e-3 * (up["gPL"] * o["phaseL"]).sum()).backward()
+            res[engine] = ({k: _np(o[k]) for k in ("YL", "YR", "QL", "QR")}, _grads(m))
+        for engine in ("fused", "fused-strict"):
+            for k, v in res["chain"][0].items():
+                assert_close(res[engine][0][k], v, 2e-5, f"B={batch} {engine} {k}")
+            for k, v in res["chain"][1].items():
+                assert rel_err(res[engine][1][k], v) <= RTOL, (batch, engine, k, rel_err(res[engine][1][k], v))
+        # the fast pass and the strict replay pass run the same arithmetic: identical bits
+        for k in ("YL", "QL", "QR"):
+            np.testing.assert_array_equal(res["fused"][0][k], res["fused-strict"][0][k])
+
+
+def test_nonfinite_q_fallback_is_batch_global(bb):
+    """model_torch.py:378-380: if ANY Q_{t+1} of an ear is non-finite, the whole batch of that ear restarts from Q0
+    with a fresh GRU state.  An Inf in one W_ih column of the LEFT controller makes only silent clips (log1p(Y) = 0
+    -> 0 * Inf = NaN) produce NaN, so the fallback must also reset the clips whose own Q was finite -- and must
+    leave the right ear alone.  Fast pass -> flags -> strict replay, against the torch chain engine."""
+    batch = 40                                             # two tiles; the silent clip sits in the second one
+    wl, wr = orc.synth_binaural(batch, seed=5)
+    wl[37] = 0.0
+    tl, tr = torch.from_numpy(wl).to(DEV), torch.from_numpy(wr).to(DEV)
+    up = torch.from_numpy(np.random.RandomState(9).standard_normal((batch, 19, 100)).astype(np.float32)).to(DEV)
+    out = {}
+    for engine in ("chain", "fused"):
+        m, _, _ = _dual(bb, 1, (11, 12), CONFIG_YAML, 0.05, engine)
+        with torch.no_grad():
+            m.fb_L.q_rnn.weight_ih_l0[5, 17] = float("inf")
+        o = m.forward_features(tl, tr)
+        ((up * torch.log(o["YR"] + 1e-8)).sum() + (up * o["QR"]).sum()).backward()
+        out[engine] = (o, _grads(m))
+    oc, of = out["chain"][0], out["fused"][0]
+    q0 = _np(m.Q0)
+    assert np.array_equal(_np(of["QL"]), np.broadcast_to(q0, (batch, 19, 100)))    # every frame fell back to Q0
+    for k in ("YL", "YR", "QL", "QR"):
+        assert torch.isfinite(of[k]).all()
+        assert_close(_np(of[k]), _np(oc[k]), 2e-5, k)
+    assert float((of["QR"] - torch.from_numpy(q0).to(DEV)).abs().max()) > 1e-3       # the right ear still adapts
+    for k, v in out["chain"][1].items():
+        if k.startswith("R."):
+            assert rel_err(out["fused"][1][k], v) <= RTOL, k
+
+
+def test_ctrl_wgrad_kernel(bb):
+    """biear_ctrl_wgrad against a float64 einsum on tile-layout operands (odd sizes, sliced operands, bias)."""
+    from biear_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(3)
+    for G, chunks, Da, do, Db, di in ((2, 37, 512, 384, 100, 100), (1, 5, 128, 128, 128, 128), (2, 144, 100, 100, 128, 128)):
+        a = torch.randn((G, chunks + 2, Da, 32), generator=g).to(DEV)
+        b = torch.randn((G, chunks + 2, Db, 32), generator=g).to(DEV)
+        dw, db = ops.ctrl_wgrad(a, do, b[:, 2:], di, chunks)
+        ref = torch.einsum("gkor,gkir->goi", a[:, :chunks, :do].double(), b[:, 2:, :di].double())
+        assert rel_err(_np(dw.double()), _np(ref)) <= 1e-5
+        assert rel_err(_np(db.double()), _np(a[:, :chunks, :do].double().sum((1, 3)))) <= 1e-5
 
 
 def test_single_controller(bb, golden):
