@@ -73,7 +73,7 @@ class ClockSampler:
     REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
                ("sw_power_cap", 0x4))
 
-    def __init__(self, gpu_index, period_s=0.02):
+    def __init__(self, gpu_index, period_s=0.01):
         self.period = period_s
         self.rows = []
         self.stop_flag = threading.Event()
@@ -190,23 +190,34 @@ def build_frontend(device):
     return m.to(device).train()
 
 
-def make_step(model, up):
-    """The public-API call a user makes: waveforms in, loss out, gradients left on the parameters."""
+def make_loss(model, up):
+    """The public-API call a user makes: waveforms in, scalar loss out (backward leaves the gradients on the
+    parameters)."""
     from biear_b200 import ops
     params = [p for p in model.parameters() if p.requires_grad]
     log_q0 = torch.log(model.Q0 + 1e-8).view(1, 1, -1)
 
-    def step(wl, wr):
-        for p in params:
-            p.grad = None
+    def loss_fn(wl, wr):
         o = model.forward_features(wl, wr, want_phase=True)
         cc = ops.cc_feature(wl, wr, FS, NBANDS, 3.0)
         x1 = torch.clamp(torch.log(o["YL"] + 1e-8), -12.0, 12.0)          # model_torch.py:1080-1083
         x2 = torch.clamp(torch.log(o["YR"] + 1e-8), -12.0, 12.0)
         lq = torch.log(0.5 * (o["QL"] + o["QR"]) + 1e-8)                   # train_biear.py:476-490
-        loss = (up["gYL"] * x1).mean() + (up["gYR"] * x2).mean() \
+        return (up["gYL"] * x1).mean() + (up["gYR"] * x2).mean() \
             + (up["gPL"] * o["phaseL"]).mean() + (up["gPR"] * o["phaseR"]).mean() + (up["gC"] * cc).mean() \
             + REG_Q_W * ((lq - log_q0) ** 2).mean() + REG_SMOOTH_W * ((lq[..., 1:] - lq[..., :-1]) ** 2).mean()
+
+    return loss_fn, params
+
+
+def make_step(model, up):
+    """Eager step (profiling tools): zero the gradients, forward, backward."""
+    loss_fn, params = make_loss(model, up)
+
+    def step(wl, wr):
+        for p in params:
+            p.grad = None
+        loss = loss_fn(wl, wr)
         loss.backward()
         return loss
 
@@ -214,7 +225,7 @@ def make_step(model, up):
 
 
 def run_ours(args):
-    from biear_b200 import _lib, ops
+    from biear_b200 import GraphedStep, _lib
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -232,7 +243,7 @@ def run_ours(args):
     up = {k: torch.from_numpy(rs.standard_normal((B, T, NBANDS)).astype(np.float32)).to(dev)
           for k in ("gYL", "gYR", "gPL", "gPR")}
     up["gC"] = torch.from_numpy(rs.standard_normal((B, NBANDS)).astype(np.float32)).to(dev)
-    step, params = make_step(model, up)
+    loss_fn, params = make_loss(model, up)
     flat_numel = sum(p.numel() for p in params)
 
     from biear_b200.dist import FlatGradAllReducer
@@ -251,6 +262,29 @@ def run_ours(args):
         dev_in.append((torch.from_numpy(np.roll(wl, sh, axis=1)).to(dev), torch.from_numpy(np.roll(wr, sh, axis=1)).to(dev)))
     pinned = [(torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()) for a, b in host]
 
+    # The step (forward + loss + backward) is captured once per resident batch as a CUDA graph (biear_b200.GraphedStep)
+    # and replayed: ~60 launches per step issued from Python are host-bound, the replay is not.  --eager times the
+    # same calls issued one by one.
+    if args.eager:
+        def eager(wl, wr):
+            for p in params:
+                p.grad = None
+            loss = loss_fn(wl, wr)
+            loss.backward()
+            return loss
+        steps_res = [lambda i=i: eager(*dev_in[i]) for i in range(N_ROTATE)]
+        e2e_graph = None
+        launches_per_step = None
+    else:
+        graphs, pool = [], None
+        for i in range(N_ROTATE):
+            gs = GraphedStep(loss_fn, dev_in[i], params, warmup=2 if i == 0 else 1, pool=pool, copy_inputs=False)
+            pool = gs.pool()
+            graphs.append(gs)
+        steps_res = [gs for gs in graphs]
+        e2e_graph = GraphedStep(loss_fn, dev_in[0], params, warmup=1, pool=pool, copy_inputs=True)
+        launches_per_step = graphs[0].launches_per_replay
+
     def sync_all():
         torch.cuda.synchronize()
         if dist is not None:
@@ -259,7 +293,7 @@ def run_ours(args):
 
     # ---- resident-input timing ----------------------------------------------------------------
     for i in range(args.warmup):
-        step(*dev_in[i % N_ROTATE])
+        steps_res[i % N_ROTATE]()
         allreduce_grads()
     sync_all()
     sampler = make_sampler(local) if rank == 0 else None
@@ -270,22 +304,32 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
-        step(*dev_in[i % N_ROTATE])
+        steps_res[i % N_ROTATE]()
         allreduce_grads()
     e1.record()
     sync_all()
-    launches = _lib.launch_count()
+    launches = _lib.launch_count() if launches_per_step is None else launches_per_step * args.steps
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end to end: pinned host waveforms in, loss out ------------------------------------------
     def e2e_step(i):
         a, b = pinned[i % 2]
-        wl = a.to(dev, non_blocking=True)
-        wr = b.to(dev, non_blocking=True)
-        loss = step(wl, wr)
+        if e2e_graph is not None:
+            loss = e2e_graph(a, b)            # H2D into the graph's static inputs, replay
+        else:
+            loss = steps_eager_e2e(a, b)
         allreduce_grads()
         return float(loss.item())            # D2H read of the step's result
+
+    def steps_eager_e2e(a, b):
+        wl = a.to(dev, non_blocking=True)
+        wr = b.to(dev, non_blocking=True)
+        for p in params:
+            p.grad = None
+        loss = loss_fn(wl, wr)
+        loss.backward()
+        return loss
 
     for i in range(max(1, args.warmup // 2)):
         e2e_step(i)
@@ -299,7 +343,7 @@ def run_ours(args):
     ms_e2e = max(e0.elapsed_time(e1), 0.0)
     wall_e2e = (time.perf_counter() - t0) * 1e3
 
-    # ---- dominant kernel alone (band stage, one frame, both ears), for the roofline line ----------
+    # ---- dominant kernel alone, for the roofline line ----------------------------------------------
     roof = kernel_roofline(model, dev_in, dev, B)
 
     times = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
@@ -323,6 +367,7 @@ def run_ours(args):
                    "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                    "l2": f"inputs rotate over {N_ROTATE} resident batches "
                          f"({N_ROTATE * B * 2 * FS * 4 / 1e6:.0f} MB > 126 MB L2)",
+                   "issue": "eager launches" if args.eager else "one CUDA graph per step (biear_b200.GraphedStep)",
                    "allreduce_floats": flat_numel if world > 1 else 0},
         "e2e": {"value": clips / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * B * FS * 4,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "wall_ms_per_step": wall_e2e / args.steps},
@@ -451,11 +496,12 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="clips per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="issue every launch from Python instead of replaying CUDA graphs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -11,7 +11,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BIEAR_B200_LIB") or os.path.join(_HERE, "lib", "libbiear_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 _p = c_void_p
 _i = c_int
@@ -32,7 +32,7 @@ class SeqParams(Structure):
             "X", "Y", "phase", "dYdQ", "dPdQ", "Q", "delta",
             "gates", "xh1", "d1", "xh2", "d2", "rstd", "yc", "H", "flags",
             "gY", "gP", "gQ",
-            "GG", "G_a1", "G_v1", "G_a2", "G_v2", "G_pre", "workspace")]
+            "GG", "G_a1", "G_v1", "G_a2", "G_v2", "G_pre", "workspace", "seed_ptr")]
     )
 
 
@@ -50,8 +50,10 @@ SIGNATURES = {
     "biear_adaptive_fwd": (_i, [POINTER(SeqParams), _p]),
     "biear_adaptive_bwd": (_i, [POINTER(SeqParams), _p]),
     "biear_adaptive_workspace_floats": (_l, [_i, _i]),
-    "biear_wgrad_scratch_floats": (_l, [_i, _i, _i, _l]),
-    "biear_ctrl_wgrad": (_i, [_p, _l, _l, _i, _p, _l, _l, _i, _i, _l, _p, _p, _p, _p]),
+    "biear_adaptive_occupancy": (_i, [_i, _i, POINTER(c_int), POINTER(c_int)]),
+    "biear_adaptive_tile_rows": (_i, []),
+    "biear_wgrad_scratch_floats": (_l, [_i, _i, _i, _l, _i]),
+    "biear_ctrl_wgrad": (_i, [_p, _l, _l, _i, _p, _l, _l, _i, _i, _l, _i, _p, _p, _p, _p]),
 }
 
 _lib = None

@@ -9,7 +9,7 @@
 //   model_torch.py:1039-1063 the second W(Q_t) build for the sub-band phase
 // (~60 library launches + 2 host syncs per frame there) and everything autograd derives from them.
 //
-// Forward:  cluster = 8 CTAs = one tile of 32 rows of one controller, resident for all T frames.  Per frame:
+// Forward:  cluster = 4 CTAs = one tile of 16 rows of one controller, resident for all T frames.  Per frame:
 //   band stage (CTA c: rows 4c..4c+3; Y/phase/Jacobians -> HBM, log1p(Y) -> every CTA's shared memory)
 //   -> GRU cell -> 2 x (Linear, LayerNorm, SiLU, Dropout) -> Linear -> tanh -> Q_{t+1} (-> HBM and -> the shared
 //   memory of the CTA that runs the band stage of that row).  Five cluster barriers per frame, no HBM round trip.
@@ -20,6 +20,10 @@
 //   them into dW with split-K GEMMs afterwards.
 //
 // See seq_dev.cuh for the cluster/thread layout and the weight images.
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "band_dev.cuh"
 #include "seq_dev.cuh"
 
@@ -41,15 +45,13 @@ __global__ void __launch_bounds__(256) pack_fwd_images_kernel(const BiearSeqPara
     for (int idx = threadIdx.x; idx < kU * 3 * N; idx += blockDim.x) {
         const int k = idx % N, gu = idx / N, gate = gu % 3, u = gu / 3;
         const long long o = gate * kHid + c * kU + u;
-        out[fwd_img_wih(N) + (k * kU + u) * 4 + gate] = fmaf(0.2f, w_ih[o * p.Kin + N + k], w_ih[o * p.Kin + k]);
+        out[fwd_img_wih(N) + (k * 3 + gate) * kU + u] = fmaf(0.2f, w_ih[o * p.Kin + N + k], w_ih[o * p.Kin + k]);
     }
-    for (int idx = threadIdx.x; idx < kU * N; idx += blockDim.x) out[fwd_img_wih(N) + idx * 4 + 3] = 0.f;
     for (int idx = threadIdx.x; idx < kU * 3 * kHid; idx += blockDim.x) {
         const int k = idx % kHid, gu = idx / kHid, gate = gu % 3, u = gu / 3;
         const int o = gate * kHid + c * kU + u;
-        out[fwd_img_whh(N) + (k * kU + u) * 4 + gate] = w_hh[o * kHid + k];
+        out[fwd_img_whh(N) + (k * 3 + gate) * kU + u] = w_hh[o * kHid + k];
     }
-    for (int idx = threadIdx.x; idx < kU * kHid; idx += blockDim.x) out[fwd_img_whh(N) + idx * 4 + 3] = 0.f;
     for (int idx = threadIdx.x; idx < kU * kHid; idx += blockDim.x) {
         const int k = idx % kHid, u = idx / kHid;
         out[fwd_img_w1(N) + k * kU + u] = w1[(c * kU + u) * kHid + k];
@@ -91,7 +93,7 @@ struct FwdSmem {   // offsets in floats
     __host__ __device__ FwdSmem(int N_, int F) : N(N_), tile(spec_tile_len(F)) {}
     __host__ __device__ int img() const { return 0; }
     __host__ __device__ int vec() const { return fwd_img_floats(N); }           // per-CTA constants, see V_*
-    __host__ __device__ int yc() const { return vec() + 1024; }                 // [128][32]; aliased by a2
+    __host__ __device__ int yc() const { return vec() + 1088; }                 // [128][32]; aliased by a2
     __host__ __device__ int h0() const { return yc() + kHid * kR; }             // [128][32] x 2 (ping-pong)
     __host__ __device__ int a1() const { return h0() + 2 * kHid * kR; }
     __host__ __device__ int red() const { return a1() + kHid * kR; }            // 16 x 128
@@ -103,8 +105,11 @@ struct FwdSmem {   // offsets in floats
     __host__ __device__ int total() const { return misc() + 16; }
 };
 // vec area
-constexpr int V_BR = 0, V_BZ = 16, V_BIN = 32, V_BHN = 48, V_B1 = 64, V_B2 = 80, V_B3 = 96, V_Q0S = 112, V_DQS = 128;
-constexpr int V_LN1G = 256, V_LN1B = 384, V_LN2G = 512, V_LN2B = 640, V_FC = 768, V_Q0 = 896;
+constexpr int V_BR = 0, V_BZ = kU, V_BIN = 2 * kU, V_BHN = 3 * kU, V_B1 = 4 * kU, V_B2 = 5 * kU, V_B3 = 6 * kU,
+              V_Q0S = 7 * kU, V_DQS = 8 * kU;
+constexpr int V_LN1G = 9 * kU, V_LN1B = V_LN1G + kHid, V_LN2G = V_LN1B + kHid, V_LN2B = V_LN2G + kHid, V_FC = V_LN2B + kHid,
+              V_Q0 = V_FC + kHid, V_END = V_Q0 + kHid;
+static_assert(V_END <= 1088, "vec area");
 
 __device__ __forceinline__ long long tile_base(const BiearSeqParams& p, int g, int t, int tiles, int tile) {
     return ((long long)(g * (p.T - 1) + t)) * tiles + tile;
@@ -117,11 +122,11 @@ __device__ __forceinline__ float* h_tile(const BiearSeqParams& p, int g, int t, 
 // LayerNorm + SiLU + Dropout over the full rows held in buf_s ([feature][32], overwritten in place with the layer
 // output).  Every CTA of the cluster does this redundantly (the next layer needs all 128 features everywhere);
 // only the warp whose 16 features are the CTA's own slice saves them.
-__device__ __forceinline__ void ln_silu_drop_fwd(const BiearSeqParams& p, float* buf_s, float* stat_s,
+__device__ __forceinline__ void ln_silu_drop_fwd(const BiearSeqParams& p, unsigned long long seed, float* buf_s, float* stat_s,
                                                  const float* __restrict__ gamma_s, const float* __restrict__ beta_s,
                                                  int layer, int t, long long grow0, int rank, float* xh_tile,
                                                  float* d_tile, float* rstd_tile) {
-    constexpr int PARTS = kSeqThreads / kR, FPP = kHid / PARTS;     // 8 parts of 16 features
+    constexpr int PARTS = kSeqThreads / kR, FPP = kHid / PARTS;     // 16 parts of 8 features
     const int row = threadIdx.x % kR, part = threadIdx.x / kR;
     const int f0 = part * FPP;
     float v[FPP];
@@ -149,12 +154,12 @@ __device__ __forceinline__ void ln_silu_drop_fwd(const BiearSeqParams& p, float*
 #pragma unroll
     for (int q = 0; q < PARTS; ++q) var += stat_s[kSeqThreads + q * kR + row];
     const float rstd = rsqrtf(var * (1.0f / kHid) + kLnEps);
-    const bool mine = part == rank;
+    const bool mine = f0 / kU == rank;
     if (rank == 0 && part == 0) rstd_tile[layer * kR + row] = rstd;
 #pragma unroll
     for (int i4 = 0; i4 < FPP / 4; ++i4) {
         float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (p.training) sc = dropout_scale4(p.seed, t, layer, grow0 + row, (f0 >> 2) + i4);
+        if (p.training) sc = dropout_scale4(seed, t, layer, grow0 + row, (f0 >> 2) + i4);
         const float scv[4] = {sc.x, sc.y, sc.z, sc.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -218,6 +223,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
     const int nu_c = max(0, min(NU, N - rank * NU));
     const int quads = (N + 3) >> 2;
     int* any_flag = p.flags + S * p.G;
+    const unsigned long long seed = p.seed_ptr ? *p.seed_ptr : p.seed;
 
     if (STRICT) {
         if (!p.force_strict && *reinterpret_cast<volatile int*>(any_flag) == 0) return;   // uniform over the grid
@@ -348,11 +354,9 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                 float ar[kRT] = {0.f, 0.f, 0.f, 0.f}, az[kRT] = {0.f, 0.f, 0.f, 0.f};
                 float ain[kRT] = {0.f, 0.f, 0.f, 0.f}, ahn[kRT] = {0.f, 0.f, 0.f, 0.f};
                 const int kh = (N + 1) >> 1;
-                dot_rows3(ar, az, ain, yc_s + rg * kRT, reinterpret_cast<const float4*>(img_s + fwd_img_wih(N)) + u,
-                          ks ? kh : 0, ks ? N : kh);
+                dot_rows3(ar, az, ain, yc_s + rg * kRT, img_s + fwd_img_wih(N) + u, ks ? kh : 0, ks ? N : kh);
                 if (!h_zero)
-                    dot_rows3(ar, az, ahn, hcur_s + rg * kRT, reinterpret_cast<const float4*>(img_s + fwd_img_whh(N)) + u,
-                              ks ? 64 : 0, ks ? 128 : 64);
+                    dot_rows3(ar, az, ahn, hcur_s + rg * kRT, img_s + fwd_img_whh(N) + u, ks ? 64 : 0, ks ? 128 : 64);
                 float acc[16];
 #pragma unroll
                 for (int i = 0; i < kRT; ++i) {
@@ -398,7 +402,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                 }
             }
             cluster.sync();   // #3
-            ln_silu_drop_fwd(p, a1_s, stat_s, vec_s + V_LN1G, vec_s + V_LN1B, 0, t, (long long)g * p.B + b0, rank,
+            ln_silu_drop_fwd(p, seed, a1_s, stat_s, vec_s + V_LN1G, vec_s + V_LN1B, 0, t, (long long)g * p.B + b0, rank,
                              p.xh1 + tb * kHid * kR, p.d1 + tb * kHid * kR, p.rstd + tb * 2 * kR);
 
             // ---- Linear 2 -> LayerNorm -> SiLU -> Dropout ------------------------------------------------------
@@ -414,7 +418,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                 }
             }
             cluster.sync();   // #4
-            ln_silu_drop_fwd(p, a2_s, stat_s, vec_s + V_LN2G, vec_s + V_LN2B, 1, t, (long long)g * p.B + b0, rank,
+            ln_silu_drop_fwd(p, seed, a2_s, stat_s, vec_s + V_LN2G, vec_s + V_LN2B, 1, t, (long long)g * p.B + b0, rank,
                              p.xh2 + tb * kHid * kR, p.d2 + tb * kHid * kR, p.rstd + tb * 2 * kR);
 
             // ---- Linear 3 -> tanh -> Q_{t+1} (model_torch.py:367-380) -------------------------------------------
@@ -477,11 +481,11 @@ struct BwdSmem {   // offsets in floats
     __host__ __device__ int dyc() const { return stage() + kRT * kHid; }           // [128][4]
     __host__ __device__ int total() const { return dyc() + kHid * kRT; }
 };
-constexpr int VB_LN1G = 0, VB_LN1B = 128, VB_LN2G = 256, VB_LN2B = 384, VB_Q0 = 512, VB_DQ = 640;
+constexpr int VB_LN1G = 0, VB_LN1B = 128, VB_LN2G = 256, VB_LN2B = 384, VB_Q0 = 512, VB_DQ = 640;   // < 1024
 
 // Backward of Dropout -> SiLU -> LayerNorm on the full rows in buf_s (dL/d(layer output) on entry, dL/d(pre-LayerNorm
 // activation) on exit).  Redundant in every CTA; the warp owning the CTA's feature slice writes the saved gradients.
-__device__ __forceinline__ void ln_silu_drop_bwd(const BiearSeqParams& p, float* buf_s, float* stat_s,
+__device__ __forceinline__ void ln_silu_drop_bwd(const BiearSeqParams& p, unsigned long long seed, float* buf_s, float* stat_s,
                                                  const float* __restrict__ gamma_s, const float* __restrict__ beta_s,
                                                  int layer, int t, long long grow0, int rank,
                                                  const float* __restrict__ xh_tile, const float* __restrict__ rstd_tile,
@@ -489,7 +493,7 @@ __device__ __forceinline__ void ln_silu_drop_bwd(const BiearSeqParams& p, float*
     constexpr int PARTS = kSeqThreads / kR, FPP = kHid / PARTS;
     const int row = threadIdx.x % kR, part = threadIdx.x / kR;
     const int f0 = part * FPP;
-    const bool mine = part == rank;
+    const bool mine = f0 / kU == rank;
     float xh[FPP], dxh[FPP];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -497,7 +501,7 @@ __device__ __forceinline__ void ln_silu_drop_bwd(const BiearSeqParams& p, float*
 #pragma unroll
     for (int i4 = 0; i4 < FPP / 4; ++i4) {
         float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (p.training) sc = dropout_scale4(p.seed, t, layer, grow0 + row, (f0 >> 2) + i4);
+        if (p.training) sc = dropout_scale4(seed, t, layer, grow0 + row, (f0 >> 2) + i4);
         const float scv[4] = {sc.x, sc.y, sc.z, sc.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -562,6 +566,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
     const int b0 = tile * kR;
     const long long grow0 = (long long)g * p.B + b0 + rank * kRT;
     const int bb0 = b0 + rank * kRT;
+    const unsigned long long seed = p.seed_ptr ? *p.seed_ptr : p.seed;
 
     copy_f4(reinterpret_cast<float4*>(img_s),
             reinterpret_cast<const float4*>(img + (long long)(g * kCS + rank) * bwd_img_floats(N)), bwd_img_floats(N) / 4);
@@ -621,7 +626,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
             if (ks == 0) broadcast_rows(cluster, bufa_s, ug, rg * kRT, acc);
         }
         cluster.sync();   // #2
-        ln_silu_drop_bwd(p, bufa_s, stat_s, vec_s + VB_LN2G, vec_s + VB_LN2B, 1, t, (long long)g * p.B + b0, rank,
+        ln_silu_drop_bwd(p, seed, bufa_s, stat_s, vec_s + VB_LN2G, vec_s + VB_LN2B, 1, t, (long long)g * p.B + b0, rank,
                          p.xh2 + tb * kHid * kR, p.rstd + tb * 2 * kR, p.G_v2 + tb * kHid * kR, p.G_a2 + tb * kHid * kR);
         // ---- Linear 2 ^T --------------------------------------------------------------------------------------
         {
@@ -631,7 +636,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
             if (ks == 0) broadcast_rows(cluster, bufb_s, ug, rg * kRT, acc);   // bufb aliases dpre: its reads ended before #2
         }
         cluster.sync();   // #3
-        ln_silu_drop_bwd(p, bufb_s, stat_s, vec_s + VB_LN1G, vec_s + VB_LN1B, 0, t, (long long)g * p.B + b0, rank,
+        ln_silu_drop_bwd(p, seed, bufb_s, stat_s, vec_s + VB_LN1G, vec_s + VB_LN1B, 0, t, (long long)g * p.B + b0, rank,
                          p.xh1 + tb * kHid * kR, p.rstd + tb * 2 * kR, p.G_v1 + tb * kHid * kR, p.G_a1 + tb * kHid * kR);
         // ---- Linear 1 ^T, GRU cell backward ------------------------------------------------------------------------
         float dh_direct[kRT] = {0.f, 0.f, 0.f, 0.f};
@@ -744,8 +749,22 @@ static int validate_seq(const BiearSeqParams* p, const char* who, bool backward)
 template <typename Kern>
 static int launch_cluster(Kern kern, const char* name, int clusters, size_t smem, cudaStream_t st,
                           const BiearSeqParams& p, const float* img) {
-    int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name);
+    // the opt-in is per device and sticky; remember the largest size set so that steady-state launches (and launches
+    // recorded into a CUDA graph) make no attribute call
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> configured;
+    int dev = 0;
+    int e = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
     if (e) return e;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        size_t& have = configured[{dev, reinterpret_cast<const void*>(kern)}];
+        if (have < smem) {
+            e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name);
+            if (e) return e;
+            have = smem;
+        }
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(clusters * kCS));
     cfg.blockDim = dim3(kSeqThreads);
@@ -765,6 +784,8 @@ static int launch_cluster(Kern kern, const char* name, int clusters, size_t smem
 }
 
 }  // namespace biear
+
+extern "C" int biear_adaptive_tile_rows(void) { return biear::kR; }
 
 extern "C" int64_t biear_adaptive_workspace_floats(int G, int N) {
     using namespace biear;
@@ -799,4 +820,37 @@ extern "C" int biear_adaptive_bwd(const BiearSeqParams* p, void* stream) {
     pack_bwd_images_kernel<<<p->G * kCS, 256, 0, st>>>(*p, p->workspace);
     BIEAR_LAUNCH_CHECK("pack_bwd_images_kernel");
     return launch_cluster(seq_bwd_kernel, "seq_bwd_kernel", p->G * tiles, smem, st, *p, p->workspace);
+}
+
+// Diagnostics: how many clusters of the persistent kernels can be resident at once on the current device.
+extern "C" int biear_adaptive_occupancy(int N, int F, int* fwd_clusters, int* bwd_clusters) {
+    using namespace biear;
+    BIEAR_REQUIRE(N >= 1 && N <= kHid && F >= 2 && fwd_clusters && bwd_clusters, "biear_adaptive_occupancy: bad arguments");
+    const size_t smem_f = sizeof(float) * (size_t)FwdSmem(N, F).total();
+    const size_t smem_b = sizeof(float) * (size_t)BwdSmem(N).total();
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    for (int pass = 0; pass < 2; ++pass) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(kCS * 64);
+        cfg.blockDim = dim3(kSeqThreads);
+        cfg.dynamicSmemBytes = pass ? smem_b : smem_f;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int n = 0;
+        cudaError_t e;
+        if (pass == 0) {
+            e = cudaFuncSetAttribute(seq_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, seq_fwd_kernel<false>, &cfg);
+        } else {
+            e = cudaFuncSetAttribute(seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, seq_bwd_kernel, &cfg);
+        }
+        if (int rc = check_cuda(e, "cudaOccupancyMaxActiveClusters")) return rc;
+        *(pass ? bwd_clusters : fwd_clusters) = n;
+    }
+    return 0;
 }

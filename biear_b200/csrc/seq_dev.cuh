@@ -1,21 +1,25 @@
 // Building blocks of the persistent adaptive-recurrence kernels (seq.cu).
 //
-// One thread-block CLUSTER of 8 CTAs owns a TILE of 32 rows (clips of one ear = one controller) for the WHOLE
+// One thread-block CLUSTER of 4 CTAs owns a TILE of 16 rows (clips of one ear = one controller) for the WHOLE
 // 19-frame recurrence: band stage of frame t -> log1p features -> GRU cell -> Linear/LayerNorm/SiLU/Dropout x2
 // -> Linear -> tanh -> Q_{t+1} -> band stage of frame t+1 ...  Nothing on the serial chain goes through HBM:
-//   * the controller's 173 k weights are SLICED across the cluster -- CTA c owns hidden units [16c, 16c+16) of
-//     every 128-wide layer and a 1/8 slice of the bands of the last layer -- and stay resident in shared memory
-//     for all steps (an 83 KB "image" per CTA, laid out by a pack kernel so that it is copied with 128-bit loads);
-//   * the (32 x 128) activations are exchanged between the CTAs through distributed shared memory;
+//   * the controller's 173 k weights are SLICED across the cluster -- CTA c owns hidden units [32c, 32c+32) of
+//     every 128-wide layer and a 1/4 slice of the bands of the last layer -- and stay resident in shared memory
+//     for all steps (a 137 KB "image" per CTA, laid out by a pack kernel so that it is copied with 128-bit loads);
+//   * the (16 x 128) activations are exchanged between the CTAs through distributed shared memory;
 //   * CTA c runs the band stage for rows 4c .. 4c+3 of the tile and broadcasts log1p(Y) to its peers; the Q of
 //     those rows comes back from the CTAs that own the corresponding bands of the last layer.
 //
-// Thread layout of the GEMM phases (256 threads): tid = ks*128 + rg*16 + u
-//   u  in [0,16)  output unit inside the CTA's slice
-//   rg in [0,8)   row group: rows 4rg .. 4rg+3 of the tile (the rows whose band stage CTA rg runs)
+// Why 4 x 16 and not 8 x 32: a B200 fits 15 clusters of 8 CTAs with this much shared memory but 36 clusters of 4
+// (cudaOccupancyMaxActiveClusters, tools/occupancy.py), and the benchmark batch (256 clips x 2 ears) needs 16 tiles
+// of 32 rows -- one more than fit, i.e. two waves -- or 32 tiles of 16 rows, which run as one wave on 128 SMs.
+//
+// Thread layout of the GEMM phases (256 threads): tid = ks*128 + rg*32 + u
+//   u  in [0,32)  output unit inside the CTA's slice
+//   rg in [0,4)   row group: rows 4rg .. 4rg+3 of the tile (the rows whose band stage CTA rg runs)
 //   ks in {0,1}   half of the contraction range; the halves are summed through shared memory
 // Activations live feature-major, [feature][32 rows], in shared memory AND in the tensors saved for the backward
-// pass ("tile layout": (G, T-1, tiles, D, 32)), so a thread moves its 4 rows of one feature with one 128-bit access.
+// pass ("tile layout": (G, T-1, tiles, D, 16)), so a thread moves its 4 rows of one feature with one 128-bit access.
 #pragma once
 #include <cooperative_groups.h>
 
@@ -26,9 +30,9 @@ namespace cg = cooperative_groups;
 
 constexpr int kHid = 128;           // GRU / MLP width (model_torch.py:256-267)
 constexpr int kSeqThreads = 256;
-constexpr int kCS = 8;              // CTAs per cluster
-constexpr int kU = kHid / kCS;      // hidden units per CTA (16)
-constexpr int kR = 32;              // rows per tile
+constexpr int kCS = 4;              // CTAs per cluster
+constexpr int kU = kHid / kCS;      // hidden units per CTA (32)
+constexpr int kR = 16;              // rows per tile
 constexpr int kRT = 4;              // rows per thread = rows per CTA in the band stage
 constexpr float kDropP = 0.1f;      // model_torch.py:261, 265
 constexpr float kLnEps = 1e-5f;
@@ -39,18 +43,18 @@ __host__ __device__ constexpr int bands_per_cta(int N) { return (N + kCS - 1) / 
 
 // ---- shared-memory weight images (offsets in floats) ------------------------------------------------------
 // forward image of CTA (g, c):
-//   wih4 [k<N][u][4]   {Weff[r,u][k], Weff[z,u][k], Weff[n,u][k], 0},  Weff = W_ih[:, :N] + 0.2 W_ih[:, N:]
-//                      (feat = [yc, 0.2*yc.detach()]  =>  W_ih feat = Weff yc)
-//   whh4 [k<128][u][4] {W_hh[r,u][k], W_hh[z,u][k], W_hh[n,u][k], 0}
+//   wih3 [k<N][gate<3][u]   Weff[gate,u][k],  Weff = W_ih[:, :N] + 0.2 W_ih[:, N:]
+//                           (feat = [yc, 0.2*yc.detach()]  =>  W_ih feat = Weff yc)
+//   whh3 [k<128][gate<3][u] W_hh[gate,u][k]
 //   w1 [k<128][u], w2 [k<128][u], w3 [k<128][u] (band c*NU+u; zero beyond the CTA's slice)
 __host__ __device__ constexpr int fwd_img_wih(int) { return 0; }
-__host__ __device__ constexpr int fwd_img_whh(int N) { return N * kU * 4; }
-__host__ __device__ constexpr int fwd_img_w1(int N) { return fwd_img_whh(N) + kHid * kU * 4; }
+__host__ __device__ constexpr int fwd_img_whh(int N) { return N * 3 * kU; }
+__host__ __device__ constexpr int fwd_img_w1(int N) { return fwd_img_whh(N) + kHid * 3 * kU; }
 __host__ __device__ constexpr int fwd_img_w2(int N) { return fwd_img_w1(N) + kHid * kU; }
 __host__ __device__ constexpr int fwd_img_w3(int N) { return fwd_img_w2(N) + kHid * kU; }
 __host__ __device__ constexpr int fwd_img_floats(int N) { return fwd_img_w3(N) + kHid * kU; }
 // backward image of CTA (g, c): column slices for the transposed products
-//   w3c [n<N][u] = W3[n][16c+u];  w2c, w1c [o<128][u] = W[o][16c+u];  whhc [o<384][u] = W_hh[o][16c+u];
+//   w3c [n<N][u] = W3[n][32c+u];  w2c, w1c [o<128][u] = W[o][32c+u];  whhc [o<384][u] = W_hh[o][32c+u];
 //   wihc [o<384][u] = W_ih[o][c*NU+u] (first N columns only: the detached half of feat carries no gradient)
 __host__ __device__ constexpr int bwd_img_w3c(int) { return 0; }
 __host__ __device__ constexpr int bwd_img_w2c(int N) { return N * kU; }
@@ -98,7 +102,7 @@ __device__ __forceinline__ void copy_f4(float4* __restrict__ dst, const float4* 
     for (; i < n4; i += kSeqThreads) dst[i] = __ldg(src + i);
 }
 
-// acc[i] += sum_{k in [k0,k1)} x_s[k*32 + i] * w_s[k*16]     (x_s / w_s already offset to the thread's rows / unit)
+// acc[i] += sum_{k in [k0,k1)} x_s[k*kR + i] * w_s[k*kU]     (x_s / w_s already offset to the thread's rows / unit)
 __device__ __forceinline__ void dot_rows(float acc[kRT], const float* __restrict__ x_s, const float* __restrict__ w_s,
                                          int k0, int k1) {
 #pragma unroll 8
@@ -112,16 +116,16 @@ __device__ __forceinline__ void dot_rows(float acc[kRT], const float* __restrict
     }
 }
 
-// Three gate rows at once: the weights of one k are a float4 {r, z, n, -}.
+// Three gate rows at once: the weights of one k are [gate][kU] (w3_s already offset to the thread's unit).
 __device__ __forceinline__ void dot_rows3(float a0[kRT], float a1[kRT], float a2[kRT], const float* __restrict__ x_s,
-                                          const float4* __restrict__ w4_s, int k0, int k1) {
+                                          const float* __restrict__ w3_s, int k0, int k1) {
 #pragma unroll 4
     for (int k = k0; k < k1; ++k) {
         const float4 x = *reinterpret_cast<const float4*>(x_s + k * kR);
-        const float4 w = w4_s[k * kU];
-        a0[0] = fmaf(w.x, x.x, a0[0]); a0[1] = fmaf(w.x, x.y, a0[1]); a0[2] = fmaf(w.x, x.z, a0[2]); a0[3] = fmaf(w.x, x.w, a0[3]);
-        a1[0] = fmaf(w.y, x.x, a1[0]); a1[1] = fmaf(w.y, x.y, a1[1]); a1[2] = fmaf(w.y, x.z, a1[2]); a1[3] = fmaf(w.y, x.w, a1[3]);
-        a2[0] = fmaf(w.z, x.x, a2[0]); a2[1] = fmaf(w.z, x.y, a2[1]); a2[2] = fmaf(w.z, x.z, a2[2]); a2[3] = fmaf(w.z, x.w, a2[3]);
+        const float w0 = w3_s[k * 3 * kU], w1 = w3_s[k * 3 * kU + kU], w2 = w3_s[k * 3 * kU + 2 * kU];
+        a0[0] = fmaf(w0, x.x, a0[0]); a0[1] = fmaf(w0, x.y, a0[1]); a0[2] = fmaf(w0, x.z, a0[2]); a0[3] = fmaf(w0, x.w, a0[3]);
+        a1[0] = fmaf(w1, x.x, a1[0]); a1[1] = fmaf(w1, x.y, a1[1]); a1[2] = fmaf(w1, x.z, a1[2]); a1[3] = fmaf(w1, x.w, a1[3]);
+        a2[0] = fmaf(w2, x.x, a2[0]); a2[1] = fmaf(w2, x.y, a2[1]); a2[2] = fmaf(w2, x.z, a2[2]); a2[3] = fmaf(w2, x.w, a2[3]);
     }
 }
 
@@ -141,7 +145,7 @@ __device__ __forceinline__ void reduce_halves(float* acc, float* red_s, int ks, 
     }
 }
 
-// Write 4 row values of one feature into the [feature][32] buffer of every CTA of the cluster.
+// Write 4 row values of one feature into the [feature][kR] buffer of every CTA of the cluster.
 __device__ __forceinline__ void broadcast_rows(cg::cluster_group& cluster, float* buf_s, int feature, int row0,
                                                const float v[kRT]) {
     const float4 val = make_float4(v[0], v[1], v[2], v[3]);

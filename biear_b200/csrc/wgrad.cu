@@ -1,5 +1,6 @@
 // Weight gradients of the controller's Linear layers from tile-layout operands (see include/biear_b200.h):
-//   dW[g][o][i] = sum_{k < chunks} sum_{r < 32} A[g][k][o][r] * Bm[g][k][i][r],   db[g][o] = sum_{k,r} A[g][k][o][r]
+//   dW[g][o][i] = sum_{k < chunks} sum_{r < R} A[g][k][o][r] * Bm[g][k][i][r],   db[g][o] = sum_{k,r} A[g][k][o][r]
+// with R = tile_rows (16 or 32; 32 / R consecutive chunks form one 32-sample slab)
 // A = per-sample pre-activation gradients written by the backward recurrence, Bm = the layer inputs saved by the
 // forward recurrence.  Both are "K-major in chunks of 32", so a 64 x 64 output tile streams [64][32] slabs of each
 // operand straight into shared memory with 128-bit loads.  The contraction length (chunks*32 = (T-1)*B samples) is
@@ -19,7 +20,8 @@ constexpr int kWgPitch = 36;         // padded slab row (floats): 16-byte aligne
 struct WgradArgs {
     const float* A; long long a_group, a_chunk; int Do;
     const float* B; long long b_group, b_chunk; int Di;
-    int G; long long chunks; int splits; long long chunks_per_split;
+    int G; long long chunks; int splits; long long chunks_per_split;   // "chunks" here = 32-sample slabs
+    long long tile_chunks; int tile_w;                                  // chunks of tile_w samples in the operands
     float* part;     // (G, splits, Do, Di)
     float* bpart;    // (G, splits, Do) or null
 };
@@ -47,10 +49,13 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_partial_kernel(const WgradAr
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int r = lr + 32 * h;
-            ra[h] = (o0 + r < a.Do) ? __ldg(reinterpret_cast<const float4*>(Ag + c * a.a_chunk + (long long)(o0 + r) * 32) + lc)
-                                    : make_float4(0.f, 0.f, 0.f, 0.f);
-            rb[h] = (i0 + r < a.Di) ? __ldg(reinterpret_cast<const float4*>(Bg + c * a.b_chunk + (long long)(i0 + r) * 32) + lc)
-                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+            const long long cc = c * (32 / a.tile_w) + (lc * 4) / a.tile_w;      // operand chunk of this float4 column
+            const int off = (lc * 4) % a.tile_w;
+            const bool live = cc < a.tile_chunks;
+            ra[h] = (live && o0 + r < a.Do) ? __ldg(reinterpret_cast<const float4*>(Ag + cc * a.a_chunk + (long long)(o0 + r) * a.tile_w + off))
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+            rb[h] = (live && i0 + r < a.Di) ? __ldg(reinterpret_cast<const float4*>(Bg + cc * a.b_chunk + (long long)(i0 + r) * a.tile_w + off))
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     };
     auto stash = [&](int buf) {
@@ -131,20 +136,21 @@ static int pick_splits(int G, int Do, int Di, long long chunks) {
 
 }  // namespace biear
 
-extern "C" int64_t biear_wgrad_scratch_floats(int G, int Do, int Di, int64_t chunks) {
+extern "C" int64_t biear_wgrad_scratch_floats(int G, int Do, int Di, int64_t chunks, int tile_rows) {
     using namespace biear;
-    if (G < 1 || Do < 1 || Di < 1 || chunks < 1) return 0;
-    const int s = pick_splits(G, Do, Di, chunks);
+    if (G < 1 || Do < 1 || Di < 1 || chunks < 1 || (tile_rows != 16 && tile_rows != 32)) return 0;
+    const int s = pick_splits(G, Do, Di, (chunks * tile_rows + 31) / 32);
     return (int64_t)G * s * ((int64_t)Do * Di + Do);
 }
 
 extern "C" int biear_ctrl_wgrad(const float* A, int64_t a_group_stride, int64_t a_chunk_stride, int Do, const float* Bm,
                                 int64_t b_group_stride, int64_t b_chunk_stride, int Di, int G, int64_t chunks,
-                                float* dW, float* db, float* scratch, void* stream) {
+                                int tile_rows, float* dW, float* db, float* scratch, void* stream) {
     using namespace biear;
     BIEAR_REQUIRE(G >= 1 && Do >= 1 && Di >= 1 && chunks >= 1, "biear_ctrl_wgrad: bad shape G=%d Do=%d Di=%d chunks=%lld", G,
                   Do, Di, (long long)chunks);
     BIEAR_REQUIRE(A && Bm && dW && scratch, "biear_ctrl_wgrad: null pointer");
+    BIEAR_REQUIRE(tile_rows == 16 || tile_rows == 32, "biear_ctrl_wgrad: tile_rows must be 16 or 32, got %d", tile_rows);
     BIEAR_REQUIRE((a_chunk_stride & 3) == 0 && (b_chunk_stride & 3) == 0 && (a_group_stride & 3) == 0 &&
                       (b_group_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(Bm) & 15) == 0,
@@ -153,9 +159,10 @@ extern "C" int biear_ctrl_wgrad(const float* A, int64_t a_group_stride, int64_t 
     WgradArgs a;
     a.A = A; a.a_group = a_group_stride; a.a_chunk = a_chunk_stride; a.Do = Do;
     a.B = Bm; a.b_group = b_group_stride; a.b_chunk = b_chunk_stride; a.Di = Di;
-    a.G = G; a.chunks = chunks;
-    a.splits = pick_splits(G, Do, Di, chunks);
-    a.chunks_per_split = (chunks + a.splits - 1) / a.splits;
+    a.G = G; a.tile_chunks = chunks; a.tile_w = tile_rows;
+    a.chunks = (chunks * tile_rows + 31) / 32;
+    a.splits = pick_splits(G, Do, Di, a.chunks);
+    a.chunks_per_split = (a.chunks + a.splits - 1) / a.splits;
     a.part = scratch;
     a.bpart = db ? scratch + (long long)G * a.splits * Do * Di : nullptr;
     const int tiles = ((Do + kWgTile - 1) / kWgTile) * ((Di + kWgTile - 1) / kWgTile);

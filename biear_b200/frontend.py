@@ -191,7 +191,8 @@ def _adaptive_chain(x: torch.Tensor, ears: int, ctrl_mods, fc, q0, dq_vec, dq_mo
              "w2": st(lambda m: m.q_out[4].weight), "b2": st(lambda m: m.q_out[4].bias),
              "ln2_g": st(lambda m: m.q_out[5].weight), "ln2_b": st(lambda m: m.q_out[5].bias),
              "w3": st(lambda m: m.q_out[8].weight), "b3": st(lambda m: m.q_out[8].bias)}
-        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if training else 0   # CPU generator: no device sync
+        # CPU generator: no device sync.  (Under CUDA-graph capture the kernels read a device-side seed instead.)
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if training else 0
         return ops.adaptive_sequence(xr, fc, q0, dq_vec, w, dq_mode == "relative", training, want_phase, cutoff,
                                      df, seed, strict=(engine == "fused-strict"))
     stack = _ControllerStack(ctrl_mods)

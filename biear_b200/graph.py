@@ -1,0 +1,63 @@
+"""CUDA-graph capture of a whole front-end training step.
+
+One step of the hot path is ~60 launches (STFT, the persistent recurrence kernels, the weight-gradient GEMMs, the
+CC kernel and the PyTorch glue of the loss); issued eagerly from Python they are host-bound on a busy box (measured:
+15 ms/step of wall time around 2 ms of kernel time).  Capturing the step once and replaying it removes the host
+from the loop.  The reference has no counterpart (it issues ~2000 eager launches and ~50 host syncs per step,
+SURVEY.md 3.1-3.2).
+
+    step = GraphedStep(fn, example_inputs, params)      # fn(*inputs) -> scalar loss; captured with its backward
+    loss = step(wavL, wavR)                             # copies the inputs into the static buffers, replays
+    # params[i].grad now hold this step's gradients; loss is a device scalar (static tensor)
+
+Dropout stays random across replays: while capturing, the front-end reads its Philox seed from a device counter that
+the graph itself advances (ops._captured_seed).
+"""
+from __future__ import annotations
+
+from typing import Callable, Iterable, Optional, Sequence
+
+import torch
+
+
+class GraphedStep:
+    def __init__(self, fn: Callable[..., torch.Tensor], example_inputs: Sequence[torch.Tensor],
+                 params: Iterable[torch.nn.Parameter], warmup: int = 3, pool=None, copy_inputs: bool = True):
+        self.params = [p for p in params if p.requires_grad]
+        self.copy_inputs = copy_inputs
+        self.static_inputs = [x.clone() for x in example_inputs] if copy_inputs else list(example_inputs)
+        dev = self.static_inputs[0].device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        # Gradients are taken with torch.autograd.grad (no AccumulateGrad nodes): those nodes remember the stream
+        # they were created on, and one left over from an earlier eager backward on the legacy default stream would
+        # make the capture illegal.
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):          # lazy one-time setup (tables, smem opt-in, allocator warm-up)
+                torch.autograd.grad(fn(*self.static_inputs), self.params, allow_unused=True)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        from . import _lib
+        n0 = _lib.launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, pool=pool):
+            self.loss = fn(*self.static_inputs)
+            grads = torch.autograd.grad(self.loss, self.params, allow_unused=True)
+        self.launches_per_replay = _lib.launch_count() - n0   # kernels of libbiear_b200.so recorded in the graph
+        self.loss = self.loss.detach()
+        self.grads = list(grads)                      # static tensors (graph pool) rewritten by every replay
+        for p, g in zip(self.params, self.grads):
+            p.grad = g
+
+    def pool(self):
+        return self.graph.pool()
+
+    def __call__(self, *inputs: torch.Tensor) -> torch.Tensor:
+        if self.copy_inputs:
+            for dst, src in zip(self.static_inputs, inputs):
+                dst.copy_(src, non_blocking=True)
+        for p, g in zip(self.params, self.grads):
+            if p.grad is not g:                       # e.g. after optimizer.zero_grad(set_to_none=True)
+                p.grad = g
+        self.graph.replay()
+        return self.loss

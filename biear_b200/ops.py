@@ -35,10 +35,28 @@ def _need_cuda(t: torch.Tensor, name: str, dtype=torch.float32):
         raise ValueError(f"biear_b200: {name} must be contiguous")
 
 
+_seed_state = {}   # device index -> int64 device tensor: dropout seed counter used while a CUDA graph is being captured
+
+
 def _prepare(device):
     idx = device.index if device.index is not None else torch.cuda.current_device()
     _lib.ensure_init(idx)
+    if idx not in _seed_state and not torch.cuda.is_current_stream_capturing():
+        base = int(torch.randint(0, 2 ** 62, (1,)).item())
+        _seed_state[idx] = torch.tensor([base], dtype=torch.int64, device=torch.device("cuda", idx))
     return _lib.load()
+
+
+def _captured_seed(device) -> torch.Tensor:
+    """Dropout seed for a forward that is being recorded into a CUDA graph: a device-side counter is advanced on
+    the stream and snapshotted, so every replay of the graph draws fresh masks and the backward of the same replay
+    sees the seed its forward used."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _seed_state:
+        raise RuntimeError("biear_b200: run the front-end once eagerly (warm-up) before capturing it in a CUDA graph")
+    st = _seed_state[idx]
+    st.add_(0x632BE59BD9B4E019)          # odd increment: a full-period walk over the 64-bit seeds
+    return st.clone()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -249,20 +267,24 @@ def _fill(params, **tensors):
         setattr(params, k, v.data_ptr() if v is not None else None)
 
 
-TILE = 32   # rows per tile of the "tile layout" tensors (G, T-1, tiles, D, 32), see include/biear_b200.h
+def tile_rows() -> int:
+    """Rows per tile (R) of the "tile layout" tensors (G, T-1, tiles, D, R), see include/biear_b200.h."""
+    return int(_lib.load().biear_adaptive_tile_rows())
 
 
 def ctrl_wgrad(a: torch.Tensor, do: int, bm: torch.Tensor, di: int, chunks: int, want_bias: bool = True):
-    """dW (G, do, di) [, db (G, do)] from tile-layout operands a (G, chunks', Da, 32) and bm (G, chunks', Db, 32):
+    """dW (G, do, di) [, db (G, do)] from tile-layout operands a (G, chunks', Da, R) and bm (G, chunks', Db, R):
     the first `do` / `di` features of each and the first `chunks` chunks are used (biear_ctrl_wgrad)."""
     G = a.shape[0]
     dev = a.device
     lib = _prepare(dev)
     dw = torch.empty((G, do, di), dtype=torch.float32, device=dev)
     db = torch.empty((G, do), dtype=torch.float32, device=dev) if want_bias else None
-    scratch = torch.empty(int(lib.biear_wgrad_scratch_floats(G, do, di, chunks)), dtype=torch.float32, device=dev)
+    R = a.shape[3]
+    assert bm.shape[3] == R
+    scratch = torch.empty(int(lib.biear_wgrad_scratch_floats(G, do, di, chunks, R)), dtype=torch.float32, device=dev)
     _lib.check(lib.biear_ctrl_wgrad(_ptr(a), a.stride(0), a.stride(1), do, _ptr(bm), bm.stride(0), bm.stride(1), di, G,
-                                    chunks, _ptr(dw), _ptr(db), _ptr(scratch), _stream(dev)), "biear_ctrl_wgrad")
+                                    chunks, R, _ptr(dw), _ptr(db), _ptr(scratch), _stream(dev)), "biear_ctrl_wgrad")
     return dw, db
 
 
@@ -300,6 +322,7 @@ class AdaptiveSequence(torch.autograd.Function):
             dY = torch.empty((rows, T, N), **f32)
             dP = torch.empty((rows, T, N), **f32) if want_phase else None
             S = max(T - 1, 1)
+            TILE = tile_rows()
             tiles = (B + TILE - 1) // TILE
             # h_t lives at step index t+1 of H; H[:, 0] = 0 is "h_{-1}", so H[:, :S] are the GRU's previous states
             H = torch.empty((G, S + 1, tiles, HID, TILE), **f32)
@@ -311,17 +334,22 @@ class AdaptiveSequence(torch.autograd.Function):
             prm = _lib.SeqParams()
             prm.G, prm.E, prm.B, prm.T, prm.N, prm.F, prm.Kin = G, G, B, T, N, F, Kin
             prm.relative, prm.training, prm.seed, prm.force_strict = int(relative), int(training), int(seed), int(strict)
+            seed_dev = _captured_seed(dev) if (training and torch.cuda.is_current_stream_capturing()) else None
             prm.df, prm.cutoff, prm.q_min, prm.q_max = float(df), float(cutoff), 0.05, 30.0
             _fill(prm, fc=fc, q0=q0, dq=dq, X=xr, Y=Y, phase=P, dYdQ=dY, dPdQ=dP, Q=Q, delta=D, flags=flags,
-                  workspace=work, H=H, **sv, **dict(zip(WEIGHT_NAMES, weights)))
+                  workspace=work, H=H, seed_ptr=seed_dev, **sv, **dict(zip(WEIGHT_NAMES, weights)))
             from ctypes import byref
             _lib.check(lib.biear_adaptive_fwd(byref(prm), _stream(dev)), "biear_adaptive_fwd")
         ctx.prm = prm
-        ctx.keep = (xr, fc, q0, dq, weights, Y, Q, D, P, dY, dP, sv, flags, work, H)   # owners of every pointer
-        ctx.dims = (G, B, T, N, Kin, tiles)
+        # owners of every pointer in prm.  The OUTPUTS go through save_for_backward: holding them as plain attributes
+        # would close a reference cycle (ctx -> output tensor -> grad_fn -> ctx) that leaks the whole graph.
+        ctx.keep = (xr, fc, q0, dq, weights, D, dY, dP, sv, flags, work, H, seed_dev)
+        ctx.has_phase = P is not None
+        ctx.dims = (G, B, T, N, Kin, tiles, TILE)
         if P is None:
             P = Y.new_empty(0)
             ctx.mark_non_differentiable(P)
+        ctx.save_for_backward(Y, Q, P)
         if not need_grad:
             ctx.mark_non_differentiable(Y, Q)
         return Y, Q, P
@@ -329,8 +357,11 @@ class AdaptiveSequence(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gY, gQ, gP):
         from ctypes import byref
-        xr, fc, q0, dq, weights, Y, Q, D, P, dY, dP, sv, flags, work, H = ctx.keep
-        G, B, T, N, Kin, tiles = ctx.dims
+        xr, fc, q0, dq, weights, D, dY, dP, sv, flags, work, H, _seed_dev = ctx.keep
+        Y, Q, P = ctx.saved_tensors                  # keeps the buffers behind prm.Y / prm.Q / prm.phase alive
+        if not ctx.has_phase:
+            P = None
+        G, B, T, N, Kin, tiles, TILE = ctx.dims
         none11 = (None,) * 11
         if T < 2 or (gY is None and gQ is None and gP is None):
             return none11 + (None,) * len(WEIGHT_NAMES)

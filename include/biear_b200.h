@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BIEAR_ABI_VERSION 4
+#define BIEAR_ABI_VERSION 5
 #define BIEAR_EINVAL (-1)
 
 /* ABI version (== BIEAR_ABI_VERSION of the library that was built). */
@@ -93,8 +93,8 @@ int biear_band_bwd(const float* X, int64_t x_stride, const float* Q, int64_t q_s
  * Replaces the frame loop of FramewiseAdaptiveGammatoneFB.forward (model_torch.py:333-380) for both ears
  * and DeepEarActiveWaveform._subband_phase_from_X (:1039-1063), and their autograd backward.
  * Row order of the row-major tensors: ear-major, row = ear * B + clip.
- * "Tile layout" tensors are (G, T-1, tiles, D, 32) with tiles = ceil(B / 32): 32 consecutive clips of one
- * controller form a tile, stored feature-major ([D][32]); rows of the last tile beyond B are padding (their
+ * "Tile layout" tensors are (G, T-1, tiles, D, R) with R = biear_adaptive_tile_rows() (16) and tiles = ceil(B / R):
+ * R consecutive clips of one controller form a tile, stored feature-major ([D][R]); rows of the last tile beyond B are padding (their
  * gradient entries are exactly zero).  The forward writes them, the backward reads them and writes the
  * per-sample pre-activation gradients in the same layout; biear_ctrl_wgrad turns those into weight gradients.
  */
@@ -120,7 +120,7 @@ typedef struct BiearSeqParams {
     float *Q, *delta;                                /* (G*B, T, N): Q used for frame t; tanh output that produced it */
     /* saved by the forward for the backward, tile layout, D = 512 (r,z,n,hn), 128 x4, 2, N */
     float *gates, *xh1, *d1, *xh2, *d2, *rstd, *yc;
-    /* GRU states (G, T, tiles, 128, 32): step index 0 is h_{-1} = 0 and must be zeroed by the caller, h_t is written
+    /* GRU states (G, T, tiles, 128, R): step index 0 is h_{-1} = 0 and must be zeroed by the caller, h_t is written
        at step index t+1 -- so H[:, :T-1] are the "previous states" and H[:, 1:] the "new states" of the T-1 steps */
     float* H;
     int32_t* flags;                                  /* ((T-1)*G + 1), zero-initialised by the caller: flags[t*G+g] != 0
@@ -133,13 +133,22 @@ typedef struct BiearSeqParams {
     float *GG, *G_a1, *G_v1, *G_a2, *G_v2, *G_pre;
     /* scratch: biear_adaptive_workspace_floats(G, N) floats (packed per-CTA weight images) */
     float* workspace;
+    /* optional DEVICE location of the dropout seed; when non-NULL it overrides `seed` and is read by the kernels at
+       run time, so that a captured CUDA graph draws fresh masks on every replay (the caller advances it on-stream) */
+    const uint64_t* seed_ptr;
 } BiearSeqParams;
 
+/* Rows per tile (R) of the tile-layout tensors. */
+int biear_adaptive_tile_rows(void);
 /* Floats of scratch the two calls below need in BiearSeqParams.workspace. */
 int64_t biear_adaptive_workspace_floats(int G, int N);
 
+/* Diagnostics: number of clusters of the forward / backward recurrence kernels that fit on the current device
+ * at once (cudaOccupancyMaxActiveClusters); a batch needs G * ceil(B / R) clusters per pass. */
+int biear_adaptive_occupancy(int N, int F, int* fwd_clusters, int* bwd_clusters);
+
 /* Whole forward recurrence in ONE persistent cluster kernel (plus a weight-packing launch and a conditional
- * replay launch that exits immediately unless a non-finite Q was produced): each cluster of 8 CTAs carries 32 rows
+ * replay launch that exits immediately unless a non-finite Q was produced): each cluster of 4 CTAs carries R rows
  * through all T frames with the controller weights and the recurrent state resident in (distributed) shared
  * memory.  No host synchronisation.
  * Non-finite fallback: the reference resets Q to Q0 and the GRU state for the WHOLE batch of an ear when any
@@ -153,16 +162,16 @@ int biear_adaptive_bwd(const BiearSeqParams* p, void* stream);
 
 /*
  * Weight gradient of one Linear layer from tile-layout operands:
- *   dW[g][o][i] = sum_{k < chunks, r < 32} A[g][k][o][r] * Bm[g][k][i][r]      (o < Do, i < Di)
+ *   dW[g][o][i] = sum_{k < chunks, r < R} A[g][k][o][r] * Bm[g][k][i][r]      (o < Do, i < Di; R = tile_rows, 16 or 32)
  *   db[g][o]    = sum_{k, r} A[g][k][o][r]                                      (db nullable)
- * A is (G, chunks, Do, 32) with chunk stride a_chunk_stride floats and group stride a_group_stride, likewise Bm;
- * `scratch` holds biear_wgrad_scratch_floats(G, Do, Di, chunks) floats of split-K partials (deterministic
+ * A is (G, chunks, Do, R) with chunk stride a_chunk_stride floats and group stride a_group_stride, likewise Bm;
+ * `scratch` holds biear_wgrad_scratch_floats(...) floats of split-K partials (deterministic
  * two-pass reduction, no atomics).  Replaces the weight-gradient GEMMs autograd runs for model_torch.py:256-267.
  */
-int64_t biear_wgrad_scratch_floats(int G, int Do, int Di, int64_t chunks);
+int64_t biear_wgrad_scratch_floats(int G, int Do, int Di, int64_t chunks, int tile_rows);
 int biear_ctrl_wgrad(const float* A, int64_t a_group_stride, int64_t a_chunk_stride, int Do,
                      const float* Bm, int64_t b_group_stride, int64_t b_chunk_stride, int Di,
-                     int G, int64_t chunks, float* dW, float* db, float* scratch, void* stream);
+                     int G, int64_t chunks, int tile_rows, float* dW, float* db, float* scratch, void* stream);
 
 /*
  * Broadband interaural cross-correlation feature.  Replaces utils.py:390-420
