@@ -8,7 +8,7 @@
 //   and what autograd derives from both for dL/dQ (closed form).
 //
 // The (B,100,513) weight tensor of the reference is never materialised: one CTA owns one (row, frame)
-// item, stages its 513-bin spectrum once in shared memory as {abs, re, im}, and each group of 8 lanes
+// item, stages its 513-bin spectrum once in shared memory as {1, abs, re, im}, and each group of 8 lanes
 // owns one band, walking only the bins with abs(u) <= cutoff.  Reductions are 3-step warp shuffles; every
 // output element is written by exactly one lane (no atomics).
 #include "band_dev.cuh"
@@ -52,8 +52,7 @@ __global__ void __launch_bounds__(kBandThreads) band_kernel(const BandArgs a) {
         for (int k = threadIdx.x; k < tile; k += kBandThreads) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (k < a.F) {
-                const float2 c = __ldg(x + k);
-                v = make_float4(sqrtf(fmaf(c.x, c.x, c.y * c.y)), c.x, c.y, 0.f);
+                v = spec_entry(__ldg(x + k));
             }
             s_spec[k] = v;
         }

@@ -6,9 +6,11 @@
 // and produces in the same pass the three u^2-moments that make the backward into Q closed-form
 // (SURVEY.md Appendix A.3), so that W is never materialised and never rebuilt.
 //
-// Spectrum tile layout in shared memory: float4 {abs(X), Re X, Im X, 0} per bin, padded with zeros to
+// Spectrum tile layout in shared memory: float4 {1, abs(X), Re X, Im X} per bin, all-zero beyond bin F-1 up to
 // a multiple of 8 bins, 16-byte aligned.  The 8 lanes of a band read 8 consecutive bins (128 B = one
-// conflict-free wavefront); the 4 band groups of the warp read the same addresses (broadcast).
+// conflict-free wavefront); the 4 band groups of the warp read the same addresses (broadcast).  The leading 1
+// makes {sum G, sum G abs(X)} and {sum G Re X, sum G Im X} two packed fp32x2 FMAs (FFMA2, sm_100) per bin, and the
+// zero padding removes the bin-range select from the loop.
 #pragma once
 #include "common.cuh"
 
@@ -57,6 +59,10 @@ __device__ __forceinline__ BandParams band_params(float fc, float q, float df, f
     return p;
 }
 
+__device__ __forceinline__ float4 spec_entry(float2 c) {   // one bin of the shared spectrum tile
+    return make_float4(1.0f, sqrtf(fmaf(c.x, c.x, c.y * c.y)), c.x, c.y);
+}
+
 // Accumulate the 8 sums of the lane's band over the quad's bin window.  `spec` is the padded tile.
 __device__ __forceinline__ BandSums band_accumulate(const float4* __restrict__ spec, int F, const BandParams& p,
                                                     int lane) {
@@ -69,34 +75,33 @@ __device__ __forceinline__ BandSums band_accumulate(const float4* __restrict__ s
     k1 = max(k1, __shfl_xor_sync(0xffffffffu, k1, 16));
     k0 &= ~7;
 
-    BandSums s = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float2 sy = make_float2(0.f, 0.f), zz = make_float2(0.f, 0.f);     // {S, Y}, {Zr, Zi}
+    float2 ma = make_float2(0.f, 0.f), z2 = make_float2(0.f, 0.f);     // {m2, a2}, {z2r, z2i}
     int k = k0 + j;
     float kf = (float)(k - p.kc);
-#pragma unroll 2
+#pragma unroll 4
     for (; k - j <= k1; k += 8, kf += 8.0f) {
-        const float4 x = spec[k];                       // k < spec_tile_len(F) always
+        const float4 x = spec[k];                       // k < spec_tile_len(F) always; zeros beyond F-1
         const float u = fmaf(kf, p.a, p.b);
         const float e = u * u;
-        float g = ex2_approx(-e);
-        g = (k < F) ? g : 0.0f;
+        const float g = ex2_approx(-e);
         const float ge = g * e;
-        s.S += g;
-        s.Y = fmaf(x.x, g, s.Y);
-        s.Zr = fmaf(x.y, g, s.Zr);
-        s.Zi = fmaf(x.z, g, s.Zi);
-        s.m2 += ge;
-        s.a2 = fmaf(x.x, ge, s.a2);
-        s.z2r = fmaf(x.y, ge, s.z2r);
-        s.z2i = fmaf(x.z, ge, s.z2i);
+        const float2 oa = make_float2(x.x, x.y), ri = make_float2(x.z, x.w);
+        const float2 gg = make_float2(g, g), gege = make_float2(ge, ge);
+        sy = __ffma2_rn(oa, gg, sy);
+        zz = __ffma2_rn(ri, gg, zz);
+        ma = __ffma2_rn(oa, gege, ma);
+        z2 = __ffma2_rn(ri, gege, z2);
     }
-    s.S = warp_sum_8(s.S);
-    s.Y = warp_sum_8(s.Y);
-    s.Zr = warp_sum_8(s.Zr);
-    s.Zi = warp_sum_8(s.Zi);
-    s.m2 = warp_sum_8(s.m2);
-    s.a2 = warp_sum_8(s.a2);
-    s.z2r = warp_sum_8(s.z2r);
-    s.z2i = warp_sum_8(s.z2i);
+    BandSums s;
+    s.S = warp_sum_8(sy.x);
+    s.Y = warp_sum_8(sy.y);
+    s.Zr = warp_sum_8(zz.x);
+    s.Zi = warp_sum_8(zz.y);
+    s.m2 = warp_sum_8(ma.x);
+    s.a2 = warp_sum_8(ma.y);
+    s.z2r = warp_sum_8(z2.x);
+    s.z2i = warp_sum_8(z2.y);
     return s;
 }
 

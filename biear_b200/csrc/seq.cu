@@ -96,8 +96,8 @@ struct FwdSmem {   // offsets in floats
     __host__ __device__ int yc() const { return vec() + 1088; }                 // [128][32]; aliased by a2
     __host__ __device__ int h0() const { return yc() + kHid * kR; }             // [128][32] x 2 (ping-pong)
     __host__ __device__ int a1() const { return h0() + 2 * kHid * kR; }
-    __host__ __device__ int red() const { return a1() + kHid * kR; }            // 16 x 128
-    __host__ __device__ int stat() const { return red() + 16 * 128; }           // 2 x 256
+    __host__ __device__ int red() const { return a1() + kHid * kR; }            // 2 x 16 x 128
+    __host__ __device__ int stat() const { return red() + 2 * 16 * 128; }       // 2 x kSeqThreads
     __host__ __device__ int q() const { return stat() + 2 * kSeqThreads; }      // [128][4]: Q_t of this CTA's 4 rows
     __host__ __device__ int ystage() const { return q() + kHid * kRT; }         // [4][128]
     __host__ __device__ int spec() const { return ystage() + kRT * kHid; }      // [4][tile] float4
@@ -126,7 +126,7 @@ __device__ __forceinline__ void ln_silu_drop_fwd(const BiearSeqParams& p, unsign
                                                  const float* __restrict__ gamma_s, const float* __restrict__ beta_s,
                                                  int layer, int t, long long grow0, int rank, float* xh_tile,
                                                  float* d_tile, float* rstd_tile) {
-    constexpr int PARTS = kSeqThreads / kR, FPP = kHid / PARTS;     // 16 parts of 8 features
+    constexpr int PARTS = kSeqThreads / kR, FPP = kHid / PARTS;     // 32 parts of 4 features
     const int row = threadIdx.x % kR, part = threadIdx.x / kR;
     const int f0 = part * FPP;
     float v[FPP];
@@ -177,15 +177,14 @@ __device__ __forceinline__ void ln_silu_drop_fwd(const BiearSeqParams& p, unsign
     __syncthreads();
 }
 
-// Spectra of this CTA's 4 rows for frame t -> shared {abs, re, im, 0} tiles (zeros for padding rows / bins).
+// Spectra of this CTA's 4 rows for frame t -> shared {1, abs, re, im} tiles (zeros for padding rows / bins).
 __device__ __forceinline__ void load_spectra(const BiearSeqParams& p, float4* spec_s, int tile, long long grow0,
                                              int b0, int t) {
     for (int idx = threadIdx.x; idx < kRT * tile; idx += kSeqThreads) {
         const int i = idx / tile, k = idx - i * tile;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (k < p.F && b0 + i < p.B) {
-            const float2 c = __ldg(reinterpret_cast<const float2*>(p.X) + ((grow0 + i) * p.T + t) * p.F + k);
-            v = make_float4(sqrtf(fmaf(c.x, c.x, c.y * c.y)), c.x, c.y, 0.f);
+            v = spec_entry(__ldg(reinterpret_cast<const float2*>(p.X) + ((grow0 + i) * p.T + t) * p.F + k));
         }
         spec_s[idx] = v;
     }
@@ -353,10 +352,11 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
             {
                 float ar[kRT] = {0.f, 0.f, 0.f, 0.f}, az[kRT] = {0.f, 0.f, 0.f, 0.f};
                 float ain[kRT] = {0.f, 0.f, 0.f, 0.f}, ahn[kRT] = {0.f, 0.f, 0.f, 0.f};
-                const int kh = (N + 1) >> 1;
-                dot_rows3(ar, az, ain, yc_s + rg * kRT, img_s + fwd_img_wih(N) + u, ks ? kh : 0, ks ? N : kh);
-                if (!h_zero)
-                    dot_rows3(ar, az, ahn, hcur_s + rg * kRT, img_s + fwd_img_whh(N) + u, ks ? 64 : 0, ks ? 128 : 64);
+                int k0, k1;
+                k_range(N, ks, k0, k1);
+                dot_rows3(ar, az, ain, yc_s + rg * kRT, img_s + fwd_img_wih(N) + u, k0, k1);
+                k_range(kHid, ks, k0, k1);
+                if (!h_zero) dot_rows3(ar, az, ahn, hcur_s + rg * kRT, img_s + fwd_img_whh(N) + u, k0, k1);
                 float acc[16];
 #pragma unroll
                 for (int i = 0; i < kRT; ++i) {
@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                     acc[8 + i] = ain[i];
                     acc[12 + i] = ahn[i];
                 }
-                reduce_halves<16>(acc, red_s, ks, slot);
+                reduce_ks<16>(acc, red_s, ks, slot);
                 if (ks == 0) {
                     const float br = vec_s[V_BR + u], bz = vec_s[V_BZ + u], bin = vec_s[V_BIN + u], bhn = vec_s[V_BHN + u];
                     float hv[kRT], vr[kRT], vz[kRT], vn[kRT], vh[kRT];
@@ -392,8 +392,10 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
             // ---- Linear 1 -> LayerNorm -> SiLU -> Dropout ------------------------------------------------------
             {
                 float acc[kRT] = {0.f, 0.f, 0.f, 0.f};
-                dot_rows(acc, hnext_s + rg * kRT, img_s + fwd_img_w1(N) + u, ks ? 64 : 0, ks ? 128 : 64);
-                reduce_halves<kRT>(acc, red_s, ks, slot);
+                int k0, k1;
+                k_range(kHid, ks, k0, k1);
+                dot_rows(acc, hnext_s + rg * kRT, img_s + fwd_img_w1(N) + u, k0, k1);
+                reduce_ks<kRT>(acc, red_s, ks, slot);
                 if (ks == 0) {
                     const float bb = vec_s[V_B1 + u];
 #pragma unroll
@@ -408,8 +410,10 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
             // ---- Linear 2 -> LayerNorm -> SiLU -> Dropout ------------------------------------------------------
             {
                 float acc[kRT] = {0.f, 0.f, 0.f, 0.f};
-                dot_rows(acc, a1_s + rg * kRT, img_s + fwd_img_w2(N) + u, ks ? 64 : 0, ks ? 128 : 64);
-                reduce_halves<kRT>(acc, red_s, ks, slot);
+                int k0, k1;
+                k_range(kHid, ks, k0, k1);
+                dot_rows(acc, a1_s + rg * kRT, img_s + fwd_img_w2(N) + u, k0, k1);
+                reduce_ks<kRT>(acc, red_s, ks, slot);
                 if (ks == 0) {
                     const float bb = vec_s[V_B2 + u];
 #pragma unroll
@@ -425,8 +429,10 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
             {
                 float acc[kRT] = {0.f, 0.f, 0.f, 0.f};
                 const bool mine = u < nu_c;
-                if (mine) dot_rows(acc, a2_s + rg * kRT, img_s + fwd_img_w3(N) + u, ks ? 64 : 0, ks ? 128 : 64);
-                reduce_halves<kRT>(acc, red_s, ks, slot);
+                int k0, k1;
+                k_range(kHid, ks, k0, k1);
+                if (mine) dot_rows(acc, a2_s + rg * kRT, img_s + fwd_img_w3(N) + u, k0, k1);
+                reduce_ks<kRT>(acc, red_s, ks, slot);
                 if (ks == 0 && mine) {
                     const int n = rank * NU + u;
                     const float bb = vec_s[V_B3 + u], q0 = vec_s[V_Q0S + u], dq = vec_s[V_DQS + u];
@@ -475,8 +481,8 @@ struct BwdSmem {   // offsets in floats
     __host__ __device__ int bufa() const { return vec() + 1024; }                  // [128][32]; first quarter of gate
     __host__ __device__ int gate() const { return bufa(); }                        // [4*128][32]: drp, dzp, dnp, dhn
     __host__ __device__ int dpre() const { return gate() + 4 * kHid * kR; }        // [128][32]; aliased by bufb
-    __host__ __device__ int red() const { return dpre() + kHid * kR; }             // 8 x 128
-    __host__ __device__ int stat() const { return red() + 8 * 128; }               // 2 x 256
+    __host__ __device__ int red() const { return dpre() + kHid * kR; }             // 2 x 8 x 128
+    __host__ __device__ int stat() const { return red() + 2 * 8 * 128; }           // 2 x kSeqThreads
     __host__ __device__ int stage() const { return stat() + 2 * kSeqThreads; }     // [4][128]
     __host__ __device__ int dyc() const { return stage() + kRT * kHid; }           // [128][4]
     __host__ __device__ int total() const { return dyc() + kHid * kRT; }
@@ -620,9 +626,10 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
         // ---- Linear 3 ^T --------------------------------------------------------------------------------------
         {
             float acc[kRT] = {0.f, 0.f, 0.f, 0.f};
-            const int nh = (N + 1) >> 1;
-            dot_rows(acc, dpre_s + rg * kRT, img_s + bwd_img_w3c(N) + u, ks ? nh : 0, ks ? N : nh);
-            reduce_halves<kRT>(acc, red_s, ks, slot);
+            int k0, k1;
+            k_range(N, ks, k0, k1);
+            dot_rows(acc, dpre_s + rg * kRT, img_s + bwd_img_w3c(N) + u, k0, k1);
+            reduce_ks<kRT>(acc, red_s, ks, slot);
             if (ks == 0) broadcast_rows(cluster, bufa_s, ug, rg * kRT, acc);
         }
         cluster.sync();   // #2
@@ -631,8 +638,10 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
         // ---- Linear 2 ^T --------------------------------------------------------------------------------------
         {
             float acc[kRT] = {0.f, 0.f, 0.f, 0.f};
-            dot_rows(acc, bufa_s + rg * kRT, img_s + bwd_img_w2c(N) + u, ks ? 64 : 0, ks ? 128 : 64);
-            reduce_halves<kRT>(acc, red_s, ks, slot);
+            int k0, k1;
+            k_range(kHid, ks, k0, k1);
+            dot_rows(acc, bufa_s + rg * kRT, img_s + bwd_img_w2c(N) + u, k0, k1);
+            reduce_ks<kRT>(acc, red_s, ks, slot);
             if (ks == 0) broadcast_rows(cluster, bufb_s, ug, rg * kRT, acc);   // bufb aliases dpre: its reads ended before #2
         }
         cluster.sync();   // #3
@@ -642,8 +651,10 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
         float dh_direct[kRT] = {0.f, 0.f, 0.f, 0.f};
         {
             float acc[kRT] = {0.f, 0.f, 0.f, 0.f};
-            dot_rows(acc, bufb_s + rg * kRT, img_s + bwd_img_w1c(N) + u, ks ? 64 : 0, ks ? 128 : 64);
-            reduce_halves<kRT>(acc, red_s, ks, slot);
+            int k0, k1;
+            k_range(kHid, ks, k0, k1);
+            dot_rows(acc, bufb_s + rg * kRT, img_s + bwd_img_w1c(N) + u, k0, k1);
+            reduce_ks<kRT>(acc, red_s, ks, slot);
             if (ks == 0) {
                 const float* gt = p.gates + tb * 4 * kHid * kR + ug * kR + rg * kRT;
                 const float4 r4 = __ldg(reinterpret_cast<const float4*>(gt));
@@ -688,16 +699,15 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
             const float* x = gate_s + rg * kRT;
             const float* whhc = img_s + bwd_img_whhc(N) + u;
             const float* wihc = img_s + bwd_img_wihc(N) + u;
-            // rows o of W_hh: [0,128) r gate, [128,256) z gate, [256,384) n gate (pairs with dhn = gate block 3)
-            if (ks == 0) {
-                dot_rows(acc, x, whhc, 0, 192);
-            } else {
-                dot_rows(acc, x, whhc, 192, 256);
-                dot_rows(acc, x + kHid * kR, whhc, 256, 384);
-            }
+            // rows o of W_hh: [0,128) r gate, [128,256) z gate, [256,384) n gate (pairs with dhn = gate block 3, i.e.
+            // gate_s rows o + 128); rows o of W_ih pair with gate_s rows o (drp, dzp, dnp)
+            int o0, o1;
+            k_range(3 * kHid, ks, o0, o1);
+            dot_rows(acc, x, whhc, min(o0, 2 * kHid), min(o1, 2 * kHid));
+            dot_rows(acc, x + kHid * kR, whhc, max(o0, 2 * kHid), max(o1, 2 * kHid));
             const bool mine = u < nu_c;
-            if (mine) dot_rows(acc + kRT, x, wihc, ks ? 192 : 0, ks ? 384 : 192);
-            reduce_halves<2 * kRT>(acc, red_s, ks, slot);
+            if (mine) dot_rows(acc + kRT, x, wihc, o0, o1);
+            reduce_ks<2 * kRT>(acc, red_s, ks, slot);
             if (ks == 0) {
 #pragma unroll
                 for (int i = 0; i < kRT; ++i) dh_carry[i] = acc[i] + dh_direct[i];

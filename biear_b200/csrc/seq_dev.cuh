@@ -14,10 +14,12 @@
 // (cudaOccupancyMaxActiveClusters, tools/occupancy.py), and the benchmark batch (256 clips x 2 ears) needs 16 tiles
 // of 32 rows -- one more than fit, i.e. two waves -- or 32 tiles of 16 rows, which run as one wave on 128 SMs.
 //
-// Thread layout of the GEMM phases (256 threads): tid = ks*128 + rg*32 + u
+// Thread layout of the GEMM phases (512 threads): tid = ks*128 + rg*32 + u
 //   u  in [0,32)  output unit inside the CTA's slice
 //   rg in [0,4)   row group: rows 4rg .. 4rg+3 of the tile (the rows whose band stage CTA rg runs)
-//   ks in {0,1}   half of the contraction range; the halves are summed through shared memory
+//   ks in [0,4)   quarter of the contraction range; the quarters are summed through shared memory
+// (16 warps per SM: the per-frame work is a chain of short dependent phases, so it is latency- not throughput-bound;
+//  with 8 warps the schedulers issued on 40 % of the cycles, ncu profiles/r1_*)
 // Activations live feature-major, [feature][32 rows], in shared memory AND in the tensors saved for the backward
 // pass ("tile layout": (G, T-1, tiles, D, 16)), so a thread moves its 4 rows of one feature with one 128-bit access.
 #pragma once
@@ -29,14 +31,15 @@ namespace biear {
 namespace cg = cooperative_groups;
 
 constexpr int kHid = 128;           // GRU / MLP width (model_torch.py:256-267)
-constexpr int kSeqThreads = 256;
+constexpr int kSeqThreads = 512;
+constexpr int kKS = 4;              // k-splits of every contraction
 constexpr int kCS = 4;              // CTAs per cluster
 constexpr int kU = kHid / kCS;      // hidden units per CTA (32)
 constexpr int kR = 16;              // rows per tile
 constexpr int kRT = 4;              // rows per thread = rows per CTA in the band stage
 constexpr float kDropP = 0.1f;      // model_torch.py:261, 265
 constexpr float kLnEps = 1e-5f;
-static_assert(2 * (kR / kRT) * kU == kSeqThreads, "thread layout");
+static_assert(kKS * (kR / kRT) * kU == kSeqThreads, "thread layout");
 static_assert(kR / kRT == kCS, "row groups == CTAs of the cluster");
 
 __host__ __device__ constexpr int bands_per_cta(int N) { return (N + kCS - 1) / kCS; }
@@ -129,10 +132,26 @@ __device__ __forceinline__ void dot_rows3(float a0[kRT], float a1[kRT], float a2
     }
 }
 
-// Sum the two k-halves: the ks == 1 threads park their accumulators, the ks == 0 threads add them.
-// red_s holds NACC floats for each of the 128 (rg,u) slots.  Contains two block barriers.
+// [k0, k1) of k-split ks over a contraction of length K
+__device__ __forceinline__ void k_range(int K, int ks, int& k0, int& k1) {
+    k0 = (K * ks) / kKS;
+    k1 = (K * (ks + 1)) / kKS;
+}
+
+// Sum the four k-splits in two rounds (ks 2,3 -> ks 0,1; then ks 1 -> ks 0); the result lands in the ks == 0 threads.
+// red_s holds 2 * NACC floats for each of the 128 (rg,u) slots.  Contains four block barriers.
 template <int NACC>
-__device__ __forceinline__ void reduce_halves(float* acc, float* red_s, int ks, int slot) {
+__device__ __forceinline__ void reduce_ks(float* acc, float* red_s, int ks, int slot) {
+    __syncthreads();
+    if (ks >= 2) {
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) red_s[((ks - 2) * NACC + i) * 128 + slot] = acc[i];
+    }
+    __syncthreads();
+    if (ks < 2) {
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) acc[i] += red_s[(ks * NACC + i) * 128 + slot];
+    }
     __syncthreads();
     if (ks == 1) {
 #pragma unroll
