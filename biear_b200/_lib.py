@@ -11,7 +11,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BIEAR_B200_LIB") or os.path.join(_HERE, "lib", "libbiear_b200.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 _p = c_void_p
 _i = c_int
@@ -36,6 +36,15 @@ class SeqParams(Structure):
     )
 
 
+class WgradJob(Structure):
+    """struct BiearWgradJob of include/biear_b200.h."""
+    _fields_ = [("A", c_void_p), ("a_group_stride", c_int64), ("a_chunk_stride", c_int64), ("Do", c_int32),
+                ("Bm", c_void_p), ("b_group_stride", c_int64), ("b_chunk_stride", c_int64), ("Di", c_int32),
+                ("chunks", c_int64), ("dW", c_void_p), ("db", c_void_p)]
+
+
+WGRAD_MAX_JOBS = 8
+
 # name -> (restype, argtypes); mirrors include/biear_b200.h one to one
 SIGNATURES = {
     "biear_abi_version": (_i, []),
@@ -52,8 +61,8 @@ SIGNATURES = {
     "biear_adaptive_workspace_floats": (_l, [_i, _i]),
     "biear_adaptive_occupancy": (_i, [_i, _i, POINTER(c_int), POINTER(c_int)]),
     "biear_adaptive_tile_rows": (_i, []),
-    "biear_wgrad_scratch_floats": (_l, [_i, _i, _i, _l, _i]),
-    "biear_ctrl_wgrad": (_i, [_p, _l, _l, _i, _p, _l, _l, _i, _i, _l, _i, _p, _p, _p, _p]),
+    "biear_wgrad_scratch_floats": (_l, [POINTER(WgradJob), _i, _i, _i]),
+    "biear_ctrl_wgrad": (_i, [POINTER(WgradJob), _i, _i, _i, _p, _p]),
 }
 
 _lib = None

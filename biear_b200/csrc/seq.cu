@@ -32,8 +32,11 @@ namespace biear {
 // ==================================================================================================
 // weight images
 // ==================================================================================================
+constexpr int kPackSlices = 16;   // CTAs per image (grid.y)
+
 __global__ void __launch_bounds__(256) pack_fwd_images_kernel(const BiearSeqParams p, float* __restrict__ img) {
     const int g = blockIdx.x / kCS, c = blockIdx.x % kCS;
+    const int tid0 = blockIdx.y * blockDim.x + threadIdx.x, stride = gridDim.y * blockDim.x;
     const int N = p.N, NU = bands_per_cta(N);
     float* out = img + (long long)blockIdx.x * fwd_img_floats(N);
     const float* w_ih = p.w_ih + (long long)g * 3 * kHid * p.Kin;
@@ -42,17 +45,17 @@ __global__ void __launch_bounds__(256) pack_fwd_images_kernel(const BiearSeqPara
     const float* w2 = p.w2 + (long long)g * kHid * kHid;
     const float* w3 = p.w3 + (long long)g * N * kHid;
     // gate images: consecutive threads walk k (the contiguous axis of the torch layout) for coalesced reads
-    for (int idx = threadIdx.x; idx < kU * 3 * N; idx += blockDim.x) {
+    for (int idx = tid0; idx < kU * 3 * N; idx += stride) {
         const int k = idx % N, gu = idx / N, gate = gu % 3, u = gu / 3;
         const long long o = gate * kHid + c * kU + u;
         out[fwd_img_wih(N) + (k * 3 + gate) * kU + u] = fmaf(0.2f, w_ih[o * p.Kin + N + k], w_ih[o * p.Kin + k]);
     }
-    for (int idx = threadIdx.x; idx < kU * 3 * kHid; idx += blockDim.x) {
+    for (int idx = tid0; idx < kU * 3 * kHid; idx += stride) {
         const int k = idx % kHid, gu = idx / kHid, gate = gu % 3, u = gu / 3;
         const int o = gate * kHid + c * kU + u;
         out[fwd_img_whh(N) + (k * 3 + gate) * kU + u] = w_hh[o * kHid + k];
     }
-    for (int idx = threadIdx.x; idx < kU * kHid; idx += blockDim.x) {
+    for (int idx = tid0; idx < kU * kHid; idx += stride) {
         const int k = idx % kHid, u = idx / kHid;
         out[fwd_img_w1(N) + k * kU + u] = w1[(c * kU + u) * kHid + k];
         out[fwd_img_w2(N) + k * kU + u] = w2[(c * kU + u) * kHid + k];
@@ -63,6 +66,7 @@ __global__ void __launch_bounds__(256) pack_fwd_images_kernel(const BiearSeqPara
 
 __global__ void __launch_bounds__(256) pack_bwd_images_kernel(const BiearSeqParams p, float* __restrict__ img) {
     const int g = blockIdx.x / kCS, c = blockIdx.x % kCS;
+    const int tid0 = blockIdx.y * blockDim.x + threadIdx.x, stride = gridDim.y * blockDim.x;
     const int N = p.N, NU = bands_per_cta(N);
     float* out = img + (long long)blockIdx.x * bwd_img_floats(N);
     const float* w_ih = p.w_ih + (long long)g * 3 * kHid * p.Kin;
@@ -70,14 +74,14 @@ __global__ void __launch_bounds__(256) pack_bwd_images_kernel(const BiearSeqPara
     const float* w1 = p.w1 + (long long)g * kHid * kHid;
     const float* w2 = p.w2 + (long long)g * kHid * kHid;
     const float* w3 = p.w3 + (long long)g * N * kHid;
-    for (int idx = threadIdx.x; idx < N * kU; idx += blockDim.x)
+    for (int idx = tid0; idx < N * kU; idx += stride)
         out[bwd_img_w3c(N) + idx] = w3[(idx / kU) * kHid + c * kU + (idx % kU)];
-    for (int idx = threadIdx.x; idx < kHid * kU; idx += blockDim.x) {
+    for (int idx = tid0; idx < kHid * kU; idx += stride) {
         const int o = idx / kU, u = idx % kU;
         out[bwd_img_w2c(N) + idx] = w2[o * kHid + c * kU + u];
         out[bwd_img_w1c(N) + idx] = w1[o * kHid + c * kU + u];
     }
-    for (int idx = threadIdx.x; idx < 3 * kHid * kU; idx += blockDim.x) {
+    for (int idx = tid0; idx < 3 * kHid * kU; idx += stride) {
         const int o = idx / kU, u = idx % kU;
         out[bwd_img_whhc(N) + idx] = w_hh[o * kHid + c * kU + u];
         const int n = c * NU + u;
@@ -811,7 +815,7 @@ extern "C" int biear_adaptive_fwd(const BiearSeqParams* p, void* stream) {
     const size_t smem = sizeof(float) * (size_t)FwdSmem(p->N, p->F).total();
     BIEAR_REQUIRE(smem <= 227 * 1024, "biear_adaptive_fwd: N=%d F=%d needs %zu B of shared memory", p->N, p->F, smem);
     const int tiles = (p->B + kR - 1) / kR;
-    pack_fwd_images_kernel<<<p->G * kCS, 256, 0, st>>>(*p, p->workspace);
+    pack_fwd_images_kernel<<<dim3(p->G * kCS, kPackSlices), 256, 0, st>>>(*p, p->workspace);
     BIEAR_LAUNCH_CHECK("pack_fwd_images_kernel");
     if (!p->force_strict)
         if (int e = launch_cluster(seq_fwd_kernel<false>, "seq_fwd_kernel", p->G * tiles, smem, st, *p, p->workspace)) return e;
@@ -827,7 +831,7 @@ extern "C" int biear_adaptive_bwd(const BiearSeqParams* p, void* stream) {
     const size_t smem = sizeof(float) * (size_t)BwdSmem(p->N).total();
     BIEAR_REQUIRE(smem <= 227 * 1024, "biear_adaptive_bwd: N=%d needs %zu B of shared memory", p->N, smem);
     const int tiles = (p->B + kR - 1) / kR;
-    pack_bwd_images_kernel<<<p->G * kCS, 256, 0, st>>>(*p, p->workspace);
+    pack_bwd_images_kernel<<<dim3(p->G * kCS, kPackSlices), 256, 0, st>>>(*p, p->workspace);
     BIEAR_LAUNCH_CHECK("pack_bwd_images_kernel");
     return launch_cluster(seq_bwd_kernel, "seq_bwd_kernel", p->G * tiles, smem, st, *p, p->workspace);
 }

@@ -1,14 +1,16 @@
-// Weight gradients of the controller's Linear layers from tile-layout operands (see include/biear_b200.h):
-//   dW[g][o][i] = sum_{k < chunks} sum_{r < R} A[g][k][o][r] * Bm[g][k][i][r],   db[g][o] = sum_{k,r} A[g][k][o][r]
-// with R = tile_rows (16 or 32; 32 / R consecutive chunks form one 32-sample slab)
+// Weight gradients of the Q controllers from tile-layout operands (see include/biear_b200.h), ALL layers in two
+// launches:
+//   matrix job    dW[g][o][i] = sum_{k < chunks} sum_{r < R} A[g][k][o][r] * Bm[g][k][i][r],   db[g][o] = sum_{k,r} A[g][k][o][r]
+//   diagonal job  dW[g][o]    = sum_{k,r} A[g][k][o][r] * Bm[g][k][o][r]     (LayerNorm gamma; db = LayerNorm beta)
 // A = per-sample pre-activation gradients written by the backward recurrence, Bm = the layer inputs saved by the
-// forward recurrence.  Both are "K-major in chunks of 32", so a 64 x 64 output tile streams [64][32] slabs of each
-// operand straight into shared memory with 128-bit loads.  The contraction length (chunks*32 = (T-1)*B samples) is
-// far longer than the outputs are wide, so the work is split along K over the grid; partials go to scratch and
-// a second kernel sums them in a fixed order (deterministic, no atomics).
+// forward recurrence; R = tile rows (16 or 32; 32/R consecutive chunks form one 32-sample slab).  Both operands are
+// "K-major in chunks", so a 64 x 64 output tile streams [64][32] slabs of each operand straight into shared memory
+// with 128-bit loads.  The contraction ((T-1)*B samples) is far longer than the outputs are wide, so every job is
+// split along K over the grid; partials go to scratch and ONE second kernel sums them in a fixed order
+// (deterministic, no atomics).  fp32 FFMA on purpose: TF32 cannot hold the 1e-4 gradient parity contract.
 //
 // Replaces what autograd + cuBLAS do for the weight gradients of model_torch.py:256-267 (GRU weight_ih / weight_hh,
-// three Linear layers) in the reference.
+// three Linear layers, two LayerNorms) in the reference: ~30 library launches per ear there.
 #include "common.cuh"
 
 namespace biear {
@@ -16,31 +18,41 @@ namespace biear {
 constexpr int kWgTile = 64;          // output tile (o and i)
 constexpr int kWgThreads = 256;      // 16 x 16 threads, 4 x 4 outputs each
 constexpr int kWgPitch = 36;         // padded slab row (floats): 16-byte aligned, conflict-free column reads
+constexpr int kWgMaxJobs = BIEAR_WGRAD_MAX_JOBS;
 
-struct WgradArgs {
+struct WgradJobPlan {
     const float* A; long long a_group, a_chunk; int Do;
-    const float* B; long long b_group, b_chunk; int Di;
-    int G; long long chunks; int splits; long long chunks_per_split;   // "chunks" here = 32-sample slabs
-    long long tile_chunks; int tile_w;                                  // chunks of tile_w samples in the operands
-    float* part;     // (G, splits, Do, Di)
-    float* bpart;    // (G, splits, Do) or null
+    const float* B; long long b_group, b_chunk; int Di;      // Di == 0: diagonal job
+    long long tile_chunks;                                    // operand chunks (of tile_w samples)
+    long long slabs;                                          // 32-sample slabs
+    int tiles_i, tiles, splits; long long slabs_per_split;
+    int cta_begin;                                            // first CTA of this job in the partial grid
+    long long part_off, bpart_off;                            // offsets into scratch (floats); bpart_off < 0: no bias
+    long long out_begin;                                      // first element of this job in the reduce index space
+    float* dW; float* db;
 };
 
-__global__ void __launch_bounds__(kWgThreads) wgrad_partial_kernel(const WgradArgs a) {
+struct WgradPlan {
+    WgradJobPlan job[kWgMaxJobs];
+    int n_jobs, G, tile_w;
+    int total_ctas;
+    long long total_out;
+    float* scratch;
+};
+
+__device__ __forceinline__ void wgrad_matrix(const WgradPlan& pl, const WgradJobPlan& a, int tile, int split, int g) {
     __shared__ __align__(16) float As[2][kWgTile * kWgPitch];
     __shared__ __align__(16) float Bs[2][kWgTile * kWgPitch];
-    const int tiles_i = (a.Di + kWgTile - 1) / kWgTile;
-    const int to = blockIdx.x / tiles_i, ti = blockIdx.x % tiles_i;
-    const int split = blockIdx.y, g = blockIdx.z;
+    const int to = tile / a.tiles_i, ti = tile % a.tiles_i;
     const int o0 = to * kWgTile, i0 = ti * kWgTile;
-    const long long c0 = (long long)split * a.chunks_per_split;
-    const long long c1 = min(a.chunks, c0 + a.chunks_per_split);
+    const long long c0 = (long long)split * a.slabs_per_split;
+    const long long c1 = min(a.slabs, c0 + a.slabs_per_split);
     const float* Ag = a.A + (long long)g * a.a_group;
     const float* Bg = a.B + (long long)g * a.b_group;
     const int tid = threadIdx.x;
     const int ty = tid / 16, tx = tid % 16;          // outputs o0 + ty + 16*{0..3}, i0 + tx + 16*{0..3}
-    // slab loader: 64 rows x 8 float4 = 512 float4 per operand, 2 per thread
-    const int lr = tid / 8, lc = tid % 8;            // rows lr and lr + 32, float4 column lc
+    const int lr = tid / 8, lc = tid % 8;            // slab loader: rows lr and lr + 32, float4 column lc
+    const int tile_w = pl.tile_w;
 
     float acc[4][4] = {};
     float bacc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -49,12 +61,12 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_partial_kernel(const WgradAr
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int r = lr + 32 * h;
-            const long long cc = c * (32 / a.tile_w) + (lc * 4) / a.tile_w;      // operand chunk of this float4 column
-            const int off = (lc * 4) % a.tile_w;
+            const long long cc = c * (32 / tile_w) + (lc * 4) / tile_w;      // operand chunk of this float4 column
+            const int off = (lc * 4) % tile_w;
             const bool live = cc < a.tile_chunks;
-            ra[h] = (live && o0 + r < a.Do) ? __ldg(reinterpret_cast<const float4*>(Ag + cc * a.a_chunk + (long long)(o0 + r) * a.tile_w + off))
+            ra[h] = (live && o0 + r < a.Do) ? __ldg(reinterpret_cast<const float4*>(Ag + cc * a.a_chunk + (long long)(o0 + r) * tile_w + off))
                                             : make_float4(0.f, 0.f, 0.f, 0.f);
-            rb[h] = (live && i0 + r < a.Di) ? __ldg(reinterpret_cast<const float4*>(Bg + cc * a.b_chunk + (long long)(i0 + r) * a.tile_w + off))
+            rb[h] = (live && i0 + r < a.Di) ? __ldg(reinterpret_cast<const float4*>(Bg + cc * a.b_chunk + (long long)(i0 + r) * tile_w + off))
                                             : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     };
@@ -100,7 +112,7 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_partial_kernel(const WgradAr
         __syncthreads();
         buf ^= 1;
     }
-    float* out = a.part + ((long long)(g * a.splits + split) * a.Do) * a.Di;
+    float* out = pl.scratch + a.part_off + ((long long)(g * a.splits + split) * a.Do) * a.Di;
 #pragma unroll
     for (int y = 0; y < 4; ++y) {
         const int o = o0 + ty + 16 * y;
@@ -110,70 +122,166 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_partial_kernel(const WgradAr
             const int i = i0 + tx + 16 * x;
             if (i < a.Di) out[(long long)o * a.Di + i] = acc[y][x];
         }
-        if (a.bpart && tx == 0 && ti == 0) a.bpart[(long long)(g * a.splits + split) * a.Do + o] = bacc[y];
+        if (a.bpart_off >= 0 && tx == 0 && ti == 0)
+            pl.scratch[a.bpart_off + (long long)(g * a.splits + split) * a.Do + o] = bacc[y];
     }
 }
 
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, int splits, long long per_group,
-                                                           int G, float* __restrict__ out) {
-    const long long total = (long long)G * per_group;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const long long g = idx / per_group, e = idx - g * per_group;
-        const float* src = part + g * splits * per_group + e;
+// Diagonal job: one CTA per (g, split) covers all Do <= 128 features; 2 threads per feature (8 of the 16 / 16 of the
+// 32 tile rows each).
+__device__ __forceinline__ void wgrad_diagonal(const WgradPlan& pl, const WgradJobPlan& a, int split, int g) {
+    const int tile_w = pl.tile_w;
+    const int f = threadIdx.x >> 1, half = threadIdx.x & 1;
+    const int per = tile_w / 2;
+    const long long per_split = a.slabs_per_split * (32 / tile_w);     // in operand chunks
+    const long long c0 = (long long)split * per_split;
+    const long long c1 = min(a.tile_chunks, c0 + per_split);
+    float dot = 0.f, sum = 0.f;
+    if (f < a.Do) {
+        const float* Ag = a.A + (long long)g * a.a_group + (long long)f * tile_w + half * per;
+        const float* Bg = a.B + (long long)g * a.b_group + (long long)f * tile_w + half * per;
+        for (long long c = c0; c < c1; ++c) {
+            for (int q = 0; q < per; q += 4) {
+                const float4 x = __ldg(reinterpret_cast<const float4*>(Ag + c * a.a_chunk + q));
+                const float4 y = __ldg(reinterpret_cast<const float4*>(Bg + c * a.b_chunk + q));
+                dot = fmaf(x.x, y.x, dot); dot = fmaf(x.y, y.y, dot); dot = fmaf(x.z, y.z, dot); dot = fmaf(x.w, y.w, dot);
+                sum += (x.x + x.y) + (x.z + x.w);
+            }
+        }
+    }
+    dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    if (f < a.Do && half == 0) {
+        pl.scratch[a.part_off + (long long)(g * a.splits + split) * a.Do + f] = dot;
+        if (a.bpart_off >= 0) pl.scratch[a.bpart_off + (long long)(g * a.splits + split) * a.Do + f] = sum;
+    }
+}
+
+__global__ void __launch_bounds__(kWgThreads) wgrad_partial_kernel(const WgradPlan pl) {
+    int j = 0;
+    while (j + 1 < pl.n_jobs && (int)blockIdx.x >= pl.job[j + 1].cta_begin) ++j;
+    const WgradJobPlan& a = pl.job[j];
+    int local = blockIdx.x - a.cta_begin;
+    const int per_g = a.tiles * a.splits;
+    const int g = local / per_g;
+    local -= g * per_g;
+    const int split = local / a.tiles, tile = local % a.tiles;
+    if (a.Di > 0)
+        wgrad_matrix(pl, a, tile, split, g);
+    else
+        wgrad_diagonal(pl, a, split, g);
+}
+
+// One pass over every output of every job: sum the split-K partials in a fixed order.
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgradPlan pl) {
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < pl.total_out;
+         idx += (long long)gridDim.x * blockDim.x) {
+        int j = 0;
+        while (j + 1 < pl.n_jobs && idx >= pl.job[j + 1].out_begin) ++j;
+        const WgradJobPlan& a = pl.job[j];
+        long long e = idx - a.out_begin;
+        const long long per_w = (long long)a.Do * (a.Di > 0 ? a.Di : 1);
+        const long long n_w = (long long)pl.G * per_w;
+        const float* src;
+        float* dst;
+        long long per;
+        if (e < n_w) {
+            per = per_w;
+            src = pl.scratch + a.part_off;
+            dst = a.dW;
+        } else {
+            e -= n_w;
+            per = a.Do;
+            src = pl.scratch + a.bpart_off;
+            dst = a.db;
+        }
+        const long long g = e / per, r = e - g * per;
+        src += g * a.splits * per + r;
         float s = 0.f;
-        for (int k = 0; k < splits; ++k) s += src[(long long)k * per_group];
-        out[idx] = s;
+        for (int k = 0; k < a.splits; ++k) s += src[(long long)k * per];
+        dst[e] = s;
     }
 }
 
-static int pick_splits(int G, int Do, int Di, long long chunks) {
-    const int tiles = ((Do + kWgTile - 1) / kWgTile) * ((Di + kWgTile - 1) / kWgTile) * G;
-    long long s = (2LL * kSmCountB200 + tiles - 1) / tiles;      // ~2 CTAs per SM over the whole grid
-    if (s > chunks) s = chunks;
-    if (s < 1) s = 1;
-    return (int)s;
+static int make_plan(const BiearWgradJob* jobs, int n_jobs, int G, int tile_rows, WgradPlan* pl, long long* scratch_floats) {
+    BIEAR_REQUIRE(jobs && n_jobs >= 1 && n_jobs <= kWgMaxJobs, "biear_ctrl_wgrad: need 1..%d jobs, got %d", kWgMaxJobs, n_jobs);
+    BIEAR_REQUIRE(G >= 1, "biear_ctrl_wgrad: G=%d", G);
+    BIEAR_REQUIRE(tile_rows == 16 || tile_rows == 32, "biear_ctrl_wgrad: tile_rows must be 16 or 32, got %d", tile_rows);
+    pl->n_jobs = n_jobs; pl->G = G; pl->tile_w = tile_rows;
+    // tiles of all matrix jobs decide how finely K is split: aim at ~3 CTAs per SM over the whole grid
+    long long tile_ctas = 0;
+    for (int j = 0; j < n_jobs; ++j) {
+        const BiearWgradJob& q = jobs[j];
+        BIEAR_REQUIRE(q.Do >= 1 && q.Di >= 0 && q.chunks >= 1, "biear_ctrl_wgrad: job %d bad shape Do=%d Di=%d chunks=%lld", j, q.Do,
+                      q.Di, (long long)q.chunks);
+        BIEAR_REQUIRE(q.A && q.Bm && q.dW, "biear_ctrl_wgrad: job %d null pointer", j);
+        BIEAR_REQUIRE(q.Di > 0 || q.Do <= kWgThreads / 2, "biear_ctrl_wgrad: diagonal job %d wider than %d", j, kWgThreads / 2);
+        BIEAR_REQUIRE((q.a_chunk_stride & 3) == 0 && (q.b_chunk_stride & 3) == 0 && (q.a_group_stride & 3) == 0 &&
+                          (q.b_group_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(q.A) & 15) == 0 &&
+                          (reinterpret_cast<uintptr_t>(q.Bm) & 15) == 0,
+                      "biear_ctrl_wgrad: job %d operands must be 16-byte aligned with strides that are multiples of 4 floats", j);
+        const int tiles = q.Di > 0 ? ((q.Do + kWgTile - 1) / kWgTile) * ((q.Di + kWgTile - 1) / kWgTile) : 1;
+        tile_ctas += (long long)tiles * G;
+    }
+    long long want = (3LL * kSmCountB200 + tile_ctas - 1) / tile_ctas;
+    long long off = 0, out = 0;
+    int cta = 0;
+    for (int j = 0; j < n_jobs; ++j) {
+        const BiearWgradJob& q = jobs[j];
+        WgradJobPlan& a = pl->job[j];
+        a.A = q.A; a.a_group = q.a_group_stride; a.a_chunk = q.a_chunk_stride; a.Do = q.Do;
+        a.B = q.Bm; a.b_group = q.b_group_stride; a.b_chunk = q.b_chunk_stride; a.Di = q.Di;
+        a.tile_chunks = q.chunks;
+        a.slabs = (q.chunks * tile_rows + 31) / 32;
+        a.tiles_i = q.Di > 0 ? (q.Di + kWgTile - 1) / kWgTile : 1;
+        a.tiles = q.Di > 0 ? ((q.Do + kWgTile - 1) / kWgTile) * a.tiles_i : 1;
+        long long s = q.Di > 0 ? want : 4 * want;
+        if (s > a.slabs) s = a.slabs;
+        if (s < 1) s = 1;
+        a.slabs_per_split = (a.slabs + s - 1) / s;
+        a.splits = (int)((a.slabs + a.slabs_per_split - 1) / a.slabs_per_split);
+        a.cta_begin = cta;
+        cta += a.tiles * a.splits * G;
+        const long long per_w = (long long)q.Do * (q.Di > 0 ? q.Di : 1);
+        a.part_off = off;
+        off += (long long)G * a.splits * per_w;
+        a.bpart_off = -1;
+        if (q.db) {
+            a.bpart_off = off;
+            off += (long long)G * a.splits * q.Do;
+        }
+        a.out_begin = out;
+        out += (long long)G * (per_w + (q.db ? q.Do : 0));
+        a.dW = q.dW; a.db = q.db;
+    }
+    pl->total_ctas = cta;
+    pl->total_out = out;
+    *scratch_floats = off;
+    return 0;
 }
 
 }  // namespace biear
 
-extern "C" int64_t biear_wgrad_scratch_floats(int G, int Do, int Di, int64_t chunks, int tile_rows) {
+extern "C" int64_t biear_wgrad_scratch_floats(const BiearWgradJob* jobs, int n_jobs, int G, int tile_rows) {
     using namespace biear;
-    if (G < 1 || Do < 1 || Di < 1 || chunks < 1 || (tile_rows != 16 && tile_rows != 32)) return 0;
-    const int s = pick_splits(G, Do, Di, (chunks * tile_rows + 31) / 32);
-    return (int64_t)G * s * ((int64_t)Do * Di + Do);
+    WgradPlan pl;
+    long long n = 0;
+    if (make_plan(jobs, n_jobs, G, tile_rows, &pl, &n)) return -1;
+    return n;
 }
 
-extern "C" int biear_ctrl_wgrad(const float* A, int64_t a_group_stride, int64_t a_chunk_stride, int Do, const float* Bm,
-                                int64_t b_group_stride, int64_t b_chunk_stride, int Di, int G, int64_t chunks,
-                                int tile_rows, float* dW, float* db, float* scratch, void* stream) {
+extern "C" int biear_ctrl_wgrad(const BiearWgradJob* jobs, int n_jobs, int G, int tile_rows, float* scratch, void* stream) {
     using namespace biear;
-    BIEAR_REQUIRE(G >= 1 && Do >= 1 && Di >= 1 && chunks >= 1, "biear_ctrl_wgrad: bad shape G=%d Do=%d Di=%d chunks=%lld", G,
-                  Do, Di, (long long)chunks);
-    BIEAR_REQUIRE(A && Bm && dW && scratch, "biear_ctrl_wgrad: null pointer");
-    BIEAR_REQUIRE(tile_rows == 16 || tile_rows == 32, "biear_ctrl_wgrad: tile_rows must be 16 or 32, got %d", tile_rows);
-    BIEAR_REQUIRE((a_chunk_stride & 3) == 0 && (b_chunk_stride & 3) == 0 && (a_group_stride & 3) == 0 &&
-                      (b_group_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
-                      (reinterpret_cast<uintptr_t>(Bm) & 15) == 0,
-                  "biear_ctrl_wgrad: operands must be 16-byte aligned with strides that are multiples of 4 floats");
+    WgradPlan pl;
+    long long n = 0;
+    if (int e = make_plan(jobs, n_jobs, G, tile_rows, &pl, &n)) return e;
+    BIEAR_REQUIRE(scratch, "biear_ctrl_wgrad: null scratch");
+    pl.scratch = scratch;
     cudaStream_t st = as_stream(stream);
-    WgradArgs a;
-    a.A = A; a.a_group = a_group_stride; a.a_chunk = a_chunk_stride; a.Do = Do;
-    a.B = Bm; a.b_group = b_group_stride; a.b_chunk = b_chunk_stride; a.Di = Di;
-    a.G = G; a.tile_chunks = chunks; a.tile_w = tile_rows;
-    a.chunks = (chunks * tile_rows + 31) / 32;
-    a.splits = pick_splits(G, Do, Di, a.chunks);
-    a.chunks_per_split = (a.chunks + a.splits - 1) / a.splits;
-    a.part = scratch;
-    a.bpart = db ? scratch + (long long)G * a.splits * Do * Di : nullptr;
-    const int tiles = ((Do + kWgTile - 1) / kWgTile) * ((Di + kWgTile - 1) / kWgTile);
-    wgrad_partial_kernel<<<dim3(tiles, a.splits, G), kWgThreads, 0, st>>>(a);
+    wgrad_partial_kernel<<<pl.total_ctas, kWgThreads, 0, st>>>(pl);
     BIEAR_LAUNCH_CHECK("wgrad_partial_kernel");
-    const long long per_w = (long long)Do * Di;
-    wgrad_reduce_kernel<<<(int)((G * per_w + 255) / 256), 256, 0, st>>>(a.part, a.splits, per_w, G, dW);
-    BIEAR_LAUNCH_CHECK("wgrad_reduce_kernel(dW)");
-    if (db) {
-        wgrad_reduce_kernel<<<(G * Do + 255) / 256, 256, 0, st>>>(a.bpart, a.splits, Do, G, db);
-        BIEAR_LAUNCH_CHECK("wgrad_reduce_kernel(db)");
-    }
+    const int blocks = (int)((pl.total_out + 255) / 256);
+    wgrad_reduce_kernel<<<blocks < 4 * kSmCountB200 ? blocks : 4 * kSmCountB200, 256, 0, st>>>(pl);
+    BIEAR_LAUNCH_CHECK("wgrad_reduce_kernel");
     return 0;
 }

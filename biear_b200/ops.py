@@ -272,20 +272,34 @@ def tile_rows() -> int:
     return int(_lib.load().biear_adaptive_tile_rows())
 
 
-def ctrl_wgrad(a: torch.Tensor, do: int, bm: torch.Tensor, di: int, chunks: int, want_bias: bool = True):
-    """dW (G, do, di) [, db (G, do)] from tile-layout operands a (G, chunks', Da, R) and bm (G, chunks', Db, R):
-    the first `do` / `di` features of each and the first `chunks` chunks are used (biear_ctrl_wgrad)."""
-    G = a.shape[0]
-    dev = a.device
+def ctrl_wgrad(jobs):
+    """Weight gradients for a list of jobs (a, do, bm, di, chunks, want_bias) in two launches (biear_ctrl_wgrad).
+
+    a (G, chunks', Da, R) and bm (G, chunks', Db, R) are tile-layout operands (views with arbitrary group / chunk
+    strides are fine); the first `do` / `di` features and the first `chunks` chunks are used.  di == 0 selects the
+    diagonal form dW[g][o] = sum a*bm (LayerNorm weight).  Returns [(dW (G,do,di) | (G,do), db (G,do) | None), ...].
+    """
+    a0 = jobs[0][0]
+    G, R, dev = a0.shape[0], a0.shape[3], a0.device
     lib = _prepare(dev)
-    dw = torch.empty((G, do, di), dtype=torch.float32, device=dev)
-    db = torch.empty((G, do), dtype=torch.float32, device=dev) if want_bias else None
-    R = a.shape[3]
-    assert bm.shape[3] == R
-    scratch = torch.empty(int(lib.biear_wgrad_scratch_floats(G, do, di, chunks, R)), dtype=torch.float32, device=dev)
-    _lib.check(lib.biear_ctrl_wgrad(_ptr(a), a.stride(0), a.stride(1), do, _ptr(bm), bm.stride(0), bm.stride(1), di, G,
-                                    chunks, R, _ptr(dw), _ptr(db), _ptr(scratch), _stream(dev)), "biear_ctrl_wgrad")
-    return dw, db
+    arr = (_lib.WgradJob * len(jobs))()
+    outs = []
+    for j, (a, do, bm, di, chunks, want_bias) in enumerate(jobs):
+        assert a.shape[0] == G and bm.shape[0] == G and a.shape[3] == R and bm.shape[3] == R
+        assert a.stride(3) == 1 and a.stride(2) == R and bm.stride(3) == 1 and bm.stride(2) == R
+        dw = torch.empty((G, do, di) if di > 0 else (G, do), dtype=torch.float32, device=dev)
+        db = torch.empty((G, do), dtype=torch.float32, device=dev) if want_bias else None
+        outs.append((dw, db))
+        q = arr[j]
+        q.A, q.a_group_stride, q.a_chunk_stride, q.Do = a.data_ptr(), a.stride(0), a.stride(1), do
+        q.Bm, q.b_group_stride, q.b_chunk_stride, q.Di = bm.data_ptr(), bm.stride(0), bm.stride(1), di
+        q.chunks, q.dW, q.db = chunks, dw.data_ptr(), (db.data_ptr() if db is not None else None)
+    n = int(lib.biear_wgrad_scratch_floats(arr, len(jobs), G, R))
+    if n < 0:
+        _lib.check(-1, "biear_wgrad_scratch_floats")
+    scratch = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+    _lib.check(lib.biear_ctrl_wgrad(arr, len(jobs), G, R, _ptr(scratch), _stream(dev)), "biear_ctrl_wgrad")
+    return outs
 
 
 class AdaptiveSequence(torch.autograd.Function):
@@ -386,19 +400,20 @@ class AdaptiveSequence(torch.autograd.Function):
             GG = fl(wk["GG"])
             Hk = H.view(G, (S + 1) * tiles, HID, TILE)      # chunk = (step, tile); group stride covers S+1 steps
             h_prev, h_cur = Hk[:, :K], Hk[:, tiles:]
-            a, d_b_ih = ctrl_wgrad(GG, 3 * HID, fl(sv["yc"]), N, K)                      # dL/dW_ih[:, :N]
+            (a, d_b_ih), (d_rz, _), (d_n, d_b_hn), (d_w1, d_b1), (d_w2, d_b2), (d_w3, d_b3), (d_g1, d_be1), (d_g2, d_be2) = \
+                ctrl_wgrad([
+                    (GG, 3 * HID, fl(sv["yc"]), N, K, True),                 # dL/dW_ih[:, :N], b_ih
+                    (GG, 2 * HID, h_prev, HID, K, False),                     # r, z rows of W_hh
+                    (GG[:, :, 3 * HID:], HID, h_prev, HID, K, True),          # n rows of W_hh, b_hn (dL/d(W_hn h + b_hn))
+                    (fl(wk["G_a1"]), HID, h_cur, HID, K, True),
+                    (fl(wk["G_a2"]), HID, fl(sv["d1"]), HID, K, True),
+                    (fl(wk["G_pre"]), N, fl(sv["d2"]), HID, K, True),
+                    (fl(wk["G_v1"]), HID, fl(sv["xh1"]), 0, K, True),          # LayerNorm 1 weight / bias
+                    (fl(wk["G_v2"]), HID, fl(sv["xh2"]), 0, K, True),
+                ])
             d_w_ih = torch.cat([a, 0.2 * a], dim=2) if Kin == 2 * N else None            # feat = [yc, 0.2 yc.detach()]
-            d_rz, _ = ctrl_wgrad(GG, 2 * HID, h_prev, HID, K, want_bias=False)           # r, z rows of W_hh
-            GGn = GG[:, :, 3 * HID:]                                                     # dL/d(W_hn h + b_hn)
-            d_n, d_b_hn = ctrl_wgrad(GGn, HID, h_prev, HID, K)
             d_w_hh = torch.cat([d_rz, d_n], dim=1)
             d_b_hh = torch.cat([d_b_ih[:, :2 * HID], d_b_hn], dim=1)
-            d_w1, d_b1 = ctrl_wgrad(fl(wk["G_a1"]), HID, h_cur, HID, K)
-            d_w2, d_b2 = ctrl_wgrad(fl(wk["G_a2"]), HID, fl(sv["d1"]), HID, K)
-            d_w3, d_b3 = ctrl_wgrad(fl(wk["G_pre"]), N, fl(sv["d2"]), HID, K)
-            gv1, gv2 = fl(wk["G_v1"]), fl(wk["G_v2"])
-            d_g1, d_be1 = (gv1 * fl(sv["xh1"])).sum((1, 3)), gv1.sum((1, 3))
-            d_g2, d_be2 = (gv2 * fl(sv["xh2"])).sum((1, 3)), gv2.sum((1, 3))
         grads = (d_w_ih, d_w_hh, d_b_ih, d_b_hh, d_w1, d_b1, d_g1, d_be1, d_w2, d_b2, d_g2, d_be2, d_w3, d_b3)
         return none11 + grads
 

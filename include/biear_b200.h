@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BIEAR_ABI_VERSION 5
+#define BIEAR_ABI_VERSION 6
 #define BIEAR_EINVAL (-1)
 
 /* ABI version (== BIEAR_ABI_VERSION of the library that was built). */
@@ -161,17 +161,25 @@ int biear_adaptive_fwd(const BiearSeqParams* p, void* stream);
 int biear_adaptive_bwd(const BiearSeqParams* p, void* stream);
 
 /*
- * Weight gradient of one Linear layer from tile-layout operands:
- *   dW[g][o][i] = sum_{k < chunks, r < R} A[g][k][o][r] * Bm[g][k][i][r]      (o < Do, i < Di; R = tile_rows, 16 or 32)
- *   db[g][o]    = sum_{k, r} A[g][k][o][r]                                      (db nullable)
- * A is (G, chunks, Do, R) with chunk stride a_chunk_stride floats and group stride a_group_stride, likewise Bm;
- * `scratch` holds biear_wgrad_scratch_floats(...) floats of split-K partials (deterministic
- * two-pass reduction, no atomics).  Replaces the weight-gradient GEMMs autograd runs for model_torch.py:256-267.
+ * Weight gradients of the controllers from tile-layout operands, all layers in two launches (split-K partials, then one
+ * fixed-order reduction; deterministic, no atomics).  One job per parameter tensor:
+ *   matrix job (Di > 0)   dW[g][o][i] = sum_{k < chunks, r < R} A[g][k][o][r] * Bm[g][k][i][r]      (o < Do, i < Di)
+ *   diagonal job (Di = 0) dW[g][o]    = sum_{k, r} A[g][k][o][r] * Bm[g][k][o][r]                    (LayerNorm weight)
+ *   both                  db[g][o]    = sum_{k, r} A[g][k][o][r]                                      (db nullable)
+ * A is (G, chunks, >=Do, R) with chunk stride a_chunk_stride floats and group stride a_group_stride, likewise Bm;
+ * R = tile_rows (16 or 32).  Outputs are dense (G, Do, Di) / (G, Do).  Replaces the weight-gradient GEMMs and
+ * reductions autograd runs for model_torch.py:256-267.
  */
-int64_t biear_wgrad_scratch_floats(int G, int Do, int Di, int64_t chunks, int tile_rows);
-int biear_ctrl_wgrad(const float* A, int64_t a_group_stride, int64_t a_chunk_stride, int Do,
-                     const float* Bm, int64_t b_group_stride, int64_t b_chunk_stride, int Di,
-                     int G, int64_t chunks, int tile_rows, float* dW, float* db, float* scratch, void* stream);
+#define BIEAR_WGRAD_MAX_JOBS 8
+typedef struct BiearWgradJob {
+    const float* A; int64_t a_group_stride, a_chunk_stride; int32_t Do;
+    const float* Bm; int64_t b_group_stride, b_chunk_stride; int32_t Di;
+    int64_t chunks;
+    float* dW; float* db;
+} BiearWgradJob;
+/* Floats of scratch biear_ctrl_wgrad needs for these jobs (-1 on invalid arguments). */
+int64_t biear_wgrad_scratch_floats(const BiearWgradJob* jobs, int n_jobs, int G, int tile_rows);
+int biear_ctrl_wgrad(const BiearWgradJob* jobs, int n_jobs, int G, int tile_rows, float* scratch, void* stream);
 
 /*
  * Broadband interaural cross-correlation feature.  Replaces utils.py:390-420

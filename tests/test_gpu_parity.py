@@ -437,17 +437,25 @@ def test_nonfinite_q_fallback_is_batch_global(bb):
 
 
 def test_ctrl_wgrad_kernel(bb):
-    """biear_ctrl_wgrad against a float64 einsum on tile-layout operands (odd sizes, sliced operands, bias)."""
+    """biear_ctrl_wgrad against float64 einsums on tile-layout operands: odd sizes, sliced operands, bias, the diagonal
+    (LayerNorm) form, several jobs per call, both tile widths."""
     from biear_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(3)
-    for G, chunks, Da, do, Db, di, R in ((2, 37, 512, 384, 100, 100, 16), (1, 5, 128, 128, 128, 128, 32),
-                                         (2, 144, 100, 100, 128, 128, 16), (1, 288, 512, 256, 128, 128, 32)):
-        a = torch.randn((G, chunks + 2, Da, R), generator=g).to(DEV)
-        b = torch.randn((G, chunks + 2, Db, R), generator=g).to(DEV)
-        dw, db = ops.ctrl_wgrad(a, do, b[:, 2:], di, chunks)
-        ref = torch.einsum("gkor,gkir->goi", a[:, :chunks, :do].double(), b[:, 2:, :di].double())
-        assert rel_err(_np(dw.double()), _np(ref)) <= 1e-5
-        assert rel_err(_np(db.double()), _np(a[:, :chunks, :do].double().sum((1, 3)))) <= 1e-5
+    for G, chunks, R in ((2, 37, 16), (1, 5, 32), (2, 288, 16)):
+        a = torch.randn((G, chunks + 2, 512, R), generator=g).to(DEV)
+        b = torch.randn((G, chunks + 2, 128, R), generator=g).to(DEV)
+        c = torch.randn((G, chunks + 2, 100, R), generator=g).to(DEV)
+        jobs = [(a, 384, c, 100, chunks, True), (a[:, :, 384:], 128, b[:, 2:], 128, chunks, False),
+                (c, 100, b, 128, chunks, True), (b, 128, a, 0, chunks, True)]
+        outs = ops.ctrl_wgrad(jobs)
+        for (x, do, y, di, k, wb), (dw, db) in zip(jobs, outs):
+            xd, yd = x[:, :k, :do].double(), y[:, :k].double()
+            ref = torch.einsum("gkor,gkir->goi", xd, yd[:, :, :di]) if di > 0 else (xd * yd[:, :, :do]).sum((1, 3))
+            assert rel_err(_np(dw.double()), _np(ref)) <= 1e-5
+            if wb:
+                assert rel_err(_np(db.double()), _np(xd.sum((1, 3)))) <= 1e-5
+            else:
+                assert db is None
 
 
 def test_autograd_node_does_not_leak(bb):
