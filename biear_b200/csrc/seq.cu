@@ -181,16 +181,38 @@ __device__ __forceinline__ void ln_silu_drop_fwd(const BiearSeqParams& p, unsign
     __syncthreads();
 }
 
-// Spectra of this CTA's 4 rows for frame t -> shared {1, abs, re, im} tiles (zeros for padding rows / bins).
-__device__ __forceinline__ void load_spectra(const BiearSeqParams& p, float4* spec_s, int tile, long long grow0,
-                                             int b0, int t) {
-    for (int idx = threadIdx.x; idx < kRT * tile; idx += kSeqThreads) {
-        const int i = idx / tile, k = idx - i * tile;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (k < p.F && b0 + i < p.B) {
-            v = spec_entry(__ldg(reinterpret_cast<const float2*>(p.X) + ((grow0 + i) * p.T + t) * p.F + k));
+// Spectra of this CTA's 4 rows for frame t -> shared {1, abs, re, im} tiles (zeros for padding rows / bins), in two
+// steps so that the HBM latency hides behind the controller phases: prefetch_spectra() issues 8-byte cp.async copies
+// of the raw complex bins straight into the {re, im} half of their tile slots; finish_spectra() (same thread -> same
+// slots) waits for them and fills in {1, abs}.
+__device__ __forceinline__ void prefetch_spectra(const BiearSeqParams& p, float4* spec_s, int tile, long long grow0,
+                                                 int b0, int t) {
+#pragma unroll
+    for (int i = 0; i < kRT; ++i) {
+        const float2* src = reinterpret_cast<const float2*>(p.X) + ((grow0 + i) * p.T + t) * p.F;
+        const bool row_ok = b0 + i < p.B;
+        for (int k = threadIdx.x; k < tile; k += kSeqThreads) {
+            float4* slot = spec_s + i * tile + k;
+            if (row_ok && k < p.F) {
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(&slot->z);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src + k) : "memory");
+            } else {
+                *slot = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
-        spec_s[idx] = v;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+__device__ __forceinline__ void finish_spectra(const BiearSeqParams& p, float4* spec_s, int tile, int b0) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < kRT; ++i) {
+        if (b0 + i >= p.B) continue;
+        for (int k = threadIdx.x; k < p.F; k += kSeqThreads) {
+            float4* slot = spec_s + i * tile + k;
+            *slot = spec_entry(make_float2(slot->z, slot->w));
+        }
     }
 }
 
@@ -219,7 +241,6 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
     float* q_s = smem + L.q();
     float* ystage_s = smem + L.ystage();
     float4* spec_s = reinterpret_cast<float4*>(smem + L.spec());
-    int* ctr_s = reinterpret_cast<int*>(smem + L.misc());
     const int tid = threadIdx.x, lane = tid & 31;
     const int ks = tid >> 7, slot = tid & 127, rg = slot / kU, u = slot % kU;
     const int ug = rank * kU + u;
@@ -302,37 +323,66 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                 float4* hdst = reinterpret_cast<float4*>(h_tile(p, g, t - 1, tiles, tile));
                 for (int i = tid; i < kHid * kR / 4; i += kSeqThreads) hdst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            if (STRICT || spec_t != t) load_spectra(p, spec_s, L.tile, grow0, bb0, t);
-            if (tid == 0) *ctr_s = 0;
+            if (STRICT || spec_t != t) prefetch_spectra(p, spec_s, L.tile, grow0, bb0, t);
+            finish_spectra(p, spec_s, L.tile, bb0);
             __syncthreads();
 
             // ---- band stage of frame t for this CTA's 4 rows (model_torch.py:340-346, 1050-1060) ---------------
-            for (;;) {
-                int item = 0;
-                if (lane == 0) item = atomicAdd(ctr_s, 1);
-                item = __shfl_sync(0xffffffffu, item, 0);
-                if (item >= kRT * quads) break;
-                const int i = item & 3;
-                const int quad = quads - 1 - (item >> 2);      // widest (highest) bands first
-                const int n = (quad << 2) + (lane >> 3);
-                const bool active = n < N;
-                const float fc = active ? vec_s[V_FC + n] : 1.0f;
-                const float q = active ? q_s[n * kRT + i] : 1.0f;
-                const BandParams bp = band_params(fc, q, p.df, p.cutoff, p.F, active);
-                const BandSums sums = band_accumulate(spec_s + i * L.tile, p.F, bp, lane);
-                const BandResult r = band_finish(sums);
-                if (!active || (lane & 7) != 0) continue;
-                ystage_s[i * kHid + n] = log1pf(fmaxf(r.Y, 0.0f));
-                if (bb0 + i >= p.B) continue;
-                const long long e = ((grow0 + i) * T + t) * N + n;
-                p.Y[e] = r.Y;
-                const float qe = q + 1e-8f;
-                const float kappa = -fc / (qe * qe * bp.bw);
-                p.dYdQ[e] = kappa * (r.a2 - r.Yraw * r.m2);
-                if (p.phase) {
-                    p.phase[e] = atan2f(r.Zi, r.Zr);
-                    const float mag2 = r.Zr * r.Zr + r.Zi * r.Zi;
-                    p.dPdQ[e] = mag2 > 0.0f ? kappa * (r.Zr * r.z2i - r.Zi * r.z2r) / mag2 : 0.0f;
+            // The 4 x quads (row, 4-band quad) pairs are dealt round-robin to the 16 warps, widest quads first and
+            // rows rotating, so every warp gets the same mix.  Lane l of a warp OWNS band (l & 3) of the warp's
+            // (l >> 2)-th pair: it computes that band's window parameters once, lends them to the 8 lanes that walk
+            // the window, gets the 8 reduced sums back and does the (expensive: 3 divisions, atan2, log1p) epilogue
+            // for it -- once per warp with up to 32 bands in flight instead of once per quad with 4.
+            {
+                const int warp = tid >> 5;
+                constexpr int kWarps = kSeqThreads / 32;
+                const int n_pairs = kRT * quads;
+                const int p_own = warp + kWarps * (lane >> 2);
+                const int row_own = ((p_own & 3) + (p_own >> 4)) & 3;
+                const int n_own = ((quads - 1 - (p_own >> 2)) << 2) + (lane & 3);
+                const bool own = p_own < n_pairs && n_own < N;
+                const float fc = own ? vec_s[V_FC + n_own] : 1.0f;
+                const float q = own ? q_s[n_own * kRT + row_own] : 1.0f;
+                const BandParams bp_own = band_params(fc, q, p.df, p.cutoff, p.F, own);
+                BandSums keep = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                for (int m = 0, pr = warp; pr < n_pairs; ++m, pr += kWarps) {
+                    const int row = ((pr & 3) + (pr >> 4)) & 3;
+                    const int src = (m << 2) + (lane >> 3);          // lane owning the band this lane helps with
+                    BandParams bp;
+                    bp.bw = 0.f;
+                    bp.a = __shfl_sync(0xffffffffu, bp_own.a, src);
+                    bp.b = __shfl_sync(0xffffffffu, bp_own.b, src);
+                    bp.kc = __shfl_sync(0xffffffffu, bp_own.kc, src);
+                    bp.k_lo = __shfl_sync(0xffffffffu, bp_own.k_lo, src);
+                    bp.k_hi = __shfl_sync(0xffffffffu, bp_own.k_hi, src);
+                    const BandSums sums = band_accumulate(spec_s + row * L.tile, p.F, bp, lane);
+                    const int from = (lane & 3) << 3;                // any lane of the group that holds my band's sums
+                    const bool mine = (lane >> 2) == m;
+                    float v;
+                    v = __shfl_sync(0xffffffffu, sums.S, from);   if (mine) keep.S = v;
+                    v = __shfl_sync(0xffffffffu, sums.Y, from);   if (mine) keep.Y = v;
+                    v = __shfl_sync(0xffffffffu, sums.Zr, from);  if (mine) keep.Zr = v;
+                    v = __shfl_sync(0xffffffffu, sums.Zi, from);  if (mine) keep.Zi = v;
+                    v = __shfl_sync(0xffffffffu, sums.m2, from);  if (mine) keep.m2 = v;
+                    v = __shfl_sync(0xffffffffu, sums.a2, from);  if (mine) keep.a2 = v;
+                    v = __shfl_sync(0xffffffffu, sums.z2r, from); if (mine) keep.z2r = v;
+                    v = __shfl_sync(0xffffffffu, sums.z2i, from); if (mine) keep.z2i = v;
+                }
+                if (own) {
+                    const BandResult r = band_finish(keep);
+                    ystage_s[row_own * kHid + n_own] = log1pf(fmaxf(r.Y, 0.0f));
+                    if (bb0 + row_own < p.B) {
+                        const long long e = ((grow0 + row_own) * T + t) * N + n_own;
+                        p.Y[e] = r.Y;
+                        const float qe = q + 1e-8f;
+                        const float kappa = -fc / (qe * qe * bp_own.bw);
+                        p.dYdQ[e] = kappa * (r.a2 - r.Yraw * r.m2);
+                        if (p.phase) {
+                            p.phase[e] = atan2f(r.Zi, r.Zr);
+                            const float mag2 = r.Zr * r.Zr + r.Zi * r.Zi;
+                            p.dPdQ[e] = mag2 > 0.0f ? kappa * (r.Zr * r.z2i - r.Zi * r.z2r) / mag2 : 0.0f;
+                        }
+                    }
                 }
             }
             if (t == T - 1) {
@@ -341,6 +391,10 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                 continue;
             }
             __syncthreads();
+            if (!STRICT) {   // the tile is free again: start fetching the next frame's spectra behind the controller phases
+                prefetch_spectra(p, spec_s, L.tile, grow0, bb0, t + 1);
+                spec_t = t + 1;
+            }
             const long long tb = tile_base(p, g, t, tiles, tile);
             if (tid < N) {   // features of my 4 rows -> every CTA of the cluster (+ saved for dW_ih)
                 const float4 v = make_float4(ystage_s[tid], ystage_s[kHid + tid], ystage_s[2 * kHid + tid],
@@ -462,10 +516,6 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                     // Q_{t+1} of rows 4rg..4rg+3 goes to the CTA that runs their band stage
                     store4(cluster.map_shared_rank(q_s, rg) + n * kRT, qv);
                 }
-            }
-            if (!STRICT && t + 1 < T) {   // overlap the next frame's spectra with the barrier
-                load_spectra(p, spec_s, L.tile, grow0, bb0, t + 1);
-                spec_t = t + 1;
             }
             if (STRICT) __threadfence();   // H / Q / flags of this step visible to the whole cluster
             cluster.sync();   // #5: Q_{t+1} delivered; a2 / yc free for the next frame

@@ -493,7 +493,7 @@ def test_graphed_step_matches_eager_and_redraws_dropout(bb):
     eager = [p.grad.clone() for p in params]
     eager_loss = float(loss_fn(tl, tr))
     step = bb.GraphedStep(loss_fn, (tl, tr), params)
-    assert step.launches_per_replay >= 10
+    assert step.launches_per_replay >= 6
     for _ in range(2):
         loss = step(tl, tr)
         assert float(loss) == eager_loss
