@@ -333,6 +333,9 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
             // (l >> 2)-th pair: it computes that band's window parameters once, lends them to the 8 lanes that walk
             // the window, gets the 8 reduced sums back and does the (expensive: 3 divisions, atan2, log1p) epilogue
             // for it -- once per warp with up to 32 bands in flight instead of once per quad with 4.
+            bool own_store = false;
+            long long own_e = 0;
+            float oY = 0.f, oJ = 0.f, oP = 0.f, oK = 0.f;
             {
                 const int warp = tid >> 5;
                 constexpr int kWarps = kSeqThreads / 32;
@@ -371,22 +374,33 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                 if (own) {
                     const BandResult r = band_finish(keep);
                     ystage_s[row_own * kHid + n_own] = log1pf(fmaxf(r.Y, 0.0f));
-                    if (bb0 + row_own < p.B) {
-                        const long long e = ((grow0 + row_own) * T + t) * N + n_own;
-                        p.Y[e] = r.Y;
-                        const float qe = q + 1e-8f;
-                        const float kappa = -fc / (qe * qe * bp_own.bw);
-                        p.dYdQ[e] = kappa * (r.a2 - r.Yraw * r.m2);
-                        if (p.phase) {
-                            p.phase[e] = atan2f(r.Zi, r.Zr);
-                            const float mag2 = r.Zr * r.Zr + r.Zi * r.Zi;
-                            p.dPdQ[e] = mag2 > 0.0f ? kappa * (r.Zr * r.z2i - r.Zi * r.z2r) / mag2 : 0.0f;
-                        }
+                    own_store = bb0 + row_own < p.B;
+                    own_e = ((grow0 + row_own) * T + t) * N + n_own;
+                    const float qe = q + 1e-8f;
+                    const float kappa = -fc / (qe * qe * bp_own.bw);
+                    oY = r.Y;
+                    oJ = kappa * (r.a2 - r.Yraw * r.m2);
+                    if (p.phase) {
+                        oP = atan2f(r.Zi, r.Zr);
+                        const float mag2 = r.Zr * r.Zr + r.Zi * r.Zi;
+                        oK = mag2 > 0.0f ? kappa * (r.Zr * r.z2i - r.Zi * r.z2r) / mag2 : 0.0f;
                     }
                 }
             }
+            // Results of this lane's band.  They go to HBM AFTER the cluster barrier below has been signalled: the
+            // barrier's release waits for every earlier global store of the thread, and nobody in the cluster needs these.
+            auto store_band_outputs = [&]() {
+                if (!own_store) return;
+                p.Y[own_e] = oY;
+                p.dYdQ[own_e] = oJ;
+                if (p.phase) {
+                    p.phase[own_e] = oP;
+                    p.dPdQ[own_e] = oK;
+                }
+            };
             if (t == T - 1) {
                 // The reference runs the controller once more and discards the result (model_torch.py:361-380).
+                store_band_outputs();
                 if (STRICT) __syncthreads();
                 continue;
             }
@@ -402,9 +416,13 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
 #pragma unroll
                 for (int dst = 0; dst < kCS; ++dst)
                     *reinterpret_cast<float4*>(cluster.map_shared_rank(yc_s, dst) + tid * kR + rank * kRT) = v;
-                *reinterpret_cast<float4*>(p.yc + tb * N * kR + tid * kR + rank * kRT) = v;
             }
-            cluster.sync();   // #1: yc complete everywhere
+            cluster.barrier_arrive();   // #1: my part of yc is delivered ...
+            if (tid < N)
+                *reinterpret_cast<float4*>(p.yc + tb * N * kR + tid * kR + rank * kRT) =
+                    make_float4(ystage_s[tid], ystage_s[kHid + tid], ystage_s[2 * kHid + tid], ystage_s[3 * kHid + tid]);
+            store_band_outputs();
+            cluster.barrier_wait();     // ... and complete everywhere
 
             // ---- GRU cell (torch gate order r, z, n; n = tanh(i_n + r * (W_hn h + b_hn))) ----------------------
             {
@@ -424,9 +442,9 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                     acc[12 + i] = ahn[i];
                 }
                 reduce_ks<16>(acc, red_s, ks, slot);
+                float hv[kRT], vr[kRT], vz[kRT], vn[kRT], vh[kRT];
                 if (ks == 0) {
                     const float br = vec_s[V_BR + u], bz = vec_s[V_BZ + u], bin = vec_s[V_BIN + u], bhn = vec_s[V_BHN + u];
-                    float hv[kRT], vr[kRT], vz[kRT], vn[kRT], vh[kRT];
 #pragma unroll
                     for (int i = 0; i < kRT; ++i) {
                         vr[i] = 1.0f / (1.0f + expf(-(acc[i] + br)));
@@ -436,16 +454,19 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                         const float hp = h_zero ? 0.0f : hcur_s[ug * kR + rg * kRT + i];
                         hv[i] = (1.0f - vz[i]) * vn[i] + vz[i] * hp;
                     }
+                    broadcast_rows(cluster, hnext_s, ug, rg * kRT, hv);
+                }
+                cluster.barrier_arrive();   // #2 signalled before the saves go out (a later release covers them)
+                if (ks == 0) {
                     store4(h_tile(p, g, t, tiles, tile) + ug * kR + rg * kRT, hv);
                     float* gt = p.gates + tb * 4 * kHid * kR + ug * kR + rg * kRT;
                     store4(gt, vr);
                     store4(gt + kHid * kR, vz);
                     store4(gt + 2 * kHid * kR, vn);
                     store4(gt + 3 * kHid * kR, vh);
-                    broadcast_rows(cluster, hnext_s, ug, rg * kRT, hv);
                 }
             }
-            cluster.sync();   // #2: h_t complete everywhere
+            cluster.barrier_wait();   // #2: h_t complete everywhere
 
             // ---- Linear 1 -> LayerNorm -> SiLU -> Dropout ------------------------------------------------------
             {
@@ -491,34 +512,48 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                 k_range(kHid, ks, k0, k1);
                 if (mine) dot_rows(acc, a2_s + rg * kRT, img_s + fwd_img_w3(N) + u, k0, k1);
                 reduce_ks<kRT>(acc, red_s, ks, slot);
-                if (ks == 0 && mine) {
-                    const int n = rank * NU + u;
+                const bool fin = ks == 0 && mine;
+                const int n = rank * NU + u;
+                float qv[kRT] = {0.f, 0.f, 0.f, 0.f}, dv[kRT] = {0.f, 0.f, 0.f, 0.f};
+                if (fin) {
                     const float bb = vec_s[V_B3 + u], q0 = vec_s[V_Q0S + u], dq = vec_s[V_DQS + u];
-                    float qv[kRT];
                     bool bad = false;
 #pragma unroll
                     for (int i = 0; i < kRT; ++i) {
-                        const int b = b0 + rg * kRT + i;
-                        const float delta = tanhf(acc[i] + bb);
-                        const float qu = p.relative ? q0 * (1.0f + dq * delta) : fmaf(dq, delta, q0);
+                        dv[i] = tanhf(acc[i] + bb);
+                        const float qu = p.relative ? q0 * (1.0f + dq * dv[i]) : fmaf(dq, dv[i], q0);
                         qv[i] = fminf(fmaxf(qu, p.q_min), p.q_max);
-                        if (b < p.B) {
-                            bad = bad || !finite_f(qu);
-                            const long long e = (((long long)g * p.B + b) * T + (t + 1)) * N + n;
-                            p.Q[e] = qv[i];
-                            p.delta[e] = delta;
-                        }
+                        bad = bad || (b0 + rg * kRT + i < p.B && !finite_f(qu));
                     }
+                    // Q_{t+1} of rows 4rg..4rg+3 goes to the CTA that runs their band stage
+                    store4(cluster.map_shared_rank(q_s, rg) + n * kRT, qv);
                     if (bad) {   // NaN / Inf: the reference falls back for the whole batch of this ear
                         atomicOr(p.flags + t * p.G + g, 1);
                         atomicOr(any_flag, 1);
                     }
-                    // Q_{t+1} of rows 4rg..4rg+3 goes to the CTA that runs their band stage
-                    store4(cluster.map_shared_rank(q_s, rg) + n * kRT, qv);
                 }
+                auto store_q = [&]() {
+                    if (!fin) return;
+#pragma unroll
+                    for (int i = 0; i < kRT; ++i) {
+                        const int b = b0 + rg * kRT + i;
+                        if (b < p.B) {
+                            const long long e = (((long long)g * p.B + b) * T + (t + 1)) * N + n;
+                            p.Q[e] = qv[i];
+                            p.delta[e] = dv[i];
+                        }
+                    }
+                };
+                // Fast pass: signal the barrier first, the row-major outputs are nobody's input inside the cluster.
+                // Strict pass: Q / flags / H are read back from global memory by other CTAs, so they must precede it.
+                if (STRICT) {
+                    store_q();
+                    __threadfence();
+                }
+                cluster.barrier_arrive();   // #5
+                if (!STRICT) store_q();
             }
-            if (STRICT) __threadfence();   // H / Q / flags of this step visible to the whole cluster
-            cluster.sync();   // #5: Q_{t+1} delivered; a2 / yc free for the next frame
+            cluster.barrier_wait();   // #5: Q_{t+1} delivered; a2 / yc free for the next frame
             if (!STRICT) hsel ^= 1;   // strict: h_{t-1} is reloaded from global memory, the buffers keep their roles
         }
     }
@@ -673,9 +708,12 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
 #pragma unroll
             for (int dst = 0; dst < kCS; ++dst)
                 *reinterpret_cast<float4*>(cluster.map_shared_rank(dpre_s, dst) + tid * kR + rank * kRT) = v;
-            *reinterpret_cast<float4*>(p.G_pre + tb * N * kR + tid * kR + rank * kRT) = v;
         }
-        cluster.sync();   // #1
+        cluster.barrier_arrive();   // #1 signalled before the saved gradients go out (nobody in the cluster reads them)
+        if (tid < N)
+            *reinterpret_cast<float4*>(p.G_pre + tb * N * kR + tid * kR + rank * kRT) =
+                make_float4(stage_s[tid], stage_s[kHid + tid], stage_s[2 * kHid + tid], stage_s[3 * kHid + tid]);
+        cluster.barrier_wait();     // #1
 
         // ---- Linear 3 ^T --------------------------------------------------------------------------------------
         {
@@ -709,6 +747,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
             k_range(kHid, ks, k0, k1);
             dot_rows(acc, bufb_s + rg * kRT, img_s + bwd_img_w1c(N) + u, k0, k1);
             reduce_ks<kRT>(acc, red_s, ks, slot);
+            float v0[kRT], v1[kRT], v2[kRT], v3[kRT];
             if (ks == 0) {
                 const float* gt = p.gates + tb * 4 * kHid * kR + ug * kR + rg * kRT;
                 const float4 r4 = __ldg(reinterpret_cast<const float4*>(gt));
@@ -721,7 +760,6 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
                 const float rr[4] = {r4.x, r4.y, r4.z, r4.w}, zz[4] = {z4.x, z4.y, z4.z, z4.w};
                 const float nn[4] = {n4.x, n4.y, n4.z, n4.w}, hn[4] = {h4.x, h4.y, h4.z, h4.w};
                 const float hp[4] = {p4.x, p4.y, p4.z, p4.w};
-                float v0[kRT], v1[kRT], v2[kRT], v3[kRT];
 #pragma unroll
                 for (int i = 0; i < kRT; ++i) {
                     float dh = acc[i];
@@ -735,18 +773,21 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
                     v2[i] = dnp;                                         // dL/d (i_n pre-activation)
                     v3[i] = dnp * rr[i];                                 // dL/d (W_hn h + b_hn)
                 }
-                float* gg = p.GG + tb * 4 * kHid * kR + ug * kR + rg * kRT;
-                store4(gg, v0);
-                store4(gg + kHid * kR, v1);
-                store4(gg + 2 * kHid * kR, v2);
-                store4(gg + 3 * kHid * kR, v3);
                 broadcast_rows(cluster, gate_s, 0 * kHid + ug, rg * kRT, v0);   // gate_s[0:128] aliases bufa: free since #3
                 broadcast_rows(cluster, gate_s, 1 * kHid + ug, rg * kRT, v1);
                 broadcast_rows(cluster, gate_s, 2 * kHid + ug, rg * kRT, v2);
                 broadcast_rows(cluster, gate_s, 3 * kHid + ug, rg * kRT, v3);
             }
+            cluster.barrier_arrive();   // #4 signalled before the saved gradients go out
+            if (ks == 0) {
+                float* gg = p.GG + tb * 4 * kHid * kR + ug * kR + rg * kRT;
+                store4(gg, v0);
+                store4(gg + kHid * kR, v1);
+                store4(gg + 2 * kHid * kR, v2);
+                store4(gg + 3 * kHid * kR, v3);
+            }
         }
-        cluster.sync();   // #4
+        cluster.barrier_wait();   // #4
         // ---- dL/dh_{t-1} = z * dh + W_hh^T [drp, dzp, dhn];  dL/dY_t = W_ih[:, :N]^T [drp, dzp, dnp] * d log1p --------
         {
             float acc[2 * kRT] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
