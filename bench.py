@@ -247,11 +247,11 @@ def run_ours(args):
     flat_numel = sum(p.numel() for p in params)
 
     from biear_b200.dist import FlatGradAllReducer
-    reducer = FlatGradAllReducer(params) if dist is not None else None
+    current = {"reducer": FlatGradAllReducer(params) if (dist is not None and args.eager) else None}
 
     def allreduce_grads():
-        if reducer is not None:
-            reducer()                     # one flat-bucket NCCL all-reduce (sum, x 1/world)
+        if current["reducer"] is not None:
+            current["reducer"]()          # one flat-bucket NCCL all-reduce (sum, x 1/world)
 
     # resident inputs: N_ROTATE distinct batches, cycled, so a step never finds its inputs in L2
     host = [synth_binaural(B, seed=1234 + 17 * rank + i) for i in range(2)]
@@ -278,12 +278,22 @@ def run_ours(args):
     else:
         graphs, pool = [], None
         for i in range(N_ROTATE):
-            gs = GraphedStep(loss_fn, dev_in[i], params, warmup=2 if i == 0 else 1, pool=pool, copy_inputs=False)
+            gs = GraphedStep(loss_fn, dev_in[i], params, warmup=2 if i == 0 else 1, pool=pool, copy_inputs=False,
+                             flat_grads=dist is not None)
             pool = gs.pool()
             graphs.append(gs)
-        steps_res = [gs for gs in graphs]
-        e2e_graph = GraphedStep(loss_fn, dev_in[0], params, warmup=1, pool=pool, copy_inputs=True)
+        e2e_graph = GraphedStep(loss_fn, dev_in[0], params, warmup=1, pool=pool, copy_inputs=True,
+                                flat_grads=dist is not None)
         launches_per_step = graphs[0].launches_per_replay
+        if dist is not None:   # every graph writes its gradients into its own flat bucket: all-reduce that, no copies
+            for gs in graphs + [e2e_graph]:
+                gs.reducer = FlatGradAllReducer(params, flat=gs.flat)
+
+        def replay(gs, *inputs):
+            loss = gs(*inputs)
+            current["reducer"] = getattr(gs, "reducer", None)
+            return loss
+        steps_res = [lambda gs=gs: replay(gs) for gs in graphs]
 
     def sync_all():
         torch.cuda.synchronize()
@@ -316,7 +326,7 @@ def run_ours(args):
     def e2e_step(i):
         a, b = pinned[i % 2]
         if e2e_graph is not None:
-            loss = e2e_graph(a, b)            # H2D into the graph's static inputs, replay
+            loss = replay(e2e_graph, a, b)    # H2D into the graph's static inputs, replay
         else:
             loss = steps_eager_e2e(a, b)
         allreduce_grads()
@@ -386,35 +396,74 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+NCU_SUMMARY = os.path.join(ROOT, "profiles", "r1_ncu_summary.json")
+# floats the forward recurrence saves per (row, step) for the backward: H 128 + gates 512 + LN in/out 4 x 128 + log1p(Y)
+# 100 + rstd 2
+SAVED_PER_ROW_STEP = 128 + 512 + 4 * 128 + NBANDS + 2
+
+
 def kernel_roofline(model, dev_in, dev, B):
-    """Time the band-stage kernel alone: one frame, both ears (2B items), rotating over frames and input
-    batches so the spectra come from HBM; CUDA events on the launching (current) stream."""
+    """The dominant kernel alone: seq_fwd_kernel, the persistent forward recurrence (band stage + controller, all 19
+    frames, both ears), timed with CUDA events around graph replays of just the recurrence call on spectra of rotating
+    input batches.  The call's two tiny companion launches (weight packing, ~5 us, and the early-exit replay check,
+    ~3 us) are inside the window: < 2 % of it.  `traffic` comes from the committed ncu capture of the same kernel."""
     from biear_b200 import ops
     fb = model.fb_L
+    mods = [model.fb_L, model.fb_R]
     with torch.no_grad():
         xs = [torch.view_as_real(fb._spectra([a, b])) for a, b in dev_in]
-        q = (fb.Q0.view(1, -1) * torch.exp(0.3 * torch.randn(2 * B, NBANDS, device=dev))).clamp(0.05, 30.0).contiguous()
-        n_launch = 0
-        for w in range(2):
-            if w == 1:
-                torch.cuda.synchronize()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-            for rep in range(3):
-                for i, xr in enumerate(xs):
-                    for t in range(T):
-                        ops.band_forward(xr, t, q, fb.fc, fb.df, fb.cutoff, True, True)
-                        n_launch += (w == 1)
+        st = lambda f: [f(m).detach() for m in mods]
+        w = {"w_ih": st(lambda m: m.q_rnn.weight_ih_l0), "w_hh": st(lambda m: m.q_rnn.weight_hh_l0),
+             "b_ih": st(lambda m: m.q_rnn.bias_ih_l0), "b_hh": st(lambda m: m.q_rnn.bias_hh_l0),
+             "w1": st(lambda m: m.q_out[0].weight), "b1": st(lambda m: m.q_out[0].bias),
+             "ln1_g": st(lambda m: m.q_out[1].weight), "ln1_b": st(lambda m: m.q_out[1].bias),
+             "w2": st(lambda m: m.q_out[4].weight), "b2": st(lambda m: m.q_out[4].bias),
+             "ln2_g": st(lambda m: m.q_out[5].weight), "ln2_b": st(lambda m: m.q_out[5].bias),
+             "w3": st(lambda m: m.q_out[8].weight), "b3": st(lambda m: m.q_out[8].bias)}
+
+        def run_all():
+            for xr in xs:
+                ops.adaptive_sequence(xr, fb.fc, fb.Q0, fb.deltaQ_vec, w, fb.deltaQ_mode == "relative", True, True,
+                                      fb.cutoff, fb.df, seed=1)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            run_all()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            run_all()
+        for _ in range(2):
+            graph.replay()
+        torch.cuda.synchronize()
+        reps = 5
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            graph.replay()
         e1.record()
         torch.cuda.synchronize()
-    us = e0.elapsed_time(e1) * 1e3 / n_launch
-    items = 2 * B
-    alg = items * (NBINS * 8 + NBANDS * 4 * 5)     # X_t in; Q in; Y, phase, dY/dQ, dphase/dQ out
+    us = e0.elapsed_time(e1) * 1e3 / (reps * len(xs))
+    rows = 2 * B
+    alg = rows * (T * NBINS * 8 + 6 * T * NBANDS * 4 + (T - 1) * SAVED_PER_ROW_STEP * 4)
     peak, peak_src = measured_peaks()
     ach = alg / (us * 1e-6) / 1e9
-    return {"kernel": "band_kernel<fwd> (one frame, both ears)", "bound": "hbm", "achieved": ach, "peak": peak,
-            "unit": "GB/s", "frac": ach / peak, "traffic": None, "us_per_launch": us,
-            "algorithmic_bytes_per_launch": alg, "peak_source": peak_src}
+    traffic, traffic_src = None, None
+    try:
+        with open(NCU_SUMMARY) as f:
+            k = json.load(f)["kernels"]
+        name = next(n for n in k if n.startswith("seq_fwd_kernel") and k[n]["duration_us"] > 50)
+        if B == 256:                       # the capture was taken at the benchmark batch
+            traffic, traffic_src = k[name]["dram_bytes"], "profiles/r1_ncu_summary.json (dram__bytes_read+write per launch)"
+    except Exception:
+        pass
+    return {"kernel": "seq_fwd_kernel (persistent forward recurrence: band stage + Q controller, 19 frames, both ears)",
+            "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+            "traffic_source": traffic_src, "us_per_launch": us, "algorithmic_bytes_per_launch": alg,
+            "peak_source": peak_src,
+            "note": "HBM is not what bounds this kernel: ~47 MFLOP of dependent fp32/MUFU work per audio-second on a "
+                    "19-step dependency chain (SURVEY.md 8(d), DESIGN.md 3.1); see profiles/ for issue-slot utilisation"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -452,6 +501,10 @@ def cpu_step_factory(sample_batch):
 
 
 def cpu_baseline(sample_batch=16, budget_s=20.0, steps=None, warmup=1):
+    try:     # every host thread this process may use (torchrun exports OMP_NUM_THREADS=1)
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:  # noqa: BLE001
+        pass
     step = cpu_step_factory(sample_batch)
     for _ in range(warmup):
         step()

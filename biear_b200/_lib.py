@@ -11,7 +11,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BIEAR_B200_LIB") or os.path.join(_HERE, "lib", "libbiear_b200.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 _p = c_void_p
 _i = c_int
@@ -20,15 +20,19 @@ _f = c_float
 
 
 
+MAX_CTRL = 2   # BIEAR_MAX_CTRL
+
+
 class SeqParams(Structure):
     """struct BiearSeqParams of include/biear_b200.h (field for field)."""
     _fields_ = (
         [(n, c_int32) for n in ("G", "E", "B", "T", "N", "F", "Kin", "relative", "training", "force_strict")]
         + [("seed", c_uint64)]
         + [(n, c_float) for n in ("df", "cutoff", "q_min", "q_max")]
+        + [(n, c_void_p) for n in ("fc", "q0", "dq")]
+        + [(n, c_void_p * MAX_CTRL) for n in (
+            "w_ih", "w_hh", "b_ih", "b_hh", "w1", "b1", "ln1_g", "ln1_b", "w2", "b2", "ln2_g", "ln2_b", "w3", "b3")]
         + [(n, c_void_p) for n in (
-            "fc", "q0", "dq",
-            "w_ih", "w_hh", "b_ih", "b_hh", "w1", "b1", "ln1_g", "ln1_b", "w2", "b2", "ln2_g", "ln2_b", "w3", "b3",
             "X", "Y", "phase", "dYdQ", "dPdQ", "Q", "delta",
             "gates", "xh1", "d1", "xh2", "d2", "rstd", "yc", "H", "flags",
             "gY", "gP", "gQ",
@@ -40,7 +44,8 @@ class WgradJob(Structure):
     """struct BiearWgradJob of include/biear_b200.h."""
     _fields_ = [("A", c_void_p), ("a_group_stride", c_int64), ("a_chunk_stride", c_int64), ("Do", c_int32),
                 ("Bm", c_void_p), ("b_group_stride", c_int64), ("b_chunk_stride", c_int64), ("Di", c_int32),
-                ("chunks", c_int64), ("dW", c_void_p), ("db", c_void_p)]
+                ("chunks", c_int64), ("dW", c_void_p), ("db", c_void_p),
+                ("dw_group_stride", c_int64), ("dw_row_stride", c_int64), ("db_group_stride", c_int64)]
 
 
 WGRAD_MAX_JOBS = 8
@@ -59,6 +64,7 @@ SIGNATURES = {
     "biear_adaptive_fwd": (_i, [POINTER(SeqParams), _p]),
     "biear_adaptive_bwd": (_i, [POINTER(SeqParams), _p]),
     "biear_adaptive_workspace_floats": (_l, [_i, _i]),
+    "biear_debug_phase_cycles": (_i, [_p]),
     "biear_adaptive_occupancy": (_i, [_i, _i, POINTER(c_int), POINTER(c_int)]),
     "biear_adaptive_tile_rows": (_i, []),
     "biear_wgrad_scratch_floats": (_l, [POINTER(WgradJob), _i, _i, _i]),

@@ -29,21 +29,42 @@
 
 namespace biear {
 
+// Optional per-phase cycle accounting (diagnostic builds: -DBIEAR_PHASE_PROF, `make prof`): thread 0 of block 0 adds
+// the clock64() time between consecutive marks to g_phase_cycles[kernel][phase]; read with biear_debug_phase_cycles.
+#ifdef BIEAR_PHASE_PROF
+__device__ unsigned long long g_phase_cycles[2][16];
+#define PHASE_INIT() long long _ph_last = clock64()
+#define PHASE_MARK(kern, i)                                            \
+    do {                                                               \
+        if (blockIdx.x == 0 && threadIdx.x == 0) {                     \
+            const long long _now = clock64();                          \
+            g_phase_cycles[kern][i] += (unsigned long long)(_now - _ph_last); \
+            _ph_last = _now;                                           \
+        }                                                              \
+    } while (0)
+#else
+#define PHASE_INIT() do {} while (0)
+#define PHASE_MARK(kern, i) do {} while (0)
+#endif
+
 // ==================================================================================================
 // weight images
 // ==================================================================================================
 constexpr int kPackSlices = 16;   // CTAs per image (grid.y)
+static_assert(BIEAR_MAX_CTRL == 2, "ctrl_ptr selects between two controllers");
+// controller g's tensor (a select, not an indexed read: indexing a kernel-parameter array spills it to local memory)
+__device__ __forceinline__ const float* ctrl_ptr(const float* const (&a)[BIEAR_MAX_CTRL], int g) { return g ? a[1] : a[0]; }
 
 __global__ void __launch_bounds__(256) pack_fwd_images_kernel(const BiearSeqParams p, float* __restrict__ img) {
     const int g = blockIdx.x / kCS, c = blockIdx.x % kCS;
     const int tid0 = blockIdx.y * blockDim.x + threadIdx.x, stride = gridDim.y * blockDim.x;
     const int N = p.N, NU = bands_per_cta(N);
     float* out = img + (long long)blockIdx.x * fwd_img_floats(N);
-    const float* w_ih = p.w_ih + (long long)g * 3 * kHid * p.Kin;
-    const float* w_hh = p.w_hh + (long long)g * 3 * kHid * kHid;
-    const float* w1 = p.w1 + (long long)g * kHid * kHid;
-    const float* w2 = p.w2 + (long long)g * kHid * kHid;
-    const float* w3 = p.w3 + (long long)g * N * kHid;
+    const float* w_ih = ctrl_ptr(p.w_ih, g);
+    const float* w_hh = ctrl_ptr(p.w_hh, g);
+    const float* w1 = ctrl_ptr(p.w1, g);
+    const float* w2 = ctrl_ptr(p.w2, g);
+    const float* w3 = ctrl_ptr(p.w3, g);
     // gate images: consecutive threads walk k (the contiguous axis of the torch layout) for coalesced reads
     for (int idx = tid0; idx < kU * 3 * N; idx += stride) {
         const int k = idx % N, gu = idx / N, gate = gu % 3, u = gu / 3;
@@ -69,11 +90,11 @@ __global__ void __launch_bounds__(256) pack_bwd_images_kernel(const BiearSeqPara
     const int tid0 = blockIdx.y * blockDim.x + threadIdx.x, stride = gridDim.y * blockDim.x;
     const int N = p.N, NU = bands_per_cta(N);
     float* out = img + (long long)blockIdx.x * bwd_img_floats(N);
-    const float* w_ih = p.w_ih + (long long)g * 3 * kHid * p.Kin;
-    const float* w_hh = p.w_hh + (long long)g * 3 * kHid * kHid;
-    const float* w1 = p.w1 + (long long)g * kHid * kHid;
-    const float* w2 = p.w2 + (long long)g * kHid * kHid;
-    const float* w3 = p.w3 + (long long)g * N * kHid;
+    const float* w_ih = ctrl_ptr(p.w_ih, g);
+    const float* w_hh = ctrl_ptr(p.w_hh, g);
+    const float* w1 = ctrl_ptr(p.w1, g);
+    const float* w2 = ctrl_ptr(p.w2, g);
+    const float* w3 = ctrl_ptr(p.w3, g);
     for (int idx = tid0; idx < N * kU; idx += stride)
         out[bwd_img_w3c(N) + idx] = w3[(idx / kU) * kHid + c * kU + (idx % kU)];
     for (int idx = tid0; idx < kHid * kU; idx += stride) {
@@ -256,6 +277,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
         __threadfence();
         cluster.sync();
     }
+    PHASE_INIT();
     const int tl_begin = STRICT ? 0 : (int)(blockIdx.x / kCS);
     const int tl_end = STRICT ? n_tiles : tl_begin + 1;
     int cur_g = -1, spec_t = -1, hsel = 0;
@@ -272,26 +294,26 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                         reinterpret_cast<const float4*>(img + (long long)(g * kCS + rank) * fwd_img_floats(N)),
                         fwd_img_floats(N) / 4);
                 for (int i = tid; i < kHid; i += kSeqThreads) {
-                    vec_s[V_LN1G + i] = p.ln1_g[g * kHid + i];
-                    vec_s[V_LN1B + i] = p.ln1_b[g * kHid + i];
-                    vec_s[V_LN2G + i] = p.ln2_g[g * kHid + i];
-                    vec_s[V_LN2B + i] = p.ln2_b[g * kHid + i];
+                    vec_s[V_LN1G + i] = ctrl_ptr(p.ln1_g, g)[i];
+                    vec_s[V_LN1B + i] = ctrl_ptr(p.ln1_b, g)[i];
+                    vec_s[V_LN2G + i] = ctrl_ptr(p.ln2_g, g)[i];
+                    vec_s[V_LN2B + i] = ctrl_ptr(p.ln2_b, g)[i];
                     vec_s[V_FC + i] = i < N ? p.fc[i] : 1.0f;
                     vec_s[V_Q0 + i] = i < N ? p.q0[i] : 1.0f;
                 }
                 if (tid < kU) {
-                    const float* b_ih = p.b_ih + g * 3 * kHid;
-                    const float* b_hh = p.b_hh + g * 3 * kHid;
+                    const float* b_ih = ctrl_ptr(p.b_ih, g);
+                    const float* b_hh = ctrl_ptr(p.b_hh, g);
                     const int o = rank * kU + tid;
                     vec_s[V_BR + tid] = b_ih[o] + b_hh[o];
                     vec_s[V_BZ + tid] = b_ih[kHid + o] + b_hh[kHid + o];
                     vec_s[V_BIN + tid] = b_ih[2 * kHid + o];
                     vec_s[V_BHN + tid] = b_hh[2 * kHid + o];
-                    vec_s[V_B1 + tid] = p.b1[g * kHid + o];
-                    vec_s[V_B2 + tid] = p.b2[g * kHid + o];
+                    vec_s[V_B1 + tid] = ctrl_ptr(p.b1, g)[o];
+                    vec_s[V_B2 + tid] = ctrl_ptr(p.b2, g)[o];
                     const int n = rank * NU + tid;
                     const bool own = tid < NU && n < N;
-                    vec_s[V_B3 + tid] = own ? p.b3[g * N + n] : 0.f;
+                    vec_s[V_B3 + tid] = own ? ctrl_ptr(p.b3, g)[n] : 0.f;
                     vec_s[V_Q0S + tid] = own ? p.q0[n] : 1.f;
                     vec_s[V_DQS + tid] = own ? p.dq[n] : 0.f;
                 }
@@ -324,8 +346,10 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                 for (int i = tid; i < kHid * kR / 4; i += kSeqThreads) hdst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
             if (STRICT || spec_t != t) prefetch_spectra(p, spec_s, L.tile, grow0, bb0, t);
+            PHASE_MARK(0, 0);    // loop head / weight load
             finish_spectra(p, spec_s, L.tile, bb0);
             __syncthreads();
+            PHASE_MARK(0, 1);    // spectra ready
 
             // ---- band stage of frame t for this CTA's 4 rows (model_torch.py:340-346, 1050-1060) ---------------
             // The 4 x quads (row, 4-band quad) pairs are dealt round-robin to the 16 warps, widest quads first and
@@ -398,6 +422,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                     p.dPdQ[own_e] = oK;
                 }
             };
+            PHASE_MARK(0, 2);    // band stage (this warp)
             if (t == T - 1) {
                 // The reference runs the controller once more and discards the result (model_torch.py:361-380).
                 store_band_outputs();
@@ -423,6 +448,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                     make_float4(ystage_s[tid], ystage_s[kHid + tid], ystage_s[2 * kHid + tid], ystage_s[3 * kHid + tid]);
             store_band_outputs();
             cluster.barrier_wait();     // ... and complete everywhere
+            PHASE_MARK(0, 3);    // band barrier + push + cluster barrier #1
 
             // ---- GRU cell (torch gate order r, z, n; n = tanh(i_n + r * (W_hn h + b_hn))) ----------------------
             {
@@ -467,6 +493,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                 }
             }
             cluster.barrier_wait();   // #2: h_t complete everywhere
+            PHASE_MARK(0, 4);    // GRU
 
             // ---- Linear 1 -> LayerNorm -> SiLU -> Dropout ------------------------------------------------------
             {
@@ -483,9 +510,11 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                 }
             }
             cluster.sync();   // #3
+            PHASE_MARK(0, 5);    // Linear 1
             ln_silu_drop_fwd(p, seed, a1_s, stat_s, vec_s + V_LN1G, vec_s + V_LN1B, 0, t, (long long)g * p.B + b0, rank,
                              p.xh1 + tb * kHid * kR, p.d1 + tb * kHid * kR, p.rstd + tb * 2 * kR);
 
+            PHASE_MARK(0, 6);    // LayerNorm 1
             // ---- Linear 2 -> LayerNorm -> SiLU -> Dropout ------------------------------------------------------
             {
                 float acc[kRT] = {0.f, 0.f, 0.f, 0.f};
@@ -501,9 +530,11 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                 }
             }
             cluster.sync();   // #4
+            PHASE_MARK(0, 7);    // Linear 2
             ln_silu_drop_fwd(p, seed, a2_s, stat_s, vec_s + V_LN2G, vec_s + V_LN2B, 1, t, (long long)g * p.B + b0, rank,
                              p.xh2 + tb * kHid * kR, p.d2 + tb * kHid * kR, p.rstd + tb * 2 * kR);
 
+            PHASE_MARK(0, 8);    // LayerNorm 2
             // ---- Linear 3 -> tanh -> Q_{t+1} (model_torch.py:367-380) -------------------------------------------
             {
                 float acc[kRT] = {0.f, 0.f, 0.f, 0.f};
@@ -554,6 +585,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                 if (!STRICT) store_q();
             }
             cluster.barrier_wait();   // #5: Q_{t+1} delivered; a2 / yc free for the next frame
+            PHASE_MARK(0, 9);    // Linear 3 + Q
             if (!STRICT) hsel ^= 1;   // strict: h_{t-1} is reloaded from global memory, the buffers keep their roles
         }
     }
@@ -666,10 +698,10 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
     copy_f4(reinterpret_cast<float4*>(img_s),
             reinterpret_cast<const float4*>(img + (long long)(g * kCS + rank) * bwd_img_floats(N)), bwd_img_floats(N) / 4);
     for (int i = tid; i < kHid; i += kSeqThreads) {
-        vec_s[VB_LN1G + i] = p.ln1_g[g * kHid + i];
-        vec_s[VB_LN1B + i] = p.ln1_b[g * kHid + i];
-        vec_s[VB_LN2G + i] = p.ln2_g[g * kHid + i];
-        vec_s[VB_LN2B + i] = p.ln2_b[g * kHid + i];
+        vec_s[VB_LN1G + i] = ctrl_ptr(p.ln1_g, g)[i];
+        vec_s[VB_LN1B + i] = ctrl_ptr(p.ln1_b, g)[i];
+        vec_s[VB_LN2G + i] = ctrl_ptr(p.ln2_g, g)[i];
+        vec_s[VB_LN2B + i] = ctrl_ptr(p.ln2_b, g)[i];
         vec_s[VB_Q0 + i] = i < N ? p.q0[i] : 1.0f;
         vec_s[VB_DQ + i] = i < N ? p.dq[i] : 0.0f;
     }
@@ -677,7 +709,9 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
     float dh_carry[kRT] = {0.f, 0.f, 0.f, 0.f};     // dL/dh_t arriving from step t+1 (owned by the ks == 0 threads)
     cluster.sync();
 
+    PHASE_INIT();
     for (int t = S - 1; t >= 0; --t) {
+        PHASE_MARK(1, 0);
         const bool flagged = p.flags[t * p.G + g] != 0;                    // Q_{t+1} was replaced by Q0, h_t dropped
         const bool h_reset = (t == 0) || (p.flags[(t - 1) * p.G + g] != 0);
         const bool has_ctrl_next = (t + 1) < S;                              // a controller step consumed Y_{t+1}
@@ -714,6 +748,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
             *reinterpret_cast<float4*>(p.G_pre + tb * N * kR + tid * kR + rank * kRT) =
                 make_float4(stage_s[tid], stage_s[kHid + tid], stage_s[2 * kHid + tid], stage_s[3 * kHid + tid]);
         cluster.barrier_wait();     // #1
+        PHASE_MARK(1, 1);    // dL/dpre assembly + push
 
         // ---- Linear 3 ^T --------------------------------------------------------------------------------------
         {
@@ -725,8 +760,10 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
             if (ks == 0) broadcast_rows(cluster, bufa_s, ug, rg * kRT, acc);
         }
         cluster.sync();   // #2
+        PHASE_MARK(1, 2);    // Linear 3 ^T
         ln_silu_drop_bwd(p, seed, bufa_s, stat_s, vec_s + VB_LN2G, vec_s + VB_LN2B, 1, t, (long long)g * p.B + b0, rank,
                          p.xh2 + tb * kHid * kR, p.rstd + tb * 2 * kR, p.G_v2 + tb * kHid * kR, p.G_a2 + tb * kHid * kR);
+        PHASE_MARK(1, 3);    // LayerNorm 2 backward
         // ---- Linear 2 ^T --------------------------------------------------------------------------------------
         {
             float acc[kRT] = {0.f, 0.f, 0.f, 0.f};
@@ -737,8 +774,10 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
             if (ks == 0) broadcast_rows(cluster, bufb_s, ug, rg * kRT, acc);   // bufb aliases dpre: its reads ended before #2
         }
         cluster.sync();   // #3
+        PHASE_MARK(1, 4);    // Linear 2 ^T
         ln_silu_drop_bwd(p, seed, bufb_s, stat_s, vec_s + VB_LN1G, vec_s + VB_LN1B, 0, t, (long long)g * p.B + b0, rank,
                          p.xh1 + tb * kHid * kR, p.rstd + tb * 2 * kR, p.G_v1 + tb * kHid * kR, p.G_a1 + tb * kHid * kR);
+        PHASE_MARK(1, 5);    // LayerNorm 1 backward
         // ---- Linear 1 ^T, GRU cell backward ------------------------------------------------------------------------
         float dh_direct[kRT] = {0.f, 0.f, 0.f, 0.f};
         {
@@ -788,6 +827,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
             }
         }
         cluster.barrier_wait();   // #4
+        PHASE_MARK(1, 6);    // Linear 1 ^T + GRU cell backward
         // ---- dL/dh_{t-1} = z * dh + W_hh^T [drp, dzp, dhn];  dL/dY_t = W_ih[:, :N]^T [drp, dzp, dnp] * d log1p --------
         {
             float acc[2 * kRT] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -821,6 +861,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
             }
         }
         cluster.sync();   // #5: dL/dY_t delivered; gate / dpre buffers free for the next step
+        PHASE_MARK(1, 7);    // W_hh^T / W_ih^T products
     }
 }
 
@@ -834,9 +875,12 @@ static int validate_seq(const BiearSeqParams* p, const char* who, bool backward)
     BIEAR_REQUIRE(p->E == p->G && p->Kin == 2 * p->N,
                   "%s: only the dual front-end (one controller per ear, Kin = 2N) is fused; got E=%d G=%d Kin=%d",
                   who, p->E, p->G, p->Kin);
-    BIEAR_REQUIRE(p->fc && p->q0 && p->dq && p->w_ih && p->w_hh && p->b_ih && p->b_hh && p->w1 && p->b1 && p->ln1_g &&
-                      p->ln1_b && p->w2 && p->b2 && p->ln2_g && p->ln2_b && p->w3 && p->b3,
-                  "%s: null constant / weight pointer", who);
+    BIEAR_REQUIRE(p->G <= BIEAR_MAX_CTRL, "%s: at most %d controllers per call, got %d", who, BIEAR_MAX_CTRL, p->G);
+    BIEAR_REQUIRE(p->fc && p->q0 && p->dq, "%s: null constant pointer", who);
+    for (int g = 0; g < p->G; ++g)
+        BIEAR_REQUIRE(p->w_ih[g] && p->w_hh[g] && p->b_ih[g] && p->b_hh[g] && p->w1[g] && p->b1[g] && p->ln1_g[g] &&
+                          p->ln1_b[g] && p->w2[g] && p->b2[g] && p->ln2_g[g] && p->ln2_b[g] && p->w3[g] && p->b3[g],
+                      "%s: null weight pointer of controller %d", who, g);
     BIEAR_REQUIRE(p->Y && p->Q && p->delta && p->dYdQ && p->flags && p->workspace, "%s: null output pointer", who);
     BIEAR_REQUIRE(!p->phase == !p->dPdQ, "%s: phase and dPdQ must be given together", who);
     if (p->T > 1)
@@ -958,4 +1002,18 @@ extern "C" int biear_adaptive_occupancy(int N, int F, int* fwd_clusters, int* bw
         *(pass ? bwd_clusters : fwd_clusters) = n;
     }
     return 0;
+}
+
+// Diagnostic builds only (-DBIEAR_PHASE_PROF): copy out and clear the per-phase cycle counters (2 x 16); returns
+// BIEAR_EINVAL in normal builds.
+extern "C" int biear_debug_phase_cycles(unsigned long long* out_host) {
+#ifdef BIEAR_PHASE_PROF
+    using namespace biear;
+    unsigned long long zero[2][16] = {};
+    if (int e = check_cuda(cudaMemcpyFromSymbol(out_host, g_phase_cycles, sizeof(zero)), "cudaMemcpyFromSymbol")) return e;
+    return check_cuda(cudaMemcpyToSymbol(g_phase_cycles, zero, sizeof(zero)), "cudaMemcpyToSymbol");
+#else
+    (void)out_host;
+    return biear::fail_invalid("biear_debug_phase_cycles: library built without BIEAR_PHASE_PROF");
+#endif
 }

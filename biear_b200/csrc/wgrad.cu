@@ -30,6 +30,7 @@ struct WgradJobPlan {
     long long part_off, bpart_off;                            // offsets into scratch (floats); bpart_off < 0: no bias
     long long out_begin;                                      // first element of this job in the reduce index space
     float* dW; float* db;
+    long long dw_group, dw_row, db_group;                    // output strides (floats)
 };
 
 struct WgradPlan {
@@ -199,7 +200,14 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgradPlan pl) {
         src += g * a.splits * per + r;
         float s = 0.f;
         for (int k = 0; k < a.splits; ++k) s += src[(long long)k * per];
-        dst[e] = s;
+        if (dst == a.db) {
+            dst[g * a.db_group + r] = s;
+        } else if (a.Di > 0) {
+            const long long o = r / a.Di, i = r - o * a.Di;
+            dst[g * a.dw_group + o * a.dw_row + i] = s;
+        } else {
+            dst[g * a.dw_group + r] = s;
+        }
     }
 }
 
@@ -253,6 +261,9 @@ static int make_plan(const BiearWgradJob* jobs, int n_jobs, int G, int tile_rows
         a.out_begin = out;
         out += (long long)G * (per_w + (q.db ? q.Do : 0));
         a.dW = q.dW; a.db = q.db;
+        a.dw_row = q.dw_row_stride ? q.dw_row_stride : (q.Di > 0 ? q.Di : 1);
+        a.dw_group = q.dw_group_stride ? q.dw_group_stride : per_w;
+        a.db_group = q.db_group_stride ? q.db_group_stride : q.Do;
     }
     pl->total_ctas = cta;
     pl->total_out = out;

@@ -29,12 +29,18 @@ class FlatGradAllReducer:
     result is the full-batch-mean gradient.
     """
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], group: Optional[dist.ProcessGroup] = None):
+    def __init__(self, params: Iterable[torch.nn.Parameter], group: Optional[dist.ProcessGroup] = None,
+                 flat: Optional[torch.Tensor] = None):
+        """flat: an existing bucket that already holds the gradients, parameter after parameter (e.g.
+        GraphedStep(..., flat_grads=True).flat, whose slices ARE the .grad tensors): no copies are made then."""
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         self.group = group
         self.numel = sum(p.numel() for p in self.params)
         p0 = self.params[0]
-        self.flat = torch.zeros(self.numel, dtype=torch.float32, device=p0.device)
+        self.aliased = flat is not None
+        if flat is not None:
+            assert flat.numel() == self.numel and flat.dtype == torch.float32
+        self.flat = flat if flat is not None else torch.zeros(self.numel, dtype=torch.float32, device=p0.device)
         self.views = []
         off = 0
         for p in self.params:
@@ -44,20 +50,22 @@ class FlatGradAllReducer:
     @torch.no_grad()
     def __call__(self, weight: Optional[float] = None) -> torch.Tensor:
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
-        for p, v in zip(self.params, self.views):
-            if p.grad is None:
-                v.zero_()
-            else:
-                v.copy_(p.grad)
+        if not self.aliased:
+            for p, v in zip(self.params, self.views):
+                if p.grad is None:
+                    v.zero_()
+                else:
+                    v.copy_(p.grad)
         if world > 1:
             if weight is not None:
                 self.flat.mul_(weight)
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
             if weight is None:
                 self.flat.mul_(1.0 / world)
-        for p, v in zip(self.params, self.views):
-            if p.grad is None:
-                p.grad = v.clone()
-            else:
-                p.grad.copy_(v)
+        if not self.aliased:
+            for p, v in zip(self.params, self.views):
+                if p.grad is None:
+                    p.grad = v.clone()
+                else:
+                    p.grad.copy_(v)
         return self.flat

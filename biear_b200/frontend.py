@@ -183,7 +183,7 @@ def _adaptive_chain(x: torch.Tensor, ears: int, ctrl_mods, fc, q0, dq_vec, dq_mo
     if engine in ("fused", "fused-strict"):
         if shared or G != ears or N > 128:
             raise NotImplementedError("the fused recurrence covers the dual front-end with at most 128 bands")
-        st = lambda f: torch.stack([f(m) for m in ctrl_mods])
+        st = lambda f: [f(m) for m in ctrl_mods]      # the parameters themselves: the C ABI takes one pointer per controller
         w = {"w_ih": st(lambda m: m.q_rnn.weight_ih_l0), "w_hh": st(lambda m: m.q_rnn.weight_hh_l0),
              "b_ih": st(lambda m: m.q_rnn.bias_ih_l0), "b_hh": st(lambda m: m.q_rnn.bias_hh_l0),
              "w1": st(lambda m: m.q_out[0].weight), "b1": st(lambda m: m.q_out[0].bias),

@@ -7,6 +7,7 @@ from the loop.  The reference has no counterpart (it issues ~2000 eager launches
 SURVEY.md 3.1-3.2).
 
     step = GraphedStep(fn, example_inputs, params)      # fn(*inputs) -> scalar loss; captured with its backward
+                                                        # (flat_grads=True: the gradients are slices of step.flat)
     loss = step(wavL, wavR)                             # copies the inputs into the static buffers, replays
     # params[i].grad now hold this step's gradients; loss is a device scalar (static tensor)
 
@@ -22,7 +23,8 @@ import torch
 
 class GraphedStep:
     def __init__(self, fn: Callable[..., torch.Tensor], example_inputs: Sequence[torch.Tensor],
-                 params: Iterable[torch.nn.Parameter], warmup: int = 3, pool=None, copy_inputs: bool = True):
+                 params: Iterable[torch.nn.Parameter], warmup: int = 3, pool=None, copy_inputs: bool = True,
+                 flat_grads: bool = False):
         self.params = [p for p in params if p.requires_grad]
         self.copy_inputs = copy_inputs
         self.static_inputs = [x.clone() for x in example_inputs] if copy_inputs else list(example_inputs)
@@ -43,6 +45,16 @@ class GraphedStep:
         with torch.cuda.graph(self.graph, pool=pool):
             self.loss = fn(*self.static_inputs)
             grads = torch.autograd.grad(self.loss, self.params, allow_unused=True)
+            if flat_grads:
+                # one contiguous bucket (written by the graph itself) whose slices become the .grad tensors: a
+                # data-parallel step then needs a single all-reduce on `flat` and no per-parameter copies
+                self.flat = torch.cat([(g if g is not None else torch.zeros_like(p)).reshape(-1)
+                                       for g, p in zip(grads, self.params)])
+                views, off = [], 0
+                for p in self.params:
+                    views.append(self.flat[off:off + p.numel()].view_as(p))
+                    off += p.numel()
+                grads = views
         self.launches_per_replay = _lib.launch_count() - n0   # kernels of libbiear_b200.so recorded in the graph
         self.loss = self.loss.detach()
         self.grads = list(grads)                      # static tensors (graph pool) rewritten by every replay

@@ -273,27 +273,39 @@ def tile_rows() -> int:
 
 
 def ctrl_wgrad(jobs):
-    """Weight gradients for a list of jobs (a, do, bm, di, chunks, want_bias) in two launches (biear_ctrl_wgrad).
+    """Weight gradients for a list of jobs in two launches (biear_ctrl_wgrad).
 
-    a (G, chunks', Da, R) and bm (G, chunks', Db, R) are tile-layout operands (views with arbitrary group / chunk
-    strides are fine); the first `do` / `di` features and the first `chunks` chunks are used.  di == 0 selects the
-    diagonal form dW[g][o] = sum a*bm (LayerNorm weight).  Returns [(dW (G,do,di) | (G,do), db (G,do) | None), ...].
+    A job is (a, do, bm, di, chunks, bias[, dw_out, db_out]).  a (G, chunks', Da, R) and bm (G, chunks', Db, R) are
+    tile-layout operands (views with arbitrary group / chunk strides are fine); the first `do` / `di` features and the
+    first `chunks` chunks are used.  di == 0 selects the diagonal form dW[g][o] = sum a*bm (LayerNorm weight).
+    Without dw_out / db_out, fresh dense outputs dW (G,do,di) | (G,do) and db (G,do) (if bias) are allocated; with them
+    the job writes into the given (possibly strided: a row block of a larger tensor) views of shape (G,do,di) / (G,do).
+    Returns [(dW, db | None), ...].
     """
     a0 = jobs[0][0]
     G, R, dev = a0.shape[0], a0.shape[3], a0.device
     lib = _prepare(dev)
     arr = (_lib.WgradJob * len(jobs))()
     outs = []
-    for j, (a, do, bm, di, chunks, want_bias) in enumerate(jobs):
+    for j, job in enumerate(jobs):
+        a, do, bm, di, chunks, want_bias = job[:6]
+        dw = job[6] if len(job) > 6 else None
+        db = job[7] if len(job) > 7 else None
         assert a.shape[0] == G and bm.shape[0] == G and a.shape[3] == R and bm.shape[3] == R
         assert a.stride(3) == 1 and a.stride(2) == R and bm.stride(3) == 1 and bm.stride(2) == R
-        dw = torch.empty((G, do, di) if di > 0 else (G, do), dtype=torch.float32, device=dev)
-        db = torch.empty((G, do), dtype=torch.float32, device=dev) if want_bias else None
+        if dw is None:
+            dw = torch.empty((G, do, di) if di > 0 else (G, do), dtype=torch.float32, device=dev)
+        if db is None and want_bias:
+            db = torch.empty((G, do), dtype=torch.float32, device=dev)
+        assert dw.stride(-1) == 1 and (db is None or db.stride(-1) == 1)
         outs.append((dw, db))
         q = arr[j]
         q.A, q.a_group_stride, q.a_chunk_stride, q.Do = a.data_ptr(), a.stride(0), a.stride(1), do
         q.Bm, q.b_group_stride, q.b_chunk_stride, q.Di = bm.data_ptr(), bm.stride(0), bm.stride(1), di
         q.chunks, q.dW, q.db = chunks, dw.data_ptr(), (db.data_ptr() if db is not None else None)
+        q.dw_group_stride = dw.stride(0)
+        q.dw_row_stride = dw.stride(1) if di > 0 else 1
+        q.db_group_stride = db.stride(0) if db is not None else 0
     n = int(lib.biear_wgrad_scratch_floats(arr, len(jobs), G, R))
     if n < 0:
         _lib.check(-1, "biear_wgrad_scratch_floats")
@@ -308,24 +320,26 @@ class AdaptiveSequence(torch.autograd.Function):
     forward : ONE persistent cluster kernel (biear_adaptive_fwd) carries every 32-row tile through all frames;
     backward: ONE persistent cluster kernel (biear_adaptive_bwd) runs the chain t = T-2 .. 0 and leaves the
               per-sample pre-activation gradients, from which biear_ctrl_wgrad forms the weight gradients.
-    Inputs : xr (E*B,T,F,2), fc/q0/dq (N), 14 weight tensors stacked over the G = E controllers.
+    Inputs : xr (E*B,T,F,2), fc/q0/dq (N), then the 14 weight tensors of every controller, name-major
+             (w_ih of controller 0, w_ih of controller 1, w_hh of controller 0, ...): the parameters themselves, no
+             stacking copy; the gradients come back in the same order.
     Outputs: Y (E*B,T,N), Q (G*B,T,N), phase (E*B,T,N) [empty when want_phase is False].
     """
 
     @staticmethod
-    def forward(ctx, xr, fc, q0, dq, relative, training, want_phase, cutoff, df, seed, strict, *weights):
+    def forward(ctx, xr, fc, q0, dq, relative, training, want_phase, cutoff, df, seed, strict, G, *weights):
         ctx.set_materialize_grads(False)
         _need_cuda(xr, "X")
         dev = xr.device
         rows, T, F, _ = xr.shape
         N = fc.numel()
-        G = weights[0].shape[0]
+        assert len(weights) == G * len(WEIGHT_NAMES) and 1 <= G <= _lib.MAX_CTRL
         B = rows // G
         weights = tuple(w.detach().contiguous() for w in weights)
-        for name, w in zip(WEIGHT_NAMES, weights):
-            _need_cuda(w, name)
-        Kin = weights[0].shape[2]
-        need_grad = any(ctx.needs_input_grad[11:])
+        for i, w in enumerate(weights):
+            _need_cuda(w, WEIGHT_NAMES[i // G])
+        Kin = weights[0].shape[1]
+        need_grad = any(ctx.needs_input_grad[12:])
         f32 = dict(dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             lib = _prepare(dev)
@@ -351,7 +365,11 @@ class AdaptiveSequence(torch.autograd.Function):
             seed_dev = _captured_seed(dev) if (training and torch.cuda.is_current_stream_capturing()) else None
             prm.df, prm.cutoff, prm.q_min, prm.q_max = float(df), float(cutoff), 0.05, 30.0
             _fill(prm, fc=fc, q0=q0, dq=dq, X=xr, Y=Y, phase=P, dYdQ=dY, dPdQ=dP, Q=Q, delta=D, flags=flags,
-                  workspace=work, H=H, seed_ptr=seed_dev, **sv, **dict(zip(WEIGHT_NAMES, weights)))
+                  workspace=work, H=H, seed_ptr=seed_dev, **sv)
+            for i, name in enumerate(WEIGHT_NAMES):
+                arr = getattr(prm, name)
+                for g in range(G):
+                    arr[g] = weights[i * G + g].data_ptr()
             from ctypes import byref
             _lib.check(lib.biear_adaptive_fwd(byref(prm), _stream(dev)), "biear_adaptive_fwd")
         ctx.prm = prm
@@ -376,9 +394,9 @@ class AdaptiveSequence(torch.autograd.Function):
         if not ctx.has_phase:
             P = None
         G, B, T, N, Kin, tiles, TILE = ctx.dims
-        none11 = (None,) * 11
+        none12 = (None,) * 12
         if T < 2 or (gY is None and gQ is None and gP is None):
-            return none11 + (None,) * len(WEIGHT_NAMES)
+            return none12 + (None,) * (G * len(WEIGHT_NAMES))
         dev = Y.device
         f32 = dict(dtype=torch.float32, device=dev)
         S = T - 1
@@ -400,28 +418,29 @@ class AdaptiveSequence(torch.autograd.Function):
             GG = fl(wk["GG"])
             Hk = H.view(G, (S + 1) * tiles, HID, TILE)      # chunk = (step, tile); group stride covers S+1 steps
             h_prev, h_cur = Hk[:, :K], Hk[:, tiles:]
-            (a, d_b_ih), (d_rz, _), (d_n, d_b_hn), (d_w1, d_b1), (d_w2, d_b2), (d_w3, d_b3), (d_g1, d_be1), (d_g2, d_be2) = \
-                ctrl_wgrad([
-                    (GG, 3 * HID, fl(sv["yc"]), N, K, True),                 # dL/dW_ih[:, :N], b_ih
-                    (GG, 2 * HID, h_prev, HID, K, False),                     # r, z rows of W_hh
-                    (GG[:, :, 3 * HID:], HID, h_prev, HID, K, True),          # n rows of W_hh, b_hn (dL/d(W_hn h + b_hn))
-                    (fl(wk["G_a1"]), HID, h_cur, HID, K, True),
-                    (fl(wk["G_a2"]), HID, fl(sv["d1"]), HID, K, True),
-                    (fl(wk["G_pre"]), N, fl(sv["d2"]), HID, K, True),
-                    (fl(wk["G_v1"]), HID, fl(sv["xh1"]), 0, K, True),          # LayerNorm 1 weight / bias
-                    (fl(wk["G_v2"]), HID, fl(sv["xh2"]), 0, K, True),
-                ])
+            d_w_hh = torch.empty((G, 3 * HID, HID), **f32)
+            d_b_hh = torch.empty((G, 3 * HID), **f32)
+            (a, d_b_ih), _, _, (d_w1, d_b1), (d_w2, d_b2), (d_w3, d_b3), (d_g1, d_be1), (d_g2, d_be2) = ctrl_wgrad([
+                (GG, 3 * HID, fl(sv["yc"]), N, K, True),                                          # dL/dW_ih[:, :N], b_ih
+                (GG, 2 * HID, h_prev, HID, K, True, d_w_hh[:, :2 * HID], d_b_hh[:, :2 * HID]),     # r, z rows of W_hh / b_hh
+                (GG[:, :, 3 * HID:], HID, h_prev, HID, K, True, d_w_hh[:, 2 * HID:], d_b_hh[:, 2 * HID:]),   # n rows: dL/d(W_hn h + b_hn)
+                (fl(wk["G_a1"]), HID, h_cur, HID, K, True),
+                (fl(wk["G_a2"]), HID, fl(sv["d1"]), HID, K, True),
+                (fl(wk["G_pre"]), N, fl(sv["d2"]), HID, K, True),
+                (fl(wk["G_v1"]), HID, fl(sv["xh1"]), 0, K, True),                                  # LayerNorm 1 weight / bias
+                (fl(wk["G_v2"]), HID, fl(sv["xh2"]), 0, K, True),
+            ])
             d_w_ih = torch.cat([a, 0.2 * a], dim=2) if Kin == 2 * N else None            # feat = [yc, 0.2 yc.detach()]
-            d_w_hh = torch.cat([d_rz, d_n], dim=1)
-            d_b_hh = torch.cat([d_b_ih[:, :2 * HID], d_b_hn], dim=1)
-        grads = (d_w_ih, d_w_hh, d_b_ih, d_b_hh, d_w1, d_b1, d_g1, d_be1, d_w2, d_b2, d_g2, d_be2, d_w3, d_b3)
-        return none11 + grads
+        stacked = (d_w_ih, d_w_hh, d_b_ih, d_b_hh, d_w1, d_b1, d_g1, d_be1, d_w2, d_b2, d_g2, d_be2, d_w3, d_b3)
+        grads = tuple(t[g] if t is not None else None for t in stacked for g in range(G))
+        return none12 + grads
 
 
 def adaptive_sequence(xr, fc, q0, dq, weights, relative: bool, training: bool, want_phase: bool,
                       cutoff: float, df: float, seed: int = 0, strict: bool = False):
-    """weights: dict name -> (G, ...) tensor (WEIGHT_NAMES).  Returns Y, Q, phase|None.
+    """weights: dict name -> list of the G controllers' tensors (WEIGHT_NAMES).  Returns Y, Q, phase|None.
     strict=True skips the fast pass and runs the batch-global-fallback replay pass only (testing)."""
-    y, q, ph = AdaptiveSequence.apply(xr, fc, q0, dq, relative, training, want_phase, cutoff, df, seed, strict,
-                                      *[weights[k] for k in WEIGHT_NAMES])
+    G = len(weights[WEIGHT_NAMES[0]])
+    y, q, ph = AdaptiveSequence.apply(xr, fc, q0, dq, relative, training, want_phase, cutoff, df, seed, strict, G,
+                                      *[w for k in WEIGHT_NAMES for w in weights[k]])
     return y, q, (ph if want_phase else None)

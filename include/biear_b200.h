@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BIEAR_ABI_VERSION 6
+#define BIEAR_ABI_VERSION 7
 #define BIEAR_EINVAL (-1)
 
 /* ABI version (== BIEAR_ABI_VERSION of the library that was built). */
@@ -98,6 +98,7 @@ int biear_band_bwd(const float* X, int64_t x_stride, const float* Q, int64_t q_s
  * gradient entries are exactly zero).  The forward writes them, the backward reads them and writes the
  * per-sample pre-activation gradients in the same layout; biear_ctrl_wgrad turns those into weight gradients.
  */
+#define BIEAR_MAX_CTRL 2   /* controllers per call: one per ear in the dual front-end */
 typedef struct BiearSeqParams {
     /* geometry */
     int32_t G, E, B, T, N, F, Kin;   /* controllers, ears, clips, frames, bands (<= 128), bins, controller input width */
@@ -108,11 +109,12 @@ typedef struct BiearSeqParams {
     float df, cutoff, q_min, q_max;
     /* constants (N) */
     const float *fc, *q0, *dq;
-    /* controller weights, stacked over the G controllers, torch layouts (out, in) */
-    const float *w_ih, *w_hh, *b_ih, *b_hh;          /* (G,384,Kin) (G,384,128) (G,384) (G,384) */
-    const float *w1, *b1, *ln1_g, *ln1_b;            /* (G,128,128) (G,128) x3 */
-    const float *w2, *b2, *ln2_g, *ln2_b;
-    const float *w3, *b3;                            /* (G,N,128) (G,N) */
+    /* controller weights: entry g < G of every array points at controller g's tensor in its torch layout (out, in),
+       i.e. straight at the nn.GRU / nn.Linear / nn.LayerNorm parameters -- no stacking copy */
+    const float *w_ih[BIEAR_MAX_CTRL], *w_hh[BIEAR_MAX_CTRL], *b_ih[BIEAR_MAX_CTRL], *b_hh[BIEAR_MAX_CTRL]; /* (384,Kin) (384,128) (384) (384) */
+    const float *w1[BIEAR_MAX_CTRL], *b1[BIEAR_MAX_CTRL], *ln1_g[BIEAR_MAX_CTRL], *ln1_b[BIEAR_MAX_CTRL];   /* (128,128) (128) x3 */
+    const float *w2[BIEAR_MAX_CTRL], *b2[BIEAR_MAX_CTRL], *ln2_g[BIEAR_MAX_CTRL], *ln2_b[BIEAR_MAX_CTRL];
+    const float *w3[BIEAR_MAX_CTRL], *b3[BIEAR_MAX_CTRL];                                                   /* (N,128) (N) */
     /* spectra (E*B, T, F, 2) */
     const float* X;
     /* forward outputs, row-major (E*B, T, N); phase / dPdQ nullable together */
@@ -147,6 +149,10 @@ int64_t biear_adaptive_workspace_floats(int G, int N);
  * at once (cudaOccupancyMaxActiveClusters); a batch needs G * ceil(B / R) clusters per pass. */
 int biear_adaptive_occupancy(int N, int F, int* fwd_clusters, int* bwd_clusters);
 
+/* Diagnostic builds only (-DBIEAR_PHASE_PROF, `make -C biear_b200/csrc prof`): per-phase clock64() totals of block 0 of
+ * the forward [0][*] and backward [1][*] recurrence kernels, copied to out_host[2*16] and cleared. */
+int biear_debug_phase_cycles(unsigned long long* out_host);
+
 /* Whole forward recurrence in ONE persistent cluster kernel (plus a weight-packing launch and a conditional
  * replay launch that exits immediately unless a non-finite Q was produced): each cluster of 4 CTAs carries R rows
  * through all T frames with the controller weights and the recurrent state resident in (distributed) shared
@@ -167,7 +173,7 @@ int biear_adaptive_bwd(const BiearSeqParams* p, void* stream);
  *   diagonal job (Di = 0) dW[g][o]    = sum_{k, r} A[g][k][o][r] * Bm[g][k][o][r]                    (LayerNorm weight)
  *   both                  db[g][o]    = sum_{k, r} A[g][k][o][r]                                      (db nullable)
  * A is (G, chunks, >=Do, R) with chunk stride a_chunk_stride floats and group stride a_group_stride, likewise Bm;
- * R = tile_rows (16 or 32).  Outputs are dense (G, Do, Di) / (G, Do).  Replaces the weight-gradient GEMMs and
+ * R = tile_rows (16 or 32).  Replaces the weight-gradient GEMMs and
  * reductions autograd runs for model_torch.py:256-267.
  */
 #define BIEAR_WGRAD_MAX_JOBS 8
@@ -176,6 +182,9 @@ typedef struct BiearWgradJob {
     const float* Bm; int64_t b_group_stride, b_chunk_stride; int32_t Di;
     int64_t chunks;
     float* dW; float* db;
+    /* output strides in floats; 0 selects dense: dW (G, Do, Di) / (G, Do), db (G, Do).  Non-zero strides let a job write
+       a row block of a larger parameter gradient (e.g. the r,z rows and the n rows of GRU weight_hh) in place. */
+    int64_t dw_group_stride, dw_row_stride, db_group_stride;
 } BiearWgradJob;
 /* Floats of scratch biear_ctrl_wgrad needs for these jobs (-1 on invalid arguments). */
 int64_t biear_wgrad_scratch_floats(const BiearWgradJob* jobs, int n_jobs, int G, int tile_rows);
