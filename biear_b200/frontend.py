@@ -97,6 +97,17 @@ class _FilterbankBase(nn.Module):
         return ops.stft(wav, self.win_fn, self.fs, self.timesteps, self.win, self.hop, self.n_fft)
 
 
+_side_streams = {}
+
+
+def _side_stream(device) -> torch.cuda.Stream:
+    """One auxiliary stream per device for work that is independent of the recurrence (the CC feature)."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _side_streams:
+        _side_streams[idx] = torch.cuda.Stream(device=device)
+    return _side_streams[idx]
+
+
 def _make_controller(in_features: int, Nbands: int):
     """Same modules, same construction order (=> same default init under a given seed) as
     model_torch.py:256-267, 283-287."""
@@ -348,10 +359,23 @@ class BinauralAdaptiveGammatoneFB(nn.Module):
         # "chain": per-frame band kernel + batched torch controller (kept as a cross-check)
         self.engine = "fused"
 
-    def forward_features(self, wavL_1s: torch.Tensor, wavR_1s: torch.Tensor, want_phase: bool = True):
+    def forward_features(self, wavL_1s: torch.Tensor, wavR_1s: torch.Tensor, want_phase: bool = True,
+                         want_cc: bool = False, cc_max_lag_ms: float = 3.0):
+        """Everything the back-end consumes, in one call: band energies, Q, spectra, sub-band phases and -- with
+        want_cc -- the broadband cross-correlation feature x3 (utils.py:390-420), which the reference precomputes
+        offline.  The CC kernel is independent of the recurrence and runs on a forked stream next to it (the
+        persistent recurrence kernels occupy 128 of the 148 SMs)."""
         fb = self.fb_L
         if wavL_1s.shape != wavR_1s.shape:
             raise ValueError(f"wavL {tuple(wavL_1s.shape)} and wavR {tuple(wavR_1s.shape)} differ")
+        cc = None
+        if want_cc:
+            cur = torch.cuda.current_stream(wavL_1s.device)
+            side = _side_stream(wavL_1s.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                cc = ops.cc_feature(wavL_1s.float().contiguous(), wavR_1s.float().contiguous(), fb.fs, fb.Nbands,
+                                    cc_max_lag_ms)
         x = fb._spectra([wavL_1s, wavR_1s])
         B = wavL_1s.shape[0]
         frozen = (not self.fixed_frontend_q) and self.fb_L.freeze_Q and self.fb_R.freeze_Q
@@ -368,6 +392,10 @@ class BinauralAdaptiveGammatoneFB(nn.Module):
         out = {"YL": y[:B], "YR": y[B:], "QL": q[:B], "QR": q[B:], "XL": x[:B], "XR": x[B:]}
         if want_phase:
             out["phaseL"], out["phaseR"] = ph[:B], ph[B:]
+        if cc is not None:
+            cur.wait_stream(side)
+            cc.record_stream(cur)
+            out["cc"] = cc
         return out
 
     def forward(self, wavL_1s: torch.Tensor, wavR_1s: torch.Tensor):

@@ -21,6 +21,14 @@ from typing import Callable, Iterable, Optional, Sequence
 import torch
 
 
+class _null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
 class GraphedStep:
     def __init__(self, fn: Callable[..., torch.Tensor], example_inputs: Sequence[torch.Tensor],
                  params: Iterable[torch.nn.Parameter], warmup: int = 3, pool=None, copy_inputs: bool = True,
@@ -64,8 +72,22 @@ class GraphedStep:
     def pool(self):
         return self.graph.pool()
 
+    def load(self, *inputs: torch.Tensor, stream: Optional[torch.cuda.Stream] = None):
+        """Copy (host or device) inputs into the graph's static input buffers, optionally on another stream so that
+        the H2D transfer of the next step overlaps this step's replay; returns an event to wait on before replay()."""
+        ctx = torch.cuda.stream(stream) if stream is not None else _null()
+        with ctx:
+            for dst, src in zip(self.static_inputs, inputs):
+                dst.copy_(src, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        return ev
+
+    def replay(self) -> torch.Tensor:
+        return self.__call__()
+
     def __call__(self, *inputs: torch.Tensor) -> torch.Tensor:
-        if self.copy_inputs:
+        if self.copy_inputs and inputs:
             for dst, src in zip(self.static_inputs, inputs):
                 dst.copy_(src, non_blocking=True)
         for p, g in zip(self.params, self.grads):
