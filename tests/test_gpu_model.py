@@ -1,0 +1,76 @@
+"""The full active model through the drop-in namespace (biear_b200.model_torch) on the GPU, against golden vectors
+produced by the unmodified reference (tests/golden/make_model_golden.py): logits / predictions and gradients of a
+fixed scalar loss.  This is BASELINE.json config 4's model (front-end + ILD/IPD encoders + heads); the back-end is plain
+PyTorch on both sides, so any difference comes from the front-end kernels."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import biear_oracle as orc
+from tests.common import RTOL, rel_err, sub
+from tests.golden.make_model_golden import GRAD_KEYS, loss_weights
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CONFIG_YAML = dict(deltaQ_base=1.0, deltaQ_low_factor=0.3, deltaQ_high_factor=5.0, deltaQ_mode="relative")
+
+
+@pytest.fixture(scope="module")
+def golden_model():
+    return np.load(os.path.join(ROOT, "tests", "golden", "model_golden.npz"))
+
+
+def _build():
+    from biear_b200 import model_torch as mt
+    torch.manual_seed(0)                     # same default initialisation as the reference under this seed
+    m = mt.build_model_active(use_cc=True, fb_alpha=0.0, fixed_frontend_q=False, **CONFIG_YAML)
+    for fb, s in ((m.bifb.fb_L, 11), (m.bifb.fb_R, 12)):
+        fb.load_state_dict({k: torch.from_numpy(v) for k, v in orc.synth_controller(s).items()}, strict=False)
+    return m.to(DEV).eval()
+
+
+def test_full_active_model_against_reference(golden_model):
+    from biear_b200 import ops
+    g = golden_model
+    m = _build()
+    wl, wr = orc.synth_binaural(3, seed=1234)
+    tl, tr = torch.from_numpy(wl).to(DEV), torch.from_numpy(wr).to(DEV)
+    x3 = ops.cc_feature(tl, tr)                                   # our CC kernel feeds cc_proj
+    assert float((x3.cpu() - torch.from_numpy(g["x3"])).abs().max()) <= 1e-6
+    with torch.backends.cudnn.flags(enabled=False):   # cuDNN refuses RNN backward in eval mode; the native GRU does not
+        sound, aoa, dist = m(tl, tr, x3)
+    assert sound.shape == (3, 8) and aoa.shape == (3, 8) and dist.shape == (3, 8, 5)
+    for name, t in (("sound", sound), ("aoa", aoa), ("dist", dist)):
+        ref32, ref64 = g[f"model32.{name}"], g[f"model64.{name}"]
+        e = rel_err(t.detach().cpu().numpy(), ref32)
+        assert e <= max(RTOL, 3 * rel_err(ref32, ref64)), (name, e)
+    assert m.last_Q is not None and m.last_Q.shape == (3, 19, 100)
+    ws, wa, wd = (torch.from_numpy(a).to(DEV) for a in loss_weights(3))
+    ((ws * sound).sum() + (wa * aoa).sum() + (wd * dist).sum()).backward()
+    params = dict(m.named_parameters())
+    for k in GRAD_KEYS:
+        ref32, ref64 = g[f"model32.grad.{k}"], g[f"model64.grad.{k}"]
+        e = rel_err(sub(params[k].grad.cpu().numpy()), ref32)
+        # gradients that pass through the sub-band phase inherit its fp32 conditioning
+        assert e <= max(RTOL, 5 * rel_err(ref32, ref64)), (k, e, rel_err(ref32, ref64))
+
+
+def test_full_model_raises_on_nonfinite_and_cpu_input():
+    m = _build()
+    wl, wr = orc.synth_binaural(2, seed=5)
+    with pytest.raises(RuntimeError):                              # no CPU path by design
+        m(torch.from_numpy(wl), torch.from_numpy(wr))
+    tl, tr = torch.from_numpy(wl).to(DEV), torch.from_numpy(wr).to(DEV)
+    with torch.no_grad():
+        # NaN recurrent weights: W_hh is unused on a fresh GRU state, so the step after every reset yields a finite Q,
+        # the next one NaN -> fallback to Q0 + state reset (model_torch.py:378-380), and so on: even frames are Q0
+        m.bifb.fb_L.q_rnn.weight_hh_l0.fill_(float("nan"))
+        s, a, d = m(tl, tr, None)
+    assert torch.isfinite(s).all() and torch.isfinite(a).all() and torch.isfinite(d).all()
+    q0 = m.bifb.Q0.view(1, 1, -1)
+    assert torch.equal(m.last_QL[:, 0::2], q0.expand_as(m.last_QL[:, 0::2]))
+    assert float((m.last_QL[:, 1::2] - q0).abs().max()) > 1e-3
+    assert float((m.last_QR[:, 2::2] - q0).abs().max()) > 1e-3       # the other ear is unaffected
