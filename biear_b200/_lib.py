@@ -67,6 +67,7 @@ SIGNATURES = {
     "biear_debug_phase_cycles": (_i, [_p]),
     "biear_adaptive_occupancy": (_i, [_i, _i, POINTER(c_int), POINTER(c_int)]),
     "biear_adaptive_tile_rows": (_i, []),
+    "biear_adaptive_supported": (_i, [_i, _i]),
     "biear_wgrad_scratch_floats": (_l, [POINTER(WgradJob), _i, _i, _i]),
     "biear_ctrl_wgrad": (_i, [POINTER(WgradJob), _i, _i, _i, _p, _p]),
 }

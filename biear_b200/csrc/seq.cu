@@ -118,11 +118,10 @@ struct FwdSmem {   // offsets in floats
     __host__ __device__ FwdSmem(int N_, int F) : N(N_), tile(spec_tile_len(F)) {}
     __host__ __device__ int img() const { return 0; }
     __host__ __device__ int vec() const { return fwd_img_floats(N); }           // per-CTA constants, see V_*
-    __host__ __device__ int yc() const { return vec() + 1088; }                 // [128][32]; aliased by a2
-    __host__ __device__ int h0() const { return yc() + kHid * kR; }             // [128][32] x 2 (ping-pong)
-    __host__ __device__ int a1() const { return h0() + 2 * kHid * kR; }
-    __host__ __device__ int red() const { return a1() + kHid * kR; }            // 2 x 16 x 128
-    __host__ __device__ int stat() const { return red() + 2 * 16 * 128; }       // 2 x kSeqThreads
+    __host__ __device__ int yc() const { return vec() + 1088; }                 // [128][kR]; aliased by a2
+    __host__ __device__ int a1() const { return yc() + kHid * kR; }             // [128][kR], directly behind yc
+    __host__ __device__ int h0() const { return a1() + kHid * kR; }             // [128][kR] x 2 (ping-pong)
+    __host__ __device__ int stat() const { return h0() + 2 * kHid * kR; }       // 2 x kSeqThreads
     __host__ __device__ int q() const { return stat() + 2 * kSeqThreads; }      // [128][4]: Q_t of this CTA's 4 rows
     __host__ __device__ int ystage() const { return q() + kHid * kRT; }         // [4][128]
     __host__ __device__ int spec() const { return ystage() + kRT * kHid; }      // [4][tile] float4
@@ -257,8 +256,15 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
     float* a2_s = yc_s;
     float* hbuf_s = smem + L.h0();
     float* a1_s = smem + L.a1();
-    float* red_s = smem + L.red();
     float* stat_s = smem + L.stat();
+    // Scratch of the k-split reductions lives in activation buffers that are idle at that point of the frame (this is
+    // what lets N = 128 fit in 227 KB): the GRU's 16 accumulators park in yc|a1 (both dead once every local dot
+    // product has passed the reduction's first barrier; peers write them only after #3 / the next #2), Linear 1 in
+    // yc (a2, its alias, is written after #3), Linear 2 and 3 in a1 (next written after the next frame's #2).
+    float* red_gru_s = yc_s;
+    float* red_l1_s = yc_s;
+    float* red_l23_s = a1_s;
+    static_assert(2 * 16 * 128 <= 2 * kHid * kR && 2 * kRT * 128 <= kHid * kR, "reduction scratch fits its hosts");
     float* q_s = smem + L.q();
     float* ystage_s = smem + L.ystage();
     float4* spec_s = reinterpret_cast<float4*>(smem + L.spec());
@@ -467,7 +473,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                     acc[8 + i] = ain[i];
                     acc[12 + i] = ahn[i];
                 }
-                reduce_ks<16>(acc, red_s, ks, slot);
+                reduce_ks<16>(acc, red_gru_s, ks, slot);
                 float hv[kRT], vr[kRT], vz[kRT], vn[kRT], vh[kRT];
                 if (ks == 0) {
                     const float br = vec_s[V_BR + u], bz = vec_s[V_BZ + u], bin = vec_s[V_BIN + u], bhn = vec_s[V_BHN + u];
@@ -501,7 +507,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                 int k0, k1;
                 k_range(kHid, ks, k0, k1);
                 dot_rows(acc, hnext_s + rg * kRT, img_s + fwd_img_w1(N) + u, k0, k1);
-                reduce_ks<kRT>(acc, red_s, ks, slot);
+                reduce_ks<kRT>(acc, red_l1_s, ks, slot);
                 if (ks == 0) {
                     const float bb = vec_s[V_B1 + u];
 #pragma unroll
@@ -521,7 +527,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                 int k0, k1;
                 k_range(kHid, ks, k0, k1);
                 dot_rows(acc, a1_s + rg * kRT, img_s + fwd_img_w2(N) + u, k0, k1);
-                reduce_ks<kRT>(acc, red_s, ks, slot);
+                reduce_ks<kRT>(acc, red_l23_s, ks, slot);
                 if (ks == 0) {
                     const float bb = vec_s[V_B2 + u];
 #pragma unroll
@@ -542,7 +548,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                 int k0, k1;
                 k_range(kHid, ks, k0, k1);
                 if (mine) dot_rows(acc, a2_s + rg * kRT, img_s + fwd_img_w3(N) + u, k0, k1);
-                reduce_ks<kRT>(acc, red_s, ks, slot);
+                reduce_ks<kRT>(acc, red_l23_s, ks, slot);
                 const bool fin = ks == 0 && mine;
                 const int n = rank * NU + u;
                 float qv[kRT] = {0.f, 0.f, 0.f, 0.f}, dv[kRT] = {0.f, 0.f, 0.f, 0.f};
@@ -935,6 +941,13 @@ static int launch_cluster(Kern kern, const char* name, int clusters, size_t smem
 }  // namespace biear
 
 extern "C" int biear_adaptive_tile_rows(void) { return biear::kR; }
+
+extern "C" int biear_adaptive_supported(int N, int F) {
+    using namespace biear;
+    if (N < 1 || N > kHid || F < 2) return 0;
+    const size_t limit = 227 * 1024;
+    return sizeof(float) * (size_t)FwdSmem(N, F).total() <= limit && sizeof(float) * (size_t)BwdSmem(N).total() <= limit;
+}
 
 extern "C" int64_t biear_adaptive_workspace_floats(int G, int N) {
     using namespace biear;

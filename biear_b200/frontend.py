@@ -192,7 +192,7 @@ def _adaptive_chain(x: torch.Tensor, ears: int, ctrl_mods, fc, q0, dq_vec, dq_mo
     N = fc.numel()
     xr = torch.view_as_real(x)
     if engine in ("fused", "fused-strict"):
-        if shared or G != ears or N > 128:
+        if shared or G != ears or not ops.fused_supported(N, Fbins):
             raise NotImplementedError("the fused recurrence covers the dual front-end with at most 128 bands")
         st = lambda f: [f(m) for m in ctrl_mods]      # the parameters themselves: the C ABI takes one pointer per controller
         w = {"w_ih": st(lambda m: m.q_rnn.weight_ih_l0), "w_hh": st(lambda m: m.q_rnn.weight_hh_l0),
@@ -282,7 +282,7 @@ class FramewiseAdaptiveGammatoneFB(_FilterbankBase):
             return y, self.Q0.view(1, 1, -1).expand(x.shape[0], self.timesteps, -1), x
         y, q, _ = _adaptive_chain(x, 1, [self], self.fc, self.Q0, self.deltaQ_vec, self.deltaQ_mode, self.df,
                                   self.training, False, False, self.band_mode, self.cutoff,
-                                  self.engine if self.Nbands <= 128 else "chain")
+                                  self.engine if ops.fused_supported(self.Nbands, self.n_fft // 2 + 1) else "chain")
         return y, q, x
 
 
@@ -386,7 +386,7 @@ class BinauralAdaptiveGammatoneFB(nn.Module):
         else:
             if self.fb_L.freeze_Q != self.fb_R.freeze_Q:
                 raise NotImplementedError("freeze_Q on one ear only")
-            engine = self.engine if fb.Nbands <= 128 else "chain"
+            engine = self.engine if ops.fused_supported(fb.Nbands, fb.n_fft // 2 + 1) else "chain"
             y, q, ph = _adaptive_chain(x, 2, [self.fb_L, self.fb_R], fb.fc, fb.Q0, fb.deltaQ_vec, fb.deltaQ_mode,
                                        fb.df, self.training, False, want_phase, fb.band_mode, fb.cutoff, engine)
         out = {"YL": y[:B], "YR": y[B:], "QL": q[:B], "QR": q[B:], "XL": x[:B], "XR": x[B:]}

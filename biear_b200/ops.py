@@ -267,6 +267,11 @@ def _fill(params, **tensors):
         setattr(params, k, v.data_ptr() if v is not None else None)
 
 
+def fused_supported(n_bands: int, n_bins: int) -> bool:
+    """Can the persistent recurrence kernels take this geometry (shared-memory budget)?"""
+    return bool(_lib.load().biear_adaptive_supported(int(n_bands), int(n_bins)))
+
+
 def tile_rows() -> int:
     """Rows per tile (R) of the "tile layout" tensors (G, T-1, tiles, D, R), see include/biear_b200.h."""
     return int(_lib.load().biear_adaptive_tile_rows())

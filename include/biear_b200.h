@@ -140,6 +140,9 @@ typedef struct BiearSeqParams {
     const uint64_t* seed_ptr;
 } BiearSeqParams;
 
+/* 1 if the persistent recurrence kernels can take N bands and F bins (their weight slices, activations and spectrum
+ * tiles must fit the 227 KB of shared memory of an SM), else 0: callers fall back to per-frame launches. */
+int biear_adaptive_supported(int N, int F);
 /* Rows per tile (R) of the tile-layout tensors. */
 int biear_adaptive_tile_rows(void);
 /* Floats of scratch the two calls below need in BiearSeqParams.workspace. */

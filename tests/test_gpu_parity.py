@@ -458,6 +458,39 @@ def test_ctrl_wgrad_kernel(bb):
                 assert db is None
 
 
+@pytest.mark.parametrize("nb", [32, 64, 128])
+def test_band_count_sweep_adaptive_against_oracle(bb, nb):
+    """BASELINE config 5: other band counts through the persistent kernels (bands per CTA, last-layer slices and the
+    band-stage dealing all depend on N) against the fp32 CPU oracle: Y, Q and controller gradients."""
+    batch = 5
+    kw = dict(CONFIG_SINGLE)
+    torch.manual_seed(0)
+    m = bb.BinauralAdaptiveGammatoneFB(Nbands=nb, alpha=0.0, **_kw(kw))
+    wts = [orc.synth_controller(41, n_bands=nb, out_std=0.05), orc.synth_controller(42, n_bands=nb, out_std=0.05)]
+    _load_ctrl(m.fb_L, wts[0])
+    _load_ctrl(m.fb_R, wts[1])
+    m = m.to(DEV).eval()
+    wl, wr = orc.synth_binaural(batch, seed=55)
+    rs = np.random.RandomState(8)
+    up = rs.standard_normal((batch, 19, nb)).astype(np.float32)
+    o = m.forward_features(torch.from_numpy(wl).to(DEV), torch.from_numpy(wr).to(DEV))
+    upd = torch.from_numpy(up).to(DEV)
+    ((upd * torch.log(o["YL"] + 1e-8)).sum() + (upd * o["QL"]).sum() + (upd * torch.log(o["YR"] + 1e-8)).sum()).backward()
+    cfg = orc.FrontEndConfig(n_bands=nb, **kw)
+    for side, wav, w, fb in (("L", wl, wts[0], m.fb_L), ("R", wr, wts[1], m.fb_R)):
+        pt = orc.to_torch(w, requires_grad=True)
+        y, q, _ = orc.adaptive_fb_forward(torch.from_numpy(wav), pt, cfg)
+        assert_close(_np(o[f"Y{side}"]), y.detach().numpy(), RTOL, f"N={nb} Y{side}")
+        assert_close(_np(o[f"Q{side}"]), q.detach().numpy(), RTOL, f"N={nb} Q{side}")
+        loss = (torch.from_numpy(up) * torch.log(y + 1e-8)).sum()
+        if side == "L":
+            loss = loss + (torch.from_numpy(up) * q).sum()
+        loss.backward()
+        for name, prm in fb.named_parameters():
+            e = rel_err(_np(prm.grad), pt[name].grad.numpy())
+            assert e <= RTOL, (nb, side, name, e)
+
+
 def test_autograd_node_does_not_leak(bb):
     """The recurrence node must not hold its own outputs (a ctx -> output -> grad_fn -> ctx cycle would keep every
     step's ~100 MB of saved state alive): allocated memory is flat across steps."""
