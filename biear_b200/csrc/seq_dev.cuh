@@ -106,30 +106,40 @@ __device__ __forceinline__ void copy_f4(float4* __restrict__ dst, const float4* 
 }
 
 // acc[i] += sum_{k in [k0,k1)} x_s[k*kR + i] * w_s[k*kU]     (x_s / w_s already offset to the thread's rows / unit)
+// The 4 rows are two packed fp32x2 FMAs (FFMA2, sm_100): same rounding as four scalar FMAs, half the issue slots.
 __device__ __forceinline__ void dot_rows(float acc[kRT], const float* __restrict__ x_s, const float* __restrict__ w_s,
                                          int k0, int k1) {
+    float2 lo = make_float2(acc[0], acc[1]), hi = make_float2(acc[2], acc[3]);
 #pragma unroll 8
     for (int k = k0; k < k1; ++k) {
         const float4 x = *reinterpret_cast<const float4*>(x_s + k * kR);
         const float wk = w_s[k * kU];
-        acc[0] = fmaf(wk, x.x, acc[0]);
-        acc[1] = fmaf(wk, x.y, acc[1]);
-        acc[2] = fmaf(wk, x.z, acc[2]);
-        acc[3] = fmaf(wk, x.w, acc[3]);
+        const float2 w2 = make_float2(wk, wk);
+        lo = __ffma2_rn(w2, make_float2(x.x, x.y), lo);
+        hi = __ffma2_rn(w2, make_float2(x.z, x.w), hi);
     }
+    acc[0] = lo.x; acc[1] = lo.y; acc[2] = hi.x; acc[3] = hi.y;
 }
 
 // Three gate rows at once: the weights of one k are [gate][kU] (w3_s already offset to the thread's unit).
 __device__ __forceinline__ void dot_rows3(float a0[kRT], float a1[kRT], float a2[kRT], const float* __restrict__ x_s,
                                           const float* __restrict__ w3_s, int k0, int k1) {
+    float2 l0 = make_float2(a0[0], a0[1]), h0 = make_float2(a0[2], a0[3]);
+    float2 l1 = make_float2(a1[0], a1[1]), h1 = make_float2(a1[2], a1[3]);
+    float2 l2 = make_float2(a2[0], a2[1]), h2 = make_float2(a2[2], a2[3]);
 #pragma unroll 4
     for (int k = k0; k < k1; ++k) {
         const float4 x = *reinterpret_cast<const float4*>(x_s + k * kR);
+        const float2 xl = make_float2(x.x, x.y), xh = make_float2(x.z, x.w);
         const float w0 = w3_s[k * 3 * kU], w1 = w3_s[k * 3 * kU + kU], w2 = w3_s[k * 3 * kU + 2 * kU];
-        a0[0] = fmaf(w0, x.x, a0[0]); a0[1] = fmaf(w0, x.y, a0[1]); a0[2] = fmaf(w0, x.z, a0[2]); a0[3] = fmaf(w0, x.w, a0[3]);
-        a1[0] = fmaf(w1, x.x, a1[0]); a1[1] = fmaf(w1, x.y, a1[1]); a1[2] = fmaf(w1, x.z, a1[2]); a1[3] = fmaf(w1, x.w, a1[3]);
-        a2[0] = fmaf(w2, x.x, a2[0]); a2[1] = fmaf(w2, x.y, a2[1]); a2[2] = fmaf(w2, x.z, a2[2]); a2[3] = fmaf(w2, x.w, a2[3]);
+        const float2 p0 = make_float2(w0, w0), p1 = make_float2(w1, w1), p2 = make_float2(w2, w2);
+        l0 = __ffma2_rn(p0, xl, l0); h0 = __ffma2_rn(p0, xh, h0);
+        l1 = __ffma2_rn(p1, xl, l1); h1 = __ffma2_rn(p1, xh, h1);
+        l2 = __ffma2_rn(p2, xl, l2); h2 = __ffma2_rn(p2, xh, h2);
     }
+    a0[0] = l0.x; a0[1] = l0.y; a0[2] = h0.x; a0[3] = h0.y;
+    a1[0] = l1.x; a1[1] = l1.y; a1[2] = h1.x; a1[3] = h1.y;
+    a2[0] = l2.x; a2[1] = l2.y; a2[2] = h2.x; a2[3] = h2.y;
 }
 
 // [k0, k1) of k-split ks over a contraction of length K
