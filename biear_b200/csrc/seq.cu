@@ -616,21 +616,35 @@ struct BwdSmem {   // offsets in floats
 };
 constexpr int VB_LN1G = 0, VB_LN1B = 128, VB_LN2G = 256, VB_LN2B = 384, VB_Q0 = 512, VB_DQ = 640;   // < 1024
 
+// The LayerNorm inputs saved by the forward (this thread's 4 features of its row) and the row's rstd: loaded by the
+// caller BEFORE the preceding GEMM phase so that the global-memory latency hides behind it.
+struct LnSaved {
+    float xh[kHid / (kSeqThreads / kR)];
+    float rstd;
+};
+__device__ __forceinline__ LnSaved load_ln_saved(const float* __restrict__ xh_tile, const float* __restrict__ rstd_tile, int layer) {
+    constexpr int PARTS = kSeqThreads / kR, FPP = kHid / PARTS;
+    const int row = threadIdx.x % kR, f0 = (threadIdx.x / kR) * FPP;
+    LnSaved v;
+#pragma unroll
+    for (int i = 0; i < FPP; ++i) v.xh[i] = __ldg(xh_tile + (f0 + i) * kR + row);
+    v.rstd = __ldg(rstd_tile + layer * kR + row);
+    return v;
+}
+
 // Backward of Dropout -> SiLU -> LayerNorm on the full rows in buf_s (dL/d(layer output) on entry, dL/d(pre-LayerNorm
 // activation) on exit).  Redundant in every CTA; the warp owning the CTA's feature slice writes the saved gradients.
 __device__ __forceinline__ void ln_silu_drop_bwd(const BiearSeqParams& p, unsigned long long seed, float* buf_s, float* stat_s,
                                                  const float* __restrict__ gamma_s, const float* __restrict__ beta_s,
                                                  int layer, int t, long long grow0, int rank,
-                                                 const float* __restrict__ xh_tile, const float* __restrict__ rstd_tile,
+                                                 const float (&xh)[kHid / (kSeqThreads / kR)], float rstd,
                                                  float* gv_tile, float* ga_tile) {
     constexpr int PARTS = kSeqThreads / kR, FPP = kHid / PARTS;
     const int row = threadIdx.x % kR, part = threadIdx.x / kR;
     const int f0 = part * FPP;
     const bool mine = f0 / kU == rank;
-    float xh[FPP], dxh[FPP];
+    float dxh[FPP];
     float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < FPP; ++i) xh[i] = __ldg(xh_tile + (f0 + i) * kR + row);
 #pragma unroll
     for (int i4 = 0; i4 < FPP / 4; ++i4) {
         float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
@@ -661,7 +675,6 @@ __device__ __forceinline__ void ln_silu_drop_bwd(const BiearSeqParams& p, unsign
     }
     m1 *= (1.0f / kHid);
     m2 *= (1.0f / kHid);
-    const float rstd = __ldg(rstd_tile + layer * kR + row);
 #pragma unroll
     for (int i = 0; i < FPP; ++i) {
         const int f = f0 + i;
@@ -713,7 +726,29 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
     }
     for (int i = tid; i < kHid * kRT; i += kSeqThreads) dyc_s[i] = 0.f;
     float dh_carry[kRT] = {0.f, 0.f, 0.f, 0.f};     // dL/dh_t arriving from step t+1 (owned by the ks == 0 threads)
-    cluster.sync();
+    static_assert(kRT * kHid <= kSeqThreads, "one (row, band) element of the dL/dpre assembly per thread");
+    // Part of dL/dpre_{t} that does not depend on the recurrence, for the element (row i, band n) this thread assembles:
+    //   ext = gY dY/dQ + gphase dphase/dQ + gQ,  jac = dY/dQ,  fac = d clamp/dQ * dQ/ddelta * d tanh  (all at frame t+1)
+    struct Pre { float ext, jac, fac; };
+    auto fetch_pre = [&](int t) {
+        Pre r = {0.f, 0.f, 0.f};
+        if (t < 0 || tid >= kRT * N) return r;
+        const int i = tid / N, n = tid - i * N;
+        if (bb0 + i >= p.B) return r;
+        const long long e = ((grow0 + i) * T + (t + 1)) * N + n;
+        r.jac = __ldg(p.dYdQ + e);
+        r.ext = (p.gY ? __ldg(p.gY + e) : 0.f) * r.jac;
+        if (p.gP) r.ext = fmaf(__ldg(p.gP + e), __ldg(p.dPdQ + e), r.ext);
+        if (p.gQ) r.ext += __ldg(p.gQ + e);
+        const float delta = __ldg(p.delta + e);
+        const float q0 = vec_s[VB_Q0 + n], dq = vec_s[VB_DQ + n];
+        const float qu = p.relative ? q0 * (1.0f + dq * delta) : fmaf(dq, delta, q0);
+        const float scale = p.relative ? q0 * dq : dq;
+        r.fac = (qu >= p.q_min && qu <= p.q_max) ? scale * (1.0f - delta * delta) : 0.f;
+        return r;
+    };
+    cluster.sync();                                  // vec_s ready (fetch_pre reads q0 / dq from it)
+    Pre pf = fetch_pre(S - 1);
 
     PHASE_INIT();
     for (int t = S - 1; t >= 0; --t) {
@@ -724,22 +759,11 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
         const long long tb = tile_base(p, g, t, tiles, tile);
 
         // ---- dL/dQ_{t+1} (external + band-stage Jacobians) -> dL/dpre, this CTA's 4 rows ---------
-        for (int idx = tid; idx < kRT * N; idx += kSeqThreads) {
-            const int i = idx / N, n = idx - i * N;
+        // dL/dpre = (ext + dyc * dY/dQ) * fac; ext, dY/dQ and fac were fetched during the previous step (pf)
+        if (tid < kRT * N) {
+            const int i = tid / N, n = tid - i * N;
             float dpre = 0.f;
-            if (bb0 + i < p.B && !flagged) {
-                const long long e = ((grow0 + i) * T + (t + 1)) * N + n;
-                float gy = p.gY ? __ldg(p.gY + e) : 0.f;
-                if (has_ctrl_next) gy += dyc_s[n * kRT + i];
-                float d = gy * __ldg(p.dYdQ + e);
-                if (p.gP) d = fmaf(__ldg(p.gP + e), __ldg(p.dPdQ + e), d);
-                if (p.gQ) d += __ldg(p.gQ + e);
-                const float delta = __ldg(p.delta + e);
-                const float q0 = vec_s[VB_Q0 + n], dq = vec_s[VB_DQ + n];
-                const float qu = p.relative ? q0 * (1.0f + dq * delta) : fmaf(dq, delta, q0);
-                const float scale = p.relative ? q0 * dq : dq;
-                if (qu >= p.q_min && qu <= p.q_max) dpre = d * scale * (1.0f - delta * delta);
-            }
+            if (!flagged) dpre = (pf.ext + (has_ctrl_next ? dyc_s[n * kRT + i] : 0.f) * pf.jac) * pf.fac;
             stage_s[i * kHid + n] = dpre;
         }
         __syncthreads();
@@ -757,6 +781,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
         PHASE_MARK(1, 1);    // dL/dpre assembly + push
 
         // ---- Linear 3 ^T --------------------------------------------------------------------------------------
+        const LnSaved ln2 = load_ln_saved(p.xh2 + tb * kHid * kR, p.rstd + tb * 2 * kR, 1);   // used after #2
         {
             float acc[kRT] = {0.f, 0.f, 0.f, 0.f};
             int k0, k1;
@@ -768,7 +793,8 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
         cluster.sync();   // #2
         PHASE_MARK(1, 2);    // Linear 3 ^T
         ln_silu_drop_bwd(p, seed, bufa_s, stat_s, vec_s + VB_LN2G, vec_s + VB_LN2B, 1, t, (long long)g * p.B + b0, rank,
-                         p.xh2 + tb * kHid * kR, p.rstd + tb * 2 * kR, p.G_v2 + tb * kHid * kR, p.G_a2 + tb * kHid * kR);
+                         ln2.xh, ln2.rstd, p.G_v2 + tb * kHid * kR, p.G_a2 + tb * kHid * kR);
+        const LnSaved ln1 = load_ln_saved(p.xh1 + tb * kHid * kR, p.rstd + tb * 2 * kR, 0);   // used after #3
         PHASE_MARK(1, 3);    // LayerNorm 2 backward
         // ---- Linear 2 ^T --------------------------------------------------------------------------------------
         {
@@ -782,11 +808,22 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
         cluster.sync();   // #3
         PHASE_MARK(1, 4);    // Linear 2 ^T
         ln_silu_drop_bwd(p, seed, bufb_s, stat_s, vec_s + VB_LN1G, vec_s + VB_LN1B, 0, t, (long long)g * p.B + b0, rank,
-                         p.xh1 + tb * kHid * kR, p.rstd + tb * 2 * kR, p.G_v1 + tb * kHid * kR, p.G_a1 + tb * kHid * kR);
+                         ln1.xh, ln1.rstd, p.G_v1 + tb * kHid * kR, p.G_a1 + tb * kHid * kR);
         PHASE_MARK(1, 5);    // LayerNorm 1 backward
         // ---- Linear 1 ^T, GRU cell backward ------------------------------------------------------------------------
         float dh_direct[kRT] = {0.f, 0.f, 0.f, 0.f};
         {
+            // the saved gates / previous state of (unit ug, rows 4rg..4rg+3): fetched before the product, used after it
+            float4 r4, z4, n4, h4, p4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ks == 0) {
+                const float* gt = p.gates + tb * 4 * kHid * kR + ug * kR + rg * kRT;
+                r4 = __ldg(reinterpret_cast<const float4*>(gt));
+                z4 = __ldg(reinterpret_cast<const float4*>(gt + kHid * kR));
+                n4 = __ldg(reinterpret_cast<const float4*>(gt + 2 * kHid * kR));
+                h4 = __ldg(reinterpret_cast<const float4*>(gt + 3 * kHid * kR));
+                if (!h_reset)
+                    p4 = __ldg(reinterpret_cast<const float4*>(h_tile(p, g, t - 1, tiles, tile) + ug * kR + rg * kRT));
+            }
             float acc[kRT] = {0.f, 0.f, 0.f, 0.f};
             int k0, k1;
             k_range(kHid, ks, k0, k1);
@@ -794,14 +831,6 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
             reduce_ks<kRT>(acc, red_s, ks, slot);
             float v0[kRT], v1[kRT], v2[kRT], v3[kRT];
             if (ks == 0) {
-                const float* gt = p.gates + tb * 4 * kHid * kR + ug * kR + rg * kRT;
-                const float4 r4 = __ldg(reinterpret_cast<const float4*>(gt));
-                const float4 z4 = __ldg(reinterpret_cast<const float4*>(gt + kHid * kR));
-                const float4 n4 = __ldg(reinterpret_cast<const float4*>(gt + 2 * kHid * kR));
-                const float4 h4 = __ldg(reinterpret_cast<const float4*>(gt + 3 * kHid * kR));
-                float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (!h_reset)
-                    p4 = __ldg(reinterpret_cast<const float4*>(h_tile(p, g, t - 1, tiles, tile) + ug * kR + rg * kRT));
                 const float rr[4] = {r4.x, r4.y, r4.z, r4.w}, zz[4] = {z4.x, z4.y, z4.z, z4.w};
                 const float nn[4] = {n4.x, n4.y, n4.z, n4.w}, hn[4] = {h4.x, h4.y, h4.z, h4.w};
                 const float hp[4] = {p4.x, p4.y, p4.z, p4.w};
@@ -834,6 +863,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
         }
         cluster.barrier_wait();   // #4
         PHASE_MARK(1, 6);    // Linear 1 ^T + GRU cell backward
+        pf = fetch_pre(t - 1);    // next step's recurrence-independent inputs: in flight during the products below
         // ---- dL/dh_{t-1} = z * dh + W_hh^T [drp, dzp, dhn];  dL/dY_t = W_ih[:, :N]^T [drp, dzp, dnp] * d log1p --------
         {
             float acc[2 * kRT] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
