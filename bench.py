@@ -198,10 +198,10 @@ def make_loss(model, up):
     log_q0 = torch.log(model.Q0 + 1e-8).view(1, 1, -1)
 
     def loss_fn(wl, wr):
-        o = model.forward_features(wl, wr, want_phase=True, want_cc=True)     # CC on a forked stream
-        cc = o["cc"]
-        x1 = torch.clamp(torch.log(o["YL"] + 1e-8), -12.0, 12.0)          # model_torch.py:1080-1083
-        x2 = torch.clamp(torch.log(o["YR"] + 1e-8), -12.0, 12.0)
+        # one call for everything the back-end consumes: log band energies (model_torch.py:1080-1083, fused into the
+        # band stage), sub-band phases, Q, and the CC feature (forked stream)
+        o = model.forward_features(wl, wr, want_phase=True, want_cc=True, want_logenergy=True)
+        cc, x1, x2 = o["cc"], o["logYL"], o["logYR"]
         lq = torch.log(0.5 * (o["QL"] + o["QR"]) + 1e-8)                   # train_biear.py:476-490
         return (up["gYL"] * x1).mean() + (up["gYR"] * x2).mean() \
             + (up["gPL"] * o["phaseL"]).mean() + (up["gPR"] * o["phaseR"]).mean() + (up["gC"] * cc).mean() \

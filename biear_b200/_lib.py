@@ -11,7 +11,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BIEAR_B200_LIB") or os.path.join(_HERE, "lib", "libbiear_b200.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 _p = c_void_p
 _i = c_int
@@ -36,7 +36,7 @@ class SeqParams(Structure):
             "X", "Y", "phase", "dYdQ", "dPdQ", "Q", "delta",
             "gates", "xh1", "d1", "xh2", "d2", "rstd", "yc", "H", "flags",
             "gY", "gP", "gQ",
-            "GG", "G_a1", "G_v1", "G_a2", "G_v2", "G_pre", "workspace", "seed_ptr")]
+            "GG", "G_a1", "G_v1", "G_a2", "G_v2", "G_pre", "workspace", "seed_ptr", "logY", "gLogY")]
     )
 
 

@@ -423,6 +423,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                 if (!own_store) return;
                 p.Y[own_e] = oY;
                 p.dYdQ[own_e] = oJ;
+                if (p.logY) p.logY[own_e] = fminf(fmaxf(logf(oY + 1e-8f), -12.0f), 12.0f);
                 if (p.phase) {
                     p.phase[own_e] = oP;
                     p.dPdQ[own_e] = oK;
@@ -737,7 +738,13 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
         if (bb0 + i >= p.B) return r;
         const long long e = ((grow0 + i) * T + (t + 1)) * N + n;
         r.jac = __ldg(p.dYdQ + e);
-        r.ext = (p.gY ? __ldg(p.gY + e) : 0.f) * r.jac;
+        float gy = p.gY ? __ldg(p.gY + e) : 0.f;
+        if (p.gLogY) {   // d clamp(log(Y + 1e-8), +-12) / dY, as autograd derives it (model_torch.py:1080-1083)
+            const float ye = __ldg(p.Y + e) + 1e-8f;
+            const float lx = logf(ye);
+            if (lx >= -12.0f && lx <= 12.0f) gy += __ldg(p.gLogY + e) / ye;
+        }
+        r.ext = gy * r.jac;
         if (p.gP) r.ext = fmaf(__ldg(p.gP + e), __ldg(p.dPdQ + e), r.ext);
         if (p.gQ) r.ext += __ldg(p.gQ + e);
         const float delta = __ldg(p.delta + e);

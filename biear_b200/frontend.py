@@ -178,13 +178,14 @@ def _next_q(delta, q0, dq, mode):
 
 
 def _adaptive_chain(x: torch.Tensor, ears: int, ctrl_mods, fc, q0, dq_vec, dq_mode, df, training,
-                    shared: bool, want_phase: bool, band_mode: str, cutoff: float, engine: str = "chain"):
+                    shared: bool, want_phase: bool, band_mode: str, cutoff: float, engine: str = "chain",
+                    want_logy: bool = False):
     """The 19-step Q recurrence for `ears` ears of B clips.
 
     x: (ears*B, T, F) complex64, ear-major.  ctrl_mods: G controller-owning modules.
       dual  : ears == G (each ear has its own controller and its own Q)       model_torch.py:314-386
       single: ears == 2, G == 1, shared=True (one Q for both ears, carried Y memory)  model_torch.py:695-776
-    Returns Y (ears*B,T,N), Q (G*B,T,N), phase (ears*B,T,N) or None.
+    Returns Y (ears*B,T,N), Q (G*B,T,N), phase (ears*B,T,N) or None, logY = clamp(log(Y + 1e-8), +-12) or None.
     """
     rows, T, Fbins = x.shape
     B = rows // ears
@@ -204,8 +205,9 @@ def _adaptive_chain(x: torch.Tensor, ears: int, ctrl_mods, fc, q0, dq_vec, dq_mo
              "w3": st(lambda m: m.q_out[8].weight), "b3": st(lambda m: m.q_out[8].bias)}
         # CPU generator: no device sync.  (Under CUDA-graph capture the kernels read a device-side seed instead.)
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if training else 0
-        return ops.adaptive_sequence(xr, fc, q0, dq_vec, w, dq_mode == "relative", training, want_phase, cutoff,
-                                     df, seed, strict=(engine == "fused-strict"))
+        res = ops.adaptive_sequence(xr, fc, q0, dq_vec, w, dq_mode == "relative", training, want_phase, cutoff,
+                                    df, seed, strict=(engine == "fused-strict"), want_logy=want_logy)
+        return res if want_logy else res + (None,)
     stack = _ControllerStack(ctrl_mods)
     q0g = q0.view(1, 1, N)
     dqg = dq_vec.view(1, 1, N)
@@ -243,7 +245,13 @@ def _adaptive_chain(x: torch.Tensor, ears: int, ctrl_mods, fc, q0, dq_vec, dq_mo
     y_all = torch.stack(ys, dim=1)
     q_all = torch.stack(qs, dim=1)
     ph_all = torch.stack(phs, dim=1) if want_phase else None
-    return y_all, q_all, ph_all
+    lx_all = _log_energy(y_all) if want_logy else None
+    return y_all, q_all, ph_all, lx_all
+
+
+def _log_energy(y: torch.Tensor) -> torch.Tensor:
+    """model_torch.py:1080-1083."""
+    return torch.clamp(torch.log(y + 1e-8), -12.0, 12.0)
 
 
 def _fixed_bands(x: torch.Tensor, fc, q_fixed, df, want_phase, cutoff):
@@ -280,7 +288,7 @@ class FramewiseAdaptiveGammatoneFB(_FilterbankBase):
         if self.freeze_Q:
             y, _ = _fixed_bands(x, self.fc, self.Q0, self.df, False, self.cutoff)
             return y, self.Q0.view(1, 1, -1).expand(x.shape[0], self.timesteps, -1), x
-        y, q, _ = _adaptive_chain(x, 1, [self], self.fc, self.Q0, self.deltaQ_vec, self.deltaQ_mode, self.df,
+        y, q, _, _ = _adaptive_chain(x, 1, [self], self.fc, self.Q0, self.deltaQ_vec, self.deltaQ_mode, self.df,
                                   self.training, False, False, self.band_mode, self.cutoff,
                                   self.engine if ops.fused_supported(self.Nbands, self.n_fft // 2 + 1) else "chain")
         return y, q, x
@@ -360,11 +368,13 @@ class BinauralAdaptiveGammatoneFB(nn.Module):
         self.engine = "fused"
 
     def forward_features(self, wavL_1s: torch.Tensor, wavR_1s: torch.Tensor, want_phase: bool = True,
-                         want_cc: bool = False, cc_max_lag_ms: float = 3.0):
+                         want_cc: bool = False, cc_max_lag_ms: float = 3.0, want_logenergy: bool = False):
         """Everything the back-end consumes, in one call: band energies, Q, spectra, sub-band phases and -- with
         want_cc -- the broadband cross-correlation feature x3 (utils.py:390-420), which the reference precomputes
         offline.  The CC kernel is independent of the recurrence and runs on a forked stream next to it (the
-        persistent recurrence kernels occupy 128 of the 148 SMs)."""
+        persistent recurrence kernels occupy 128 of the 148 SMs).  With want_logenergy the log band energies
+        clamp(log(Y + 1e-8), +-12) (model_torch.py:1080-1083) come out of the band stage's epilogue as "logYL" / "logYR"
+        and their gradient is folded into the backward kernel."""
         fb = self.fb_L
         if wavL_1s.shape != wavR_1s.shape:
             raise ValueError(f"wavL {tuple(wavL_1s.shape)} and wavR {tuple(wavR_1s.shape)} differ")
@@ -383,15 +393,19 @@ class BinauralAdaptiveGammatoneFB(nn.Module):
             qf = fb.Q0 if frozen else torch.clamp(fb.Q0, Q_MIN, Q_MAX)
             y, ph = _fixed_bands(x, fb.fc, qf, fb.df, want_phase, fb.cutoff)
             q = qf.view(1, 1, -1).expand(2 * B, fb.timesteps, -1)
+            lx = _log_energy(y) if want_logenergy else None
         else:
             if self.fb_L.freeze_Q != self.fb_R.freeze_Q:
                 raise NotImplementedError("freeze_Q on one ear only")
             engine = self.engine if ops.fused_supported(fb.Nbands, fb.n_fft // 2 + 1) else "chain"
-            y, q, ph = _adaptive_chain(x, 2, [self.fb_L, self.fb_R], fb.fc, fb.Q0, fb.deltaQ_vec, fb.deltaQ_mode,
-                                       fb.df, self.training, False, want_phase, fb.band_mode, fb.cutoff, engine)
+            y, q, ph, lx = _adaptive_chain(x, 2, [self.fb_L, self.fb_R], fb.fc, fb.Q0, fb.deltaQ_vec, fb.deltaQ_mode,
+                                           fb.df, self.training, False, want_phase, fb.band_mode, fb.cutoff, engine,
+                                           want_logy=want_logenergy)
         out = {"YL": y[:B], "YR": y[B:], "QL": q[:B], "QR": q[B:], "XL": x[:B], "XR": x[B:]}
         if want_phase:
             out["phaseL"], out["phaseR"] = ph[:B], ph[B:]
+        if want_logenergy:
+            out["logYL"], out["logYR"] = lx[:B], lx[B:]
         if cc is not None:
             cur.wait_stream(side)
             cc.record_stream(cur)
@@ -432,7 +446,7 @@ class BinauralAdaptiveGammatoneFB_SingleController(_FilterbankBase):
             self.fb_L = mk()
             self.fb_R = mk()
 
-    def forward_features(self, wavL_1s, wavR_1s, want_phase: bool = True):
+    def forward_features(self, wavL_1s, wavR_1s, want_phase: bool = True, want_logenergy: bool = False):
         x = self._spectra([wavL_1s, wavR_1s])
         B = wavL_1s.shape[0]
         if self.fixed_frontend_q or self.freeze_Q:
@@ -440,11 +454,13 @@ class BinauralAdaptiveGammatoneFB_SingleController(_FilterbankBase):
             y, ph = _fixed_bands(x, self.fc, qf, self.df, want_phase, self.cutoff)
             q = qf.view(1, 1, -1).expand(B, self.timesteps, -1)
         else:
-            y, q, ph = _adaptive_chain(x, 2, [self], self.fc, self.Q0, self.deltaQ_vec, self.deltaQ_mode, self.df,
-                                       self.training, True, want_phase, self.band_mode, self.cutoff)
+            y, q, ph, _ = _adaptive_chain(x, 2, [self], self.fc, self.Q0, self.deltaQ_vec, self.deltaQ_mode, self.df,
+                                          self.training, True, want_phase, self.band_mode, self.cutoff)
         out = {"YL": y[:B], "YR": y[B:], "QL": q, "QR": q, "XL": x[:B], "XR": x[B:]}
         if want_phase:
             out["phaseL"], out["phaseR"] = ph[:B], ph[B:]
+        if want_logenergy:
+            out["logYL"], out["logYR"] = _log_energy(y[:B]), _log_energy(y[B:])
         return out
 
     def forward(self, wavL_1s, wavR_1s):

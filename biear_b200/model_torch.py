@@ -167,15 +167,14 @@ class DeepEarActiveWaveform(_BackEnd):
         wavL_1s = wavL_1s.float()
         wavR_1s = wavR_1s.float()
         if hasattr(self.bifb, "forward_features"):
-            o = self.bifb.forward_features(wavL_1s, wavR_1s, want_phase=True)
+            o = self.bifb.forward_features(wavL_1s, wavR_1s, want_phase=True, want_logenergy=True)
             YL, YR, QL, QR, ph_l, ph_r = o["YL"], o["YR"], o["QL"], o["QR"], o["phaseL"], o["phaseR"]
         else:   # a foreign bifb_class that only implements the reference's 6-tuple protocol
             raise TypeError("bifb_class must provide forward_features(wavL, wavR, want_phase) "
                             "(biear_b200 front-ends do); the reference's own classes run on its own model")
         self._assert_finite((("YL", YL), ("YR", YR), ("QL", QL), ("QR", QR)))
         self.last_QL, self.last_QR, self.last_Q = QL, QR, 0.5 * (QL + QR)
-        x1 = torch.clamp(torch.log(YL + 1e-8), -12.0, 12.0)
-        x2 = torch.clamp(torch.log(YR + 1e-8), -12.0, 12.0)
+        x1, x2 = o["logYL"], o["logYR"]          # clamp(log(Y + 1e-8), +-12), fused into the band stage (:1080-1083)
         if self.use_cc:
             if x3 is None:
                 x3 = torch.zeros(wavL_1s.size(0), DATA_DIM, device=wavL_1s.device)

@@ -328,11 +328,12 @@ class AdaptiveSequence(torch.autograd.Function):
     Inputs : xr (E*B,T,F,2), fc/q0/dq (N), then the 14 weight tensors of every controller, name-major
              (w_ih of controller 0, w_ih of controller 1, w_hh of controller 0, ...): the parameters themselves, no
              stacking copy; the gradients come back in the same order.
-    Outputs: Y (E*B,T,N), Q (G*B,T,N), phase (E*B,T,N) [empty when want_phase is False].
+    Outputs: Y (E*B,T,N), Q (G*B,T,N), phase (E*B,T,N) [empty when want_phase is False],
+             logY = clamp(log(Y + 1e-8), +-12) (E*B,T,N) [empty when want_logy is False].
     """
 
     @staticmethod
-    def forward(ctx, xr, fc, q0, dq, relative, training, want_phase, cutoff, df, seed, strict, G, *weights):
+    def forward(ctx, xr, fc, q0, dq, relative, training, want_phase, cutoff, df, seed, strict, want_logy, G, *weights):
         ctx.set_materialize_grads(False)
         _need_cuda(xr, "X")
         dev = xr.device
@@ -344,7 +345,7 @@ class AdaptiveSequence(torch.autograd.Function):
         for i, w in enumerate(weights):
             _need_cuda(w, WEIGHT_NAMES[i // G])
         Kin = weights[0].shape[1]
-        need_grad = any(ctx.needs_input_grad[12:])
+        need_grad = any(ctx.needs_input_grad[13:])
         f32 = dict(dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             lib = _prepare(dev)
@@ -352,6 +353,7 @@ class AdaptiveSequence(torch.autograd.Function):
             Q = torch.empty((rows, T, N), **f32)
             D = torch.empty((rows, T, N), **f32)
             P = torch.empty((rows, T, N), **f32) if want_phase else None
+            LX = torch.empty((rows, T, N), **f32) if want_logy else None
             dY = torch.empty((rows, T, N), **f32)
             dP = torch.empty((rows, T, N), **f32) if want_phase else None
             S = max(T - 1, 1)
@@ -370,7 +372,7 @@ class AdaptiveSequence(torch.autograd.Function):
             seed_dev = _captured_seed(dev) if (training and torch.cuda.is_current_stream_capturing()) else None
             prm.df, prm.cutoff, prm.q_min, prm.q_max = float(df), float(cutoff), 0.05, 30.0
             _fill(prm, fc=fc, q0=q0, dq=dq, X=xr, Y=Y, phase=P, dYdQ=dY, dPdQ=dP, Q=Q, delta=D, flags=flags,
-                  workspace=work, H=H, seed_ptr=seed_dev, **sv)
+                  workspace=work, H=H, seed_ptr=seed_dev, logY=LX, **sv)
             for i, name in enumerate(WEIGHT_NAMES):
                 arr = getattr(prm, name)
                 for g in range(G):
@@ -382,25 +384,29 @@ class AdaptiveSequence(torch.autograd.Function):
         # would close a reference cycle (ctx -> output tensor -> grad_fn -> ctx) that leaks the whole graph.
         ctx.keep = (xr, fc, q0, dq, weights, D, dY, dP, sv, flags, work, H, seed_dev)
         ctx.has_phase = P is not None
+        ctx.has_logy = LX is not None
         ctx.dims = (G, B, T, N, Kin, tiles, TILE)
         if P is None:
             P = Y.new_empty(0)
             ctx.mark_non_differentiable(P)
+        if LX is None:
+            LX = Y.new_empty(0)
+            ctx.mark_non_differentiable(LX)
         ctx.save_for_backward(Y, Q, P)
         if not need_grad:
             ctx.mark_non_differentiable(Y, Q)
-        return Y, Q, P
+        return Y, Q, P, LX
 
     @staticmethod
-    def backward(ctx, gY, gQ, gP):
+    def backward(ctx, gY, gQ, gP, gLX):
         from ctypes import byref
         xr, fc, q0, dq, weights, D, dY, dP, sv, flags, work, H, _seed_dev = ctx.keep
         Y, Q, P = ctx.saved_tensors                  # keeps the buffers behind prm.Y / prm.Q / prm.phase alive
         if not ctx.has_phase:
             P = None
         G, B, T, N, Kin, tiles, TILE = ctx.dims
-        none12 = (None,) * 12
-        if T < 2 or (gY is None and gQ is None and gP is None):
+        none12 = (None,) * 13
+        if T < 2 or (gY is None and gQ is None and gP is None and gLX is None):
             return none12 + (None,) * (G * len(WEIGHT_NAMES))
         dev = Y.device
         f32 = dict(dtype=torch.float32, device=dev)
@@ -408,14 +414,15 @@ class AdaptiveSequence(torch.autograd.Function):
         gY = gY.contiguous() if gY is not None else None
         gQ = gQ.contiguous() if gQ is not None else None
         gP = gP.contiguous() if (gP is not None and P is not None) else None
+        gLX = gLX.contiguous() if (gLX is not None and ctx.has_logy) else None
         with torch.cuda.device(dev):
             lib = _prepare(dev)
             wk = {k: torch.empty((G, S, tiles, d, TILE), **f32) for k, d in
                   (("GG", 4 * HID), ("G_a1", HID), ("G_v1", HID), ("G_a2", HID), ("G_v2", HID), ("G_pre", N))}
             prm = ctx.prm
-            _fill(prm, gY=gY, gQ=gQ, gP=gP, **wk)
+            _fill(prm, gY=gY, gQ=gQ, gP=gP, gLogY=gLX, **wk)
             _lib.check(lib.biear_adaptive_bwd(byref(prm), _stream(dev)), "biear_adaptive_bwd")
-            _fill(prm, gY=None, gQ=None, gP=None)
+            _fill(prm, gY=None, gQ=None, gP=None, gLogY=None)
 
             # ---- weight gradients: split-K GEMMs over all (step, tile) chunks, off the serial chain ----
             K = S * tiles
@@ -442,10 +449,12 @@ class AdaptiveSequence(torch.autograd.Function):
 
 
 def adaptive_sequence(xr, fc, q0, dq, weights, relative: bool, training: bool, want_phase: bool,
-                      cutoff: float, df: float, seed: int = 0, strict: bool = False):
-    """weights: dict name -> list of the G controllers' tensors (WEIGHT_NAMES).  Returns Y, Q, phase|None.
+                      cutoff: float, df: float, seed: int = 0, strict: bool = False, want_logy: bool = False):
+    """weights: dict name -> list of the G controllers' tensors (WEIGHT_NAMES).  Returns Y, Q, phase|None[, logY].
     strict=True skips the fast pass and runs the batch-global-fallback replay pass only (testing)."""
     G = len(weights[WEIGHT_NAMES[0]])
-    y, q, ph = AdaptiveSequence.apply(xr, fc, q0, dq, relative, training, want_phase, cutoff, df, seed, strict, G,
-                                      *[w for k in WEIGHT_NAMES for w in weights[k]])
+    y, q, ph, lx = AdaptiveSequence.apply(xr, fc, q0, dq, relative, training, want_phase, cutoff, df, seed, strict,
+                                          want_logy, G, *[w for k in WEIGHT_NAMES for w in weights[k]])
+    if want_logy:
+        return y, q, (ph if want_phase else None), lx
     return y, q, (ph if want_phase else None)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BIEAR_ABI_VERSION 7
+#define BIEAR_ABI_VERSION 8
 #define BIEAR_EINVAL (-1)
 
 /* ABI version (== BIEAR_ABI_VERSION of the library that was built). */
@@ -138,6 +138,11 @@ typedef struct BiearSeqParams {
     /* optional DEVICE location of the dropout seed; when non-NULL it overrides `seed` and is read by the kernels at
        run time, so that a captured CUDA graph draws fresh masks on every replay (the caller advances it on-stream) */
     const uint64_t* seed_ptr;
+    /* optional fused log-energy features (model_torch.py:1080-1083): logY = clamp(log(Y + 1e-8), -12, 12), row-major
+       (E*B, T, N), written by the forward band stage when non-NULL; gLogY = dL/dlogY for the backward (nullable): its
+       contribution gLogY / (Y + 1e-8) (zero where the clamp is active) is added to dL/dY inside the kernel */
+    float* logY;
+    const float* gLogY;
 } BiearSeqParams;
 
 /* 1 if the persistent recurrence kernels can take N bands and F bins (their weight slices, activations and spectrum

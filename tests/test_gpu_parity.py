@@ -491,6 +491,31 @@ def test_band_count_sweep_adaptive_against_oracle(bb, nb):
             assert e <= RTOL, (nb, side, name, e)
 
 
+@pytest.mark.parametrize("engine", ["fused", "chain"])
+def test_fused_log_energy_features(bb, engine):
+    """want_logenergy: clamp(log(Y + 1e-8), +-12) out of the band stage's epilogue, gradient folded into the backward
+    kernel -- against the same expression written in PyTorch on Y (values and controller gradients), including
+    entries where the clamp is active (a silent clip: log(1e-8) = -18.4 -> -12, zero gradient)."""
+    m, tl, tr = _dual(bb, 3, (11, 12), CONFIG_YAML, 0.05, engine)
+    tl = tl.clone()
+    tl[1] = 0.0
+    up = torch.from_numpy(upstream(3)["gYL"]).to(DEV)
+    res = []
+    for fused in (True, False):
+        for p in m.parameters():
+            p.grad = None
+        o = m.forward_features(tl, tr, want_logenergy=fused)
+        x1 = o["logYL"] if fused else torch.clamp(torch.log(o["YL"] + 1e-8), -12.0, 12.0)
+        x2 = o["logYR"] if fused else torch.clamp(torch.log(o["YR"] + 1e-8), -12.0, 12.0)
+        ((up * x1).sum() + (up * x2).sum() + 0.1 * (up * o["YR"]).sum()).backward()
+        res.append((x1.detach(), x2.detach(), _grads(m)))
+    assert float(res[0][0][1].max()) == -12.0 and float(res[0][0][1].min()) == -12.0      # the silent clip is clamped
+    for a, b in zip(res[0][:2], res[1][:2]):
+        assert float((a - b).abs().max()) <= 2e-6
+    for k, v in res[1][2].items():
+        assert rel_err(res[0][2][k], v) <= 1e-5, (k, rel_err(res[0][2][k], v))
+
+
 def test_autograd_node_does_not_leak(bb):
     """The recurrence node must not hold its own outputs (a ctx -> output -> grad_fn -> ctx cycle would keep every
     step's ~100 MB of saved state alive): allocated memory is flat across steps."""
