@@ -254,10 +254,17 @@ def _log_energy(y: torch.Tensor) -> torch.Tensor:
     return torch.clamp(torch.log(y + 1e-8), -12.0, 12.0)
 
 
+FIXED_ENGINE = "gemm"   # "gemm": shared-weight dense contraction (csrc/band_fixed.cu); "item": per-item band kernel,
+                        # bit-identical to the adaptive path at Q == Q0 (kept for that identity and as a cross-check)
+
+
 def _fixed_bands(x: torch.Tensor, fc, q_fixed, df, want_phase, cutoff):
-    """Fixed-Q path: every (row, frame) item in one launch with a broadcast Q vector."""
-    y, ph, _, _ = ops.band_forward(torch.view_as_real(x), None, q_fixed.contiguous(), fc, df, cutoff,
-                                   want_phase, False)
+    """Fixed-Q path: every (row, frame) item in one launch.  All items share one Q vector, so the band weights are
+    one (N x F) matrix and the stage is a GEMM (model_torch.py:451-487 rebuilds that matrix 19 times per call)."""
+    xr = torch.view_as_real(x)
+    if FIXED_ENGINE == "gemm" and fc.numel() <= 128:
+        return ops.band_fixed_forward(xr, q_fixed.contiguous(), fc, df, cutoff, want_phase)
+    y, ph, _, _ = ops.band_forward(xr, None, q_fixed.contiguous(), fc, df, cutoff, want_phase, False)
     return y, ph
 
 

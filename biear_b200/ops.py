@@ -125,6 +125,28 @@ def band_forward(xr: torch.Tensor, t: Optional[int], q: torch.Tensor, fc: torch.
     return y, ph, dy, dp
 
 
+def band_fixed_forward(xr: torch.Tensor, q: torch.Tensor, fc: torch.Tensor, df: float,
+                       cutoff: float = DEFAULT_CUTOFF, want_phase: bool = True):
+    """Fixed-Q band stage for ALL (row, frame) items as one dense contraction (biear_band_fixed_fwd).
+    xr (rows, T, F, 2), q (N,) shared by every item -> Y (rows, T, N), phase (rows, T, N) | None."""
+    _need_cuda(xr, "X")
+    _need_cuda(q, "Q")
+    _need_cuda(fc, "fc")
+    rows, T, F, _ = xr.shape
+    N = fc.numel()
+    if q.shape != (N,):
+        raise ValueError(f"Q must be ({N},), got {tuple(q.shape)}")
+    dev = xr.device
+    with torch.cuda.device(dev):
+        lib = _prepare(dev)
+        y = torch.empty((rows, T, N), dtype=torch.float32, device=dev)
+        ph = torch.empty((rows, T, N), dtype=torch.float32, device=dev) if want_phase else None
+        work = torch.empty(int(lib.biear_band_fixed_workspace_floats(F)), dtype=torch.float32, device=dev)
+        _lib.check(lib.biear_band_fixed_fwd(_ptr(xr), 2 * F, _ptr(q), _ptr(fc), rows * T, N, F, float(df), float(cutoff),
+                                            _ptr(y), N, _ptr(ph), N, _ptr(work), _stream(dev)), "biear_band_fixed_fwd")
+    return y, ph
+
+
 def band_backward(xr: torch.Tensor, t: Optional[int], q: torch.Tensor, fc: torch.Tensor, df: float,
                   g_y: Optional[torch.Tensor], g_phase: Optional[torch.Tensor],
                   cutoff: float = DEFAULT_CUTOFF) -> torch.Tensor:

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BIEAR_ABI_VERSION 8
+#define BIEAR_ABI_VERSION 9
 #define BIEAR_EINVAL (-1)
 
 /* ABI version (== BIEAR_ABI_VERSION of the library that was built). */
@@ -75,6 +75,19 @@ int biear_band_fwd(const float* X, int64_t x_stride, const float* Q, int64_t q_s
                    const float* fc, int64_t items, int N, int F, float df, float cutoff,
                    float* Y, int64_t y_stride, float* phase, int64_t phase_stride,
                    float* dYdQ, float* dPdQ, int64_t jac_stride, void* stream);
+
+/*
+ * Fixed-Q band stage as one dense contraction: every item uses the SAME Q vector (N), so the Gaussian weights are a
+ * single (N x F) matrix and Y = abs(X) W^T, Z = X W^T is a GEMM over all (row, frame) items at once.
+ * Replaces model_torch.py:451-487 (FramewiseFixedGammatoneFB), :161-195 (AuralNetGammatoneFB) and, with phase != NULL,
+ * :1039-1063 for fixed Q.  Same window truncation and normalisation as biear_band_fwd.
+ *   X (items, F, 2) with item stride x_stride floats; Q, fc (N <= 128); Y / phase (items, N) with item strides;
+ *   workspace: biear_band_fixed_workspace_floats(F) floats, 16-byte aligned (the packed weight matrix).
+ */
+int64_t biear_band_fixed_workspace_floats(int F);
+int biear_band_fixed_fwd(const float* X, int64_t x_stride, const float* Q, const float* fc, int64_t items, int N, int F,
+                         float df, float cutoff, float* Y, int64_t y_stride, float* phase, int64_t phase_stride,
+                         float* workspace, void* stream);
 
 /*
  * Backward of biear_band_fwd into Q by recomputation (nothing saved by the forward):

@@ -74,3 +74,31 @@ def test_full_model_raises_on_nonfinite_and_cpu_input():
     assert torch.equal(m.last_QL[:, 0::2], q0.expand_as(m.last_QL[:, 0::2]))
     assert float((m.last_QL[:, 1::2] - q0).abs().max()) > 1e-3
     assert float((m.last_QR[:, 2::2] - q0).abs().max()) > 1e-3       # the other ear is unaffected
+
+
+def test_precompute_wire_format_against_oracle():
+    """biear_b200.precompute (BASELINE config 3): chunked host->host feature precompute in the reference's H5 wire
+    format, against the CPU oracle (fixed-Q filterbank + phase + CC) on a few clips, with a chunk size that does not
+    divide the clip count."""
+    from biear_b200 import precompute
+    wl, wr = orc.synth_binaural(7, seed=21)
+    y = np.arange(7 * 56, dtype=np.float32).reshape(7, 56)
+    out = precompute.precompute(wl, wr, y, fmt="passive", chunk=3)
+    assert {k: v.shape for k, v in out.items()} == {"x1": (7, 19, 100), "x2": (7, 19, 100), "x3": (7, 100), "x4": (7, 19, 100),
+                                                    "x5": (7, 19, 100), "y": (7, 56)}
+    cfg = orc.FrontEndConfig()
+    yl, ql, xl = orc.fixed_fb_forward(torch.from_numpy(wl), cfg)
+    c = orc.constants(cfg)
+    assert rel_err(out["x1"], orc.log_energy(yl).numpy()) <= RTOL
+    assert float(np.max(np.abs(out["x3"] - orc.cc_feature_batch(wl, wr)))) <= 1e-6
+    # phase against the float64 truth, weighted by its conditioning abs(Z)/Y (see tests/test_gpu_parity.py)
+    c64 = orc.constants(cfg, torch.float64)
+    x64 = orc.stft_frames(torch.from_numpy(wl).double(), cfg, c64["win_fn"])
+    q64 = torch.clamp(c64["Q0"], orc.Q_MIN, orc.Q_MAX).expand(7, -1)
+    mom = [orc.band_moments(x64[:, t], q64, c64["fc"], c64["f_fft"]) for t in range(19)]
+    z = torch.stack([m_["Z"] for m_ in mom], 1)
+    wgt = (z.abs() / torch.stack([m_["Y"] for m_ in mom], 1)).numpy()
+    d = np.abs(out["x4"].astype(np.float64) - torch.atan2(z.imag, z.real).numpy()) % (2 * np.pi)
+    assert float(np.max(np.minimum(d, 2 * np.pi - d) * wgt)) <= 1e-6
+    act = precompute.precompute(wl, wr, y, fmt="active", chunk=4)
+    assert act["x1"].shape == (7, 16000) and np.array_equal(act["x3"], out["x3"]) and np.array_equal(act["x1"], wl)

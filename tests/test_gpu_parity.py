@@ -593,14 +593,30 @@ def test_properties_full_size(bb):
     B = 256
     wl, wr = orc.synth_binaural(B, seed=4321)
     tl, tr = torch.from_numpy(wl).to(DEV), torch.from_numpy(wr).to(DEV)
+    from biear_b200 import frontend
     torch.manual_seed(0)
     adaptive = bb.BinauralAdaptiveGammatoneFB(**_kw(CONFIG_YAML)).to(DEV).eval()   # zero-init last layer: Q == Q0
     fixed = bb.BinauralAdaptiveGammatoneFB(fixed_frontend_q=True).to(DEV).eval()
     with torch.no_grad():
         ya, _, qa, _, xa, _ = adaptive(tl, tr)
+        # (1) adaptive at initialisation == fixed: bit for bit with the per-item band
+        #     kernel (same arithmetic as the adaptive path), to rounding with the shared-weight GEMM form
+        frontend.FIXED_ENGINE = "item"
+        try:
+            yi, _, qf, _, xf, _ = fixed(tl, tr)
+        finally:
+            frontend.FIXED_ENGINE = "gemm"
+        assert torch.equal(qa, qf.expand_as(qa)) and torch.equal(ya, yi) and torch.equal(xa, xf)
         yf, yfr, qf, _, xf, _ = fixed(tl, tr)
-        # (1) adaptive at initialisation == fixed, bit for bit
-        assert torch.equal(qa, qf.expand_as(qa)) and torch.equal(ya, yf) and torch.equal(xa, xf)
+        assert float((yf - yi).abs().max() / yi.abs().max()) <= 2e-6
+        oi = fixed.forward_features(tl[:8], tr[:8])
+        frontend.FIXED_ENGINE = "item"
+        try:
+            og = fixed.forward_features(tl[:8], tr[:8])
+        finally:
+            frontend.FIXED_ENGINE = "gemm"
+        dph = (oi["phaseL"] - og["phaseL"]).abs()
+        assert float(torch.minimum(dph, 2 * np.pi - dph).median()) <= 1e-5     # same phases up to fp32 conditioning
         # (2) a 10 s input gives the result of its first second (section 4 item 5)
         y10 = fixed(torch.cat([tl, tl.flip(1)], 1), torch.cat([tr, tr], 1))[0]
         assert torch.equal(y10, yf)
