@@ -30,17 +30,23 @@ struct StftArgs {
 
 __global__ void __launch_bounds__(kStftThreads) stft_fwd_kernel(const StftArgs a) {
     __shared__ float2 s_tw[kNfft];
+    __shared__ float s_win[kNfft];
     __shared__ float2 s_buf[kFramesPerCta][kFftSlots];
 
-    for (int i = threadIdx.x; i < kNfft; i += kStftThreads) s_tw[i] = a.tw[i];
+    for (int i = threadIdx.x; i < kNfft; i += kStftThreads) {
+        s_tw[i] = a.tw[i];
+        s_win[i] = i < a.win ? a.win_fn[i] : 0.0f;
+    }
 
     const int g = threadIdx.x / kFftThreads;
     const int j = threadIdx.x % kFftThreads;
     float2* buf = s_buf[g];
     const int valid_len = min(min(a.win, kNfft), a.limit);
+    const long long stride = (long long)gridDim.x * kFramesPerCta;
 
-    for (long long base = (long long)blockIdx.x * kFramesPerCta; base < a.n_frames;
-         base += (long long)gridDim.x * kFramesPerCta) {
+    // Raw samples of one frame (this thread's 16), NOT yet windowed: issued one trip ahead so that the HBM latency of
+    // the next frame group hides behind the three FFT passes of the current one.
+    auto fetch = [&](long long base, float2 (&raw)[8]) {
         const long long fi = base + g;
         const bool live = fi < a.n_frames;
         const long long row = live ? fi / a.T : 0;
@@ -48,22 +54,34 @@ __global__ void __launch_bounds__(kStftThreads) stft_fwd_kernel(const StftArgs a
         const bool frame_valid = live && t < a.n_avail;
         const long long start = (long long)t * a.hop;
         const float* wrow = a.wav + row * a.row_stride;
-
-        // pass 1 (Ns = 1): packed, windowed samples straight from global memory
-        float2 v[8];
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
             const int i0 = 2 * (j + r * 64);
             float x0 = 0.f, x1 = 0.f;
             if (frame_valid) {
                 const long long s0 = start + i0;
-                if (i0 < valid_len && s0 < a.limit && s0 < a.nsamp) x0 = __ldg(wrow + s0) * __ldg(a.win_fn + i0);
-                if (i0 + 1 < valid_len && s0 + 1 < a.limit && s0 + 1 < a.nsamp)
-                    x1 = __ldg(wrow + s0 + 1) * __ldg(a.win_fn + i0 + 1);
+                if (i0 < valid_len && s0 < a.limit && s0 < a.nsamp) x0 = __ldg(wrow + s0);
+                if (i0 + 1 < valid_len && s0 + 1 < a.limit && s0 + 1 < a.nsamp) x1 = __ldg(wrow + s0 + 1);
             }
-            v[r] = make_float2(x0, x1);
+            raw[r] = make_float2(x0, x1);
         }
-        __syncthreads();   // twiddles loaded (first trip) / previous trip's unpack reads done
+    };
+
+    float2 nxt[8];
+    long long base = (long long)blockIdx.x * kFramesPerCta;
+    if (base < a.n_frames) fetch(base, nxt);
+    __syncthreads();   // twiddles and window in shared memory
+    for (; base < a.n_frames; base += stride) {
+        const long long fi = base + g;
+        const bool live = fi < a.n_frames;
+        // pass 1 (Ns = 1): packed, windowed samples
+        float2 v[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int i0 = 2 * (j + r * 64);
+            v[r] = make_float2(nxt[r].x * s_win[i0], nxt[r].y * s_win[i0 + 1]);
+        }
+        if (base + stride < a.n_frames) fetch(base + stride, nxt);
         fft512_butterfly(v, j, 1, s_tw);
         fft512_scatter<true>(v, buf, j, 1);
         __syncthreads();
@@ -94,6 +112,7 @@ __global__ void __launch_bounds__(kStftThreads) stft_fwd_kernel(const StftArgs a
                 out[256] = xk;
             }
         }
+        __syncthreads();   // unpack reads done before the next trip scatters into the buffer
     }
 }
 
@@ -129,7 +148,7 @@ extern "C" int biear_stft_fwd(const float* wav, int64_t rows, int64_t nsamp, int
     a.X = reinterpret_cast<float2*>(X);
     a.n_frames = rows * T;
     const long long ctas_needed = (a.n_frames + kFramesPerCta - 1) / kFramesPerCta;
-    const long long cap = (long long)kSmCountB200 * 8;
+    const long long cap = (long long)kSmCountB200 * 4;   // ~2 resident CTAs per SM, each pipelining over its frame groups
     const int grid = (int)(ctas_needed < cap ? ctas_needed : cap);
     stft_fwd_kernel<<<grid, kStftThreads, 0, st>>>(a);
     BIEAR_LAUNCH_CHECK("stft_fwd_kernel");

@@ -86,15 +86,14 @@ class _FilterbankBase(nn.Module):
         return (self.fs / 2) / (self.n_fft // 2)
 
     def _spectra(self, wavs: List[torch.Tensor]) -> torch.Tensor:
-        """[(B,Nsamp)] * E -> X (E*B, T, F) complex64, one launch for all ears."""
+        """[(B,Nsamp)] * E -> X (E*B, T, F) complex64: one launch per ear into one output tensor (no waveform concat)."""
         for w in wavs:
             if w.dim() != 2:
                 raise ValueError(f"Expected wav_1s (B,N), got {w.shape}")
-        wav = wavs[0] if len(wavs) == 1 else torch.cat(wavs, dim=0)
-        if wav.requires_grad:
-            raise RuntimeError("biear_b200: gradients with respect to the waveform are not implemented")
-        wav = wav.float().contiguous()
-        return ops.stft(wav, self.win_fn, self.fs, self.timesteps, self.win, self.hop, self.n_fft)
+            if w.requires_grad:
+                raise RuntimeError("biear_b200: gradients with respect to the waveform are not implemented")
+        return ops.stft([w.float().contiguous() for w in wavs], self.win_fn, self.fs, self.timesteps, self.win, self.hop,
+                        self.n_fft)
 
 
 _side_streams = {}

@@ -62,20 +62,28 @@ def _captured_seed(device) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 # STFT
 # ------------------------------------------------------------------------------------------------
-def stft(wav: torch.Tensor, win_fn: torch.Tensor, fs: int, timesteps: int, win: int, hop: int,
-         n_fft: int) -> torch.Tensor:
-    """(rows, nsamp) fp32 -> X (rows, T, n_fft//2+1) complex64.  model_torch.py:289-312, 334-335."""
-    if wav.dim() != 2:
-        raise ValueError(f"Expected wav_1s (B,N), got {tuple(wav.shape)}")
-    _need_cuda(wav, "wav")
+def stft(wav, win_fn: torch.Tensor, fs: int, timesteps: int, win: int, hop: int, n_fft: int) -> torch.Tensor:
+    """(rows, nsamp) fp32 -> X (rows, T, n_fft//2+1) complex64.  model_torch.py:289-312, 334-335.
+    `wav` may be a list of equally shaped (B, nsamp) tensors (the ears): their spectra are written one after the other
+    into ONE output tensor (E*B, T, F) without concatenating the waveforms first."""
+    wavs = list(wav) if isinstance(wav, (list, tuple)) else [wav]
+    for w in wavs:
+        if w.dim() != 2:
+            raise ValueError(f"Expected wav_1s (B,N), got {tuple(w.shape)}")
+        if w.shape != wavs[0].shape:
+            raise ValueError(f"waveform shapes differ: {tuple(w.shape)} vs {tuple(wavs[0].shape)}")
+        _need_cuda(w, "wav")
     _need_cuda(win_fn, "win_fn")
-    with torch.cuda.device(wav.device):
-        lib = _prepare(wav.device)
-        rows, nsamp = wav.shape
+    dev = wavs[0].device
+    with torch.cuda.device(dev):
+        lib = _prepare(dev)
+        rows, nsamp = wavs[0].shape
         nbins = n_fft // 2 + 1
-        xr = torch.empty((rows, timesteps, nbins, 2), dtype=torch.float32, device=wav.device)
-        _lib.check(lib.biear_stft_fwd(_ptr(wav), rows, nsamp, nsamp, _ptr(win_fn), fs, timesteps, win, hop,
-                                      n_fft, _ptr(xr), _stream(wav.device)), "biear_stft_fwd")
+        xr = torch.empty((len(wavs) * rows, timesteps, nbins, 2), dtype=torch.float32, device=dev)
+        for e, w in enumerate(wavs):
+            out = c_void_p(xr.data_ptr() + 4 * e * rows * timesteps * nbins * 2)
+            _lib.check(lib.biear_stft_fwd(_ptr(w), rows, nsamp, nsamp, _ptr(win_fn), fs, timesteps, win, hop,
+                                          n_fft, out, _stream(dev)), "biear_stft_fwd")
     return torch.view_as_complex(xr)
 
 
