@@ -79,7 +79,7 @@ __device__ __forceinline__ BandSums band_accumulate(const float4* __restrict__ s
     float2 ma = make_float2(0.f, 0.f), z2 = make_float2(0.f, 0.f);     // {m2, a2}, {z2r, z2i}
     int k = k0 + j;
     float kf = (float)(k - p.kc);
-#pragma unroll 4
+#pragma unroll 8
     for (; k - j <= k1; k += 8, kf += 8.0f) {
         const float4 x = spec[k];                       // k < spec_tile_len(F) always; zeros beyond F-1
         const float u = fmaf(kf, p.a, p.b);
