@@ -458,6 +458,32 @@ def test_ctrl_wgrad_kernel(bb):
                 assert db is None
 
 
+@pytest.mark.parametrize("fs,T,hop_ratio", [(16000, 25, 1.0), (8000, 19, 1.0), (16000, 10, 0.5)])
+def test_monaural_adaptive_other_geometries(bb, fs, T, hop_ratio):
+    """FramewiseAdaptiveGammatoneFB on its own (one controller, G = 1) through the persistent kernels, with other frame
+    counts / sample rates / hops (win = round(fs / T): 640, 421 and 1600 > n_fft samples), against the fp32 CPU oracle."""
+    batch = 4
+    cfg = orc.FrontEndConfig(fs=fs, timesteps=T, hop_ratio=hop_ratio, **CONFIG_YAML)
+    torch.manual_seed(0)
+    m = bb.FramewiseAdaptiveGammatoneFB(fs=fs, timesteps=T, hop_ratio=hop_ratio, **_kw(CONFIG_YAML))
+    w = orc.synth_controller(51, out_std=0.05)
+    _load_ctrl(m, w)
+    m = m.to(DEV).eval()
+    assert m.engine == "fused"
+    wl, _ = orc.synth_binaural(batch, seed=91, n=fs)
+    y, q, x = m(torch.from_numpy(wl).to(DEV))
+    assert y.shape == (batch, T, 100) and q.shape == (batch, T, 100) and x.shape == (batch, T, 513)
+    up = torch.from_numpy(np.random.RandomState(2).standard_normal((batch, T, 100)).astype(np.float32))
+    ((up.to(DEV) * torch.log(y + 1e-8)).sum() + (up.to(DEV) * q).sum()).backward()
+    pt = orc.to_torch(w, requires_grad=True)
+    yo, qo, _ = orc.adaptive_fb_forward(torch.from_numpy(wl), pt, cfg)
+    assert_close(_np(y), yo.detach().numpy(), RTOL, "Y")
+    assert_close(_np(q), qo.detach().numpy(), RTOL, "Q")
+    ((up * torch.log(yo + 1e-8)).sum() + (up * qo).sum()).backward()
+    for name, prm in m.named_parameters():
+        assert rel_err(_np(prm.grad), pt[name].grad.numpy()) <= RTOL, name
+
+
 @pytest.mark.parametrize("nb", [32, 64, 128])
 def test_band_count_sweep_adaptive_against_oracle(bb, nb):
     """BASELINE config 5: other band counts through the persistent kernels (bands per CTA, last-layer slices and the
