@@ -121,7 +121,7 @@ struct FwdSmem {   // offsets in floats
     __host__ __device__ int yc() const { return vec() + 1088; }                 // [128][kR]; aliased by a2
     __host__ __device__ int a1() const { return yc() + kHid * kR; }             // [128][kR], directly behind yc
     __host__ __device__ int h0() const { return a1() + kHid * kR; }             // [128][kR] x 2 (ping-pong)
-    __host__ __device__ int stat() const { return h0() + 2 * kHid * kR; }       // 2 x kSeqThreads
+    __host__ __device__ int stat() const { return h0() + 2 * kHid * kR; }       // 2 x kSeqThreads (LayerNorm partials)
     __host__ __device__ int q() const { return stat() + 2 * kSeqThreads; }      // [128][4]: Q_t of this CTA's 4 rows
     __host__ __device__ int ystage() const { return q() + kHid * kRT; }         // [4][128]
     __host__ __device__ int spec() const { return ystage() + kRT * kHid; }      // [4][tile] float4
@@ -151,32 +151,37 @@ __device__ __forceinline__ void ln_silu_drop_fwd(const BiearSeqParams& p, unsign
                                                  int layer, int t, long long grow0, int rank, float* xh_tile,
                                                  float* d_tile, float* rstd_tile) {
     constexpr int PARTS = kSeqThreads / kR, FPP = kHid / PARTS;     // 32 parts of 4 features
+    static_assert(kR == 16 && PARTS == 2 * (kSeqThreads / 32), "lanes l and l^16 of a warp hold two parts of one row");
     const int row = threadIdx.x % kR, part = threadIdx.x / kR;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int f0 = part * FPP;
+    // One pass over the row: sum and sum of squares of x - pivot (pivot = the row's feature 0; the shift keeps
+    // E[x^2] - E[x]^2 well conditioned), the two parts of a warp combined by a shuffle, the 16 warps through shared memory.
+    const float pivot = buf_s[row];
     float v[FPP];
-    float s = 0.f;
+    float s = 0.f, ss = 0.f;
 #pragma unroll
     for (int i = 0; i < FPP; ++i) {
-        v[i] = buf_s[(f0 + i) * kR + row];
+        v[i] = buf_s[(f0 + i) * kR + row] - pivot;
         s += v[i];
-    }
-    stat_s[part * kR + row] = s;
-    __syncthreads();
-    float mean = 0.f;
-#pragma unroll
-    for (int q = 0; q < PARTS; ++q) mean += stat_s[q * kR + row];
-    mean *= (1.0f / kHid);
-    float ss = 0.f;
-#pragma unroll
-    for (int i = 0; i < FPP; ++i) {
-        v[i] -= mean;
         ss = fmaf(v[i], v[i], ss);
     }
-    stat_s[kSeqThreads + part * kR + row] = ss;
+    s += __shfl_xor_sync(0xffffffffu, s, 16);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 16);
+    float2* stat2 = reinterpret_cast<float2*>(stat_s);               // [row][17] float2: conflict-free both ways
+    if (lane < kR) stat2[row * 17 + warp] = make_float2(s, ss);
     __syncthreads();
-    float var = 0.f;
+    float S = 0.f, SS = 0.f;
 #pragma unroll
-    for (int q = 0; q < PARTS; ++q) var += stat_s[kSeqThreads + q * kR + row];
+    for (int w = 0; w < kSeqThreads / 32; ++w) {
+        const float2 q = stat2[row * 17 + w];
+        S += q.x;
+        SS += q.y;
+    }
+    const float mean = S * (1.0f / kHid);
+    const float var = fmaxf(fmaf(-mean, mean, SS * (1.0f / kHid)), 0.0f) * kHid;   // sum of squared deviations
+#pragma unroll
+    for (int i = 0; i < FPP; ++i) v[i] -= mean;
     const float rstd = rsqrtf(var * (1.0f / kHid) + kLnEps);
     const bool mine = f0 / kU == rank;
     if (rank == 0 && part == 0) rstd_tile[layer * kR + row] = rstd;
@@ -665,14 +670,17 @@ __device__ __forceinline__ void ln_silu_drop_bwd(const BiearSeqParams& p, unsign
             s2 = fmaf(dxh[i], xh[i], s2);
         }
     }
-    stat_s[part * kR + row] = s1;
-    stat_s[kSeqThreads + part * kR + row] = s2;
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 16);                     // lanes l and l^16 hold two parts of one row
+    s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+    float2* stat2 = reinterpret_cast<float2*>(stat_s);               // [row][17] float2
+    if ((threadIdx.x & 31) < kR) stat2[row * 17 + (threadIdx.x >> 5)] = make_float2(s1, s2);
     __syncthreads();
     float m1 = 0.f, m2 = 0.f;
 #pragma unroll
-    for (int q = 0; q < PARTS; ++q) {
-        m1 += stat_s[q * kR + row];
-        m2 += stat_s[kSeqThreads + q * kR + row];
+    for (int w = 0; w < kSeqThreads / 32; ++w) {
+        const float2 q = stat2[row * 17 + w];
+        m1 += q.x;
+        m2 += q.y;
     }
     m1 *= (1.0f / kHid);
     m2 *= (1.0f / kHid);

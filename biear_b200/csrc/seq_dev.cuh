@@ -109,6 +109,9 @@ __device__ __forceinline__ void copy_f4(float4* __restrict__ dst, const float4* 
 // The 4 rows are two packed fp32x2 FMAs (FFMA2, sm_100): same rounding as four scalar FMAs, half the issue slots.
 __device__ __forceinline__ void dot_rows(float acc[kRT], const float* __restrict__ x_s, const float* __restrict__ w_s,
                                          int k0, int k1) {
+#ifdef BIEAR_SKIP_DOTS   // timing experiment only: what the phases cost without their contractions
+    k1 = k0;
+#endif
     float2 lo = make_float2(acc[0], acc[1]), hi = make_float2(acc[2], acc[3]);
 #pragma unroll 8
     for (int k = k0; k < k1; ++k) {
@@ -124,6 +127,9 @@ __device__ __forceinline__ void dot_rows(float acc[kRT], const float* __restrict
 // Three gate rows at once: the weights of one k are [gate][kU] (w3_s already offset to the thread's unit).
 __device__ __forceinline__ void dot_rows3(float a0[kRT], float a1[kRT], float a2[kRT], const float* __restrict__ x_s,
                                           const float* __restrict__ w3_s, int k0, int k1) {
+#ifdef BIEAR_SKIP_DOTS
+    k1 = k0;
+#endif
     float2 l0 = make_float2(a0[0], a0[1]), h0 = make_float2(a0[2], a0[3]);
     float2 l1 = make_float2(a1[0], a1[1]), h1 = make_float2(a1[2], a1[3]);
     float2 l2 = make_float2(a2[0], a2[1]), h2 = make_float2(a2[2], a2[3]);
