@@ -195,7 +195,7 @@ __device__ __forceinline__ void ln_silu_drop_fwd(const BiearSeqParams& p, unsign
             const int i = i4 * 4 + j, f = f0 + i;
             const float xh = v[i] * rstd;
             const float y = fmaf(xh, gamma_s[f], beta_s[f]);
-            const float o = (y / (1.0f + expf(-y))) * scv[j];
+            const float o = (y * sigmoid_fast(y)) * scv[j];
             buf_s[f * kR + row] = o;
             if (mine) {
                 xh_tile[f * kR + row] = xh;
@@ -485,8 +485,8 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                     const float br = vec_s[V_BR + u], bz = vec_s[V_BZ + u], bin = vec_s[V_BIN + u], bhn = vec_s[V_BHN + u];
 #pragma unroll
                     for (int i = 0; i < kRT; ++i) {
-                        vr[i] = 1.0f / (1.0f + expf(-(acc[i] + br)));
-                        vz[i] = 1.0f / (1.0f + expf(-(acc[4 + i] + bz)));
+                        vr[i] = sigmoid_fast(acc[i] + br);
+                        vz[i] = sigmoid_fast(acc[4 + i] + bz);
                         vh[i] = acc[12 + i] + bhn;
                         vn[i] = tanhf(acc[8 + i] + bin + vr[i] * vh[i]);
                         const float hp = h_zero ? 0.0f : hcur_s[ug * kR + rg * kRT + i];
@@ -661,7 +661,7 @@ __device__ __forceinline__ void ln_silu_drop_bwd(const BiearSeqParams& p, unsign
             const int i = i4 * 4 + j, f = f0 + i;
             const float gm = gamma_s[f];
             const float y = fmaf(xh[i], gm, beta_s[f]);
-            const float sg = 1.0f / (1.0f + expf(-y));
+            const float sg = sigmoid_fast(y);
             const float d = buf_s[f * kR + row] * scv[j];
             const float dv = d * sg * (1.0f + y * (1.0f - sg));
             if (mine) gv_tile[f * kR + row] = dv;
