@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
     float* red_gru_s = yc_s;
     float* red_l1_s = yc_s;
     float* red_l23_s = a1_s;
-    static_assert(2 * 16 * 128 <= 2 * kHid * kR && 2 * kRT * 128 <= kHid * kR, "reduction scratch fits its hosts");
+    static_assert(2 * 16 * 128 <= 2 * kHid * kR && (kKS - 1) * kRT * 128 <= kHid * kR, "reduction scratch fits its hosts");
     float* q_s = smem + L.q();
     float* ystage_s = smem + L.ystage();
     float4* spec_s = reinterpret_cast<float4*>(smem + L.spec());
@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                 int k0, k1;
                 k_range(kHid, ks, k0, k1);
                 dot_rows(acc, hnext_s + rg * kRT, img_s + fwd_img_w1(N) + u, k0, k1);
-                reduce_ks<kRT>(acc, red_l1_s, ks, slot);
+                reduce_ks1<kRT>(acc, red_l1_s, ks, slot);
                 if (ks == 0) {
                     const float bb = vec_s[V_B1 + u];
 #pragma unroll
@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                 int k0, k1;
                 k_range(kHid, ks, k0, k1);
                 dot_rows(acc, a1_s + rg * kRT, img_s + fwd_img_w2(N) + u, k0, k1);
-                reduce_ks<kRT>(acc, red_l23_s, ks, slot);
+                reduce_ks1<kRT>(acc, red_l23_s, ks, slot);
                 if (ks == 0) {
                     const float bb = vec_s[V_B2 + u];
 #pragma unroll
@@ -554,7 +554,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                 int k0, k1;
                 k_range(kHid, ks, k0, k1);
                 if (mine) dot_rows(acc, a2_s + rg * kRT, img_s + fwd_img_w3(N) + u, k0, k1);
-                reduce_ks<kRT>(acc, red_l23_s, ks, slot);
+                reduce_ks1<kRT>(acc, red_l23_s, ks, slot);
                 const bool fin = ks == 0 && mine;
                 const int n = rank * NU + u;
                 float qv[kRT] = {0.f, 0.f, 0.f, 0.f}, dv[kRT] = {0.f, 0.f, 0.f, 0.f};
@@ -614,8 +614,8 @@ struct BwdSmem {   // offsets in floats
     __host__ __device__ int bufa() const { return vec() + 1024; }                  // [128][32]; first quarter of gate
     __host__ __device__ int gate() const { return bufa(); }                        // [4*128][32]: drp, dzp, dnp, dhn
     __host__ __device__ int dpre() const { return gate() + 4 * kHid * kR; }        // [128][32]; aliased by bufb
-    __host__ __device__ int red() const { return dpre() + kHid * kR; }             // 2 x 8 x 128
-    __host__ __device__ int stat() const { return red() + 2 * 8 * 128; }           // 2 x kSeqThreads
+    __host__ __device__ int red() const { return dpre() + kHid * kR; }             // (kKS - 1) x 8 x 128
+    __host__ __device__ int stat() const { return red() + (kKS - 1) * 8 * 128; }   // 2 x kSeqThreads
     __host__ __device__ int stage() const { return stat() + 2 * kSeqThreads; }     // [4][128]
     __host__ __device__ int dyc() const { return stage() + kRT * kHid; }           // [128][4]
     __host__ __device__ int total() const { return dyc() + kHid * kRT; }
@@ -802,7 +802,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
             int k0, k1;
             k_range(N, ks, k0, k1);
             dot_rows(acc, dpre_s + rg * kRT, img_s + bwd_img_w3c(N) + u, k0, k1);
-            reduce_ks<kRT>(acc, red_s, ks, slot);
+            reduce_ks1<kRT>(acc, red_s, ks, slot);
             if (ks == 0) broadcast_rows(cluster, bufa_s, ug, rg * kRT, acc);
         }
         cluster.sync();   // #2
@@ -817,7 +817,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
             int k0, k1;
             k_range(kHid, ks, k0, k1);
             dot_rows(acc, bufa_s + rg * kRT, img_s + bwd_img_w2c(N) + u, k0, k1);
-            reduce_ks<kRT>(acc, red_s, ks, slot);
+            reduce_ks1<kRT>(acc, red_s, ks, slot);
             if (ks == 0) broadcast_rows(cluster, bufb_s, ug, rg * kRT, acc);   // bufb aliases dpre: its reads ended before #2
         }
         cluster.sync();   // #3
@@ -843,7 +843,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
             int k0, k1;
             k_range(kHid, ks, k0, k1);
             dot_rows(acc, bufb_s + rg * kRT, img_s + bwd_img_w1c(N) + u, k0, k1);
-            reduce_ks<kRT>(acc, red_s, ks, slot);
+            reduce_ks1<kRT>(acc, red_s, ks, slot);
             float v0[kRT], v1[kRT], v2[kRT], v3[kRT];
             if (ks == 0) {
                 const float rr[4] = {r4.x, r4.y, r4.z, r4.w}, zz[4] = {z4.x, z4.y, z4.z, z4.w};
@@ -893,7 +893,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
             dot_rows(acc, x + kHid * kR, whhc, max(o0, 2 * kHid), max(o1, 2 * kHid));
             const bool mine = u < nu_c;
             if (mine) dot_rows(acc + kRT, x, wihc, o0, o1);
-            reduce_ks<2 * kRT>(acc, red_s, ks, slot);
+            reduce_ks1<2 * kRT>(acc, red_s, ks, slot);
             if (ks == 0) {
 #pragma unroll
                 for (int i = 0; i < kRT; ++i) dh_carry[i] = acc[i] + dh_direct[i];

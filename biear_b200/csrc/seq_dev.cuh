@@ -180,6 +180,24 @@ __device__ __forceinline__ void reduce_ks(float* acc, float* red_s, int ks, int 
     }
 }
 
+// Same sum in ONE round: every ks > 0 thread parks its accumulators, the ks == 0 thread adds the three of them in a
+// fixed order.  Needs (kKS - 1) * NACC floats per slot of scratch but only two block barriers.
+template <int NACC>
+__device__ __forceinline__ void reduce_ks1(float* acc, float* red_s, int ks, int slot) {
+    __syncthreads();
+    if (ks > 0) {
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) red_s[((ks - 1) * NACC + i) * 128 + slot] = acc[i];
+    }
+    __syncthreads();
+    if (ks == 0) {
+#pragma unroll
+        for (int k = 0; k < kKS - 1; ++k)
+#pragma unroll
+            for (int i = 0; i < NACC; ++i) acc[i] += red_s[(k * NACC + i) * 128 + slot];
+    }
+}
+
 // Write 4 row values of one feature into the [feature][kR] buffer of every CTA of the cluster.
 __device__ __forceinline__ void broadcast_rows(cg::cluster_group& cluster, float* buf_s, int feature, int row0,
                                                const float v[kRT]) {
