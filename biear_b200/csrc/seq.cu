@@ -356,10 +356,12 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                 float4* hdst = reinterpret_cast<float4*>(h_tile(p, g, t - 1, tiles, tile));
                 for (int i = tid; i < kHid * kR / 4; i += kSeqThreads) hdst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            if (STRICT || spec_t != t) prefetch_spectra(p, spec_s, L.tile, grow0, bb0, t);
             PHASE_MARK(0, 0);    // loop head / weight load
-            finish_spectra(p, spec_s, L.tile, bb0);
-            __syncthreads();
+            if (STRICT || spec_t != t) {   // first frame / strict pass: fetch and convert now (also orders the q_s fill)
+                prefetch_spectra(p, spec_s, L.tile, grow0, bb0, t);
+                finish_spectra(p, spec_s, L.tile, bb0);
+                __syncthreads();
+            }   // otherwise frame t's tile was fetched behind frame t-1's controller phases and converted before its barrier #5
             PHASE_MARK(0, 1);    // spectra ready
 
             // ---- band stage of frame t for this CTA's 4 rows (model_torch.py:340-346, 1050-1060) ---------------
@@ -592,6 +594,10 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                 if (STRICT) {
                     store_q();
                     __threadfence();
+                } else {
+                    // finish the next frame's spectrum tile (cp.async data has long arrived) BEFORE signalling: once #5
+                    // completes, every thread of this CTA has converted its slots, so the band stage can start at once
+                    finish_spectra(p, spec_s, L.tile, bb0);
                 }
                 cluster.barrier_arrive();   // #5
                 if (!STRICT) store_q();
@@ -739,31 +745,50 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
     // Part of dL/dpre_{t} that does not depend on the recurrence, for the element (row i, band n) this thread assembles:
     //   ext = gY dY/dQ + gphase dphase/dQ + gQ,  jac = dY/dQ,  fac = d clamp/dQ * dQ/ddelta * d tanh  (all at frame t+1)
     struct Pre { float ext, jac, fac; };
-    auto fetch_pre = [&](int t) {
-        Pre r = {0.f, 0.f, 0.f};
+    struct PreRaw { float gy, jac, gp, dp, gq, delta, y, glx; bool live; };
+    // issue_pre: only the global loads (so that they are in flight during whatever comes next);
+    // finish_pre: the arithmetic, called when the values are needed.
+    auto issue_pre = [&](int t) {
+        PreRaw r = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, false};
         if (t < 0 || tid >= kRT * N) return r;
         const int i = tid / N, n = tid - i * N;
         if (bb0 + i >= p.B) return r;
         const long long e = ((grow0 + i) * T + (t + 1)) * N + n;
+        r.live = true;
         r.jac = __ldg(p.dYdQ + e);
-        float gy = p.gY ? __ldg(p.gY + e) : 0.f;
-        if (p.gLogY) {   // d clamp(log(Y + 1e-8), +-12) / dY, as autograd derives it (model_torch.py:1080-1083)
-            const float ye = __ldg(p.Y + e) + 1e-8f;
-            const float lx = logf(ye);
-            if (lx >= -12.0f && lx <= 12.0f) gy += __ldg(p.gLogY + e) / ye;
+        if (p.gY) r.gy = __ldg(p.gY + e);
+        if (p.gLogY) {
+            r.y = __ldg(p.Y + e);
+            r.glx = __ldg(p.gLogY + e);
         }
-        r.ext = gy * r.jac;
-        if (p.gP) r.ext = fmaf(__ldg(p.gP + e), __ldg(p.dPdQ + e), r.ext);
-        if (p.gQ) r.ext += __ldg(p.gQ + e);
-        const float delta = __ldg(p.delta + e);
+        if (p.gP) {
+            r.gp = __ldg(p.gP + e);
+            r.dp = __ldg(p.dPdQ + e);
+        }
+        if (p.gQ) r.gq = __ldg(p.gQ + e);
+        r.delta = __ldg(p.delta + e);
+        return r;
+    };
+    auto finish_pre = [&](const PreRaw& w) {
+        Pre r = {0.f, 0.f, 0.f};
+        if (!w.live) return r;
+        const int n = tid % N;
+        float gy = w.gy;
+        if (p.gLogY) {   // d clamp(log(Y + 1e-8), +-12) / dY, as autograd derives it (model_torch.py:1080-1083)
+            const float ye = w.y + 1e-8f;
+            const float lx = logf(ye);
+            if (lx >= -12.0f && lx <= 12.0f) gy += w.glx / ye;
+        }
+        r.jac = w.jac;
+        r.ext = fmaf(w.gp, w.dp, gy * w.jac) + w.gq;
         const float q0 = vec_s[VB_Q0 + n], dq = vec_s[VB_DQ + n];
-        const float qu = p.relative ? q0 * (1.0f + dq * delta) : fmaf(dq, delta, q0);
+        const float qu = p.relative ? q0 * (1.0f + dq * w.delta) : fmaf(dq, w.delta, q0);
         const float scale = p.relative ? q0 * dq : dq;
-        r.fac = (qu >= p.q_min && qu <= p.q_max) ? scale * (1.0f - delta * delta) : 0.f;
+        r.fac = (qu >= p.q_min && qu <= p.q_max) ? scale * (1.0f - w.delta * w.delta) : 0.f;
         return r;
     };
     cluster.sync();                                  // vec_s ready (fetch_pre reads q0 / dq from it)
-    Pre pf = fetch_pre(S - 1);
+    Pre pf = finish_pre(issue_pre(S - 1));
 
     PHASE_INIT();
     for (int t = S - 1; t >= 0; --t) {
@@ -878,7 +903,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
         }
         cluster.barrier_wait();   // #4
         PHASE_MARK(1, 6);    // Linear 1 ^T + GRU cell backward
-        pf = fetch_pre(t - 1);    // next step's recurrence-independent inputs: in flight during the products below
+        const PreRaw pf_raw = issue_pre(t - 1);    // next step's recurrence-independent inputs: in flight during the products below
         // ---- dL/dh_{t-1} = z * dh + W_hh^T [drp, dzp, dhn];  dL/dY_t = W_ih[:, :N]^T [drp, dzp, dnp] * d log1p --------
         {
             float acc[2 * kRT] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -892,24 +917,28 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
             dot_rows(acc, x, whhc, min(o0, 2 * kHid), min(o1, 2 * kHid));
             dot_rows(acc, x + kHid * kR, whhc, max(o0, 2 * kHid), max(o1, 2 * kHid));
             const bool mine = u < nu_c;
+            const int n = rank * NU + u;
+            float yv[kRT] = {0.f, 0.f, 0.f, 0.f};       // Y_t of this thread's 4 rows (for d log1p): fetched before the products
+            if (ks == 0 && mine) {
+#pragma unroll
+                for (int i = 0; i < kRT; ++i) {
+                    const int b = b0 + rg * kRT + i;
+                    if (b < p.B) yv[i] = __ldg(p.Y + (((long long)g * p.B + b) * T + t) * N + n);
+                }
+            }
             if (mine) dot_rows(acc + kRT, x, wihc, o0, o1);
             reduce_ks1<2 * kRT>(acc, red_s, ks, slot);
             if (ks == 0) {
 #pragma unroll
                 for (int i = 0; i < kRT; ++i) dh_carry[i] = acc[i] + dh_direct[i];
                 if (mine) {
-                    const int n = rank * NU + u;
                     float dy[kRT];
 #pragma unroll
-                    for (int i = 0; i < kRT; ++i) {
-                        const int b = b0 + rg * kRT + i;
-                        float y = 0.f;
-                        if (b < p.B) y = __ldg(p.Y + (((long long)g * p.B + b) * T + t) * N + n);
-                        dy[i] = y >= 0.0f ? acc[kRT + i] / (1.0f + y) : 0.0f;
-                    }
+                    for (int i = 0; i < kRT; ++i) dy[i] = yv[i] >= 0.0f ? acc[kRT + i] / (1.0f + yv[i]) : 0.0f;
                     store4(cluster.map_shared_rank(dyc_s, rg) + n * kRT, dy);
                 }
             }
+            pf = finish_pre(pf_raw);
         }
         cluster.sync();   // #5: dL/dY_t delivered; gate / dpre buffers free for the next step
         PHASE_MARK(1, 7);    // W_hh^T / W_ih^T products
