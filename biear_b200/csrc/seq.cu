@@ -622,9 +622,8 @@ struct BwdSmem {   // offsets in floats
     __host__ __device__ int dpre() const { return gate() + 4 * kHid * kR; }        // [128][32]; aliased by bufb
     __host__ __device__ int red() const { return dpre() + kHid * kR; }             // (kKS - 1) x 8 x 128
     __host__ __device__ int stat() const { return red() + (kKS - 1) * 8 * 128; }   // 2 x kSeqThreads
-    __host__ __device__ int stage() const { return stat() + 2 * kSeqThreads; }     // [4][128]
-    __host__ __device__ int dyc() const { return stage() + kRT * kHid; }           // [128][4]
-    __host__ __device__ int total() const { return dyc() + kHid * kRT; }
+    __host__ __device__ int pre() const { return stat() + 2 * kSeqThreads; }       // [3][kR][kU]: ext, jac, fac
+    __host__ __device__ int total() const { return pre() + 3 * kR * kU; }
 };
 constexpr int VB_LN1G = 0, VB_LN1B = 128, VB_LN2G = 256, VB_LN2B = 384, VB_Q0 = 512, VB_DQ = 640;   // < 1024
 
@@ -716,8 +715,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
     float* bufb_s = dpre_s;
     float* red_s = smem + L.red();
     float* stat_s = smem + L.stat();
-    float* stage_s = smem + L.stage();
-    float* dyc_s = smem + L.dyc();
+    float* pre_s = smem + L.pre();
     const int tid = threadIdx.x;
     const int ks = tid >> 7, slot = tid & 127, rg = slot / kU, u = slot % kU;
     const int ug = rank * kU + u;
@@ -739,7 +737,6 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
         vec_s[VB_Q0 + i] = i < N ? p.q0[i] : 1.0f;
         vec_s[VB_DQ + i] = i < N ? p.dq[i] : 0.0f;
     }
-    for (int i = tid; i < kHid * kRT; i += kSeqThreads) dyc_s[i] = 0.f;
     float dh_carry[kRT] = {0.f, 0.f, 0.f, 0.f};     // dL/dh_t arriving from step t+1 (owned by the ks == 0 threads)
     static_assert(kRT * kHid <= kSeqThreads, "one (row, band) element of the dL/dpre assembly per thread");
     // Part of dL/dpre_{t} that does not depend on the recurrence, for the element (row i, band n) this thread assembles:
@@ -748,12 +745,12 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
     struct PreRaw { float gy, jac, gp, dp, gq, delta, y, glx; bool live; };
     // issue_pre: only the global loads (so that they are in flight during whatever comes next);
     // finish_pre: the arithmetic, called when the values are needed.
+    static_assert(kR * kU == kSeqThreads, "one (tile row, band of the CTA's slice) element per thread");
+    const int pre_r = tid / kU, pre_u = tid % kU;                 // element this thread fetches: row pre_r, band rank*NU + pre_u
     auto issue_pre = [&](int t) {
         PreRaw r = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, false};
-        if (t < 0 || tid >= kRT * N) return r;
-        const int i = tid / N, n = tid - i * N;
-        if (bb0 + i >= p.B) return r;
-        const long long e = ((grow0 + i) * T + (t + 1)) * N + n;
+        if (t < 0 || pre_u >= nu_c || b0 + pre_r >= p.B) return r;
+        const long long e = ((((long long)g * p.B + b0 + pre_r) * T) + (t + 1)) * N + rank * NU + pre_u;
         r.live = true;
         r.jac = __ldg(p.dYdQ + e);
         if (p.gY) r.gy = __ldg(p.gY + e);
@@ -772,7 +769,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
     auto finish_pre = [&](const PreRaw& w) {
         Pre r = {0.f, 0.f, 0.f};
         if (!w.live) return r;
-        const int n = tid % N;
+        const int n = rank * NU + pre_u;
         float gy = w.gy;
         if (p.gLogY) {   // d clamp(log(Y + 1e-8), +-12) / dY, as autograd derives it (model_torch.py:1080-1083)
             const float ye = w.y + 1e-8f;
@@ -788,37 +785,41 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
         return r;
     };
     cluster.sync();                                  // vec_s ready (fetch_pre reads q0 / dq from it)
-    Pre pf = finish_pre(issue_pre(S - 1));
+    // dL/dpre of step t for (band n of this CTA's slice, rows 4rg..4rg+3), from the pre-fetched recurrence-independent
+    // parts in pre_s and dL/dY_{t+1} through the controller (dyc, zero for the last step): broadcast to every CTA of the
+    // cluster (the next Linear^T contracts over all bands) and saved for dW3.  Returns the values for the deferred store.
+    auto push_dpre = [&](int t, const float dyc[kRT], float (&dp)[kRT]) {
+        const bool flagged_t = p.flags[t * p.G + g] != 0;           // Q_{t+1} was replaced by Q0: no gradient through it
+#pragma unroll
+        for (int i = 0; i < kRT; ++i) {
+            const int r = rg * kRT + i;
+            dp[i] = flagged_t ? 0.f
+                              : (pre_s[r * kU + u] + dyc[i] * pre_s[kR * kU + r * kU + u]) * pre_s[2 * kR * kU + r * kU + u];
+        }
+        broadcast_rows(cluster, dpre_s, rank * NU + u, rg * kRT, dp);
+    };
+    {   // prologue: dL/dpre of the last step (nothing arrives through a later controller step)
+        const Pre pf = finish_pre(issue_pre(S - 1));
+        pre_s[pre_r * kU + pre_u] = pf.ext;
+        pre_s[kR * kU + pre_r * kU + pre_u] = pf.jac;
+        pre_s[2 * kR * kU + pre_r * kU + pre_u] = pf.fac;
+        __syncthreads();
+        if (ks == 0 && u < nu_c) {
+            const float zero[kRT] = {0.f, 0.f, 0.f, 0.f};
+            float dp[kRT];
+            push_dpre(S - 1, zero, dp);
+            store4(p.G_pre + tile_base(p, g, S - 1, tiles, tile) * N * kR + (rank * NU + u) * kR + rg * kRT, dp);
+        }
+        cluster.sync();
+    }
 
     PHASE_INIT();
     for (int t = S - 1; t >= 0; --t) {
         PHASE_MARK(1, 0);
         const bool flagged = p.flags[t * p.G + g] != 0;                    // Q_{t+1} was replaced by Q0, h_t dropped
         const bool h_reset = (t == 0) || (p.flags[(t - 1) * p.G + g] != 0);
-        const bool has_ctrl_next = (t + 1) < S;                              // a controller step consumed Y_{t+1}
         const long long tb = tile_base(p, g, t, tiles, tile);
-
-        // ---- dL/dQ_{t+1} (external + band-stage Jacobians) -> dL/dpre, this CTA's 4 rows ---------
-        // dL/dpre = (ext + dyc * dY/dQ) * fac; ext, dY/dQ and fac were fetched during the previous step (pf)
-        if (tid < kRT * N) {
-            const int i = tid / N, n = tid - i * N;
-            float dpre = 0.f;
-            if (!flagged) dpre = (pf.ext + (has_ctrl_next ? dyc_s[n * kRT + i] : 0.f) * pf.jac) * pf.fac;
-            stage_s[i * kHid + n] = dpre;
-        }
-        __syncthreads();
-        if (tid < N) {
-            const float4 v = make_float4(stage_s[tid], stage_s[kHid + tid], stage_s[2 * kHid + tid], stage_s[3 * kHid + tid]);
-#pragma unroll
-            for (int dst = 0; dst < kCS; ++dst)
-                *reinterpret_cast<float4*>(cluster.map_shared_rank(dpre_s, dst) + tid * kR + rank * kRT) = v;
-        }
-        cluster.barrier_arrive();   // #1 signalled before the saved gradients go out (nobody in the cluster reads them)
-        if (tid < N)
-            *reinterpret_cast<float4*>(p.G_pre + tb * N * kR + tid * kR + rank * kRT) =
-                make_float4(stage_s[tid], stage_s[kHid + tid], stage_s[2 * kHid + tid], stage_s[3 * kHid + tid]);
-        cluster.barrier_wait();     // #1
-        PHASE_MARK(1, 1);    // dL/dpre assembly + push
+        PHASE_MARK(1, 1);    // (dL/dpre of this step was assembled and pushed at the end of the previous one)
 
         // ---- Linear 3 ^T --------------------------------------------------------------------------------------
         const LnSaved ln2 = load_ln_saved(p.xh2 + tb * kHid * kR, p.rstd + tb * 2 * kR, 1);   // used after #2
@@ -927,20 +928,30 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
                 }
             }
             if (mine) dot_rows(acc + kRT, x, wihc, o0, o1);
-            reduce_ks1<2 * kRT>(acc, red_s, ks, slot);
+            // the recurrence-independent parts of the NEXT step's dL/dpre (step t-1) have arrived: publish them CTA-wide
+            if (t > 0) {
+                const Pre pf = finish_pre(pf_raw);
+                pre_s[pre_r * kU + pre_u] = pf.ext;
+                pre_s[kR * kU + pre_r * kU + pre_u] = pf.jac;
+                pre_s[2 * kR * kU + pre_r * kU + pre_u] = pf.fac;
+            }
+            reduce_ks1<2 * kRT>(acc, red_s, ks, slot);   // (its barriers also order the pre_s writes before the reads below)
+            float dp[kRT] = {0.f, 0.f, 0.f, 0.f};
+            const bool fin = ks == 0 && mine && t > 0;
             if (ks == 0) {
 #pragma unroll
                 for (int i = 0; i < kRT; ++i) dh_carry[i] = acc[i] + dh_direct[i];
-                if (mine) {
+                if (fin) {   // dL/dY_t through the controller (d log1p), straight into dL/dpre of step t-1: no exchange needed
                     float dy[kRT];
 #pragma unroll
                     for (int i = 0; i < kRT; ++i) dy[i] = yv[i] >= 0.0f ? acc[kRT + i] / (1.0f + yv[i]) : 0.0f;
-                    store4(cluster.map_shared_rank(dyc_s, rg) + n * kRT, dy);
+                    push_dpre(t - 1, dy, dp);
                 }
             }
-            pf = finish_pre(pf_raw);
+            cluster.barrier_arrive();   // #5: dL/dpre of step t-1 is on its way everywhere; gate buffers free again
+            if (fin) store4(p.G_pre + tile_base(p, g, t - 1, tiles, tile) * N * kR + n * kR + rg * kRT, dp);
         }
-        cluster.sync();   // #5: dL/dY_t delivered; gate / dpre buffers free for the next step
+        cluster.barrier_wait();
         PHASE_MARK(1, 7);    // W_hh^T / W_ih^T products
     }
 }
