@@ -203,8 +203,12 @@ def make_loss(model, up):
         o = model.forward_features(wl, wr, want_phase=True, want_cc=True, want_logenergy=True)
         cc, x1, x2 = o["cc"], o["logYL"], o["logYR"]
         lq = torch.log(0.5 * (o["QL"] + o["QR"]) + 1e-8)                   # train_biear.py:476-490
-        return (up["gYL"] * x1).mean() + (up["gYR"] * x2).mean() \
-            + (up["gPL"] * o["phaseL"]).mean() + (up["gPR"] * o["phaseR"]).mean() + (up["gC"] * cc).mean() \
+        # a random linear functional of every feature stands in for the back-end (it makes all upstream gradients dense
+        # and non-trivial); mean(up * x) written as one dot product per feature ...
+        lin = lambda w, x: torch.dot(w.reshape(-1), x.reshape(-1)) / x.numel()
+        # ... plus the reference's Q regularisers, as train_biear.py:476-490 writes them
+        return lin(up["gYL"], x1) + lin(up["gYR"], x2) + lin(up["gPL"], o["phaseL"]) + lin(up["gPR"], o["phaseR"]) \
+            + lin(up["gC"], cc) \
             + REG_Q_W * ((lq - log_q0) ** 2).mean() + REG_SMOOTH_W * ((lq[..., 1:] - lq[..., :-1]) ** 2).mean()
 
     return loss_fn, params

@@ -915,8 +915,11 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
             // gate_s rows o + 128); rows o of W_ih pair with gate_s rows o (drp, dzp, dnp)
             int o0, o1;
             k_range(3 * kHid, ks, o0, o1);
-            dot_rows(acc, x, whhc, min(o0, 2 * kHid), min(o1, 2 * kHid));
+            // o < 256: both products read gate_s row o (one load); o >= 256: W_hh pairs with row o + 128, W_ih with row o.
+            // (Bands beyond the CTA's slice have zero W_ih columns in the image: computing them is harmless.)
+            dot_rows_pair(acc, acc + kRT, x, whhc, wihc, min(o0, 2 * kHid), min(o1, 2 * kHid));
             dot_rows(acc, x + kHid * kR, whhc, max(o0, 2 * kHid), max(o1, 2 * kHid));
+            dot_rows(acc + kRT, x, wihc, max(o0, 2 * kHid), max(o1, 2 * kHid));
             const bool mine = u < nu_c;
             const int n = rank * NU + u;
             float yv[kRT] = {0.f, 0.f, 0.f, 0.f};       // Y_t of this thread's 4 rows (for d log1p): fetched before the products
@@ -927,7 +930,6 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
                     if (b < p.B) yv[i] = __ldg(p.Y + (((long long)g * p.B + b) * T + t) * N + n);
                 }
             }
-            if (mine) dot_rows(acc + kRT, x, wihc, o0, o1);
             // the recurrence-independent parts of the NEXT step's dL/dpre (step t-1) have arrived: publish them CTA-wide
             if (t > 0) {
                 const Pre pf = finish_pre(pf_raw);

@@ -124,6 +124,28 @@ __device__ __forceinline__ void dot_rows(float acc[kRT], const float* __restrict
     acc[0] = lo.x; acc[1] = lo.y; acc[2] = hi.x; acc[3] = hi.y;
 }
 
+// Two contractions that share the activations (rows k of x_s) but not the weights:
+//   accA[i] += sum_k x_s[k*kR+i] * wa_s[k*kU],   accB[i] += sum_k x_s[k*kR+i] * wb_s[k*kU]        (one x load per k)
+__device__ __forceinline__ void dot_rows_pair(float accA[kRT], float accB[kRT], const float* __restrict__ x_s,
+                                              const float* __restrict__ wa_s, const float* __restrict__ wb_s, int k0, int k1) {
+#ifdef BIEAR_SKIP_DOTS
+    k1 = k0;
+#endif
+    float2 al = make_float2(accA[0], accA[1]), ah = make_float2(accA[2], accA[3]);
+    float2 bl = make_float2(accB[0], accB[1]), bh = make_float2(accB[2], accB[3]);
+#pragma unroll 8
+    for (int k = k0; k < k1; ++k) {
+        const float4 x = *reinterpret_cast<const float4*>(x_s + k * kR);
+        const float2 xl = make_float2(x.x, x.y), xh = make_float2(x.z, x.w);
+        const float wa = wa_s[k * kU], wb = wb_s[k * kU];
+        const float2 pa = make_float2(wa, wa), pb = make_float2(wb, wb);
+        al = __ffma2_rn(pa, xl, al); ah = __ffma2_rn(pa, xh, ah);
+        bl = __ffma2_rn(pb, xl, bl); bh = __ffma2_rn(pb, xh, bh);
+    }
+    accA[0] = al.x; accA[1] = al.y; accA[2] = ah.x; accA[3] = ah.y;
+    accB[0] = bl.x; accB[1] = bl.y; accB[2] = bh.x; accB[3] = bh.y;
+}
+
 // Three gate rows at once: the weights of one k are [gate][kU] (w3_s already offset to the thread's unit).
 __device__ __forceinline__ void dot_rows3(float a0[kRT], float a1[kRT], float a2[kRT], const float* __restrict__ x_s,
                                           const float* __restrict__ w3_s, int k0, int k1) {
