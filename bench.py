@@ -443,9 +443,11 @@ def kernel_roofline(model, dev_in, dev, B):
              "w3": st(lambda m: m.q_out[8].weight), "b3": st(lambda m: m.q_out[8].bias)}
 
         def run_all():
+            keep = []
             for xr in xs:
-                ops.adaptive_sequence(xr, fb.fc, fb.Q0, fb.deltaQ_vec, w, fb.deltaQ_mode == "relative", True, True,
-                                      fb.cutoff, fb.df, seed=1)
+                keep.append(ops.adaptive_sequence(xr, fb.fc, fb.Q0, fb.deltaQ_vec, w, fb.deltaQ_mode == "relative", True,
+                                                  True, fb.cutoff, fb.df, seed=1))
+            return keep
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):

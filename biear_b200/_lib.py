@@ -11,7 +11,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BIEAR_B200_LIB") or os.path.join(_HERE, "lib", "libbiear_b200.so")
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 _p = c_void_p
 _i = c_int
@@ -32,11 +32,11 @@ class SeqParams(Structure):
         + [(n, c_void_p) for n in ("fc", "q0", "dq")]
         + [(n, c_void_p * MAX_CTRL) for n in (
             "w_ih", "w_hh", "b_ih", "b_hh", "w1", "b1", "ln1_g", "ln1_b", "w2", "b2", "ln2_g", "ln2_b", "w3", "b3")]
-        + [(n, c_void_p) for n in (
-            "X", "Y", "phase", "dYdQ", "dPdQ", "Q", "delta",
-            "gates", "xh1", "d1", "xh2", "d2", "rstd", "yc", "H", "flags",
-            "gY", "gP", "gQ",
-            "GG", "G_a1", "G_v1", "G_a2", "G_v2", "G_pre", "workspace", "seed_ptr", "logY", "gLogY")]
+        + [(n, c_void_p) for n in ("X", "Y", "phase", "dYdQ", "dPdQ", "Q", "delta",
+                                   "gates", "xh1", "d1", "xh2", "d2", "rstd", "yc", "H", "flags")]
+        + [(n, c_void_p * MAX_CTRL) for n in ("gY", "gP", "gQ")]
+        + [(n, c_void_p) for n in ("GG", "G_a1", "G_v1", "G_a2", "G_v2", "G_pre", "workspace", "seed_ptr", "logY")]
+        + [("gLogY", c_void_p * MAX_CTRL)]
     )
 
 

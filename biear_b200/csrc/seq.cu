@@ -741,6 +741,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
     static_assert(kRT * kHid <= kSeqThreads, "one (row, band) element of the dL/dpre assembly per thread");
     // Part of dL/dpre_{t} that does not depend on the recurrence, for the element (row i, band n) this thread assembles:
     //   ext = gY dY/dQ + gphase dphase/dQ + gQ,  jac = dY/dQ,  fac = d clamp/dQ * dQ/ddelta * d tanh  (all at frame t+1)
+    const float *gY_g = ctrl_ptr(p.gY, g), *gP_g = ctrl_ptr(p.gP, g), *gQ_g = ctrl_ptr(p.gQ, g), *gLogY_g = ctrl_ptr(p.gLogY, g);
     struct Pre { float ext, jac, fac; };
     struct PreRaw { float gy, jac, gp, dp, gq, delta, y, glx; bool live; };
     // issue_pre: only the global loads (so that they are in flight during whatever comes next);
@@ -750,19 +751,20 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
     auto issue_pre = [&](int t) {
         PreRaw r = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, false};
         if (t < 0 || pre_u >= nu_c || b0 + pre_r >= p.B) return r;
-        const long long e = ((((long long)g * p.B + b0 + pre_r) * T) + (t + 1)) * N + rank * NU + pre_u;
+        const long long el = (((long long)(b0 + pre_r) * T) + (t + 1)) * N + rank * NU + pre_u;   // within this ear's tensors
+        const long long e = el + (long long)g * p.B * T * N;                                        // within the (E*B,T,N) ones
         r.live = true;
         r.jac = __ldg(p.dYdQ + e);
-        if (p.gY) r.gy = __ldg(p.gY + e);
-        if (p.gLogY) {
+        if (gY_g) r.gy = __ldg(gY_g + el);
+        if (gLogY_g) {
             r.y = __ldg(p.Y + e);
-            r.glx = __ldg(p.gLogY + e);
+            r.glx = __ldg(gLogY_g + el);
         }
-        if (p.gP) {
-            r.gp = __ldg(p.gP + e);
+        if (gP_g) {
+            r.gp = __ldg(gP_g + el);
             r.dp = __ldg(p.dPdQ + e);
         }
-        if (p.gQ) r.gq = __ldg(p.gQ + e);
+        if (gQ_g) r.gq = __ldg(gQ_g + el);
         r.delta = __ldg(p.delta + e);
         return r;
     };
@@ -771,7 +773,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
         if (!w.live) return r;
         const int n = rank * NU + pre_u;
         float gy = w.gy;
-        if (p.gLogY) {   // d clamp(log(Y + 1e-8), +-12) / dY, as autograd derives it (model_torch.py:1080-1083)
+        if (gLogY_g) {   // d clamp(log(Y + 1e-8), +-12) / dY, as autograd derives it (model_torch.py:1080-1083)
             const float ye = w.y + 1e-8f;
             const float lx = logf(ye);
             if (lx >= -12.0f && lx <= 12.0f) gy += w.glx / ye;
@@ -981,7 +983,8 @@ static int validate_seq(const BiearSeqParams* p, const char* who, bool backward)
                       "%s: null saved-state pointer", who);
     if (backward) {
         BIEAR_REQUIRE(p->GG && p->G_a1 && p->G_v1 && p->G_a2 && p->G_v2 && p->G_pre, "%s: null backward buffer", who);
-        BIEAR_REQUIRE(!p->gP || p->dPdQ, "%s: gphase given but the forward saved no dphase/dQ", who);
+        for (int g = 0; g < p->G; ++g)
+            BIEAR_REQUIRE(!p->gP[g] || p->dPdQ, "%s: gphase given but the forward saved no dphase/dQ", who);
     } else {
         BIEAR_REQUIRE(p->X, "%s: null spectra", who);
     }

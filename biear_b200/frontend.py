@@ -184,7 +184,8 @@ def _adaptive_chain(x: torch.Tensor, ears: int, ctrl_mods, fc, q0, dq_vec, dq_mo
     x: (ears*B, T, F) complex64, ear-major.  ctrl_mods: G controller-owning modules.
       dual  : ears == G (each ear has its own controller and its own Q)       model_torch.py:314-386
       single: ears == 2, G == 1, shared=True (one Q for both ears, carried Y memory)  model_torch.py:695-776
-    Returns Y (ears*B,T,N), Q (G*B,T,N), phase (ears*B,T,N) or None, logY = clamp(log(Y + 1e-8), +-12) or None.
+    Returns per-ear LISTS of (B,T,N) tensors: Y [ears], Q [G], phase [ears] or None, logY = clamp(log(Y + 1e-8), +-12)
+    [ears] or None.
     """
     rows, T, Fbins = x.shape
     B = rows // ears
@@ -245,7 +246,8 @@ def _adaptive_chain(x: torch.Tensor, ears: int, ctrl_mods, fc, q0, dq_vec, dq_mo
     q_all = torch.stack(qs, dim=1)
     ph_all = torch.stack(phs, dim=1) if want_phase else None
     lx_all = _log_energy(y_all) if want_logy else None
-    return y_all, q_all, ph_all, lx_all
+    split = lambda t, k: [t[i * B:(i + 1) * B] for i in range(k)] if t is not None else None
+    return split(y_all, ears), split(q_all, G), split(ph_all, ears), split(lx_all, ears)
 
 
 def _log_energy(y: torch.Tensor) -> torch.Tensor:
@@ -295,9 +297,9 @@ class FramewiseAdaptiveGammatoneFB(_FilterbankBase):
             y, _ = _fixed_bands(x, self.fc, self.Q0, self.df, False, self.cutoff)
             return y, self.Q0.view(1, 1, -1).expand(x.shape[0], self.timesteps, -1), x
         y, q, _, _ = _adaptive_chain(x, 1, [self], self.fc, self.Q0, self.deltaQ_vec, self.deltaQ_mode, self.df,
-                                  self.training, False, False, self.band_mode, self.cutoff,
-                                  self.engine if ops.fused_supported(self.Nbands, self.n_fft // 2 + 1) else "chain")
-        return y, q, x
+                                     self.training, False, False, self.band_mode, self.cutoff,
+                                     self.engine if ops.fused_supported(self.Nbands, self.n_fft // 2 + 1) else "chain")
+        return y[0], q[0], x
 
 
 class FramewiseFixedGammatoneFB(_FilterbankBase):
@@ -400,6 +402,8 @@ class BinauralAdaptiveGammatoneFB(nn.Module):
             y, ph = _fixed_bands(x, fb.fc, qf, fb.df, want_phase, fb.cutoff)
             q = qf.view(1, 1, -1).expand(2 * B, fb.timesteps, -1)
             lx = _log_energy(y) if want_logenergy else None
+            halves = lambda t: [t[:B], t[B:]] if t is not None else None
+            y, q, ph, lx = halves(y), halves(q), halves(ph), halves(lx)
         else:
             if self.fb_L.freeze_Q != self.fb_R.freeze_Q:
                 raise NotImplementedError("freeze_Q on one ear only")
@@ -407,11 +411,11 @@ class BinauralAdaptiveGammatoneFB(nn.Module):
             y, q, ph, lx = _adaptive_chain(x, 2, [self.fb_L, self.fb_R], fb.fc, fb.Q0, fb.deltaQ_vec, fb.deltaQ_mode,
                                            fb.df, self.training, False, want_phase, fb.band_mode, fb.cutoff, engine,
                                            want_logy=want_logenergy)
-        out = {"YL": y[:B], "YR": y[B:], "QL": q[:B], "QR": q[B:], "XL": x[:B], "XR": x[B:]}
+        out = {"YL": y[0], "YR": y[1], "QL": q[0], "QR": q[1], "XL": x[:B], "XR": x[B:]}     # per-ear lists
         if want_phase:
-            out["phaseL"], out["phaseR"] = ph[:B], ph[B:]
+            out["phaseL"], out["phaseR"] = ph
         if want_logenergy:
-            out["logYL"], out["logYR"] = lx[:B], lx[B:]
+            out["logYL"], out["logYR"] = lx
         if cc is not None:
             cur.wait_stream(side)
             cc.record_stream(cur)
@@ -459,14 +463,16 @@ class BinauralAdaptiveGammatoneFB_SingleController(_FilterbankBase):
             qf = torch.clamp(self.Q0, Q_MIN, Q_MAX) if self.fixed_frontend_q else self.Q0
             y, ph = _fixed_bands(x, self.fc, qf, self.df, want_phase, self.cutoff)
             q = qf.view(1, 1, -1).expand(B, self.timesteps, -1)
+            y, ph = [y[:B], y[B:]], ([ph[:B], ph[B:]] if ph is not None else None)
         else:
             y, q, ph, _ = _adaptive_chain(x, 2, [self], self.fc, self.Q0, self.deltaQ_vec, self.deltaQ_mode, self.df,
                                           self.training, True, want_phase, self.band_mode, self.cutoff)
-        out = {"YL": y[:B], "YR": y[B:], "QL": q, "QR": q, "XL": x[:B], "XR": x[B:]}
+            q = q[0]
+        out = {"YL": y[0], "YR": y[1], "QL": q, "QR": q, "XL": x[:B], "XR": x[B:]}
         if want_phase:
-            out["phaseL"], out["phaseR"] = ph[:B], ph[B:]
+            out["phaseL"], out["phaseR"] = ph
         if want_logenergy:
-            out["logYL"], out["logYR"] = _log_energy(y[:B]), _log_energy(y[B:])
+            out["logYL"], out["logYR"] = _log_energy(y[0]), _log_energy(y[1])
         return out
 
     def forward(self, wavL_1s, wavR_1s):

@@ -358,8 +358,11 @@ class AdaptiveSequence(torch.autograd.Function):
     Inputs : xr (E*B,T,F,2), fc/q0/dq (N), then the 14 weight tensors of every controller, name-major
              (w_ih of controller 0, w_ih of controller 1, w_hh of controller 0, ...): the parameters themselves, no
              stacking copy; the gradients come back in the same order.
-    Outputs: Y (E*B,T,N), Q (G*B,T,N), phase (E*B,T,N) [empty when want_phase is False],
-             logY = clamp(log(Y + 1e-8), +-12) (E*B,T,N) [empty when want_logy is False].
+    Outputs: PER EAR (B,T,N) views of the contiguous (E*B,T,N) result buffers, ear-major:
+             Y_0..Y_{E-1}, Q_0.., phase_0.. [empty when want_phase is False], logY_0.. [clamp(log(Y + 1e-8), +-12);
+             empty when want_logy is False].  Returning the ears as separate outputs means autograd hands the backward
+             the per-ear gradients as they are (the C ABI takes one pointer per ear) instead of scattering them into
+             zero-filled full-size tensors and adding those.
     """
 
     @staticmethod
@@ -410,49 +413,55 @@ class AdaptiveSequence(torch.autograd.Function):
             from ctypes import byref
             _lib.check(lib.biear_adaptive_fwd(byref(prm), _stream(dev)), "biear_adaptive_fwd")
         ctx.prm = prm
-        # owners of every pointer in prm.  The OUTPUTS go through save_for_backward: holding them as plain attributes
-        # would close a reference cycle (ctx -> output tensor -> grad_fn -> ctx) that leaks the whole graph.
-        ctx.keep = (xr, fc, q0, dq, weights, D, dY, dP, sv, flags, work, H, seed_dev)
+        # owners of every pointer in prm (the per-ear outputs are views of Y / Q / P / LX, which are not outputs
+        # themselves, so holding them here closes no reference cycle)
+        ctx.keep = (xr, fc, q0, dq, weights, Y, Q, P, LX, D, dY, dP, sv, flags, work, H, seed_dev)
         ctx.has_phase = P is not None
         ctx.has_logy = LX is not None
         ctx.dims = (G, B, T, N, Kin, tiles, TILE)
-        if P is None:
-            P = Y.new_empty(0)
-            ctx.mark_non_differentiable(P)
-        if LX is None:
-            LX = Y.new_empty(0)
-            ctx.mark_non_differentiable(LX)
-        ctx.save_for_backward(Y, Q, P)
+        empty = Y.new_empty(0)
+        ears = lambda t: tuple(t[e * B:(e + 1) * B] for e in range(G)) if t is not None else tuple(empty for _ in range(G))
+        outs = ears(Y) + ears(Q) + ears(P) + ears(LX)
+        nd = [o for o in outs if o.numel() == 0]
         if not need_grad:
-            ctx.mark_non_differentiable(Y, Q)
-        return Y, Q, P, LX
+            nd = list(outs)
+        if nd:
+            ctx.mark_non_differentiable(*nd)
+        return outs
 
     @staticmethod
-    def backward(ctx, gY, gQ, gP, gLX):
+    def backward(ctx, *grads):
         from ctypes import byref
-        xr, fc, q0, dq, weights, D, dY, dP, sv, flags, work, H, _seed_dev = ctx.keep
-        Y, Q, P = ctx.saved_tensors                  # keeps the buffers behind prm.Y / prm.Q / prm.phase alive
-        if not ctx.has_phase:
-            P = None
+        xr, fc, q0, dq, weights, Y, Q, P, LX, D, dY, dP, sv, flags, work, H, _seed_dev = ctx.keep
         G, B, T, N, Kin, tiles, TILE = ctx.dims
-        none12 = (None,) * 13
-        if T < 2 or (gY is None and gQ is None and gP is None and gLX is None):
-            return none12 + (None,) * (G * len(WEIGHT_NAMES))
+        none13 = (None,) * 13
+        gY, gQ, gP, gLX = (list(grads[i * G:(i + 1) * G]) for i in range(4))
+        if not ctx.has_phase:
+            gP = [None] * G
+        if not ctx.has_logy:
+            gLX = [None] * G
+        if T < 2 or all(g is None for g in gY + gQ + gP + gLX):
+            return none13 + (None,) * (G * len(WEIGHT_NAMES))
         dev = Y.device
         f32 = dict(dtype=torch.float32, device=dev)
         S = T - 1
-        gY = gY.contiguous() if gY is not None else None
-        gQ = gQ.contiguous() if gQ is not None else None
-        gP = gP.contiguous() if (gP is not None and P is not None) else None
-        gLX = gLX.contiguous() if (gLX is not None and ctx.has_logy) else None
+        cont = lambda lst: [g.contiguous() if g is not None else None for g in lst]
+        gY, gQ, gP, gLX = cont(gY), cont(gQ), cont(gP), cont(gLX)
         with torch.cuda.device(dev):
             lib = _prepare(dev)
             wk = {k: torch.empty((G, S, tiles, d, TILE), **f32) for k, d in
                   (("GG", 4 * HID), ("G_a1", HID), ("G_v1", HID), ("G_a2", HID), ("G_v2", HID), ("G_pre", N))}
             prm = ctx.prm
-            _fill(prm, gY=gY, gQ=gQ, gP=gP, gLogY=gLX, **wk)
+            _fill(prm, **wk)
+            for name, lst in (("gY", gY), ("gQ", gQ), ("gP", gP), ("gLogY", gLX)):
+                arr = getattr(prm, name)
+                for g in range(_lib.MAX_CTRL):
+                    arr[g] = lst[g].data_ptr() if (g < G and lst[g] is not None) else None
             _lib.check(lib.biear_adaptive_bwd(byref(prm), _stream(dev)), "biear_adaptive_bwd")
-            _fill(prm, gY=None, gQ=None, gP=None, gLogY=None)
+            for name in ("gY", "gQ", "gP", "gLogY"):
+                arr = getattr(prm, name)
+                for g in range(_lib.MAX_CTRL):
+                    arr[g] = None
 
             # ---- weight gradients: split-K GEMMs over all (step, tile) chunks, off the serial chain ----
             K = S * tiles
@@ -475,16 +484,18 @@ class AdaptiveSequence(torch.autograd.Function):
             d_w_ih = torch.cat([a, 0.2 * a], dim=2) if Kin == 2 * N else None            # feat = [yc, 0.2 yc.detach()]
         stacked = (d_w_ih, d_w_hh, d_b_ih, d_b_hh, d_w1, d_b1, d_g1, d_be1, d_w2, d_b2, d_g2, d_be2, d_w3, d_b3)
         grads = tuple(t[g] if t is not None else None for t in stacked for g in range(G))
-        return none12 + grads
+        return none13 + grads
 
 
 def adaptive_sequence(xr, fc, q0, dq, weights, relative: bool, training: bool, want_phase: bool,
                       cutoff: float, df: float, seed: int = 0, strict: bool = False, want_logy: bool = False):
-    """weights: dict name -> list of the G controllers' tensors (WEIGHT_NAMES).  Returns Y, Q, phase|None[, logY].
+    """weights: dict name -> list of the G controllers' tensors (WEIGHT_NAMES).  Returns Y, Q, phase|None[, logY], each a
+    LIST with one (B,T,N) tensor per ear / controller.
     strict=True skips the fast pass and runs the batch-global-fallback replay pass only (testing)."""
     G = len(weights[WEIGHT_NAMES[0]])
-    y, q, ph, lx = AdaptiveSequence.apply(xr, fc, q0, dq, relative, training, want_phase, cutoff, df, seed, strict,
-                                          want_logy, G, *[w for k in WEIGHT_NAMES for w in weights[k]])
+    outs = AdaptiveSequence.apply(xr, fc, q0, dq, relative, training, want_phase, cutoff, df, seed, strict,
+                                  want_logy, G, *[w for k in WEIGHT_NAMES for w in weights[k]])
+    y, q, ph, lx = (list(outs[i * G:(i + 1) * G]) for i in range(4))
     if want_logy:
         return y, q, (ph if want_phase else None), lx
     return y, q, (ph if want_phase else None)

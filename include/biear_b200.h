@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BIEAR_ABI_VERSION 9
+#define BIEAR_ABI_VERSION 10
 #define BIEAR_EINVAL (-1)
 
 /* ABI version (== BIEAR_ABI_VERSION of the library that was built). */
@@ -141,8 +141,10 @@ typedef struct BiearSeqParams {
     int32_t* flags;                                  /* ((T-1)*G + 1), zero-initialised by the caller: flags[t*G+g] != 0
                                                         <=> the non-finite-Q fallback (model_torch.py:378-380) was
                                                         taken after step t for controller g; last entry: any */
-    /* backward inputs (nullable): dL/dY, dL/dphase (E*B,T,N), dL/dQ (G*B,T,N) */
-    const float *gY, *gP, *gQ;
+    /* backward inputs, ONE POINTER PER EAR / CONTROLLER g (each nullable, each a contiguous (B,T,N) tensor): dL/dY,
+       dL/dphase, dL/dQ.  Separate pointers let a framework hand over the per-ear gradients as they are, without
+       concatenating them first. */
+    const float *gY[BIEAR_MAX_CTRL], *gP[BIEAR_MAX_CTRL], *gQ[BIEAR_MAX_CTRL];
     /* backward outputs, tile layout: dL/d[r_pre, z_pre, n_in_pre, hn] (D = 512); dL/d pre-LN and dL/d LN-output of
        layers 1, 2 (D = 128 each); dL/d(pre-tanh output) (D = N) */
     float *GG, *G_a1, *G_v1, *G_a2, *G_v2, *G_pre;
@@ -152,10 +154,11 @@ typedef struct BiearSeqParams {
        run time, so that a captured CUDA graph draws fresh masks on every replay (the caller advances it on-stream) */
     const uint64_t* seed_ptr;
     /* optional fused log-energy features (model_torch.py:1080-1083): logY = clamp(log(Y + 1e-8), -12, 12), row-major
-       (E*B, T, N), written by the forward band stage when non-NULL; gLogY = dL/dlogY for the backward (nullable): its
-       contribution gLogY / (Y + 1e-8) (zero where the clamp is active) is added to dL/dY inside the kernel */
+       (E*B, T, N), written by the forward band stage when non-NULL; gLogY[g] = dL/dlogY of ear g for the backward
+       ((B,T,N), nullable): its contribution gLogY / (Y + 1e-8) (zero where the clamp is active) is added to dL/dY
+       inside the kernel */
     float* logY;
-    const float* gLogY;
+    const float* gLogY[BIEAR_MAX_CTRL];
 } BiearSeqParams;
 
 /* 1 if the persistent recurrence kernels can take N bands and F bins (their weight slices, activations and spectrum
