@@ -195,21 +195,20 @@ def make_loss(model, up):
     parameters)."""
     from biear_b200 import ops
     params = [p for p in model.parameters() if p.requires_grad]
-    log_q0 = torch.log(model.Q0 + 1e-8).view(1, 1, -1)
+    # a random linear functional of every feature stands in for the back-end (it makes all upstream gradients dense and
+    # non-trivial): mean(up * x) per feature, written as ONE dot product with the 1/numel folded into the fixed weights
+    wts = {k: (v / v.numel()).reshape(-1) for k, v in up.items()}
 
     def loss_fn(wl, wr):
         # one call for everything the back-end consumes: log band energies (model_torch.py:1080-1083, fused into the
         # band stage), sub-band phases, Q, and the CC feature (forked stream)
         o = model.forward_features(wl, wr, want_phase=True, want_cc=True, want_logenergy=True)
-        cc, x1, x2 = o["cc"], o["logYL"], o["logYR"]
-        lq = torch.log(0.5 * (o["QL"] + o["QR"]) + 1e-8)                   # train_biear.py:476-490
-        # a random linear functional of every feature stands in for the back-end (it makes all upstream gradients dense
-        # and non-trivial); mean(up * x) written as one dot product per feature ...
-        lin = lambda w, x: torch.dot(w.reshape(-1), x.reshape(-1)) / x.numel()
-        # ... plus the reference's Q regularisers, as train_biear.py:476-490 writes them
-        return lin(up["gYL"], x1) + lin(up["gYR"], x2) + lin(up["gPL"], o["phaseL"]) + lin(up["gPR"], o["phaseR"]) \
-            + lin(up["gC"], cc) \
-            + REG_Q_W * ((lq - log_q0) ** 2).mean() + REG_SMOOTH_W * ((lq[..., 1:] - lq[..., :-1]) ** 2).mean()
+        lin = lambda k, x: torch.dot(wts[k], x.reshape(-1))
+        # ... plus the reference's Q regularisers on (QL + QR) / 2 (train_biear.py:476-490): value and gradient from one
+        # kernel (biear_q_regularizers)
+        reg = ops.q_regularizers(o["QL"], o["QR"], model.Q0, REG_Q_W, REG_SMOOTH_W)[0]
+        return torch.stack([lin("gYL", o["logYL"]), lin("gYR", o["logYR"]), lin("gPL", o["phaseL"]),
+                            lin("gPR", o["phaseR"]), lin("gC", o["cc"]), reg]).sum()
 
     return loss_fn, params
 

@@ -13,9 +13,9 @@ from .frontend import (AuralNetGammatoneFB, BinauralAdaptiveGammatoneFB,  # noqa
                        BinauralAdaptiveGammatoneFB_SingleController, FramewiseAdaptiveGammatoneFB,
                        FramewiseFixedGammatoneFB)
 from .graph import GraphedStep  # noqa: F401
-from .ops import cc_feature  # noqa: F401
+from .ops import cc_feature, q_regularizers  # noqa: F401
 
 __all__ = [
     "AuralNetGammatoneFB", "BinauralAdaptiveGammatoneFB", "BinauralAdaptiveGammatoneFB_SingleController",
-    "FramewiseAdaptiveGammatoneFB", "FramewiseFixedGammatoneFB", "GraphedStep", "cc_feature",
+    "FramewiseAdaptiveGammatoneFB", "FramewiseFixedGammatoneFB", "GraphedStep", "cc_feature", "q_regularizers",
 ]

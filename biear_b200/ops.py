@@ -286,6 +286,68 @@ def cc_feature(wav_l: torch.Tensor, wav_r: torch.Tensor, fs: float = 16000, num_
 
 
 # ------------------------------------------------------------------------------------------------
+# Q regularisers (train_biear.py:476-490)
+# ------------------------------------------------------------------------------------------------
+_qreg_ws = {}   # device index -> workspace (its counter word zeroed once; the kernel leaves it zero)
+
+
+def _qreg_workspace(dev, lib):
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    ws = _qreg_ws.get(idx)
+    if ws is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("biear_b200: run q_regularizers once eagerly (warm-up) before capturing it in a CUDA graph")
+        ws = torch.zeros(int(lib.biear_q_regularizers_workspace_floats()), dtype=torch.float32, device=dev)
+        _qreg_ws[idx] = ws
+    return ws
+
+
+class QRegularizers(torch.autograd.Function):
+    """loss = w_reg * mean((logQ - logQ0)^2) + w_smooth * mean(diff_band(logQ)^2) on Q = (QL + QR) / 2, value and
+    d loss / dQ from one kernel (biear_q_regularizers); the backward is one scaling by the upstream gradient."""
+
+    @staticmethod
+    def forward(ctx, ql, qr, q0, w_reg, w_smooth):
+        _need_cuda(ql, "QL")
+        _need_cuda(q0, "Q0")
+        if qr is not None:
+            _need_cuda(qr, "QR")
+            if qr.shape != ql.shape:
+                raise ValueError(f"QL {tuple(ql.shape)} and QR {tuple(qr.shape)} differ")
+        N = ql.shape[-1]
+        if q0.numel() != N:
+            raise ValueError(f"Q0 has {q0.numel()} bands, Q has {N}")
+        dev = ql.device
+        need = ql.requires_grad or (qr is not None and qr.requires_grad)
+        with torch.cuda.device(dev):
+            lib = _prepare(dev)
+            ws = _qreg_workspace(dev, lib)
+            out = torch.empty(3, dtype=torch.float32, device=dev)
+            gq = torch.empty_like(ql) if need else None
+            _lib.check(lib.biear_q_regularizers(_ptr(ql), _ptr(qr), _ptr(q0), ql.numel() // N, N, float(w_reg),
+                                                float(w_smooth), _ptr(out), _ptr(gq), _ptr(ws), _stream(dev)),
+                       "biear_q_regularizers")
+        ctx.gq = gq
+        ctx.two = qr is not None
+        loss, reg_q, reg_smooth = out[0], out[1], out[2]
+        ctx.mark_non_differentiable(reg_q, reg_smooth)
+        return loss, reg_q, reg_smooth
+
+    @staticmethod
+    def backward(ctx, g, _g1, _g2):
+        if ctx.gq is None or g is None:
+            return None, None, None, None, None
+        grad = ctx.gq * g
+        return grad, (grad if ctx.two else None), None, None, None
+
+
+def q_regularizers(ql: torch.Tensor, qr: Optional[torch.Tensor], q0: torch.Tensor, w_reg: float, w_smooth: float):
+    """The two Q regularisers of train_biear.py:476-490 on Q = (QL + QR) / 2 (qr None: Q = QL).
+    Returns (w_reg * reg_q + w_smooth * reg_smooth [differentiable], reg_q, reg_smooth) as 0-d tensors."""
+    return QRegularizers.apply(ql, qr, q0, w_reg, w_smooth)
+
+
+# ------------------------------------------------------------------------------------------------
 # fused adaptive recurrence (dual front-end)
 # ------------------------------------------------------------------------------------------------
 WEIGHT_NAMES = ("w_ih", "w_hh", "b_ih", "b_hh", "w1", "b1", "ln1_g", "ln1_b", "w2", "b2", "ln2_g", "ln2_b", "w3", "b3")

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BIEAR_ABI_VERSION 10
+#define BIEAR_ABI_VERSION 11
 #define BIEAR_EINVAL (-1)
 
 /* ABI version (== BIEAR_ABI_VERSION of the library that was built). */
@@ -226,6 +226,20 @@ int biear_ctrl_wgrad(const BiearWgradJob* jobs, int n_jobs, int G, int tile_rows
 int biear_cc_fwd(const float* wavL, const float* wavR, int64_t B, int64_t nsamp, int64_t row_stride,
                  int k_min, int k_max, const int32_t* interp_idx, const float* interp_frac,
                  int num_lags, float* cc, void* stream);
+
+/*
+ * Q regularisers of the training loss, value and gradient in one launch.  Replaces train_biear.py:476-490 on
+ * Q = (QA + QB) / 2 (model.last_Q, model_torch.py:1076-1078; QB == NULL: Q = QA):
+ *   reg_q = mean((log(Q + 1e-8) - log(Q0 + 1e-8))^2) over (rows, N);  reg_smooth = mean of the squared first difference
+ *   of log(Q + 1e-8) along the band axis over (rows, N - 1).
+ *   out[0] = w_reg * reg_q + w_smooth * reg_smooth, out[1] = reg_q, out[2] = reg_smooth.
+ *   gQ (rows, N), nullable: d out[0] / d QA (identical to d out[0] / d QB when QB is given).
+ *   workspace: biear_q_regularizers_workspace_floats() floats whose first 4 bytes the caller zeroes ONCE; the kernel
+ *   leaves them zero again (launches sharing a workspace must be stream-ordered).  Deterministic for given sizes.
+ */
+int64_t biear_q_regularizers_workspace_floats(void);
+int biear_q_regularizers(const float* QA, const float* QB, const float* Q0, int64_t rows, int N, float w_reg,
+                         float w_smooth, float* out, float* gQ, float* workspace, void* stream);
 
 #ifdef __cplusplus
 }

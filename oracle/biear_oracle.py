@@ -343,6 +343,16 @@ def log_energy(y):
     return torch.clamp(torch.log(y + 1e-8), -12.0, 12.0)
 
 
+def q_regularizers(q: torch.Tensor, q0: torch.Tensor):
+    """The two Q regularisers of the training loss (train_biear.py:476-490) on Q = model.last_Q = (QL + QR) / 2
+    (model_torch.py:1076-1078): returns (reg_q, reg_smooth); loss += REG_Q_W * reg_q + REG_SMOOTH_W * reg_smooth."""
+    log_q = torch.log(q + 1e-8)
+    log_q0 = torch.log(q0.view(1, 1, -1) + 1e-8)
+    reg_q = ((log_q - log_q0) ** 2).mean()
+    reg_smooth = ((log_q[:, :, 1:] - log_q[:, :, :-1]) ** 2).mean()
+    return reg_q, reg_smooth
+
+
 def cc_feature(left: np.ndarray, right: np.ndarray, fs=16000, num_lags=100, max_lag_ms=3.0) -> np.ndarray:
     """Broadband interaural cross-correlation cropped to +-max_lag, max-abs normalised, resampled to
     num_lags points by linear interpolation.  float64 arithmetic, float32 result."""

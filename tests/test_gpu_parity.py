@@ -691,3 +691,41 @@ def test_randomised_controller_full_size_against_oracle_rows(bb):
     assert_close(_np(o["YR"])[rows], yr.numpy(), RTOL, "YR rows")
     assert_close(_np(o["QL"])[rows], ql.numpy(), RTOL, "QL rows")
     assert_close(_np(o["QR"])[rows], qr.numpy(), RTOL, "QR rows")
+
+
+@pytest.mark.parametrize("rows_shape,n,two", [((3, 19), 100, True), ((5, 7), 32, False), ((256, 19), 100, True),
+                                              ((2, 19), 2, True), ((4000, 19), 100, True)])
+def test_q_regularizers_against_oracle(bb, rows_shape, n, two):
+    """biear_q_regularizers (value + gradient in one launch) against the oracle's restatement of
+    train_biear.py:476-490 in float64, and against torch autograd of the same formula for the gradient."""
+    from biear_b200 import ops
+    rs = np.random.RandomState(5)
+    q0 = np.exp(rs.uniform(-1.0, 2.0, size=n)).astype(np.float32)
+    ql = np.clip(q0 * (1.0 + 0.8 * rs.uniform(-1, 1, size=rows_shape + (n,))), 0.05, 30.0).astype(np.float32)
+    qr = np.clip(q0 * (1.0 + 0.8 * rs.uniform(-1, 1, size=rows_shape + (n,))), 0.05, 30.0).astype(np.float32)
+    w_reg, w_smooth = 1e-3, 2e-3
+    tl = torch.from_numpy(ql).to(DEV).requires_grad_(True)
+    tr = torch.from_numpy(qr).to(DEV).requires_grad_(True) if two else None
+    t0 = torch.from_numpy(q0).to(DEV)
+    for rep in range(2):                                       # twice: the kernel must leave its counter word reset
+        tl.grad = None
+        if two:
+            tr.grad = None
+        loss, reg_q, reg_smooth = ops.q_regularizers(tl, tr, t0, w_reg, w_smooth)
+        (3.0 * loss).backward()                                # non-trivial upstream gradient
+        dl = torch.from_numpy(ql).double().requires_grad_(True)
+        dr = torch.from_numpy(qr).double().requires_grad_(True)
+        qq = 0.5 * (dl + dr) if two else dl
+        r1, r2 = orc.q_regularizers(qq, torch.from_numpy(q0).double())
+        ref = w_reg * r1 + w_smooth * r2
+        (3.0 * ref).backward()
+        assert abs(float(reg_q) - float(r1)) <= 1e-5 * abs(float(r1))
+        assert abs(float(reg_smooth) - float(r2)) <= 1e-5 * abs(float(r2))
+        assert abs(float(loss) - float(ref)) <= 1e-5 * abs(float(ref))
+        assert_close(_np(tl.grad), dl.grad.numpy(), what="dloss/dQL")
+        assert elem_rel_err(_np(tl.grad), dl.grad.numpy()) <= RTOL
+        if two:
+            assert_close(_np(tr.grad), dr.grad.numpy(), what="dloss/dQR")
+    a = ops.q_regularizers(tl, tr, t0, w_reg, w_smooth)[0]
+    b = ops.q_regularizers(tl, tr, t0, w_reg, w_smooth)[0]
+    assert float(a) == float(b)                                # fixed-order reduction: bitwise repeatable

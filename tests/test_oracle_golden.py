@@ -190,3 +190,20 @@ def test_dq_closed_form_matches_autograd():
     m = orc.band_moments(x, q.detach(), c["fc"], c["f_fft"])
     dq = orc.dq_closed_form(m, q.detach(), c["fc"], gy, gp)
     assert rel_err(dq, q.grad) < 1e-10
+
+
+def test_q_regularizers_known_answer():
+    """train_biear.py:476-490 (the script runs at import and cannot be imported as a module, so this is a known-answer
+    check of the restatement): Q == Q0 gives reg_q = 0 and reg_smooth = mean(diff(log Q0)^2); scaling one band of every
+    row by e adds exactly 1/N to reg_q."""
+    q0 = torch.tensor([1.0, 2.0, 4.0, 8.0], dtype=torch.float64)
+    q = q0.view(1, 1, -1).repeat(3, 5, 1)
+    r1, r2 = orc.q_regularizers(q, q0)
+    assert float(r1) == 0.0
+    assert abs(float(r2) - np.log(2.0) ** 2) < 1e-7
+    q2 = q.clone()
+    q2[:, :, 1] *= np.e
+    r1, r2 = orc.q_regularizers(q2, q0)
+    assert abs(float(r1) - 0.25) < 1e-7
+    d = np.array([np.log(2.0) + 1.0, np.log(2.0) - 1.0, np.log(2.0)])
+    assert abs(float(r2) - np.mean(d ** 2)) < 1e-7
