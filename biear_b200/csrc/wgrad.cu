@@ -41,34 +41,51 @@ struct WgradPlan {
     float* scratch;
 };
 
-__device__ __forceinline__ void wgrad_matrix(const WgradPlan& pl, const WgradJobPlan& a, int tile, int split, int g) {
-    __shared__ __align__(16) float As[2][kWgTile * kWgPitch];
-    __shared__ __align__(16) float Bs[2][kWgTile * kWgPitch];
+template <int TILE_W>
+__device__ __forceinline__ void wgrad_matrix(const WgradPlan& pl, const WgradJobPlan& a, int tile, int split, int g,
+                                             float (*As)[kWgTile * kWgPitch], float (*Bs)[kWgTile * kWgPitch]) {
+    static_assert(TILE_W == 16 || TILE_W == 32, "tile rows");
     const int to = tile / a.tiles_i, ti = tile % a.tiles_i;
     const int o0 = to * kWgTile, i0 = ti * kWgTile;
     const long long c0 = (long long)split * a.slabs_per_split;
     const long long c1 = min(a.slabs, c0 + a.slabs_per_split);
-    const float* Ag = a.A + (long long)g * a.a_group;
-    const float* Bg = a.B + (long long)g * a.b_group;
     const int tid = threadIdx.x;
     const int ty = tid / 16, tx = tid % 16;          // outputs o0 + ty + 16*{0..3}, i0 + tx + 16*{0..3}
     const int lr = tid / 8, lc = tid % 8;            // slab loader: rows lr and lr + 32, float4 column lc
-    const int tile_w = pl.tile_w;
+    // this thread's two rows of each operand inside a slab: operand chunk (lc*4)/TILE_W of the slab, offset (lc*4)%TILE_W
+    constexpr int kPerSlab = 32 / TILE_W;
+    const int sub = (lc * 4) / TILE_W, off = (lc * 4) % TILE_W;
+    const float* ap[2];
+    const float* bp[2];
+    bool aok[2], bok[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int r = lr + 32 * h;
+        aok[h] = o0 + r < a.Do;
+        bok[h] = i0 + r < a.Di;
+        ap[h] = a.A + (long long)g * a.a_group + (long long)(o0 + r) * TILE_W + off;
+        bp[h] = a.B + (long long)g * a.b_group + (long long)(i0 + r) * TILE_W + off;
+    }
 
-    float acc[4][4] = {};
-    float bacc[4] = {0.f, 0.f, 0.f, 0.f};
+    float2 acc[4][4];                                // {even-sample, odd-sample} partial sums of output (y, x)
+#pragma unroll
+    for (int y = 0; y < 4; ++y)
+#pragma unroll
+        for (int x = 0; x < 4; ++x) acc[y][x] = make_float2(0.f, 0.f);
+    // bias (sum of A over the samples): lane l of warp w sums 8 samples of row 8w + l/4 per slab; combined at the end
+    const bool want_bias = a.bpart_off >= 0 && ti == 0;
+    const int brow = (tid >> 5) * 8 + ((tid & 31) >> 2), bcol = (tid & 3) * 8;
+    float bsum = 0.f;
     float4 ra[2], rb[2];
     auto fetch = [&](long long c) {
+        const long long cc = c * kPerSlab + sub;                             // operand chunk of this float4 column
+        const bool live = cc < a.tile_chunks;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const int r = lr + 32 * h;
-            const long long cc = c * (32 / tile_w) + (lc * 4) / tile_w;      // operand chunk of this float4 column
-            const int off = (lc * 4) % tile_w;
-            const bool live = cc < a.tile_chunks;
-            ra[h] = (live && o0 + r < a.Do) ? __ldg(reinterpret_cast<const float4*>(Ag + cc * a.a_chunk + (long long)(o0 + r) * tile_w + off))
-                                            : make_float4(0.f, 0.f, 0.f, 0.f);
-            rb[h] = (live && i0 + r < a.Di) ? __ldg(reinterpret_cast<const float4*>(Bg + cc * a.b_chunk + (long long)(i0 + r) * tile_w + off))
-                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+            ra[h] = (live && aok[h]) ? __ldg(reinterpret_cast<const float4*>(ap[h] + cc * a.a_chunk))
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+            rb[h] = (live && bok[h]) ? __ldg(reinterpret_cast<const float4*>(bp[h] + cc * a.b_chunk))
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     };
     auto stash = [&](int buf) {
@@ -97,17 +114,24 @@ __device__ __forceinline__ void wgrad_matrix(const WgradPlan& pl, const WgradJob
                 av[j] = *reinterpret_cast<const float4*>(as + j * 16 * kWgPitch + r4 * 4);
                 bv[j] = *reinterpret_cast<const float4*>(bs + j * 16 * kWgPitch + r4 * 4);
             }
+            // the two updates of one accumulator are 16 instructions apart (no back-to-back dependent FFMA2)
 #pragma unroll
             for (int y = 0; y < 4; ++y) {
+                const float2 alo = make_float2(av[y].x, av[y].y);
 #pragma unroll
-                for (int x = 0; x < 4; ++x) {
-                    acc[y][x] = fmaf(av[y].x, bv[x].x, acc[y][x]);
-                    acc[y][x] = fmaf(av[y].y, bv[x].y, acc[y][x]);
-                    acc[y][x] = fmaf(av[y].z, bv[x].z, acc[y][x]);
-                    acc[y][x] = fmaf(av[y].w, bv[x].w, acc[y][x]);
-                }
-                if (tx == 0) bacc[y] += (av[y].x + av[y].y) + (av[y].z + av[y].w);
+                for (int x = 0; x < 4; ++x) acc[y][x] = __ffma2_rn(alo, make_float2(bv[x].x, bv[x].y), acc[y][x]);
             }
+#pragma unroll
+            for (int y = 0; y < 4; ++y) {
+                const float2 ahi = make_float2(av[y].z, av[y].w);
+#pragma unroll
+                for (int x = 0; x < 4; ++x) acc[y][x] = __ffma2_rn(ahi, make_float2(bv[x].z, bv[x].w), acc[y][x]);
+            }
+        }
+        if (want_bias) {
+            const float4 u = *reinterpret_cast<const float4*>(&As[buf][brow * kWgPitch + bcol]);
+            const float4 v = *reinterpret_cast<const float4*>(&As[buf][brow * kWgPitch + bcol + 4]);
+            bsum += ((u.x + u.y) + (u.z + u.w)) + ((v.x + v.y) + (v.z + v.w));
         }
         if (c + 1 < c1) stash(buf ^ 1);
         __syncthreads();
@@ -121,10 +145,14 @@ __device__ __forceinline__ void wgrad_matrix(const WgradPlan& pl, const WgradJob
 #pragma unroll
         for (int x = 0; x < 4; ++x) {
             const int i = i0 + tx + 16 * x;
-            if (i < a.Di) out[(long long)o * a.Di + i] = acc[y][x];
+            if (i < a.Di) out[(long long)o * a.Di + i] = acc[y][x].x + acc[y][x].y;
         }
-        if (a.bpart_off >= 0 && tx == 0 && ti == 0)
-            pl.scratch[a.bpart_off + (long long)(g * a.splits + split) * a.Do + o] = bacc[y];
+    }
+    if (want_bias) {
+        bsum += __shfl_xor_sync(0xffffffffu, bsum, 1);
+        bsum += __shfl_xor_sync(0xffffffffu, bsum, 2);
+        if ((tid & 3) == 0 && o0 + brow < a.Do)
+            pl.scratch[a.bpart_off + (long long)(g * a.splits + split) * a.Do + o0 + brow] = bsum;
     }
 }
 
@@ -167,9 +195,14 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_partial_kernel(const WgradPl
     const int g = local / per_g;
     local -= g * per_g;
     const int split = local / a.tiles, tile = local % a.tiles;
-    if (a.Di > 0)
-        wgrad_matrix(pl, a, tile, split, g);
-    else
+    __shared__ __align__(16) float As[2][kWgTile * kWgPitch];
+    __shared__ __align__(16) float Bs[2][kWgTile * kWgPitch];
+    if (a.Di > 0) {
+        if (pl.tile_w == 16)
+            wgrad_matrix<16>(pl, a, tile, split, g, As, Bs);
+        else
+            wgrad_matrix<32>(pl, a, tile, split, g, As, Bs);
+    } else
         wgrad_diagonal(pl, a, split, g);
 }
 
@@ -216,7 +249,7 @@ static int make_plan(const BiearWgradJob* jobs, int n_jobs, int G, int tile_rows
     BIEAR_REQUIRE(G >= 1, "biear_ctrl_wgrad: G=%d", G);
     BIEAR_REQUIRE(tile_rows == 16 || tile_rows == 32, "biear_ctrl_wgrad: tile_rows must be 16 or 32, got %d", tile_rows);
     pl->n_jobs = n_jobs; pl->G = G; pl->tile_w = tile_rows;
-    // tiles of all matrix jobs decide how finely K is split: aim at ~3 CTAs per SM over the whole grid
+    // tiles of all matrix jobs decide how finely K is split
     long long tile_ctas = 0;
     for (int j = 0; j < n_jobs; ++j) {
         const BiearWgradJob& q = jobs[j];
@@ -229,9 +262,11 @@ static int make_plan(const BiearWgradJob* jobs, int n_jobs, int G, int tile_rows
                           (reinterpret_cast<uintptr_t>(q.Bm) & 15) == 0,
                       "biear_ctrl_wgrad: job %d operands must be 16-byte aligned with strides that are multiples of 4 floats", j);
         const int tiles = q.Di > 0 ? ((q.Do + kWgTile - 1) / kWgTile) * ((q.Di + kWgTile - 1) / kWgTile) : 1;
-        tile_ctas += (long long)tiles * G;
+        if (q.Di > 0) tile_ctas += (long long)tiles * G;      // the (short) diagonal CTAs fill in behind
     }
-    long long want = (3LL * kSmCountB200 + tile_ctas - 1) / tile_ctas;
+    // 2 CTAs per SM are resident (124 registers x 256 threads): split K so that the matrix CTAs fill one wave
+    long long want = tile_ctas > 0 ? (2LL * kSmCountB200) / tile_ctas : 1;
+    if (want < 1) want = 1;
     long long off = 0, out = 0;
     int cta = 0;
     for (int j = 0; j < n_jobs; ++j) {
