@@ -11,7 +11,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BIEAR_B200_LIB") or os.path.join(_HERE, "lib", "libbiear_b200.so")
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 _p = c_void_p
 _i = c_int
@@ -37,6 +37,7 @@ class SeqParams(Structure):
         + [(n, c_void_p * MAX_CTRL) for n in ("gY", "gP", "gQ")]
         + [(n, c_void_p) for n in ("GG", "G_a1", "G_v1", "G_a2", "G_v2", "G_pre", "workspace", "seed_ptr", "logY")]
         + [("gLogY", c_void_p * MAX_CTRL)]
+        + [("prepared", c_int32)]
     )
 
 
@@ -63,6 +64,7 @@ SIGNATURES = {
     "biear_band_fixed_workspace_floats": (_l, [_i]),
     "biear_band_fixed_fwd": (_i, [_p, _l, _p, _p, _l, _i, _i, _f, _f, _p, _l, _p, _l, _p, _p]),
     "biear_cc_fwd": (_i, [_p, _p, _l, _l, _l, _i, _i, _p, _p, _i, _p, _p]),
+    "biear_adaptive_prepare": (_i, [POINTER(SeqParams), _p]),
     "biear_adaptive_fwd": (_i, [POINTER(SeqParams), _p]),
     "biear_adaptive_bwd": (_i, [POINTER(SeqParams), _p]),
     "biear_adaptive_workspace_floats": (_l, [_i, _i]),

@@ -55,11 +55,10 @@ static_assert(BIEAR_MAX_CTRL == 2, "ctrl_ptr selects between two controllers");
 // controller g's tensor (a select, not an indexed read: indexing a kernel-parameter array spills it to local memory)
 __device__ __forceinline__ const float* ctrl_ptr(const float* const (&a)[BIEAR_MAX_CTRL], int g) { return g ? a[1] : a[0]; }
 
-__global__ void __launch_bounds__(256) pack_fwd_images_kernel(const BiearSeqParams p, float* __restrict__ img) {
-    const int g = blockIdx.x / kCS, c = blockIdx.x % kCS;
+// image of CTA rank c of controller g for the forward kernel (one slice of kPackSlices per CTA of the packing grid)
+__device__ __forceinline__ void pack_fwd_image(const BiearSeqParams& p, float* __restrict__ out, int g, int c) {
     const int tid0 = blockIdx.y * blockDim.x + threadIdx.x, stride = gridDim.y * blockDim.x;
     const int N = p.N, NU = bands_per_cta(N);
-    float* out = img + (long long)blockIdx.x * fwd_img_floats(N);
     const float* w_ih = ctrl_ptr(p.w_ih, g);
     const float* w_hh = ctrl_ptr(p.w_hh, g);
     const float* w1 = ctrl_ptr(p.w1, g);
@@ -85,11 +84,9 @@ __global__ void __launch_bounds__(256) pack_fwd_images_kernel(const BiearSeqPara
     }
 }
 
-__global__ void __launch_bounds__(256) pack_bwd_images_kernel(const BiearSeqParams p, float* __restrict__ img) {
-    const int g = blockIdx.x / kCS, c = blockIdx.x % kCS;
+__device__ __forceinline__ void pack_bwd_image(const BiearSeqParams& p, float* __restrict__ out, int g, int c) {
     const int tid0 = blockIdx.y * blockDim.x + threadIdx.x, stride = gridDim.y * blockDim.x;
     const int N = p.N, NU = bands_per_cta(N);
-    float* out = img + (long long)blockIdx.x * bwd_img_floats(N);
     const float* w_ih = ctrl_ptr(p.w_ih, g);
     const float* w_hh = ctrl_ptr(p.w_hh, g);
     const float* w1 = ctrl_ptr(p.w1, g);
@@ -107,6 +104,32 @@ __global__ void __launch_bounds__(256) pack_bwd_images_kernel(const BiearSeqPara
         out[bwd_img_whhc(N) + idx] = w_hh[o * kHid + c * kU + u];
         const int n = c * NU + u;
         out[bwd_img_wihc(N) + idx] = (u < NU && n < N) ? w_ih[(long long)o * p.Kin + n] : 0.f;
+    }
+}
+
+// Workspace layout: [G * kCS forward images][G * kCS backward images].
+__host__ __device__ inline long long bwd_images_offset(int G, int N) { return (long long)G * kCS * fwd_img_floats(N); }
+
+// Everything the recurrence needs that does not depend on the spectra, in ONE launch (so that a caller can run it on
+// a forked stream next to the STFT): both sets of weight images, the zero initial GRU state H[:, 0] and the cleared
+// fallback flags.  want: bit 0 forward images + H0 + flags, bit 1 backward images.
+__global__ void __launch_bounds__(256) prepare_kernel(const BiearSeqParams p, float* __restrict__ ws, int want) {
+    const int n_img = p.G * kCS;
+    const int bx = blockIdx.x;
+    if (bx < n_img) {
+        if (want & 1) pack_fwd_image(p, ws + (long long)bx * fwd_img_floats(p.N), bx / kCS, bx % kCS);
+    } else if (bx < 2 * n_img) {
+        const int b = bx - n_img;
+        if (want & 2) pack_bwd_image(p, ws + bwd_images_offset(p.G, p.N) + (long long)b * bwd_img_floats(p.N), b / kCS, b % kCS);
+    } else if (want & 1) {
+        const int tid0 = blockIdx.y * blockDim.x + threadIdx.x, stride = gridDim.y * blockDim.x;
+        const int tiles = (p.B + kR - 1) / kR;
+        const long long per_g = (long long)tiles * kHid * kR / 4;
+        for (int g = 0; g < p.G; ++g) {
+            float4* h0 = reinterpret_cast<float4*>(p.H + (long long)g * p.T * tiles * kHid * kR);
+            for (long long i = tid0; i < per_g; i += stride) h0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        for (int i = tid0; i < (p.T - 1) * p.G + 1; i += stride) p.flags[i] = 0;
     }
 }
 
@@ -1042,8 +1065,28 @@ extern "C" int biear_adaptive_supported(int N, int F) {
 extern "C" int64_t biear_adaptive_workspace_floats(int G, int N) {
     using namespace biear;
     if (G < 1 || N < 1 || N > kHid) return 0;
-    const int per_cta = fwd_img_floats(N) > bwd_img_floats(N) ? fwd_img_floats(N) : bwd_img_floats(N);
-    return (int64_t)G * kCS * per_cta;
+    return (int64_t)G * kCS * (fwd_img_floats(N) + bwd_img_floats(N));
+}
+
+namespace biear {
+static int launch_prepare(const BiearSeqParams* p, int want, cudaStream_t st) {
+    prepare_kernel<<<dim3(2 * p->G * kCS + 1, kPackSlices), 256, 0, st>>>(*p, p->workspace, want);
+    BIEAR_LAUNCH_CHECK("prepare_kernel");
+    return 0;
+}
+}  // namespace biear
+
+extern "C" int biear_adaptive_prepare(const BiearSeqParams* p, void* stream) {
+    using namespace biear;
+    BIEAR_REQUIRE(p != nullptr, "biear_adaptive_prepare: null parameter block");
+    BIEAR_REQUIRE(p->G >= 1 && p->G <= BIEAR_MAX_CTRL && p->B >= 1 && p->T >= 1 && p->N >= 1 && p->N <= kHid &&
+                      p->Kin == 2 * p->N,
+                  "biear_adaptive_prepare: bad geometry G=%d B=%d T=%d N=%d Kin=%d", p->G, p->B, p->T, p->N, p->Kin);
+    for (int g = 0; g < p->G; ++g)
+        BIEAR_REQUIRE(p->w_ih[g] && p->w_hh[g] && p->w1[g] && p->w2[g] && p->w3[g],
+                      "biear_adaptive_prepare: null weight pointer of controller %d", g);
+    BIEAR_REQUIRE(p->workspace && p->H && p->flags, "biear_adaptive_prepare: null workspace / H / flags");
+    return launch_prepare(p, 3, as_stream(stream));
 }
 
 extern "C" int biear_adaptive_fwd(const BiearSeqParams* p, void* stream) {
@@ -1053,8 +1096,8 @@ extern "C" int biear_adaptive_fwd(const BiearSeqParams* p, void* stream) {
     const size_t smem = sizeof(float) * (size_t)FwdSmem(p->N, p->F).total();
     BIEAR_REQUIRE(smem <= 227 * 1024, "biear_adaptive_fwd: N=%d F=%d needs %zu B of shared memory", p->N, p->F, smem);
     const int tiles = (p->B + kR - 1) / kR;
-    pack_fwd_images_kernel<<<dim3(p->G * kCS, kPackSlices), 256, 0, st>>>(*p, p->workspace);
-    BIEAR_LAUNCH_CHECK("pack_fwd_images_kernel");
+    if (!p->prepared)
+        if (int e = launch_prepare(p, 1, st)) return e;
     if (!p->force_strict)
         if (int e = launch_cluster(seq_fwd_kernel<false>, "seq_fwd_kernel", p->G * tiles, smem, st, *p, p->workspace)) return e;
     // replay with batch-global fallback semantics; returns immediately unless a non-finite Q was recorded
@@ -1069,9 +1112,10 @@ extern "C" int biear_adaptive_bwd(const BiearSeqParams* p, void* stream) {
     const size_t smem = sizeof(float) * (size_t)BwdSmem(p->N).total();
     BIEAR_REQUIRE(smem <= 227 * 1024, "biear_adaptive_bwd: N=%d needs %zu B of shared memory", p->N, smem);
     const int tiles = (p->B + kR - 1) / kR;
-    pack_bwd_images_kernel<<<dim3(p->G * kCS, kPackSlices), 256, 0, st>>>(*p, p->workspace);
-    BIEAR_LAUNCH_CHECK("pack_bwd_images_kernel");
-    return launch_cluster(seq_bwd_kernel, "seq_bwd_kernel", p->G * tiles, smem, st, *p, p->workspace);
+    if (!p->prepared)
+        if (int e = launch_prepare(p, 2, st)) return e;
+    return launch_cluster(seq_bwd_kernel, "seq_bwd_kernel", p->G * tiles, smem, st, *p,
+                          p->workspace + bwd_images_offset(p->G, p->N));
 }
 
 // Diagnostics: how many clusters of the persistent kernels can be resident at once on the current device.

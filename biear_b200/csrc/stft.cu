@@ -28,14 +28,12 @@ struct StftArgs {
     long long n_frames;
 };
 
-__global__ void __launch_bounds__(kStftThreads) stft_fwd_kernel(const StftArgs a) {
+__global__ void __launch_bounds__(kStftThreads, 3) stft_fwd_kernel(const StftArgs a) {
     __shared__ float2 s_tw[kNfft];
-    __shared__ float s_win[kNfft];
     __shared__ float2 s_buf[kFramesPerCta][kFftSlots];
 
     for (int i = threadIdx.x; i < kNfft; i += kStftThreads) {
         s_tw[i] = a.tw[i];
-        s_win[i] = i < a.win ? a.win_fn[i] : 0.0f;
     }
 
     const int g = threadIdx.x / kFftThreads;
@@ -70,7 +68,14 @@ __global__ void __launch_bounds__(kStftThreads) stft_fwd_kernel(const StftArgs a
     float2 nxt[8];
     long long base = (long long)blockIdx.x * kFramesPerCta;
     if (base < a.n_frames) fetch(base, nxt);
-    __syncthreads();   // twiddles and window in shared memory
+    // this thread's 16 window taps are the same for every frame it touches: registers, not shared memory
+    float2 wreg[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int i0 = 2 * (j + r * 64);
+        wreg[r] = make_float2(i0 < a.win ? __ldg(a.win_fn + i0) : 0.0f, i0 + 1 < a.win ? __ldg(a.win_fn + i0 + 1) : 0.0f);
+    }
+    __syncthreads();   // twiddles in shared memory
     for (; base < a.n_frames; base += stride) {
         const long long fi = base + g;
         const bool live = fi < a.n_frames;
@@ -78,8 +83,7 @@ __global__ void __launch_bounds__(kStftThreads) stft_fwd_kernel(const StftArgs a
         float2 v[8];
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-            const int i0 = 2 * (j + r * 64);
-            v[r] = make_float2(nxt[r].x * s_win[i0], nxt[r].y * s_win[i0 + 1]);
+            v[r] = make_float2(nxt[r].x * wreg[r].x, nxt[r].y * wreg[r].y);
         }
         if (base + stride < a.n_frames) fetch(base + stride, nxt);
         fft512_butterfly(v, j, 1, s_tw);
@@ -148,8 +152,11 @@ extern "C" int biear_stft_fwd(const float* wav, int64_t rows, int64_t nsamp, int
     a.X = reinterpret_cast<float2*>(X);
     a.n_frames = rows * T;
     const long long ctas_needed = (a.n_frames + kFramesPerCta - 1) / kFramesPerCta;
-    const long long cap = (long long)kSmCountB200 * 4;   // ~2 resident CTAs per SM, each pipelining over its frame groups
-    const int grid = (int)(ctas_needed < cap ? ctas_needed : cap);
+    // 3 resident CTAs per SM (<= 85 registers, 26 KB of shared memory each), every CTA pipelining over the same number of
+    // frame groups: one even wave instead of a ragged one
+    const long long cap = (long long)kSmCountB200 * 3;
+    const long long trips = (ctas_needed + cap - 1) / cap;
+    const int grid = (int)((ctas_needed + trips - 1) / trips);
     stft_fwd_kernel<<<grid, kStftThreads, 0, st>>>(a);
     BIEAR_LAUNCH_CHECK("stft_fwd_kernel");
     return 0;

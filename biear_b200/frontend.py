@@ -176,9 +176,21 @@ def _next_q(delta, q0, dq, mode):
     return torch.clamp(q, Q_MIN, Q_MAX)
 
 
+def _controller_weights(ctrl_mods):
+    """name -> list of the controllers' parameters themselves (the C ABI takes one pointer per controller)."""
+    st = lambda f: [f(m) for m in ctrl_mods]
+    return {"w_ih": st(lambda m: m.q_rnn.weight_ih_l0), "w_hh": st(lambda m: m.q_rnn.weight_hh_l0),
+            "b_ih": st(lambda m: m.q_rnn.bias_ih_l0), "b_hh": st(lambda m: m.q_rnn.bias_hh_l0),
+            "w1": st(lambda m: m.q_out[0].weight), "b1": st(lambda m: m.q_out[0].bias),
+            "ln1_g": st(lambda m: m.q_out[1].weight), "ln1_b": st(lambda m: m.q_out[1].bias),
+            "w2": st(lambda m: m.q_out[4].weight), "b2": st(lambda m: m.q_out[4].bias),
+            "ln2_g": st(lambda m: m.q_out[5].weight), "ln2_b": st(lambda m: m.q_out[5].bias),
+            "w3": st(lambda m: m.q_out[8].weight), "b3": st(lambda m: m.q_out[8].bias)}
+
+
 def _adaptive_chain(x: torch.Tensor, ears: int, ctrl_mods, fc, q0, dq_vec, dq_mode, df, training,
                     shared: bool, want_phase: bool, band_mode: str, cutoff: float, engine: str = "chain",
-                    want_logy: bool = False):
+                    want_logy: bool = False, prep=None):
     """The 19-step Q recurrence for `ears` ears of B clips.
 
     x: (ears*B, T, F) complex64, ear-major.  ctrl_mods: G controller-owning modules.
@@ -195,18 +207,11 @@ def _adaptive_chain(x: torch.Tensor, ears: int, ctrl_mods, fc, q0, dq_vec, dq_mo
     if engine in ("fused", "fused-strict"):
         if shared or G != ears or not ops.fused_supported(N, Fbins):
             raise NotImplementedError("the fused recurrence covers the dual front-end with at most 128 bands")
-        st = lambda f: [f(m) for m in ctrl_mods]      # the parameters themselves: the C ABI takes one pointer per controller
-        w = {"w_ih": st(lambda m: m.q_rnn.weight_ih_l0), "w_hh": st(lambda m: m.q_rnn.weight_hh_l0),
-             "b_ih": st(lambda m: m.q_rnn.bias_ih_l0), "b_hh": st(lambda m: m.q_rnn.bias_hh_l0),
-             "w1": st(lambda m: m.q_out[0].weight), "b1": st(lambda m: m.q_out[0].bias),
-             "ln1_g": st(lambda m: m.q_out[1].weight), "ln1_b": st(lambda m: m.q_out[1].bias),
-             "w2": st(lambda m: m.q_out[4].weight), "b2": st(lambda m: m.q_out[4].bias),
-             "ln2_g": st(lambda m: m.q_out[5].weight), "ln2_b": st(lambda m: m.q_out[5].bias),
-             "w3": st(lambda m: m.q_out[8].weight), "b3": st(lambda m: m.q_out[8].bias)}
+        w = _controller_weights(ctrl_mods)
         # CPU generator: no device sync.  (Under CUDA-graph capture the kernels read a device-side seed instead.)
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if training else 0
         res = ops.adaptive_sequence(xr, fc, q0, dq_vec, w, dq_mode == "relative", training, want_phase, cutoff,
-                                    df, seed, strict=(engine == "fused-strict"), want_logy=want_logy)
+                                    df, seed, strict=(engine == "fused-strict"), want_logy=want_logy, prep=prep)
         return res if want_logy else res + (None,)
     stack = _ControllerStack(ctrl_mods)
     q0g = q0.view(1, 1, N)
@@ -386,17 +391,29 @@ class BinauralAdaptiveGammatoneFB(nn.Module):
         fb = self.fb_L
         if wavL_1s.shape != wavR_1s.shape:
             raise ValueError(f"wavL {tuple(wavL_1s.shape)} and wavR {tuple(wavR_1s.shape)} differ")
+        if not (wavL_1s.is_cuda and wavR_1s.is_cuda):
+            raise RuntimeError(f"biear_b200: waveforms must be CUDA tensors (got {wavL_1s.device}, {wavR_1s.device}); "
+                               "there is no CPU path")
         cc = None
-        if want_cc:
+        prep = None
+        B = wavL_1s.shape[0]
+        frozen = (not self.fixed_frontend_q) and self.fb_L.freeze_Q and self.fb_R.freeze_Q
+        fused = (not self.fixed_frontend_q) and not frozen and self.engine in ("fused", "fused-strict") \
+            and self.fb_L.freeze_Q == self.fb_R.freeze_Q and ops.fused_supported(fb.Nbands, fb.n_fft // 2 + 1)
+        if want_cc or fused:
             cur = torch.cuda.current_stream(wavL_1s.device)
             side = _side_stream(wavL_1s.device)
+        if fused:
+            # the spectra-independent part of the recurrence step (weight images, zero state, flags, dropout seed) runs
+            # on the forked stream next to the STFT
+            prep = ops.adaptive_prepare(_controller_weights([self.fb_L, self.fb_R]), B, fb.timesteps, fb.Nbands,
+                                        self.training, stream=side)
+        if want_cc:
             side.wait_stream(cur)
             with torch.cuda.stream(side):
                 cc = ops.cc_feature(wavL_1s.float().contiguous(), wavR_1s.float().contiguous(), fb.fs, fb.Nbands,
                                     cc_max_lag_ms)
         x = fb._spectra([wavL_1s, wavR_1s])
-        B = wavL_1s.shape[0]
-        frozen = (not self.fixed_frontend_q) and self.fb_L.freeze_Q and self.fb_R.freeze_Q
         if self.fixed_frontend_q or frozen:
             qf = fb.Q0 if frozen else torch.clamp(fb.Q0, Q_MIN, Q_MAX)
             y, ph = _fixed_bands(x, fb.fc, qf, fb.df, want_phase, fb.cutoff)
@@ -410,7 +427,7 @@ class BinauralAdaptiveGammatoneFB(nn.Module):
             engine = self.engine if ops.fused_supported(fb.Nbands, fb.n_fft // 2 + 1) else "chain"
             y, q, ph, lx = _adaptive_chain(x, 2, [self.fb_L, self.fb_R], fb.fc, fb.Q0, fb.deltaQ_vec, fb.deltaQ_mode,
                                            fb.df, self.training, False, want_phase, fb.band_mode, fb.cutoff, engine,
-                                           want_logy=want_logenergy)
+                                           want_logy=want_logenergy, prep=prep if engine == self.engine else None)
         out = {"YL": y[0], "YR": y[1], "QL": q[0], "QR": q[1], "XL": x[:B], "XR": x[B:]}     # per-ear lists
         if want_phase:
             out["phaseL"], out["phaseR"] = ph

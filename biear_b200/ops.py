@@ -411,6 +411,56 @@ def ctrl_wgrad(jobs):
     return outs
 
 
+class PreparedSequence:
+    """What biear_adaptive_prepare leaves behind for one step: the packed weight images (workspace), the GRU state
+    tensor with its zeroed step 0, the cleared fallback flags, the snapshotted dropout seed -- and the event that marks
+    the preparation launch on the stream it ran on."""
+    __slots__ = ("work", "H", "flags", "seed_dev", "event", "stream", "key")
+
+
+def adaptive_prepare(weights, B: int, T: int, N: int, training: bool, stream: Optional[torch.cuda.Stream] = None):
+    """Run the spectra-independent part of a recurrence step (weight-image packing for the forward AND the backward
+    kernel, H[:, 0] = 0, flags = 0, dropout-seed snapshot) as one launch, on `stream` if given: the front-end issues
+    it on a forked stream so that it overlaps the STFT.  Pass the result to adaptive_sequence(prep=...).
+    weights: dict name -> list of the G controllers' tensors."""
+    G = len(weights[WEIGHT_NAMES[0]])
+    ws = [w.detach() for k in WEIGHT_NAMES for w in weights[k]]
+    dev = ws[0].device
+    for i, w in enumerate(ws):
+        _need_cuda(w, WEIGHT_NAMES[i // G])
+    f32 = dict(dtype=torch.float32, device=dev)
+    S = max(T - 1, 1)
+    TILE = tile_rows()
+    tiles = (B + TILE - 1) // TILE
+    cur = torch.cuda.current_stream(dev)
+    run = stream if stream is not None else cur
+    out = PreparedSequence()
+    with torch.cuda.device(dev):
+        lib = _prepare(dev)
+        if stream is not None:
+            stream.wait_stream(cur)                      # the weights (e.g. an optimizer step) are ordered before us
+        with torch.cuda.stream(run):
+            # h_t lives at step index t+1 of H; H[:, 0] = 0 is "h_{-1}", so H[:, :S] are the GRU's previous states
+            out.H = torch.empty((G, S + 1, tiles, HID, TILE), **f32)
+            out.flags = torch.empty((S * G + 1,), dtype=torch.int32, device=dev)
+            out.work = torch.empty(int(lib.biear_adaptive_workspace_floats(G, N)), **f32)
+            out.seed_dev = _captured_seed(dev) if (training and torch.cuda.is_current_stream_capturing()) else None
+            prm = _lib.SeqParams()
+            prm.G, prm.E, prm.B, prm.T, prm.N, prm.F, prm.Kin = G, G, B, T, N, 2, ws[0].shape[1]
+            _fill(prm, workspace=out.work, H=out.H, flags=out.flags)
+            for i, name in enumerate(WEIGHT_NAMES):
+                arr = getattr(prm, name)
+                for g in range(G):
+                    arr[g] = ws[i * G + g].data_ptr()
+            from ctypes import byref
+            _lib.check(lib.biear_adaptive_prepare(byref(prm), c_void_p(run.cuda_stream)), "biear_adaptive_prepare")
+            out.event = torch.cuda.Event()
+            out.event.record(run)
+    out.stream = run
+    out.key = (G, B, T, N, tuple(w.data_ptr() for w in ws))
+    return out
+
+
 class AdaptiveSequence(torch.autograd.Function):
     """The whole 19-frame Q recurrence of the dual front-end as one autograd node.
 
@@ -428,7 +478,7 @@ class AdaptiveSequence(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, xr, fc, q0, dq, relative, training, want_phase, cutoff, df, seed, strict, want_logy, G, *weights):
+    def forward(ctx, xr, fc, q0, dq, relative, training, want_phase, cutoff, df, seed, strict, want_logy, G, prep, *weights):
         ctx.set_materialize_grads(False)
         _need_cuda(xr, "X")
         dev = xr.device
@@ -440,7 +490,7 @@ class AdaptiveSequence(torch.autograd.Function):
         for i, w in enumerate(weights):
             _need_cuda(w, WEIGHT_NAMES[i // G])
         Kin = weights[0].shape[1]
-        need_grad = any(ctx.needs_input_grad[13:])
+        need_grad = any(ctx.needs_input_grad[14:])
         f32 = dict(dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             lib = _prepare(dev)
@@ -454,17 +504,24 @@ class AdaptiveSequence(torch.autograd.Function):
             S = max(T - 1, 1)
             TILE = tile_rows()
             tiles = (B + TILE - 1) // TILE
-            # h_t lives at step index t+1 of H; H[:, 0] = 0 is "h_{-1}", so H[:, :S] are the GRU's previous states
-            H = torch.empty((G, S + 1, tiles, HID, TILE), **f32)
-            H[:, 0].zero_()
+            wdict = {name: list(weights[i * G:(i + 1) * G]) for i, name in enumerate(WEIGHT_NAMES)}
+            if prep is None:
+                prep = adaptive_prepare(wdict, B, T, N, training)
+            elif prep.key != (G, B, T, N, tuple(w.data_ptr() for w in weights)):
+                raise ValueError("biear_b200: adaptive_prepare was called for another geometry / other weights")
+            cur = torch.cuda.current_stream(dev)
+            if prep.stream != cur:                       # prepared on a forked stream: join it here
+                cur.wait_event(prep.event)
+                for t_ in (prep.work, prep.H, prep.flags, prep.seed_dev):
+                    if t_ is not None:
+                        t_.record_stream(cur)
+            H, flags, work, seed_dev = prep.H, prep.flags, prep.work, prep.seed_dev
             sv = {k: torch.empty((G, S, tiles, d, TILE), **f32) for k, d in
                   (("gates", 4 * HID), ("xh1", HID), ("d1", HID), ("xh2", HID), ("d2", HID), ("rstd", 2), ("yc", N))}
-            flags = torch.zeros((S * G + 1,), dtype=torch.int32, device=dev)
-            work = torch.empty(int(lib.biear_adaptive_workspace_floats(G, N)), **f32)
             prm = _lib.SeqParams()
             prm.G, prm.E, prm.B, prm.T, prm.N, prm.F, prm.Kin = G, G, B, T, N, F, Kin
             prm.relative, prm.training, prm.seed, prm.force_strict = int(relative), int(training), int(seed), int(strict)
-            seed_dev = _captured_seed(dev) if (training and torch.cuda.is_current_stream_capturing()) else None
+            prm.prepared = 1
             prm.df, prm.cutoff, prm.q_min, prm.q_max = float(df), float(cutoff), 0.05, 30.0
             _fill(prm, fc=fc, q0=q0, dq=dq, X=xr, Y=Y, phase=P, dYdQ=dY, dPdQ=dP, Q=Q, delta=D, flags=flags,
                   workspace=work, H=H, seed_ptr=seed_dev, logY=LX, **sv)
@@ -496,7 +553,7 @@ class AdaptiveSequence(torch.autograd.Function):
         from ctypes import byref
         xr, fc, q0, dq, weights, Y, Q, P, LX, D, dY, dP, sv, flags, work, H, _seed_dev = ctx.keep
         G, B, T, N, Kin, tiles, TILE = ctx.dims
-        none13 = (None,) * 13
+        none13 = (None,) * 14
         gY, gQ, gP, gLX = (list(grads[i * G:(i + 1) * G]) for i in range(4))
         if not ctx.has_phase:
             gP = [None] * G
@@ -550,13 +607,15 @@ class AdaptiveSequence(torch.autograd.Function):
 
 
 def adaptive_sequence(xr, fc, q0, dq, weights, relative: bool, training: bool, want_phase: bool,
-                      cutoff: float, df: float, seed: int = 0, strict: bool = False, want_logy: bool = False):
+                      cutoff: float, df: float, seed: int = 0, strict: bool = False, want_logy: bool = False,
+                      prep: Optional[PreparedSequence] = None):
     """weights: dict name -> list of the G controllers' tensors (WEIGHT_NAMES).  Returns Y, Q, phase|None[, logY], each a
     LIST with one (B,T,N) tensor per ear / controller.
-    strict=True skips the fast pass and runs the batch-global-fallback replay pass only (testing)."""
+    strict=True skips the fast pass and runs the batch-global-fallback replay pass only (testing).
+    prep: result of adaptive_prepare (same weights / geometry) issued earlier, typically on a forked stream."""
     G = len(weights[WEIGHT_NAMES[0]])
     outs = AdaptiveSequence.apply(xr, fc, q0, dq, relative, training, want_phase, cutoff, df, seed, strict,
-                                  want_logy, G, *[w for k in WEIGHT_NAMES for w in weights[k]])
+                                  want_logy, G, prep, *[w for k in WEIGHT_NAMES for w in weights[k]])
     y, q, ph, lx = (list(outs[i * G:(i + 1) * G]) for i in range(4))
     if want_logy:
         return y, q, (ph if want_phase else None), lx

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BIEAR_ABI_VERSION 11
+#define BIEAR_ABI_VERSION 12
 #define BIEAR_EINVAL (-1)
 
 /* ABI version (== BIEAR_ABI_VERSION of the library that was built). */
@@ -135,10 +135,10 @@ typedef struct BiearSeqParams {
     float *Q, *delta;                                /* (G*B, T, N): Q used for frame t; tanh output that produced it */
     /* saved by the forward for the backward, tile layout, D = 512 (r,z,n,hn), 128 x4, 2, N */
     float *gates, *xh1, *d1, *xh2, *d2, *rstd, *yc;
-    /* GRU states (G, T, tiles, 128, R): step index 0 is h_{-1} = 0 and must be zeroed by the caller, h_t is written
+    /* GRU states (G, T, tiles, 128, R): step index 0 is h_{-1} = 0 (zeroed by the preparation launch), h_t is written
        at step index t+1 -- so H[:, :T-1] are the "previous states" and H[:, 1:] the "new states" of the T-1 steps */
     float* H;
-    int32_t* flags;                                  /* ((T-1)*G + 1), zero-initialised by the caller: flags[t*G+g] != 0
+    int32_t* flags;                                  /* ((T-1)*G + 1), cleared by the preparation launch: flags[t*G+g] != 0
                                                         <=> the non-finite-Q fallback (model_torch.py:378-380) was
                                                         taken after step t for controller g; last entry: any */
     /* backward inputs, ONE POINTER PER EAR / CONTROLLER g (each nullable, each a contiguous (B,T,N) tensor): dL/dY,
@@ -148,7 +148,8 @@ typedef struct BiearSeqParams {
     /* backward outputs, tile layout: dL/d[r_pre, z_pre, n_in_pre, hn] (D = 512); dL/d pre-LN and dL/d LN-output of
        layers 1, 2 (D = 128 each); dL/d(pre-tanh output) (D = N) */
     float *GG, *G_a1, *G_v1, *G_a2, *G_v2, *G_pre;
-    /* scratch: biear_adaptive_workspace_floats(G, N) floats (packed per-CTA weight images) */
+    /* scratch: biear_adaptive_workspace_floats(G, N) floats (packed per-CTA weight images, forward then backward);
+       must stay untouched between the forward and the backward of one step */
     float* workspace;
     /* optional DEVICE location of the dropout seed; when non-NULL it overrides `seed` and is read by the kernels at
        run time, so that a captured CUDA graph draws fresh masks on every replay (the caller advances it on-stream) */
@@ -159,6 +160,9 @@ typedef struct BiearSeqParams {
        inside the kernel */
     float* logY;
     const float* gLogY[BIEAR_MAX_CTRL];
+    /* non-zero: biear_adaptive_prepare has already run on this block's workspace / H / flags (stream-ordered before
+       the forward), so biear_adaptive_fwd / _bwd skip their own preparation launch */
+    int32_t prepared;
 } BiearSeqParams;
 
 /* 1 if the persistent recurrence kernels can take N bands and F bins (their weight slices, activations and spectrum
@@ -166,8 +170,14 @@ typedef struct BiearSeqParams {
 int biear_adaptive_supported(int N, int F);
 /* Rows per tile (R) of the tile-layout tensors. */
 int biear_adaptive_tile_rows(void);
-/* Floats of scratch the two calls below need in BiearSeqParams.workspace. */
+/* Floats of scratch the calls below need in BiearSeqParams.workspace. */
 int64_t biear_adaptive_workspace_floats(int G, int N);
+/* Everything of a step that does not depend on the spectra, in ONE launch: the per-CTA weight images of the forward
+ * and the backward kernel (from the controllers' nn.GRU / nn.Linear parameters), H[:, 0] = 0, flags = 0.  Needs only
+ * the geometry, the weight pointers, workspace, H and flags of the block.  Optional: a caller that runs it on a forked
+ * stream next to the STFT sets `prepared` = 1 afterwards; with `prepared` == 0 the forward / backward do the same work
+ * themselves on their own stream. */
+int biear_adaptive_prepare(const BiearSeqParams* p, void* stream);
 
 /* Diagnostics: number of clusters of the forward / backward recurrence kernels that fit on the current device
  * at once (cudaOccupancyMaxActiveClusters); a batch needs G * ceil(B / R) clusters per pass. */

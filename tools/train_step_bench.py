@@ -49,26 +49,49 @@ def loss_fn(a, b):
     l_sound = F.binary_cross_entropy_with_logits(sound, pres, pos_weight=pos_w)
     l_aoa = (F.smooth_l1_loss(aoa, y[..., 1], beta=0.02, reduction="none") * pres).sum() / pres.sum().clamp_min(1.0)
     l_dist = (F.cross_entropy(dl.reshape(-1, 5), dist_cls.reshape(-1), reduction="none") * pres.reshape(-1)).sum() / pres.sum().clamp_min(1.0)
-    lq = torch.log(model.last_Q + 1e-8)
-    return 0.2 * l_sound + 0.45 * l_aoa + 0.35 * l_dist + 1e-3 * ((lq - log_q0) ** 2).mean() \
-        + 1e-3 * ((lq[..., 1:] - lq[..., :-1]) ** 2).mean()
+    reg = ops.q_regularizers(model.last_QL, model.last_QR, model.bifb.Q0, 1e-3, 1e-3)[0]      # train_biear.py:476-490
+    return 0.2 * l_sound + 0.45 * l_aoa + 0.35 * l_dist + reg
 
 model._assert_finite = lambda tensors: None      # the finiteness read-back is a host sync: not capturable (checked eagerly below)
 step = GraphedStep(loss_fn, (wl, wr), params, warmup=3, flat_grads=world > 1)
 red = FlatGradAllReducer(params, flat=step.flat) if world > 1 else None
 
-def full_step():
-    loss = step(wl, wr)
-    if red is not None:
-        red()
+def update():
     torch.nn.utils.clip_grad_norm_(fb_params, 0.2, foreach=True)
     torch.nn.utils.clip_grad_norm_(be_params, 3.0, foreach=True)
     opt.step()
+
+EAGER_UPDATE = os.environ.get("BIEAR_EAGER_UPDATE") == "1"
+update_graph = None
+
+def full_step():
+    loss = step(wl, wr)
+    if red is not None:
+        red()                      # one flat-bucket NCCL all-reduce between the two graphs
+    if update_graph is None:
+        update()
+    else:
+        update_graph.replay()
     return loss
 
 for _ in range(5):
     full_step()
 torch.cuda.synchronize()
+if not EAGER_UPDATE:
+    # the two global-norm clips + Adam (capturable) as a second CUDA graph over the static gradient tensors: ~300 tiny
+    # foreach launches that are host-bound when issued eagerly
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        update()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize()
+    update_graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(update_graph, pool=step.pool()):
+        update()
+    for _ in range(3):
+        full_step()
+    torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(steps):
@@ -82,7 +105,8 @@ for _ in range(steps):
 g1.record(); torch.cuda.synchronize()
 if rank == 0:
     print(f"full active training step, batch {B} x {world} GPU(s): {ms:.3f} ms/step = {B * world / ms * 1e3:.0f} audio-s/s "
-          f"(graph replay fwd+bwd alone {g0.elapsed_time(g1) / steps:.3f} ms; loss {float(loss):.4f}; "
+          f"(graph replay fwd+bwd alone {g0.elapsed_time(g1) / steps:.3f} ms; clips + Adam "
+          f"{'eager' if update_graph is None else 'as a second graph'}; loss {float(loss):.4f}; "
           f"{step.launches_per_replay} launches of ours per step)")
 if dist is not None:
     dist.destroy_process_group()
