@@ -11,7 +11,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BIEAR_B200_LIB") or os.path.join(_HERE, "lib", "libbiear_b200.so")
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 _p = c_void_p
 _i = c_int
@@ -63,6 +63,8 @@ SIGNATURES = {
     "biear_band_bwd": (_i, [_p, _l, _p, _l, _p, _l, _i, _i, _f, _f, _p, _l, _p, _l, _p, _l, _i, _p]),
     "biear_band_fixed_workspace_floats": (_l, [_i]),
     "biear_band_fixed_fwd": (_i, [_p, _l, _p, _p, _l, _i, _i, _f, _f, _p, _l, _p, _l, _p, _p]),
+    "biear_band_fixed_tc_workspace_floats": (_l, [_i]),
+    "biear_band_fixed_fwd_tc": (_i, [_p, _l, _p, _p, _l, _i, _i, _f, _f, _p, _l, _p, _l, _p, _p]),
     "biear_cc_fwd": (_i, [_p, _p, _l, _l, _l, _i, _i, _p, _p, _i, _p, _p]),
     "biear_adaptive_prepare": (_i, [POINTER(SeqParams), _p]),
     "biear_adaptive_fwd": (_i, [POINTER(SeqParams), _p]),

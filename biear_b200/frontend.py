@@ -391,6 +391,8 @@ class BinauralAdaptiveGammatoneFB(nn.Module):
         fb = self.fb_L
         if wavL_1s.shape != wavR_1s.shape:
             raise ValueError(f"wavL {tuple(wavL_1s.shape)} and wavR {tuple(wavR_1s.shape)} differ")
+        if wavL_1s.dim() != 2:
+            raise ValueError(f"Expected wav_1s (B,N), got {tuple(wavL_1s.shape)}")
         if not (wavL_1s.is_cuda and wavR_1s.is_cuda):
             raise RuntimeError(f"biear_b200: waveforms must be CUDA tensors (got {wavL_1s.device}, {wavR_1s.device}); "
                                "there is no CPU path")

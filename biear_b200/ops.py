@@ -6,6 +6,7 @@ no fallback path.
 """
 from __future__ import annotations
 
+import os
 from ctypes import c_void_p
 from functools import lru_cache
 from typing import Optional, Tuple
@@ -133,9 +134,13 @@ def band_forward(xr: torch.Tensor, t: Optional[int], q: torch.Tensor, fc: torch.
     return y, ph, dy, dp
 
 
+FIXED_VARIANT = os.environ.get("BIEAR_FIXED_VARIANT", "tc")   # "tc": tcgen05 / TMEM 3xTF32 GEMM (csrc/band_fixed_tc.cu); "ffma": fp32 FFMA2 GEMM (csrc/band_fixed.cu).
+                       # Picked by measured throughput (profiles/): the tensor-core variant wins at every batch size.
+
+
 def band_fixed_forward(xr: torch.Tensor, q: torch.Tensor, fc: torch.Tensor, df: float,
-                       cutoff: float = DEFAULT_CUTOFF, want_phase: bool = True):
-    """Fixed-Q band stage for ALL (row, frame) items as one dense contraction (biear_band_fixed_fwd).
+                       cutoff: float = DEFAULT_CUTOFF, want_phase: bool = True, variant: Optional[str] = None):
+    """Fixed-Q band stage for ALL (row, frame) items as one dense contraction (biear_band_fixed_fwd[_tc]).
     xr (rows, T, F, 2), q (N,) shared by every item -> Y (rows, T, N), phase (rows, T, N) | None."""
     _need_cuda(xr, "X")
     _need_cuda(q, "Q")
@@ -144,14 +149,24 @@ def band_fixed_forward(xr: torch.Tensor, q: torch.Tensor, fc: torch.Tensor, df: 
     N = fc.numel()
     if q.shape != (N,):
         raise ValueError(f"Q must be ({N},), got {tuple(q.shape)}")
+    variant = variant or FIXED_VARIANT
+    if variant not in ("tc", "ffma"):
+        raise ValueError(f"unknown fixed-Q variant {variant!r}")
     dev = xr.device
     with torch.cuda.device(dev):
         lib = _prepare(dev)
         y = torch.empty((rows, T, N), dtype=torch.float32, device=dev)
         ph = torch.empty((rows, T, N), dtype=torch.float32, device=dev) if want_phase else None
-        work = torch.empty(int(lib.biear_band_fixed_workspace_floats(F)), dtype=torch.float32, device=dev)
-        _lib.check(lib.biear_band_fixed_fwd(_ptr(xr), 2 * F, _ptr(q), _ptr(fc), rows * T, N, F, float(df), float(cutoff),
-                                            _ptr(y), N, _ptr(ph), N, _ptr(work), _stream(dev)), "biear_band_fixed_fwd")
+        if variant == "tc":
+            work = torch.empty(int(lib.biear_band_fixed_tc_workspace_floats(F)), dtype=torch.float32, device=dev)
+            _lib.check(lib.biear_band_fixed_fwd_tc(_ptr(xr), 2 * F, _ptr(q), _ptr(fc), rows * T, N, F, float(df),
+                                                   float(cutoff), _ptr(y), N, _ptr(ph), N, _ptr(work), _stream(dev)),
+                       "biear_band_fixed_fwd_tc")
+        else:
+            work = torch.empty(int(lib.biear_band_fixed_workspace_floats(F)), dtype=torch.float32, device=dev)
+            _lib.check(lib.biear_band_fixed_fwd(_ptr(xr), 2 * F, _ptr(q), _ptr(fc), rows * T, N, F, float(df),
+                                                float(cutoff), _ptr(y), N, _ptr(ph), N, _ptr(work), _stream(dev)),
+                       "biear_band_fixed_fwd")
     return y, ph
 
 

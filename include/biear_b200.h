@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BIEAR_ABI_VERSION 12
+#define BIEAR_ABI_VERSION 13
 #define BIEAR_EINVAL (-1)
 
 /* ABI version (== BIEAR_ABI_VERSION of the library that was built). */
@@ -88,6 +88,13 @@ int64_t biear_band_fixed_workspace_floats(int F);
 int biear_band_fixed_fwd(const float* X, int64_t x_stride, const float* Q, const float* fc, int64_t items, int N, int F,
                          float df, float cutoff, float* Y, int64_t y_stride, float* phase, int64_t phase_stride,
                          float* workspace, void* stream);
+/* The same contraction on the tcgen05 tensor cores: three 128 x 128 fp32 accumulators in TMEM, TF32 operands with the
+ * 3-way hi/lo split (fp32-accurate: the 1e-4 contract holds), A tiles built on the fly from X, B tiles by bulk async
+ * copy.  Same arguments; workspace: biear_band_fixed_tc_workspace_floats(F) floats, 16-byte aligned. */
+int64_t biear_band_fixed_tc_workspace_floats(int F);
+int biear_band_fixed_fwd_tc(const float* X, int64_t x_stride, const float* Q, const float* fc, int64_t items, int N, int F,
+                            float df, float cutoff, float* Y, int64_t y_stride, float* phase, int64_t phase_stride,
+                            float* workspace, void* stream);
 
 /*
  * Backward of biear_band_fwd into Q by recomputation (nothing saved by the forward):
