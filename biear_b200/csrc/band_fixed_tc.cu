@@ -40,6 +40,13 @@ __host__ __device__ constexpr int tc_tile_off(int r, int kk) {
     return (kk >> 2) * (kTcLBO / 4) + (r >> 3) * (kTcSBO / 4) + (r & 7) * 4 + (kk & 3);
 }
 
+// sqrt.approx: <= 1 ulp-level error (2^-23 relative), a fraction of the instructions of the IEEE sqrtf sequence
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
 // W^T image: for k-block kb, part p (0 hi, 1 lo): tile at ((kb * 2 + p) * kTcTileBytes / 4) floats.
@@ -167,7 +174,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) band_fixed_tc_kernel(const Fixe
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool want_phase = a.phase != nullptr;
     const int planes = want_phase ? 3 : 1;
+#ifdef BIEAR_TC_ONE_KB               // (timing experiments only)
+    const int nkb = 1;
+#else
     const int nkb = tc_kblocks(a.F);
+#endif
     const long long m0 = (long long)blockIdx.x * kTcM;
 
     if (tid == 0) {
@@ -210,14 +221,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) band_fixed_tc_kernel(const Fixe
             mbar_wait(bar_empty + 8 * s, ph ^ 1);              // the MMAs that read this stage have completed
             unsigned char* stage = smem + s * kTcStageBytes;
             if (tid == 0) {                                     // B operand of this k-block: one 16 KB bulk copy
+#ifdef BIEAR_TC_SKIP_BCOPY           // (timing experiments only)
+                mbar_arrive(bar_full + 8 * s);
+            }
+            if (false) {
+#endif
                 mbar_arrive_expect_tx(bar_full + 8 * s, kTcBBytes);
                 bulk_g2s(smem_base + s * kTcStageBytes + kTcABytes, a.Wimg + (long long)kb * (kTcBBytes / 4), kTcBBytes,
                          bar_full + 8 * s);
             }
+#ifndef BIEAR_TC_SKIP_PRODUCER     // (timing experiments only)
             float v[3][8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                v[0][i] = sqrtf(fmaf(x[i].x, x[i].x, x[i].y * x[i].y));
+                v[0][i] = sqrt_approx(fmaf(x[i].x, x[i].x, x[i].y * x[i].y));
                 v[1][i] = x[i].x;
                 v[2][i] = x[i].y;
             }
@@ -239,6 +256,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) band_fixed_tc_kernel(const Fixe
                     *reinterpret_cast<float4*>(t_lo) = make_float4(lo[0], lo[1], lo[2], lo[3]);
                 }
             }
+#endif
             fence_proxy_async();                                // generic-proxy stores -> visible to the tensor core
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_full + 8 * s);
@@ -249,6 +267,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) band_fixed_tc_kernel(const Fixe
         const int q = warp & 3, colh = warp >> 2;               // TMEM lane quarter (rows 32q..32q+31), band half
         const long long me = m0 + 32 * q + lane;
         const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16);
+        const bool vec_ok = ((a.y_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.Y) & 15) == 0) &&
+                            (!want_phase || (((a.p_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.phase) & 15) == 0)));
 #pragma unroll 1
         for (int cb = 0; cb < 4; ++cb) {
             const int n0 = colh * 64 + cb * 16;
@@ -260,11 +280,39 @@ __global__ void __launch_bounds__(kTcThreads, 1) band_fixed_tc_kernel(const Fixe
                 tc_ld16(trow + 2 * kTcN + n0, zi);
             }
             if (me < a.items) {
+                float ph[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    if (n0 + j >= a.N) break;
-                    a.Y[me * a.y_stride + n0 + j] = sanitize(y[j]);
-                    if (want_phase) a.phase[me * a.p_stride + n0 + j] = atan2f(zi[j], zr[j]);
+                    y[j] = sanitize(y[j]);
+                    ph[j] = want_phase ? atan2f(zi[j], zr[j]) : 0.f;
+                }
+                float* yrow = a.Y + me * a.y_stride + n0;
+                float* prow = want_phase ? a.phase + me * a.p_stride + n0 : nullptr;
+                if (vec_ok) {       // 128-bit stores: 4 instead of 16 store instructions per 16 bands and plane
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        if (n0 + j + 3 < a.N) {
+                            *reinterpret_cast<float4*>(yrow + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+                            if (want_phase)
+                                *reinterpret_cast<float4*>(prow + j) = make_float4(ph[j], ph[j + 1], ph[j + 2], ph[j + 3]);
+                        } else {
+#pragma unroll
+                            for (int i = j; i < j + 4; ++i) {
+                                if (n0 + i < a.N) {
+                                    yrow[i] = y[i];
+                                    if (want_phase) prow[i] = ph[i];
+                                }
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (n0 + j < a.N) {
+                            yrow[j] = y[j];
+                            if (want_phase) prow[j] = ph[j];
+                        }
+                    }
                 }
             }
         }
@@ -288,9 +336,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) band_fixed_tc_kernel(const Fixe
                         const uint64_t a_hi = tc_smem_desc(sa + (2 * pl) * kTcTileBytes + koff);
                         const uint64_t a_lo = tc_smem_desc(sa + (2 * pl + 1) * kTcTileBytes + koff);
                         const uint32_t d = tmem + pl * kTcN;
+#ifndef BIEAR_TC_SKIP_MMA          // (timing experiments only)
                         tc_mma_tf32(d, a_lo, b_hi, idesc, (kb | j) != 0);   // small terms first
                         tc_mma_tf32(d, a_hi, b_lo, idesc, 1u);
                         tc_mma_tf32(d, a_hi, b_hi, idesc, 1u);
+#endif
                     }
                 }
                 tc_commit(bar_empty + 8 * s);                   // stage free once these MMAs have read it

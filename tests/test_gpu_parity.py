@@ -729,3 +729,31 @@ def test_q_regularizers_against_oracle(bb, rows_shape, n, two):
     a = ops.q_regularizers(tl, tr, t0, w_reg, w_smooth)[0]
     b = ops.q_regularizers(tl, tr, t0, w_reg, w_smooth)[0]
     assert float(a) == float(b)                                # fixed-order reduction: bitwise repeatable
+
+
+@pytest.mark.parametrize("variant", ["tc", "ffma"])
+@pytest.mark.parametrize("rows,n_bands,want_phase", [(1, 100, True), (7, 100, True), (14, 100, False), (27, 64, True),
+                                                      (3, 128, True), (60, 32, True)])
+def test_band_fixed_variants_against_float64(bb, variant, rows, n_bands, want_phase):
+    """Both fixed-Q contractions (tcgen05 3xTF32 in TMEM, fp32 FFMA2) against the float64 contraction with the oracle's
+    weights on random tilted spectra; item counts straddle the 128-item tile of the tensor-core kernel."""
+    from biear_b200 import ops
+    cfg = orc.FrontEndConfig(n_bands=n_bands)
+    c = orc.constants(cfg, dtype=torch.float64)
+    g = torch.Generator().manual_seed(100 * rows + n_bands)
+    x = torch.randn((rows, 19, 513, 2), generator=g) * torch.linspace(3.0, 0.2, 513).view(1, 1, -1, 1)
+    q = torch.clamp(c["Q0"] * (1.0 + 0.5 * torch.rand(n_bands, generator=g, dtype=torch.float64)), orc.Q_MIN, orc.Q_MAX)
+    y, ph = ops.band_fixed_forward(x.to(DEV).contiguous(), q.float().to(DEV), c["fc"].float().to(DEV),
+                                   float(cfg.fs / 2 / 512), 6.0, want_phase, variant=variant)
+    w = orc.band_weights(q.float().double().view(1, -1), c["fc"].float().double(), c["f_fft"], sanitize=True)[0]
+    xc = torch.view_as_complex(x.double().contiguous()).reshape(-1, 513)
+    y64 = (xc.abs() @ w.T).reshape(rows, 19, n_bands).numpy()
+    assert_close(_np(y), y64, 1e-5, f"fixed-Q Y ({variant})")
+    assert elem_rel_err(_np(y), y64) <= RTOL
+    if want_phase:
+        z64 = (xc @ w.T.to(torch.complex128)).reshape(rows, 19, n_bands)
+        wgt = (z64.abs() / z64.abs().max()).numpy()
+        d = np.abs(_np(ph) - torch.atan2(z64.imag, z64.real).numpy()) % (2 * np.pi)
+        assert float((np.minimum(d, 2 * np.pi - d) * wgt).max()) <= 2e-6
+    else:
+        assert ph is None
