@@ -642,7 +642,9 @@ def test_properties_full_size(bb):
         finally:
             frontend.FIXED_ENGINE = "gemm"
         dph = (oi["phaseL"] - og["phaseL"]).abs()
-        assert float(torch.minimum(dph, 2 * np.pi - dph).median()) <= 1e-5     # same phases up to fp32 conditioning
+        # same phases up to fp32 conditioning (the tensor-core GEMM's 3xTF32 products and truncating fp32 accumulation
+        # are ~4x the rounding error of the FFMA form: 2e-6 instead of 5e-7 on Y)
+        assert float(torch.minimum(dph, 2 * np.pi - dph).median()) <= 5e-5
         # (2) a 10 s input gives the result of its first second (section 4 item 5)
         y10 = fixed(torch.cat([tl, tl.flip(1)], 1), torch.cat([tr, tr], 1))[0]
         assert torch.equal(y10, yf)
