@@ -11,7 +11,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BIEAR_B200_LIB") or os.path.join(_HERE, "lib", "libbiear_b200.so")
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 _p = c_void_p
 _i = c_int
@@ -76,6 +76,8 @@ SIGNATURES = {
     "biear_adaptive_supported": (_i, [_i, _i]),
     "biear_wgrad_scratch_floats": (_l, [POINTER(WgradJob), _i, _i, _i]),
     "biear_ctrl_wgrad": (_i, [POINTER(WgradJob), _i, _i, _i, _p, _p]),
+    "biear_wgrad_scratch_floats_tc": (_l, [POINTER(WgradJob), _i, _i, _i]),
+    "biear_ctrl_wgrad_tc": (_i, [POINTER(WgradJob), _i, _i, _i, _p, _p]),
     "biear_q_regularizers_workspace_floats": (_l, []),
     "biear_q_regularizers": (_i, [_p, _p, _p, _l, _i, _f, _f, _p, _p, _p, _p]),
 }

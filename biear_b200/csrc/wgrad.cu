@@ -12,6 +12,7 @@
 // Replaces what autograd + cuBLAS do for the weight gradients of model_torch.py:256-267 (GRU weight_ih / weight_hh,
 // three Linear layers, two LayerNorms) in the reference: ~30 library launches per ear there.
 #include "common.cuh"
+#include "tc_dev.cuh"
 
 namespace biear {
 
@@ -26,6 +27,7 @@ struct WgradJobPlan {
     long long tile_chunks;                                    // operand chunks (of tile_w samples)
     long long slabs;                                          // 32-sample slabs
     int tiles_i, tiles, splits; long long slabs_per_split;
+    long long diag_chunks_per_split;                          // diagonal jobs: operand chunks per split
     int cta_begin;                                            // first CTA of this job in the partial grid
     long long part_off, bpart_off;                            // offsets into scratch (floats); bpart_off < 0: no bias
     long long out_begin;                                      // first element of this job in the reduce index space
@@ -162,7 +164,7 @@ __device__ __forceinline__ void wgrad_diagonal(const WgradPlan& pl, const WgradJ
     const int tile_w = pl.tile_w;
     const int f = threadIdx.x >> 1, half = threadIdx.x & 1;
     const int per = tile_w / 2;
-    const long long per_split = a.slabs_per_split * (32 / tile_w);     // in operand chunks
+    const long long per_split = a.diag_chunks_per_split;               // in operand chunks
     const long long c0 = (long long)split * per_split;
     const long long c1 = min(a.tile_chunks, c0 + per_split);
     float dot = 0.f, sum = 0.f;
@@ -206,6 +208,180 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_partial_kernel(const WgradPl
         wgrad_diagonal(pl, a, split, g);
 }
 
+// ==================================================================================================
+// tensor-core variant (tcgen05 + TMEM, 3xTF32 split: fp32-accurate)
+// ==================================================================================================
+// One CTA = one 128 x Di output tile of one (job, controller, K split).  Warps 0-7 stream the two operands' 16-sample
+// slabs (both are K-major: [feature][sample]) from HBM/L2, split every value x = hi + lo and store the four TF32 tiles
+// {A.hi, A.lo, B.hi, B.lo} in the UMMA core-matrix layout (tc_dev.cuh); warp 8 issues six tcgen05.mma per slab
+// (lo*hi, hi*lo, hi*hi for each of the two K = 8 steps) into one 128 x 128 fp32 accumulator in TMEM; a 4-stage mbarrier
+// ring decouples them.  The bias sums (sum over the samples of A) are accumulated by the producers on the way.
+constexpr int kWtStages = 4;
+constexpr int kWtProducerWarps = 8;
+constexpr int kWtThreads = (kWtProducerWarps + 1) * 32;
+constexpr int kWtStageBytes = 4 * kTcTileBytes;                   // 32 KB
+constexpr int kWtSmemBytes = kWtStages * kWtStageBytes + 1024;    // + barriers / TMEM pointer (and alignment slack)
+
+__device__ __forceinline__ void wgrad_matrix_tc(const WgradPlan& pl, const WgradJobPlan& a, int tile, int split, int g) {
+    extern __shared__ __align__(128) unsigned char wt_smem_raw[];
+    const uint32_t smem_base = (smem_u32(wt_smem_raw) + 127u) & ~127u;
+    unsigned char* smem = wt_smem_raw + (smem_base - smem_u32(wt_smem_raw));
+    const uint32_t bars = smem_base + kWtStages * kWtStageBytes;
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * kWtStages, bar_acc = bars + 16 * kWtStages;
+    volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + kWtStages * kWtStageBytes + 16 * kWtStages + 8);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int o0 = tile * kTcRows;
+    const int tile_w = pl.tile_w, per = tile_w / kTcKB;           // 16-sample slabs per operand chunk
+    const long long c0 = (long long)split * a.slabs_per_split;
+    const long long c1 = min(a.slabs, c0 + a.slabs_per_split);
+    const int n_slabs = (int)(c1 - c0);
+    const bool want_bias = a.bpart_off >= 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < kWtStages; ++s) {
+            mbar_init(bar_full + 8 * s, kWtProducerWarps);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        mbar_init(bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kWtProducerWarps) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_ptr_s)),
+                     "r"(128u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_ptr_s;
+
+    if (warp < kWtProducerWarps) {
+        const int r = tid & (kTcRows - 1), half = tid >> 7;       // operand row; samples 8*half .. 8*half+7 of the slab
+        const bool a_ok = o0 + r < a.Do, b_ok = r < a.Di;
+        const float* ap = a.A + (long long)g * a.a_group + (long long)(o0 + r) * tile_w + half * 8;
+        const float* bp = a.B + (long long)g * a.b_group + (long long)r * tile_w + half * 8;
+        float4 xa[2], xb[2];
+        auto fetch = [&](long long q) {
+            const long long cc = q / per;
+            const int sub = (int)(q % per) * kTcKB;
+            const bool live = cc < a.tile_chunks;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                xa[c] = (live && a_ok) ? __ldg(reinterpret_cast<const float4*>(ap + cc * a.a_chunk + sub) + c)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+                xb[c] = (live && b_ok) ? __ldg(reinterpret_cast<const float4*>(bp + cc * a.b_chunk + sub) + c)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        float bsum = 0.f;
+        if (n_slabs > 0) fetch(c0);
+        for (int i = 0; i < n_slabs; ++i) {
+            const int s = i % kWtStages;
+            const uint32_t ph = (i / kWtStages) & 1;
+            mbar_wait(bar_empty + 8 * s, ph ^ 1);
+            float* stage = reinterpret_cast<float*>(smem + s * kWtStageBytes);
+            float4 va[2] = {xa[0], xa[1]}, vb[2] = {xb[0], xb[1]};
+            if (i + 1 < n_slabs) fetch(c0 + i + 1);               // next slab's loads in flight behind the stores
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int off = tc_tile_off(r, half * 8 + c * 4);
+                const float4 ah = make_float4(tf32_hi(va[c].x), tf32_hi(va[c].y), tf32_hi(va[c].z), tf32_hi(va[c].w));
+                const float4 bh = make_float4(tf32_hi(vb[c].x), tf32_hi(vb[c].y), tf32_hi(vb[c].z), tf32_hi(vb[c].w));
+                *reinterpret_cast<float4*>(stage + off) = ah;
+                *reinterpret_cast<float4*>(stage + kTcTileBytes / 4 + off) =
+                    make_float4(va[c].x - ah.x, va[c].y - ah.y, va[c].z - ah.z, va[c].w - ah.w);
+                *reinterpret_cast<float4*>(stage + 2 * (kTcTileBytes / 4) + off) = bh;
+                *reinterpret_cast<float4*>(stage + 3 * (kTcTileBytes / 4) + off) =
+                    make_float4(vb[c].x - bh.x, vb[c].y - bh.y, vb[c].z - bh.z, vb[c].w - bh.w);
+                bsum += (va[c].x + va[c].y) + (va[c].z + va[c].w);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_full + 8 * s);
+        }
+        // ---- epilogue: TMEM -> registers -> split-K partials ----
+        if (n_slabs > 0) {
+            mbar_wait(bar_acc, 0);
+            tc_fence_after();
+        }
+        float* out = pl.scratch + a.part_off + ((long long)(g * a.splits + split) * a.Do) * a.Di;
+        const int q4 = warp & 3, colh = warp >> 2;
+        const int o = o0 + 32 * q4 + lane;
+        const uint32_t trow = tmem + ((uint32_t)(32 * q4) << 16);
+#pragma unroll 1
+        for (int cb = 0; cb < 4; ++cb) {
+            const int n0 = colh * 64 + cb * 16;
+            if (n0 >= a.Di) break;                                // warp-uniform
+            float v[16];
+            if (n_slabs > 0) {
+                tc_ld16(trow + n0, v);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = 0.f;
+            }
+            if (o < a.Do) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    if (n0 + j < a.Di)                            // Di is a multiple of 4
+                        *reinterpret_cast<float4*>(out + (long long)o * a.Di + n0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+        }
+        if (want_bias) {                                          // the two sample halves of a row, through shared memory
+            float* bias_s = reinterpret_cast<float*>(smem);       // stage 0 is free: every MMA has completed
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            bias_s[tid] = bsum;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (half == 0 && a_ok)
+                pl.scratch[a.bpart_off + (long long)(g * a.splits + split) * a.Do + o0 + r] = bias_s[r] + bias_s[r + kTcRows];
+        }
+    } else {
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcRows >> 3) << 17) | ((uint32_t)(kTcRows >> 4) << 24);
+        for (int i = 0; i < n_slabs; ++i) {
+            const int s = i % kWtStages;
+            const uint32_t ph = (i / kWtStages) & 1;
+            mbar_wait(bar_full + 8 * s, ph);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t sa = smem_base + s * kWtStageBytes;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const uint32_t koff = j * 2 * kTcLBO;
+                    const uint64_t a_hi = tc_smem_desc(sa + koff), a_lo = tc_smem_desc(sa + kTcTileBytes + koff);
+                    const uint64_t b_hi = tc_smem_desc(sa + 2 * kTcTileBytes + koff), b_lo = tc_smem_desc(sa + 3 * kTcTileBytes + koff);
+                    tc_mma_tf32(tmem, a_lo, b_hi, idesc, (i | j) != 0);
+                    tc_mma_tf32(tmem, a_hi, b_lo, idesc, 1u);
+                    tc_mma_tf32(tmem, a_hi, b_hi, idesc, 1u);
+                }
+                tc_commit(bar_empty + 8 * s);
+                if (i == n_slabs - 1) tc_commit(bar_acc);
+            }
+            __syncwarp();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kWtProducerWarps)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u) : "memory");
+}
+
+__global__ void __launch_bounds__(kWtThreads, 1) wgrad_tc_kernel(const WgradPlan pl) {
+    int j = 0;
+    while (j + 1 < pl.n_jobs && (int)blockIdx.x >= pl.job[j + 1].cta_begin) ++j;
+    const WgradJobPlan& a = pl.job[j];
+    int local = blockIdx.x - a.cta_begin;
+    const int per_g = a.tiles * a.splits;
+    const int g = local / per_g;
+    local -= g * per_g;
+    const int split = local / a.tiles, tile = local % a.tiles;
+    if (a.Di > 0) {
+        wgrad_matrix_tc(pl, a, tile, split, g);
+    } else if (threadIdx.x < kWgThreads) {      // whole warps 0-7: the diagonal form is plain FFMA
+        wgrad_diagonal(pl, a, split, g);
+    }
+}
+
 // One pass over every output of every job: sum the split-K partials in a fixed order.
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgradPlan pl) {
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < pl.total_out;
@@ -244,7 +420,12 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgradPlan pl) {
     }
 }
 
-static int make_plan(const BiearWgradJob* jobs, int n_jobs, int G, int tile_rows, WgradPlan* pl, long long* scratch_floats) {
+// tc == false: 64 x 64 output tiles, 32-sample slabs, 2 resident CTAs per SM (FFMA kernel)
+// tc == true : 128 x Di output tiles (Di <= 128), 16-sample slabs, 1 CTA per SM (tcgen05 kernel)
+static int make_plan(const BiearWgradJob* jobs, int n_jobs, int G, int tile_rows, WgradPlan* pl, long long* scratch_floats,
+                     bool tc = false) {
+    const int tile_o = tc ? kTcRows : kWgTile;
+    const int slab = tc ? kTcKB : 32;
     BIEAR_REQUIRE(jobs && n_jobs >= 1 && n_jobs <= kWgMaxJobs, "biear_ctrl_wgrad: need 1..%d jobs, got %d", kWgMaxJobs, n_jobs);
     BIEAR_REQUIRE(G >= 1, "biear_ctrl_wgrad: G=%d", G);
     BIEAR_REQUIRE(tile_rows == 16 || tile_rows == 32, "biear_ctrl_wgrad: tile_rows must be 16 or 32, got %d", tile_rows);
@@ -261,11 +442,13 @@ static int make_plan(const BiearWgradJob* jobs, int n_jobs, int G, int tile_rows
                           (q.b_group_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(q.A) & 15) == 0 &&
                           (reinterpret_cast<uintptr_t>(q.Bm) & 15) == 0,
                       "biear_ctrl_wgrad: job %d operands must be 16-byte aligned with strides that are multiples of 4 floats", j);
-        const int tiles = q.Di > 0 ? ((q.Do + kWgTile - 1) / kWgTile) * ((q.Di + kWgTile - 1) / kWgTile) : 1;
+        BIEAR_REQUIRE(!tc || (q.Di <= kTcRows && (q.Di & 3) == 0),
+                      "biear_ctrl_wgrad_tc: job %d needs Di <= %d and a multiple of 4, got %d", j, kTcRows, q.Di);
+        const int tiles = q.Di > 0 ? ((q.Do + tile_o - 1) / tile_o) * (tc ? 1 : (q.Di + kWgTile - 1) / kWgTile) : 1;
         if (q.Di > 0) tile_ctas += (long long)tiles * G;      // the (short) diagonal CTAs fill in behind
     }
     // 2 CTAs per SM are resident (124 registers x 256 threads): split K so that the matrix CTAs fill one wave
-    long long want = tile_ctas > 0 ? (2LL * kSmCountB200) / tile_ctas : 1;
+    long long want = tile_ctas > 0 ? ((tc ? 1LL : 2LL) * kSmCountB200) / tile_ctas : 1;
     if (want < 1) want = 1;
     long long off = 0, out = 0;
     int cta = 0;
@@ -275,23 +458,24 @@ static int make_plan(const BiearWgradJob* jobs, int n_jobs, int G, int tile_rows
         a.A = q.A; a.a_group = q.a_group_stride; a.a_chunk = q.a_chunk_stride; a.Do = q.Do;
         a.B = q.Bm; a.b_group = q.b_group_stride; a.b_chunk = q.b_chunk_stride; a.Di = q.Di;
         a.tile_chunks = q.chunks;
-        a.slabs = (q.chunks * tile_rows + 31) / 32;
-        a.tiles_i = q.Di > 0 ? (q.Di + kWgTile - 1) / kWgTile : 1;
-        a.tiles = q.Di > 0 ? ((q.Do + kWgTile - 1) / kWgTile) * a.tiles_i : 1;
+        a.slabs = (q.chunks * tile_rows + slab - 1) / slab;
+        a.tiles_i = (q.Di > 0 && !tc) ? (q.Di + kWgTile - 1) / kWgTile : 1;
+        a.tiles = q.Di > 0 ? ((q.Do + tile_o - 1) / tile_o) * a.tiles_i : 1;
         long long s = q.Di > 0 ? want : 4 * want;
         if (s > a.slabs) s = a.slabs;
         if (s < 1) s = 1;
         a.slabs_per_split = (a.slabs + s - 1) / s;
         a.splits = (int)((a.slabs + a.slabs_per_split - 1) / a.slabs_per_split);
+        a.diag_chunks_per_split = (a.slabs_per_split * slab + tile_rows - 1) / tile_rows;
         a.cta_begin = cta;
         cta += a.tiles * a.splits * G;
         const long long per_w = (long long)q.Do * (q.Di > 0 ? q.Di : 1);
         a.part_off = off;
-        off += (long long)G * a.splits * per_w;
+        off += ((long long)G * a.splits * per_w + 3) & ~3LL;      // every region starts 16-byte aligned
         a.bpart_off = -1;
         if (q.db) {
             a.bpart_off = off;
-            off += (long long)G * a.splits * q.Do;
+            off += ((long long)G * a.splits * q.Do + 3) & ~3LL;
         }
         a.out_begin = out;
         out += (long long)G * (per_w + (q.db ? q.Do : 0));
@@ -326,6 +510,39 @@ extern "C" int biear_ctrl_wgrad(const BiearWgradJob* jobs, int n_jobs, int G, in
     cudaStream_t st = as_stream(stream);
     wgrad_partial_kernel<<<pl.total_ctas, kWgThreads, 0, st>>>(pl);
     BIEAR_LAUNCH_CHECK("wgrad_partial_kernel");
+    const int blocks = (int)((pl.total_out + 255) / 256);
+    wgrad_reduce_kernel<<<blocks < 4 * kSmCountB200 ? blocks : 4 * kSmCountB200, 256, 0, st>>>(pl);
+    BIEAR_LAUNCH_CHECK("wgrad_reduce_kernel");
+    return 0;
+}
+
+extern "C" int64_t biear_wgrad_scratch_floats_tc(const BiearWgradJob* jobs, int n_jobs, int G, int tile_rows) {
+    using namespace biear;
+    WgradPlan pl;
+    long long n = 0;
+    if (make_plan(jobs, n_jobs, G, tile_rows, &pl, &n, true)) return -1;
+    return n;
+}
+
+extern "C" int biear_ctrl_wgrad_tc(const BiearWgradJob* jobs, int n_jobs, int G, int tile_rows, float* scratch, void* stream) {
+    using namespace biear;
+    WgradPlan pl;
+    long long n = 0;
+    if (int e = make_plan(jobs, n_jobs, G, tile_rows, &pl, &n, true)) return e;
+    BIEAR_REQUIRE(scratch && (reinterpret_cast<uintptr_t>(scratch) & 15) == 0, "biear_ctrl_wgrad_tc: scratch must be 16-byte aligned");
+    pl.scratch = scratch;
+    cudaStream_t st = as_stream(stream);
+    static bool configured[64] = {false};
+    int dev = 0;
+    if (int e = check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return e;
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+        if (int e = check_cuda(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWtSmemBytes),
+                               "cudaFuncSetAttribute(wgrad_tc_kernel)"))
+            return e;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+    wgrad_tc_kernel<<<pl.total_ctas, kWtThreads, kWtSmemBytes, st>>>(pl);
+    BIEAR_LAUNCH_CHECK("wgrad_tc_kernel");
     const int blocks = (int)((pl.total_out + 255) / 256);
     wgrad_reduce_kernel<<<blocks < 4 * kSmCountB200 ? blocks : 4 * kSmCountB200, 256, 0, st>>>(pl);
     BIEAR_LAUNCH_CHECK("wgrad_reduce_kernel");

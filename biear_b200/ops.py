@@ -384,8 +384,11 @@ def tile_rows() -> int:
     return int(_lib.load().biear_adaptive_tile_rows())
 
 
-def ctrl_wgrad(jobs):
-    """Weight gradients for a list of jobs in two launches (biear_ctrl_wgrad).
+WGRAD_VARIANT = os.environ.get("BIEAR_WGRAD_VARIANT", "tc")   # "tc": tcgen05 / TMEM 3xTF32 (wgrad_tc_kernel); "ffma": fp32 FFMA2
+
+
+def ctrl_wgrad(jobs, variant: Optional[str] = None):
+    """Weight gradients for a list of jobs in two launches (biear_ctrl_wgrad[_tc]).
 
     A job is (a, do, bm, di, chunks, bias[, dw_out, db_out]).  a (G, chunks', Da, R) and bm (G, chunks', Db, R) are
     tile-layout operands (views with arbitrary group / chunk strides are fine); the first `do` / `di` features and the
@@ -418,11 +421,16 @@ def ctrl_wgrad(jobs):
         q.dw_group_stride = dw.stride(0)
         q.dw_row_stride = dw.stride(1) if di > 0 else 1
         q.db_group_stride = db.stride(0) if db is not None else 0
-    n = int(lib.biear_wgrad_scratch_floats(arr, len(jobs), G, R))
+    variant = variant or WGRAD_VARIANT
+    if variant == "tc" and any(job[3] > 128 or job[3] % 4 for job in jobs):
+        variant = "ffma"                      # wider / odd inputs: the FFMA kernel takes any shape
+    sizer, runner = ((lib.biear_wgrad_scratch_floats_tc, lib.biear_ctrl_wgrad_tc) if variant == "tc"
+                     else (lib.biear_wgrad_scratch_floats, lib.biear_ctrl_wgrad))
+    n = int(sizer(arr, len(jobs), G, R))
     if n < 0:
         _lib.check(-1, "biear_wgrad_scratch_floats")
-    scratch = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
-    _lib.check(lib.biear_ctrl_wgrad(arr, len(jobs), G, R, _ptr(scratch), _stream(dev)), "biear_ctrl_wgrad")
+    scratch = torch.empty(max(n, 4), dtype=torch.float32, device=dev)
+    _lib.check(runner(arr, len(jobs), G, R, _ptr(scratch), _stream(dev)), "biear_ctrl_wgrad")
     return outs
 
 

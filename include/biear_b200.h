@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BIEAR_ABI_VERSION 13
+#define BIEAR_ABI_VERSION 14
 #define BIEAR_EINVAL (-1)
 
 /* ABI version (== BIEAR_ABI_VERSION of the library that was built). */
@@ -230,6 +230,11 @@ typedef struct BiearWgradJob {
 /* Floats of scratch biear_ctrl_wgrad needs for these jobs (-1 on invalid arguments). */
 int64_t biear_wgrad_scratch_floats(const BiearWgradJob* jobs, int n_jobs, int G, int tile_rows);
 int biear_ctrl_wgrad(const BiearWgradJob* jobs, int n_jobs, int G, int tile_rows, float* scratch, void* stream);
+/* The same jobs on the tcgen05 tensor cores (128 x Di output tiles accumulated in TMEM, TF32 operands with the 3-way
+ * hi/lo split: fp32-accurate).  Matrix jobs need Di <= 128 and Di % 4 == 0; scratch 16-byte aligned, sized by
+ * biear_wgrad_scratch_floats_tc. */
+int64_t biear_wgrad_scratch_floats_tc(const BiearWgradJob* jobs, int n_jobs, int G, int tile_rows);
+int biear_ctrl_wgrad_tc(const BiearWgradJob* jobs, int n_jobs, int G, int tile_rows, float* scratch, void* stream);
 
 /*
  * Broadband interaural cross-correlation feature.  Replaces utils.py:390-420

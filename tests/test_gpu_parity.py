@@ -436,8 +436,9 @@ def test_nonfinite_q_fallback_is_batch_global(bb):
             assert rel_err(out["fused"][1][k], v) <= RTOL, k
 
 
-def test_ctrl_wgrad_kernel(bb):
-    """biear_ctrl_wgrad against float64 einsums on tile-layout operands: odd sizes, sliced operands, bias, the diagonal
+@pytest.mark.parametrize("variant", ["tc", "ffma"])
+def test_ctrl_wgrad_kernel(bb, variant):
+    """biear_ctrl_wgrad / biear_ctrl_wgrad_tc against float64 einsums on tile-layout operands: odd sizes, sliced operands, bias, the diagonal
     (LayerNorm) form, several jobs per call, both tile widths."""
     from biear_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(3)
@@ -447,7 +448,7 @@ def test_ctrl_wgrad_kernel(bb):
         c = torch.randn((G, chunks + 2, 100, R), generator=g).to(DEV)
         jobs = [(a, 384, c, 100, chunks, True), (a[:, :, 384:], 128, b[:, 2:], 128, chunks, False),
                 (c, 100, b, 128, chunks, True), (b, 128, a, 0, chunks, True)]
-        outs = ops.ctrl_wgrad(jobs)
+        outs = ops.ctrl_wgrad(jobs, variant=variant)
         for (x, do, y, di, k, wb), (dw, db) in zip(jobs, outs):
             xd, yd = x[:, :k, :do].double(), y[:, :k].double()
             ref = torch.einsum("gkor,gkir->goi", xd, yd[:, :, :di]) if di > 0 else (xd * yd[:, :, :do]).sum((1, 3))
