@@ -14,7 +14,7 @@
 namespace biear {
 
 constexpr int kQregThreads = 256;
-constexpr int kQregMaxBlocks = 8 * kSmCountB200;
+constexpr int kQregMaxBlocks = 4 * kSmCountB200;
 
 struct QRegArgs {
     const float* qa;
@@ -81,17 +81,31 @@ __global__ void __launch_bounds__(kQregThreads) q_reg_kernel(const QRegArgs a) {
         last_s = atomicAdd(a.counter, 1u) == gridDim.x - 1;
     }
     __syncthreads();
-    if (!last_s || warp != 0) return;
+    if (!last_s) return;
     __threadfence();
+    // fixed order: thread-strided over the blocks (independent loads: one L2 round trip, not one per block), then the
+    // same shuffle tree / warp order as above
     float t1 = 0.f, t2 = 0.f;
-    for (int b = lane; b < (int)gridDim.x; b += 32) {           // fixed order: lane-strided, then a shuffle tree
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += kQregThreads) {
         t1 += __ldcg(a.partials + 2 * b);
         t2 += __ldcg(a.partials + 2 * b + 1);
     }
     t1 = warp_sum(t1);
     t2 = warp_sum(t2);
+    __syncthreads();                                             // red_s is reused
     if (lane == 0) {
-        const float r1 = t1 * inv1, r2 = t2 * inv2;
+        red_s[0][warp] = t1;
+        red_s[1][warp] = t2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float u1 = 0.f, u2 = 0.f;
+#pragma unroll
+        for (int w = 0; w < kQregThreads / 32; ++w) {
+            u1 += red_s[0][w];
+            u2 += red_s[1][w];
+        }
+        const float r1 = u1 * inv1, r2 = u2 * inv2;
         a.out[0] = fmaf(a.w_reg, r1, a.w_smooth * r2);
         a.out[1] = r1;
         a.out[2] = r2;

@@ -262,44 +262,54 @@ __device__ __forceinline__ void wgrad_matrix_tc(const WgradPlan& pl, const Wgrad
         const bool a_ok = o0 + r < a.Do, b_ok = r < a.Di;
         const float* ap = a.A + (long long)g * a.a_group + (long long)(o0 + r) * tile_w + half * 8;
         const float* bp = a.B + (long long)g * a.b_group + (long long)r * tile_w + half * 8;
-        float4 xa[2], xb[2];
-        auto fetch = [&](long long q) {
+        // register prefetch ring, kWtAhead slabs deep: a slab is little work, so the loads of several slabs must be in
+        // flight at once to cover the L2 / HBM latency
+        constexpr int kWtAhead = 3;
+        float4 xa[kWtAhead][2], xb[kWtAhead][2];
+        auto fetch = [&](long long q, float4 (&ra)[2], float4 (&rb)[2]) {
             const long long cc = q / per;
             const int sub = (int)(q % per) * kTcKB;
             const bool live = cc < a.tile_chunks;
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
-                xa[c] = (live && a_ok) ? __ldg(reinterpret_cast<const float4*>(ap + cc * a.a_chunk + sub) + c)
+                ra[c] = (live && a_ok) ? __ldg(reinterpret_cast<const float4*>(ap + cc * a.a_chunk + sub) + c)
                                        : make_float4(0.f, 0.f, 0.f, 0.f);
-                xb[c] = (live && b_ok) ? __ldg(reinterpret_cast<const float4*>(bp + cc * a.b_chunk + sub) + c)
+                rb[c] = (live && b_ok) ? __ldg(reinterpret_cast<const float4*>(bp + cc * a.b_chunk + sub) + c)
                                        : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
         float bsum = 0.f;
-        if (n_slabs > 0) fetch(c0);
-        for (int i = 0; i < n_slabs; ++i) {
-            const int s = i % kWtStages;
-            const uint32_t ph = (i / kWtStages) & 1;
-            mbar_wait(bar_empty + 8 * s, ph ^ 1);
-            float* stage = reinterpret_cast<float*>(smem + s * kWtStageBytes);
-            float4 va[2] = {xa[0], xa[1]}, vb[2] = {xb[0], xb[1]};
-            if (i + 1 < n_slabs) fetch(c0 + i + 1);               // next slab's loads in flight behind the stores
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const int off = tc_tile_off(r, half * 8 + c * 4);
-                const float4 ah = make_float4(tf32_hi(va[c].x), tf32_hi(va[c].y), tf32_hi(va[c].z), tf32_hi(va[c].w));
-                const float4 bh = make_float4(tf32_hi(vb[c].x), tf32_hi(vb[c].y), tf32_hi(vb[c].z), tf32_hi(vb[c].w));
-                *reinterpret_cast<float4*>(stage + off) = ah;
-                *reinterpret_cast<float4*>(stage + kTcTileBytes / 4 + off) =
-                    make_float4(va[c].x - ah.x, va[c].y - ah.y, va[c].z - ah.z, va[c].w - ah.w);
-                *reinterpret_cast<float4*>(stage + 2 * (kTcTileBytes / 4) + off) = bh;
-                *reinterpret_cast<float4*>(stage + 3 * (kTcTileBytes / 4) + off) =
-                    make_float4(vb[c].x - bh.x, vb[c].y - bh.y, vb[c].z - bh.z, vb[c].w - bh.w);
-                bsum += (va[c].x + va[c].y) + (va[c].z + va[c].w);
+        for (int u = 0; u < kWtAhead; ++u)
+            if (u < n_slabs) fetch(c0 + u, xa[u], xb[u]);
+        for (int i0 = 0; i0 < n_slabs; i0 += kWtAhead) {
+#pragma unroll
+            for (int u = 0; u < kWtAhead; ++u) {
+                const int i = i0 + u;
+                if (i >= n_slabs) break;
+                const int s = i % kWtStages;
+                const uint32_t ph = (i / kWtStages) & 1;
+                mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                float* stage = reinterpret_cast<float*>(smem + s * kWtStageBytes);
+                const float4 va[2] = {xa[u][0], xa[u][1]}, vb[2] = {xb[u][0], xb[u][1]};
+                if (i + kWtAhead < n_slabs) fetch(c0 + i + kWtAhead, xa[u], xb[u]);
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int off = tc_tile_off(r, half * 8 + c * 4);
+                    const float4 ah = make_float4(tf32_hi(va[c].x), tf32_hi(va[c].y), tf32_hi(va[c].z), tf32_hi(va[c].w));
+                    const float4 bh = make_float4(tf32_hi(vb[c].x), tf32_hi(vb[c].y), tf32_hi(vb[c].z), tf32_hi(vb[c].w));
+                    *reinterpret_cast<float4*>(stage + off) = ah;
+                    *reinterpret_cast<float4*>(stage + kTcTileBytes / 4 + off) =
+                        make_float4(va[c].x - ah.x, va[c].y - ah.y, va[c].z - ah.z, va[c].w - ah.w);
+                    *reinterpret_cast<float4*>(stage + 2 * (kTcTileBytes / 4) + off) = bh;
+                    *reinterpret_cast<float4*>(stage + 3 * (kTcTileBytes / 4) + off) =
+                        make_float4(vb[c].x - bh.x, vb[c].y - bh.y, vb[c].z - bh.z, vb[c].w - bh.w);
+                    bsum += (va[c].x + va[c].y) + (va[c].z + va[c].w);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_full + 8 * s);
             }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_full + 8 * s);
         }
         // ---- epilogue: TMEM -> registers -> split-K partials ----
         if (n_slabs > 0) {
