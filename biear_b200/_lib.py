@@ -11,7 +11,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BIEAR_B200_LIB") or os.path.join(_HERE, "lib", "libbiear_b200.so")
-ABI_VERSION = 14
+ABI_VERSION = 15
 
 _p = c_void_p
 _i = c_int
@@ -46,7 +46,8 @@ class WgradJob(Structure):
     _fields_ = [("A", c_void_p), ("a_group_stride", c_int64), ("a_chunk_stride", c_int64), ("Do", c_int32),
                 ("Bm", c_void_p), ("b_group_stride", c_int64), ("b_chunk_stride", c_int64), ("Di", c_int32),
                 ("chunks", c_int64), ("dW", c_void_p), ("db", c_void_p),
-                ("dw_group_stride", c_int64), ("dw_row_stride", c_int64), ("db_group_stride", c_int64)]
+                ("dw_group_stride", c_int64), ("dw_row_stride", c_int64), ("db_group_stride", c_int64),
+                ("dW2", c_void_p), ("scale2", c_float)]
 
 
 WGRAD_MAX_JOBS = 8

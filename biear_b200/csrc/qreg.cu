@@ -14,7 +14,7 @@
 namespace biear {
 
 constexpr int kQregThreads = 256;
-constexpr int kQregMaxBlocks = 4 * kSmCountB200;
+constexpr int kQregMaxBlocks = 16 * kSmCountB200;   // one element per thread at the benchmark size: one memory round trip
 
 struct QRegArgs {
     const float* qa;

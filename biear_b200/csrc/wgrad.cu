@@ -33,6 +33,7 @@ struct WgradJobPlan {
     long long out_begin;                                      // first element of this job in the reduce index space
     float* dW; float* db;
     long long dw_group, dw_row, db_group;                    // output strides (floats)
+    float* dW2; float scale2;                                 // optional scaled second copy (matrix jobs)
 };
 
 struct WgradPlan {
@@ -424,6 +425,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgradPlan pl) {
         } else if (a.Di > 0) {
             const long long o = r / a.Di, i = r - o * a.Di;
             dst[g * a.dw_group + o * a.dw_row + i] = s;
+            if (a.dW2) a.dW2[g * a.dw_group + o * a.dw_row + i] = a.scale2 * s;
         } else {
             dst[g * a.dw_group + r] = s;
         }
@@ -490,6 +492,7 @@ static int make_plan(const BiearWgradJob* jobs, int n_jobs, int G, int tile_rows
         a.out_begin = out;
         out += (long long)G * (per_w + (q.db ? q.Do : 0));
         a.dW = q.dW; a.db = q.db;
+        a.dW2 = q.Di > 0 ? q.dW2 : nullptr; a.scale2 = q.scale2;
         a.dw_row = q.dw_row_stride ? q.dw_row_stride : (q.Di > 0 ? q.Di : 1);
         a.dw_group = q.dw_group_stride ? q.dw_group_stride : per_w;
         a.db_group = q.db_group_stride ? q.db_group_stride : q.Do;

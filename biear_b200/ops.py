@@ -390,12 +390,12 @@ WGRAD_VARIANT = os.environ.get("BIEAR_WGRAD_VARIANT", "tc")   # "tc": tcgen05 / 
 def ctrl_wgrad(jobs, variant: Optional[str] = None):
     """Weight gradients for a list of jobs in two launches (biear_ctrl_wgrad[_tc]).
 
-    A job is (a, do, bm, di, chunks, bias[, dw_out, db_out]).  a (G, chunks', Da, R) and bm (G, chunks', Db, R) are
+    A job is (a, do, bm, di, chunks, bias[, dw_out, db_out[, dw2_out, scale2]]).  a (G, chunks', Da, R) and bm (G, chunks', Db, R) are
     tile-layout operands (views with arbitrary group / chunk strides are fine); the first `do` / `di` features and the
     first `chunks` chunks are used.  di == 0 selects the diagonal form dW[g][o] = sum a*bm (LayerNorm weight).
     Without dw_out / db_out, fresh dense outputs dW (G,do,di) | (G,do) and db (G,do) (if bias) are allocated; with them
     the job writes into the given (possibly strided: a row block of a larger tensor) views of shape (G,do,di) / (G,do).
-    Returns [(dW, db | None), ...].
+    dw2_out (same shape / strides as dw_out) receives scale2 * dW as well.  Returns [(dW, db | None), ...].
     """
     a0 = jobs[0][0]
     G, R, dev = a0.shape[0], a0.shape[3], a0.device
@@ -418,6 +418,10 @@ def ctrl_wgrad(jobs, variant: Optional[str] = None):
         q.A, q.a_group_stride, q.a_chunk_stride, q.Do = a.data_ptr(), a.stride(0), a.stride(1), do
         q.Bm, q.b_group_stride, q.b_chunk_stride, q.Di = bm.data_ptr(), bm.stride(0), bm.stride(1), di
         q.chunks, q.dW, q.db = chunks, dw.data_ptr(), (db.data_ptr() if db is not None else None)
+        dw2 = job[8] if len(job) > 8 else None
+        if dw2 is not None:
+            assert di > 0 and dw2.shape == dw.shape and dw2.stride() == dw.stride()
+            q.dW2, q.scale2 = dw2.data_ptr(), float(job[9])
         q.dw_group_stride = dw.stride(0)
         q.dw_row_stride = dw.stride(1) if di > 0 else 1
         q.db_group_stride = db.stride(0) if db is not None else 0
@@ -438,13 +442,16 @@ class PreparedSequence:
     """What biear_adaptive_prepare leaves behind for one step: the packed weight images (workspace), the GRU state
     tensor with its zeroed step 0, the cleared fallback flags, the snapshotted dropout seed -- and the event that marks
     the preparation launch on the stream it ran on."""
-    __slots__ = ("work", "H", "flags", "seed_dev", "event", "stream", "key")
+    __slots__ = ("work", "H", "flags", "seed_dev", "event", "stream", "key", "launched")
 
 
-def adaptive_prepare(weights, B: int, T: int, N: int, training: bool, stream: Optional[torch.cuda.Stream] = None):
+def adaptive_prepare(weights, B: int, T: int, N: int, training: bool, stream: Optional[torch.cuda.Stream] = None,
+                     launch: bool = True):
     """Run the spectra-independent part of a recurrence step (weight-image packing for the forward AND the backward
     kernel, H[:, 0] = 0, flags = 0, dropout-seed snapshot) as one launch, on `stream` if given: the front-end issues
     it on a forked stream so that it overlaps the STFT.  Pass the result to adaptive_sequence(prep=...).
+    launch=False only allocates (the buffers are poisoned): biear_adaptive_fwd / _bwd then prepare on their own stream,
+    the path a C caller that never calls biear_adaptive_prepare takes (testing).
     weights: dict name -> list of the G controllers' tensors."""
     G = len(weights[WEIGHT_NAMES[0]])
     ws = [w.detach() for k in WEIGHT_NAMES for w in weights[k]]
@@ -476,7 +483,13 @@ def adaptive_prepare(weights, B: int, T: int, N: int, training: bool, stream: Op
                 for g in range(G):
                     arr[g] = ws[i * G + g].data_ptr()
             from ctypes import byref
-            _lib.check(lib.biear_adaptive_prepare(byref(prm), c_void_p(run.cuda_stream)), "biear_adaptive_prepare")
+            if launch:
+                _lib.check(lib.biear_adaptive_prepare(byref(prm), c_void_p(run.cuda_stream)), "biear_adaptive_prepare")
+            else:
+                out.H.fill_(float("nan"))
+                out.flags.fill_(1)
+                out.work.fill_(float("nan"))
+            out.launched = launch
             out.event = torch.cuda.Event()
             out.event.record(run)
     out.stream = run
@@ -544,7 +557,7 @@ class AdaptiveSequence(torch.autograd.Function):
             prm = _lib.SeqParams()
             prm.G, prm.E, prm.B, prm.T, prm.N, prm.F, prm.Kin = G, G, B, T, N, F, Kin
             prm.relative, prm.training, prm.seed, prm.force_strict = int(relative), int(training), int(seed), int(strict)
-            prm.prepared = 1
+            prm.prepared = int(prep.launched)
             prm.df, prm.cutoff, prm.q_min, prm.q_max = float(df), float(cutoff), 0.05, 30.0
             _fill(prm, fc=fc, q0=q0, dq=dq, X=xr, Y=Y, phase=P, dYdQ=dY, dPdQ=dP, Q=Q, delta=D, flags=flags,
                   workspace=work, H=H, seed_ptr=seed_dev, logY=LX, **sv)
@@ -613,8 +626,11 @@ class AdaptiveSequence(torch.autograd.Function):
             h_prev, h_cur = Hk[:, :K], Hk[:, tiles:]
             d_w_hh = torch.empty((G, 3 * HID, HID), **f32)
             d_b_hh = torch.empty((G, 3 * HID), **f32)
+            fold = Kin == 2 * N                   # feat = [yc, 0.2 yc.detach()]: dW_ih[:, N:] = 0.2 dW_ih[:, :N]
+            d_w_ih = torch.empty((G, 3 * HID, Kin), **f32) if fold else None
+            ih_out = (d_w_ih[:, :, :N], None, d_w_ih[:, :, N:], 0.2) if fold else ()
             (a, d_b_ih), _, _, (d_w1, d_b1), (d_w2, d_b2), (d_w3, d_b3), (d_g1, d_be1), (d_g2, d_be2) = ctrl_wgrad([
-                (GG, 3 * HID, fl(sv["yc"]), N, K, True),                                          # dL/dW_ih[:, :N], b_ih
+                (GG, 3 * HID, fl(sv["yc"]), N, K, True) + ih_out,                                 # dL/dW_ih (both halves), b_ih
                 (GG, 2 * HID, h_prev, HID, K, True, d_w_hh[:, :2 * HID], d_b_hh[:, :2 * HID]),     # r, z rows of W_hh / b_hh
                 (GG[:, :, 3 * HID:], HID, h_prev, HID, K, True, d_w_hh[:, 2 * HID:], d_b_hh[:, 2 * HID:]),   # n rows: dL/d(W_hn h + b_hn)
                 (fl(wk["G_a1"]), HID, h_cur, HID, K, True),
@@ -623,7 +639,6 @@ class AdaptiveSequence(torch.autograd.Function):
                 (fl(wk["G_v1"]), HID, fl(sv["xh1"]), 0, K, True),                                  # LayerNorm 1 weight / bias
                 (fl(wk["G_v2"]), HID, fl(sv["xh2"]), 0, K, True),
             ])
-            d_w_ih = torch.cat([a, 0.2 * a], dim=2) if Kin == 2 * N else None            # feat = [yc, 0.2 yc.detach()]
         stacked = (d_w_ih, d_w_hh, d_b_ih, d_b_hh, d_w1, d_b1, d_g1, d_be1, d_w2, d_b2, d_g2, d_be2, d_w3, d_b3)
         grads = tuple(t[g] if t is not None else None for t in stacked for g in range(G))
         return none13 + grads

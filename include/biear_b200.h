@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BIEAR_ABI_VERSION 14
+#define BIEAR_ABI_VERSION 15
 #define BIEAR_EINVAL (-1)
 
 /* ABI version (== BIEAR_ABI_VERSION of the library that was built). */
@@ -226,6 +226,10 @@ typedef struct BiearWgradJob {
     /* output strides in floats; 0 selects dense: dW (G, Do, Di) / (G, Do), db (G, Do).  Non-zero strides let a job write
        a row block of a larger parameter gradient (e.g. the r,z rows and the n rows of GRU weight_hh) in place. */
     int64_t dw_group_stride, dw_row_stride, db_group_stride;
+    /* optional second copy of a matrix job's result, scaled: dW2[g][o][i] = scale2 * dW[g][o][i] with the same strides
+       (NULL: none).  The dual controller's input is [c, 0.2 c.detach()] (model_torch.py:351-359), so the gradient of
+       weight_ih[:, N:] is 0.2 x that of weight_ih[:, :N]: one job fills both halves of the parameter's gradient. */
+    float* dW2; float scale2;
 } BiearWgradJob;
 /* Floats of scratch biear_ctrl_wgrad needs for these jobs (-1 on invalid arguments). */
 int64_t biear_wgrad_scratch_floats(const BiearWgradJob* jobs, int n_jobs, int G, int tile_rows);

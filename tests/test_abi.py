@@ -37,7 +37,7 @@ def test_ctypes_structs_match_the_header(tmp_path):
     from biear_b200 import _lib
     probe = tmp_path / "probe.c"
     fields_seq = ["G", "seed", "df", "fc", "w_ih", "b3", "X", "Q", "delta", "gates", "H", "flags", "gY", "GG", "workspace", "seed_ptr", "gLogY", "prepared"]
-    fields_job = ["A", "Do", "Bm", "Di", "chunks", "dW", "db", "dw_group_stride", "db_group_stride"]
+    fields_job = ["A", "Do", "Bm", "Di", "chunks", "dW", "db", "dw_group_stride", "db_group_stride", "dW2", "scale2"]
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){",
              'printf("%zu %zu\\n", sizeof(BiearSeqParams), sizeof(BiearWgradJob));']
     lines += [f'printf("%zu\\n", offsetof(BiearSeqParams, {f}));' for f in fields_seq]

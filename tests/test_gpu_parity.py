@@ -760,3 +760,30 @@ def test_band_fixed_variants_against_float64(bb, variant, rows, n_bands, want_ph
         assert float((np.minimum(d, 2 * np.pi - d) * wgt).max()) <= 2e-6
     else:
         assert ph is None
+
+
+def test_recurrence_prepares_itself_without_biear_adaptive_prepare(bb):
+    """A C caller that never calls biear_adaptive_prepare (BiearSeqParams.prepared == 0): biear_adaptive_fwd / _bwd pack
+    their weight images, zero H[:, 0] and clear the flags themselves -- same results and gradients, bit for bit, as
+    the prepared path (the buffers are poisoned with NaN / ones beforehand)."""
+    from biear_b200 import frontend, ops
+    m, tl, tr = _dual(bb, 3, (11, 12), CONFIG_YAML)
+    fb = m.fb_L
+    x = torch.view_as_real(fb._spectra([tl, tr]))
+    w = frontend._controller_weights([m.fb_L, m.fb_R])
+    up = upstream(3)
+    res = []
+    for launch in (True, False):
+        for p in m.parameters():
+            p.grad = None
+        prep = ops.adaptive_prepare(w, 3, fb.timesteps, fb.Nbands, False, launch=launch)
+        y, q, ph = ops.adaptive_sequence(x, fb.fc, fb.Q0, fb.deltaQ_vec, w, True, False, True, fb.cutoff, fb.df, prep=prep)
+        loss = sum((torch.from_numpy(up[k]).to(DEV) * t).sum() for k, t in
+                   (("gYL", y[0]), ("gYR", y[1]), ("gPL", ph[0]), ("gPR", ph[1]), ("gQL", q[0]), ("gQR", q[1])))
+        loss.backward()
+        res.append(([t.detach().clone() for t in y + q + ph], [p.grad.clone() for p in m.parameters()]))
+    for a, b in zip(res[0][0], res[1][0]):
+        assert torch.equal(a, b)
+    for a, b in zip(res[0][1], res[1][1]):
+        assert torch.equal(a, b)
+    assert all(torch.isfinite(g).all() for g in res[1][1])
