@@ -410,12 +410,16 @@ class BinauralAdaptiveGammatoneFB(nn.Module):
             # on the forked stream next to the STFT
             prep = ops.adaptive_prepare(_controller_weights([self.fb_L, self.fb_R]), B, fb.timesteps, fb.Nbands,
                                         self.training, stream=side)
+        x = fb._spectra([wavL_1s, wavR_1s])
         if want_cc:
+            # The CC kernel is forked BEHIND the STFT: it becomes eligible together with the recurrence kernel, and when
+            # the caller's stream has a higher priority than the (lowest-priority) side stream -- GraphedStep captures on
+            # such a stream -- the recurrence's 128 persistent CTAs are placed first and the CC kernel's CTAs run on the 20
+            # SMs they leave idle instead of delaying them.
             side.wait_stream(cur)
             with torch.cuda.stream(side):
                 cc = ops.cc_feature(wavL_1s.float().contiguous(), wavR_1s.float().contiguous(), fb.fs, fb.Nbands,
                                     cc_max_lag_ms)
-        x = fb._spectra([wavL_1s, wavR_1s])
         if self.fixed_frontend_q or frozen:
             qf = fb.Q0 if frozen else torch.clamp(fb.Q0, Q_MIN, Q_MAX)
             y, ph = _fixed_bands(x, fb.fc, qf, fb.df, want_phase, fb.cutoff)

@@ -37,7 +37,10 @@ class GraphedStep:
         self.copy_inputs = copy_inputs
         self.static_inputs = [x.clone() for x in example_inputs] if copy_inputs else list(example_inputs)
         dev = self.static_inputs[0].device
-        side = torch.cuda.Stream(device=dev)
+        # warm-up and capture run on a HIGH-priority stream: the kernels the front-end forks onto its own (lowest-priority)
+        # side stream -- the CC feature -- then yield the SMs to the persistent recurrence kernels whenever both are
+        # eligible, and fill the SMs those leave idle
+        side = torch.cuda.Stream(device=dev, priority=-1)
         side.wait_stream(torch.cuda.current_stream(dev))
         # Gradients are taken with torch.autograd.grad (no AccumulateGrad nodes): those nodes remember the stream
         # they were created on, and one left over from an earlier eager backward on the legacy default stream would
@@ -50,7 +53,7 @@ class GraphedStep:
         from . import _lib
         n0 = _lib.launch_count()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph, pool=pool):
+        with torch.cuda.graph(self.graph, pool=pool, stream=side):
             self.loss = fn(*self.static_inputs)
             grads = torch.autograd.grad(self.loss, self.params, allow_unused=True)
             if flat_grads:
