@@ -75,6 +75,14 @@ BIEAR_HD void fft512_butterfly(float2 v[8], int j, int Ns, const float2* tw1024)
     bfly8(v);
 }
 
+// The same with the 7 twiddles of the pass already in registers (they depend on the thread and the pass only, not on
+// the frame: tw[r - 1] = tw1024[r * (j & (Ns - 1)) * (1024 / (8 Ns))]).
+BIEAR_HD void fft512_butterfly_reg(float2 v[8], const float2 tw[7]) {
+#pragma unroll
+    for (int r = 1; r < 8; ++r) v[r] = cmul(v[r], tw[r - 1]);
+    bfly8(v);
+}
+
 // Scatter the butterfly outputs to their Stockham positions (through the slot map when Padded).
 template <bool Padded>
 BIEAR_HD void fft512_scatter(const float2 v[8], float2* out, int j, int Ns) {

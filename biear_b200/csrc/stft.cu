@@ -28,7 +28,7 @@ struct StftArgs {
     long long n_frames;
 };
 
-__global__ void __launch_bounds__(kStftThreads, 3) stft_fwd_kernel(const StftArgs a) {
+__global__ void __launch_bounds__(kStftThreads, 2) stft_fwd_kernel(const StftArgs a) {
     __shared__ float2 s_tw[kNfft];
     __shared__ float2 s_buf[kFramesPerCta][kFftSlots];
 
@@ -76,6 +76,13 @@ __global__ void __launch_bounds__(kStftThreads, 3) stft_fwd_kernel(const StftArg
         wreg[r] = make_float2(i0 < a.win ? __ldg(a.win_fn + i0) : 0.0f, i0 + 1 < a.win ? __ldg(a.win_fn + i0 + 1) : 0.0f);
     }
     __syncthreads();   // twiddles in shared memory
+    // the twiddles of passes 2 and 3 depend on the thread only: registers, not 14 shared loads per frame
+    float2 tw8[7], tw64[7];
+#pragma unroll
+    for (int r = 1; r < 8; ++r) {
+        tw8[r - 1] = s_tw[r * (j & 7) * (kNfft / 64)];
+        tw64[r - 1] = s_tw[r * (j & 63) * (kNfft / 512)];
+    }
     for (; base < a.n_frames; base += stride) {
         const long long fi = base + g;
         const bool live = fi < a.n_frames;
@@ -90,12 +97,12 @@ __global__ void __launch_bounds__(kStftThreads, 3) stft_fwd_kernel(const StftArg
         fft512_scatter<true>(v, buf, j, 1);
         __syncthreads();
         fft512_gather<true>(v, buf, j);
-        fft512_butterfly(v, j, 8, s_tw);
+        fft512_butterfly_reg(v, tw8);
         __syncthreads();
         fft512_scatter<true>(v, buf, j, 8);
         __syncthreads();
         fft512_gather<true>(v, buf, j);
-        fft512_butterfly(v, j, 64, s_tw);
+        fft512_butterfly_reg(v, tw64);
         __syncthreads();
         fft512_scatter<true>(v, buf, j, 64);
         __syncthreads();
@@ -152,9 +159,9 @@ extern "C" int biear_stft_fwd(const float* wav, int64_t rows, int64_t nsamp, int
     a.X = reinterpret_cast<float2*>(X);
     a.n_frames = rows * T;
     const long long ctas_needed = (a.n_frames + kFramesPerCta - 1) / kFramesPerCta;
-    // 3 resident CTAs per SM (<= 85 registers, 26 KB of shared memory each), every CTA pipelining over the same number of
+    // 2 resident CTAs per SM (window taps and twiddles in registers, 26 KB of shared memory each), every CTA pipelining over the same number of
     // frame groups: one even wave instead of a ragged one
-    const long long cap = (long long)kSmCountB200 * 3;
+    const long long cap = (long long)kSmCountB200 * 2;
     const long long trips = (ctas_needed + cap - 1) / cap;
     const int grid = (int)((ctas_needed + trips - 1) / trips);
     stft_fwd_kernel<<<grid, kStftThreads, 0, st>>>(a);
