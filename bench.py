@@ -227,6 +227,26 @@ def make_step(model, up):
     return step, params
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Run this rank's host threads on the CPUs next to its GPU (NVML's ideal affinity), so that the pinned staging
+    buffers of the end-to-end path are allocated on the GPU's own NUMA node: with 8 ranks each pushing 32.8 MB per step
+    through the host, cross-socket traffic is what limits the H2D streams.  Best effort: containers may forbid it."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].isdigit() else gpu_index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+    except Exception:  # noqa: BLE001
+        pass
+
+
 def run_ours(args):
     from biear_b200 import GraphedStep, _lib
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -240,6 +260,7 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
+    bind_to_gpu_numa_node(local)
     B = args.batch
     model = build_frontend(dev)
     rs = np.random.RandomState(3)
