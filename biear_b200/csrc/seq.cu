@@ -130,6 +130,8 @@ __global__ void __launch_bounds__(256) prepare_kernel(const BiearSeqParams p, fl
             for (long long i = tid0; i < per_g; i += stride) h0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         for (int i = tid0; i < (p.T - 1) * p.G + 1; i += stride) p.flags[i] = 0;
+        if (p.x_ready)
+            for (long long i = tid0; i < (long long)p.E * p.B * p.T + 4; i += stride) p.x_ready[i] = 0;   // + work counter
     }
 }
 
@@ -224,6 +226,24 @@ __device__ __forceinline__ void ln_silu_drop_fwd(const BiearSeqParams& p, unsign
                 xh_tile[f * kR + row] = xh;
                 d_tile[f * kR + row] = o;
             }
+        }
+    }
+    __syncthreads();
+}
+
+// Streaming hand-over of the spectra (BiearSeqParams.x_ready): wait until the concurrently running STFT has published
+// frame t of this CTA's rows.  One thread per row polls (acquire), the block barrier hands the ordering to everybody.
+// The spin is bounded: a broken protocol must end in a launch failure, never in a hung GPU.
+__device__ __forceinline__ void wait_spectra(const BiearSeqParams& p, long long grow0, int b0, int t) {
+    if (!p.x_ready) return;
+    if (threadIdx.x < kRT && b0 + (int)threadIdx.x < p.B) {
+        const int32_t* flag = p.x_ready + (grow0 + threadIdx.x) * p.T + t;
+        int v = 0;
+        for (unsigned spin = 0; ; ++spin) {
+            asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+            if (v != 0) break;
+            if (spin > (1u << 24)) __trap();
+            __nanosleep(64);
         }
     }
     __syncthreads();
@@ -381,6 +401,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
             }
             PHASE_MARK(0, 0);    // loop head / weight load
             if (STRICT || spec_t != t) {   // first frame / strict pass: fetch and convert now (also orders the q_s fill)
+                wait_spectra(p, grow0, bb0, t);
                 prefetch_spectra(p, spec_s, L.tile, grow0, bb0, t);
                 finish_spectra(p, spec_s, L.tile, bb0);
                 __syncthreads();
@@ -468,6 +489,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
             }
             __syncthreads();
             if (!STRICT) {   // the tile is free again: start fetching the next frame's spectra behind the controller phases
+                wait_spectra(p, grow0, bb0, t + 1);
                 prefetch_spectra(p, spec_s, L.tile, grow0, bb0, t + 1);
                 spec_t = t + 1;
             }

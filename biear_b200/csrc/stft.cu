@@ -18,6 +18,11 @@ constexpr int kStftThreads = kFramesPerCta * kFftThreads;
 
 struct StftArgs {
     const float* wav;
+    const float* wav2;    // rows >= rows_first come from wav2 (the second ear), row index rebased; nullable
+    long long rows_first;
+    int32_t* ready;       // nullable: ready[row * T + t] = 1 once X[row][t] is complete (release order)
+    void* counter;        // with ready: 8-byte work counter behind the flags (cleared with them)
+    int frame_major;      // work order: 1 = frame 0 of every row first, then frame 1, ... (streaming consumers)
     long long rows, nsamp, row_stride;
     const float* win_fn;
     const float2* tw;
@@ -42,16 +47,30 @@ __global__ void __launch_bounds__(kStftThreads, 2) stft_fwd_kernel(const StftArg
     const int valid_len = min(min(a.win, kNfft), a.limit);
     const long long stride = (long long)gridDim.x * kFramesPerCta;
 
+    // work item -> (row, frame)
+    auto item_of = [&](long long fi, bool live, long long& row, int& t) {
+        if (!live) {
+            row = 0;
+            t = 0;
+        } else if (a.frame_major) {
+            t = (int)(fi / a.rows);
+            row = fi % a.rows;
+        } else {
+            row = fi / a.T;
+            t = (int)(fi % a.T);
+        }
+    };
     // Raw samples of one frame (this thread's 16), NOT yet windowed: issued one trip ahead so that the HBM latency of
     // the next frame group hides behind the three FFT passes of the current one.
     auto fetch = [&](long long base, float2 (&raw)[8]) {
         const long long fi = base + g;
         const bool live = fi < a.n_frames;
-        const long long row = live ? fi / a.T : 0;
-        const int t = live ? (int)(fi % a.T) : 0;
+        long long row;
+        int t;
+        item_of(fi, live, row, t);
         const bool frame_valid = live && t < a.n_avail;
         const long long start = (long long)t * a.hop;
-        const float* wrow = a.wav + row * a.row_stride;
+        const float* wrow = (row < a.rows_first ? a.wav + row * a.row_stride : a.wav2 + (row - a.rows_first) * a.row_stride);
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
             const int i0 = 2 * (j + r * 64);
@@ -65,8 +84,24 @@ __global__ void __launch_bounds__(kStftThreads, 2) stft_fwd_kernel(const StftArg
         }
     };
 
+    // Work distribution.  Static (no ready flags): CTA c takes frame groups c, c + grid, ...  Dynamic (streaming hand-over):
+    // groups are claimed from a device counter in order, so that frame-major order holds no matter how many CTAs are
+    // resident at a time (next to a persistent kernel only the SMs it leaves idle take CTAs of this one).
+    __shared__ long long s_claim[2];
+    unsigned long long* counter = reinterpret_cast<unsigned long long*>(a.counter);
+    const bool dynamic = counter != nullptr;
+    auto claim = [&]() { return (long long)atomicAdd(counter, 1ull) * kFramesPerCta; };
     float2 nxt[8];
-    long long base = (long long)blockIdx.x * kFramesPerCta;
+    long long base = (long long)blockIdx.x * kFramesPerCta, next_base = base + stride;
+    if (dynamic) {
+        if (threadIdx.x == 0) {
+            s_claim[0] = claim();
+            s_claim[1] = claim();
+        }
+        __syncthreads();
+        base = s_claim[0];
+        next_base = s_claim[1];
+    }
     if (base < a.n_frames) fetch(base, nxt);
     // this thread's 16 window taps are the same for every frame it touches: registers, not shared memory
     float2 wreg[8];
@@ -83,7 +118,7 @@ __global__ void __launch_bounds__(kStftThreads, 2) stft_fwd_kernel(const StftArg
         tw8[r - 1] = s_tw[r * (j & 7) * (kNfft / 64)];
         tw64[r - 1] = s_tw[r * (j & 63) * (kNfft / 512)];
     }
-    for (; base < a.n_frames; base += stride) {
+    for (int trip = 0; base < a.n_frames; ++trip) {
         const long long fi = base + g;
         const bool live = fi < a.n_frames;
         // pass 1 (Ns = 1): packed, windowed samples
@@ -92,10 +127,12 @@ __global__ void __launch_bounds__(kStftThreads, 2) stft_fwd_kernel(const StftArg
         for (int r = 0; r < 8; ++r) {
             v[r] = make_float2(nxt[r].x * wreg[r].x, nxt[r].y * wreg[r].y);
         }
-        if (base + stride < a.n_frames) fetch(base + stride, nxt);
+        if (next_base < a.n_frames) fetch(next_base, nxt);
         fft512_butterfly(v, j, 1, s_tw);
         fft512_scatter<true>(v, buf, j, 1);
         __syncthreads();
+        // (dynamic) claim the group after next: slot trip & 1 was consumed as this trip's base before the barrier above
+        if (dynamic && threadIdx.x == 0) s_claim[trip & 1] = claim();
         fft512_gather<true>(v, buf, j);
         fft512_butterfly_reg(v, tw8);
         __syncthreads();
@@ -107,8 +144,11 @@ __global__ void __launch_bounds__(kStftThreads, 2) stft_fwd_kernel(const StftArg
         fft512_scatter<true>(v, buf, j, 64);
         __syncthreads();
 
+        long long orow;
+        int ot;
+        item_of(fi, live, orow, ot);
         if (live) {
-            float2* out = a.X + fi * kBins;
+            float2* out = a.X + (orow * a.T + ot) * kBins;
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 const int k = j + r * 64;          // 0..255
@@ -123,15 +163,20 @@ __global__ void __launch_bounds__(kStftThreads, 2) stft_fwd_kernel(const StftArg
                 out[256] = xk;
             }
         }
+        if (a.ready) __threadfence();   // this thread's part of the frame is visible device-wide ...
         __syncthreads();   // unpack reads done before the next trip scatters into the buffer
+        if (a.ready && live && j == 0)   // ... every thread's is: publish the frame
+            *reinterpret_cast<volatile int32_t*>(a.ready + orow * a.T + ot) = 1;
+        base = next_base;
+        next_base = dynamic ? s_claim[trip & 1] : next_base + stride;   // written before the barrier above
     }
 }
 
 }  // namespace biear
 
-extern "C" int biear_stft_fwd(const float* wav, int64_t rows, int64_t nsamp, int64_t wav_row_stride,
-                              const float* win_fn, int fs, int T, int win, int hop, int n_fft, float* X,
-                              void* stream) {
+static int stft_launch(const float* wav, const float* wav2, int64_t rows_first, int64_t rows, int64_t nsamp,
+                       int64_t wav_row_stride, const float* win_fn, int fs, int T, int win, int hop, int n_fft, float* X,
+                       int32_t* ready, int frame_major, void* stream, const char* who) {
     using namespace biear;
     BIEAR_REQUIRE(n_fft == kNfft, "biear_stft_fwd: n_fft=%d unsupported (only 1024)", n_fft);
     BIEAR_REQUIRE(rows >= 0 && nsamp >= 0 && fs >= 1 && T >= 1 && win >= 1 && hop >= 1,
@@ -147,6 +192,11 @@ extern "C" int biear_stft_fwd(const float* wav, int64_t rows, int64_t nsamp, int
     a.tw = twiddle_table(st, &err);
     if (err) return err;
     a.wav = wav;
+    a.wav2 = wav2;
+    a.rows_first = rows_first;
+    a.ready = ready;
+    a.counter = ready ? reinterpret_cast<void*>(ready + ((rows * T + 1) & ~1LL)) : nullptr;
+    a.frame_major = frame_major;
     a.rows = rows;
     a.nsamp = nsamp;
     a.row_stride = wav_row_stride;
@@ -163,8 +213,25 @@ extern "C" int biear_stft_fwd(const float* wav, int64_t rows, int64_t nsamp, int
     // frame groups: one even wave instead of a ragged one
     const long long cap = (long long)kSmCountB200 * 2;
     const long long trips = (ctas_needed + cap - 1) / cap;
-    const int grid = (int)((ctas_needed + trips - 1) / trips);
+    const int grid = ready ? (int)(ctas_needed < cap ? ctas_needed : cap)      // dynamic claiming: any grid is in order
+                           : (int)((ctas_needed + trips - 1) / trips);
+    (void)who;
     stft_fwd_kernel<<<grid, kStftThreads, 0, st>>>(a);
     BIEAR_LAUNCH_CHECK("stft_fwd_kernel");
     return 0;
+}
+
+extern "C" int biear_stft_fwd(const float* wav, int64_t rows, int64_t nsamp, int64_t wav_row_stride,
+                              const float* win_fn, int fs, int T, int win, int hop, int n_fft, float* X,
+                              void* stream) {
+    return stft_launch(wav, nullptr, rows, rows, nsamp, wav_row_stride, win_fn, fs, T, win, hop, n_fft, X, nullptr, 0, stream,
+                       "biear_stft_fwd");
+}
+
+extern "C" int biear_stft_fwd_pair(const float* wavA, const float* wavB, int64_t rows_each, int64_t nsamp,
+                                   int64_t wav_row_stride, const float* win_fn, int fs, int T, int win, int hop, int n_fft,
+                                   float* X, int32_t* ready, void* stream) {
+    BIEAR_REQUIRE(wavB != nullptr || rows_each == 0, "biear_stft_fwd_pair: null second waveform");
+    return stft_launch(wavA, wavB, rows_each, 2 * rows_each, nsamp, wav_row_stride, win_fn, fs, T, win, hop, n_fft, X, ready,
+                       1, stream, "biear_stft_fwd_pair");
 }

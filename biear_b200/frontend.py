@@ -18,6 +18,8 @@ All compute requires CUDA tensors; there is no CPU fallback.
 """
 from __future__ import annotations
 
+import os
+
 from typing import List, Optional, Tuple
 
 import numpy as np
@@ -260,6 +262,7 @@ def _log_energy(y: torch.Tensor) -> torch.Tensor:
     return torch.clamp(torch.log(y + 1e-8), -12.0, 12.0)
 
 
+STREAM_SPECTRA = os.environ.get("BIEAR_STREAM_SPECTRA", "1") != "0"   # STFT next to the recurrence (flag hand-over)
 FIXED_ENGINE = "gemm"   # "gemm": shared-weight dense contraction (csrc/band_fixed.cu); "item": per-item band kernel,
                         # bit-identical to the adaptive path at Q == Q0 (kept for that identity and as a cross-check)
 
@@ -405,12 +408,26 @@ class BinauralAdaptiveGammatoneFB(nn.Module):
         if want_cc or fused:
             cur = torch.cuda.current_stream(wavL_1s.device)
             side = _side_stream(wavL_1s.device)
+        stft_done = None
         if fused:
-            # the spectra-independent part of the recurrence step (weight images, zero state, flags, dropout seed) runs
-            # on the forked stream next to the STFT
+            # The spectra-independent part of the recurrence step (weight images, zero state, flags, dropout seed) runs on
+            # the forked stream, and BEHIND it, on the same lowest-priority stream, the STFT of both ears in frame-major
+            # order with per-(row, frame) ready flags: the recurrence kernel is launched right after the preparation and
+            # waits, frame by frame, for the spectra it needs -- the STFT then runs on the SMs the persistent kernel
+            # leaves idle instead of in front of it (when the caller's stream has a higher priority, e.g. GraphedStep).
+            for w in (wavL_1s, wavR_1s):
+                if w.requires_grad:
+                    raise RuntimeError("biear_b200: gradients with respect to the waveform are not implemented")
             prep = ops.adaptive_prepare(_controller_weights([self.fb_L, self.fb_R]), B, fb.timesteps, fb.Nbands,
-                                        self.training, stream=side)
-        x = fb._spectra([wavL_1s, wavR_1s])
+                                        self.training, stream=side, streamed_spectra=STREAM_SPECTRA)
+            if STREAM_SPECTRA:
+                with torch.cuda.stream(side):
+                    x = ops.stft_pair(wavL_1s.float().contiguous(), wavR_1s.float().contiguous(), fb.win_fn, fb.fs,
+                                      fb.timesteps, fb.win, fb.hop, fb.n_fft, ready=prep.x_ready)
+                    stft_done = torch.cuda.Event()
+                    stft_done.record(side)
+        if stft_done is None:
+            x = fb._spectra([wavL_1s, wavR_1s])
         if want_cc:
             # The CC kernel is forked BEHIND the STFT: it becomes eligible together with the recurrence kernel, and when
             # the caller's stream has a higher priority than the (lowest-priority) side stream -- GraphedStep captures on
@@ -434,6 +451,9 @@ class BinauralAdaptiveGammatoneFB(nn.Module):
             y, q, ph, lx = _adaptive_chain(x, 2, [self.fb_L, self.fb_R], fb.fc, fb.Q0, fb.deltaQ_vec, fb.deltaQ_mode,
                                            fb.df, self.training, False, want_phase, fb.band_mode, fb.cutoff, engine,
                                            want_logy=want_logenergy, prep=prep if engine == self.engine else None)
+        if stft_done is not None:           # every later reader of X (the caller included) is ordered behind the STFT
+            cur.wait_event(stft_done)
+            x.record_stream(cur)
         out = {"YL": y[0], "YR": y[1], "QL": q[0], "QR": q[1], "XL": x[:B], "XR": x[B:]}     # per-ear lists
         if want_phase:
             out["phaseL"], out["phaseR"] = ph

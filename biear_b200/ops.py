@@ -88,6 +88,31 @@ def stft(wav, win_fn: torch.Tensor, fs: int, timesteps: int, win: int, hop: int,
     return torch.view_as_complex(xr)
 
 
+def stft_pair(wav_a: torch.Tensor, wav_b: torch.Tensor, win_fn: torch.Tensor, fs: int, timesteps: int, win: int, hop: int,
+              n_fft: int, ready: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Both ears in one launch, frame-major work order: X (2B, T, F) complex64 (rows of wav_a first).  `ready` ((2B*T + 4,)
+    int32, cleared beforehand; the last entries are the kernel's work counter) receives a 1 per finished (row, frame): the streaming hand-over to the recurrence kernel
+    (BiearSeqParams.x_ready), which may then run CONCURRENTLY with this launch."""
+    for w in (wav_a, wav_b):
+        if w.dim() != 2:
+            raise ValueError(f"Expected wav_1s (B,N), got {tuple(w.shape)}")
+        _need_cuda(w, "wav")
+    if wav_a.shape != wav_b.shape:
+        raise ValueError(f"waveform shapes differ: {tuple(wav_a.shape)} vs {tuple(wav_b.shape)}")
+    _need_cuda(win_fn, "win_fn")
+    dev = wav_a.device
+    with torch.cuda.device(dev):
+        lib = _prepare(dev)
+        rows, nsamp = wav_a.shape
+        nbins = n_fft // 2 + 1
+        xr = torch.empty((2 * rows, timesteps, nbins, 2), dtype=torch.float32, device=dev)
+        if ready is not None:
+            assert ready.dtype == torch.int32 and ready.numel() == 2 * rows * timesteps + 4 and ready.is_contiguous()
+        _lib.check(lib.biear_stft_fwd_pair(_ptr(wav_a), _ptr(wav_b), rows, nsamp, nsamp, _ptr(win_fn), fs, timesteps, win, hop,
+                                           n_fft, _ptr(xr), _ptr(ready), _stream(dev)), "biear_stft_fwd_pair")
+    return torch.view_as_complex(xr)
+
+
 # ------------------------------------------------------------------------------------------------
 # band stage
 # ------------------------------------------------------------------------------------------------
@@ -442,14 +467,16 @@ class PreparedSequence:
     """What biear_adaptive_prepare leaves behind for one step: the packed weight images (workspace), the GRU state
     tensor with its zeroed step 0, the cleared fallback flags, the snapshotted dropout seed -- and the event that marks
     the preparation launch on the stream it ran on."""
-    __slots__ = ("work", "H", "flags", "seed_dev", "event", "stream", "key", "launched")
+    __slots__ = ("work", "H", "flags", "seed_dev", "event", "stream", "key", "launched", "x_ready")
 
 
 def adaptive_prepare(weights, B: int, T: int, N: int, training: bool, stream: Optional[torch.cuda.Stream] = None,
-                     launch: bool = True):
+                     launch: bool = True, streamed_spectra: bool = False):
     """Run the spectra-independent part of a recurrence step (weight-image packing for the forward AND the backward
     kernel, H[:, 0] = 0, flags = 0, dropout-seed snapshot) as one launch, on `stream` if given: the front-end issues
     it on a forked stream so that it overlaps the STFT.  Pass the result to adaptive_sequence(prep=...).
+    streamed_spectra=True also allocates and clears the (G*B*T) ready flags of the streaming spectra hand-over
+    (stft_pair(ready=prep.x_ready) then runs next to the recurrence instead of before it).
     launch=False only allocates (the buffers are poisoned): biear_adaptive_fwd / _bwd then prepare on their own stream,
     the path a C caller that never calls biear_adaptive_prepare takes (testing).
     weights: dict name -> list of the G controllers' tensors."""
@@ -475,9 +502,10 @@ def adaptive_prepare(weights, B: int, T: int, N: int, training: bool, stream: Op
             out.flags = torch.empty((S * G + 1,), dtype=torch.int32, device=dev)
             out.work = torch.empty(int(lib.biear_adaptive_workspace_floats(G, N)), **f32)
             out.seed_dev = _captured_seed(dev) if (training and torch.cuda.is_current_stream_capturing()) else None
+            out.x_ready = torch.empty((G * B * T + 4,), dtype=torch.int32, device=dev) if (streamed_spectra and launch) else None
             prm = _lib.SeqParams()
             prm.G, prm.E, prm.B, prm.T, prm.N, prm.F, prm.Kin = G, G, B, T, N, 2, ws[0].shape[1]
-            _fill(prm, workspace=out.work, H=out.H, flags=out.flags)
+            _fill(prm, workspace=out.work, H=out.H, flags=out.flags, x_ready=out.x_ready)
             for i, name in enumerate(WEIGHT_NAMES):
                 arr = getattr(prm, name)
                 for g in range(G):
@@ -548,7 +576,7 @@ class AdaptiveSequence(torch.autograd.Function):
             cur = torch.cuda.current_stream(dev)
             if prep.stream != cur:                       # prepared on a forked stream: join it here
                 cur.wait_event(prep.event)
-                for t_ in (prep.work, prep.H, prep.flags, prep.seed_dev):
+                for t_ in (prep.work, prep.H, prep.flags, prep.seed_dev, prep.x_ready):
                     if t_ is not None:
                         t_.record_stream(cur)
             H, flags, work, seed_dev = prep.H, prep.flags, prep.work, prep.seed_dev
@@ -560,7 +588,7 @@ class AdaptiveSequence(torch.autograd.Function):
             prm.prepared = int(prep.launched)
             prm.df, prm.cutoff, prm.q_min, prm.q_max = float(df), float(cutoff), 0.05, 30.0
             _fill(prm, fc=fc, q0=q0, dq=dq, X=xr, Y=Y, phase=P, dYdQ=dY, dPdQ=dP, Q=Q, delta=D, flags=flags,
-                  workspace=work, H=H, seed_ptr=seed_dev, logY=LX, **sv)
+                  workspace=work, H=H, seed_ptr=seed_dev, logY=LX, x_ready=prep.x_ready, **sv)
             for i, name in enumerate(WEIGHT_NAMES):
                 arr = getattr(prm, name)
                 for g in range(G):
@@ -570,7 +598,7 @@ class AdaptiveSequence(torch.autograd.Function):
         ctx.prm = prm
         # owners of every pointer in prm (the per-ear outputs are views of Y / Q / P / LX, which are not outputs
         # themselves, so holding them here closes no reference cycle)
-        ctx.keep = (xr, fc, q0, dq, weights, Y, Q, P, LX, D, dY, dP, sv, flags, work, H, seed_dev)
+        ctx.keep = (xr, fc, q0, dq, weights, Y, Q, P, LX, D, dY, dP, sv, flags, work, H, seed_dev, prep.x_ready)
         ctx.has_phase = P is not None
         ctx.has_logy = LX is not None
         ctx.dims = (G, B, T, N, Kin, tiles, TILE)
@@ -587,7 +615,7 @@ class AdaptiveSequence(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *grads):
         from ctypes import byref
-        xr, fc, q0, dq, weights, Y, Q, P, LX, D, dY, dP, sv, flags, work, H, _seed_dev = ctx.keep
+        xr, fc, q0, dq, weights, Y, Q, P, LX, D, dY, dP, sv, flags, work, H, _seed_dev, _x_ready = ctx.keep
         G, B, T, N, Kin, tiles, TILE = ctx.dims
         none13 = (None,) * 14
         gY, gQ, gP, gLX = (list(grads[i * G:(i + 1) * G]) for i in range(4))

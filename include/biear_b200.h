@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BIEAR_ABI_VERSION 15
+#define BIEAR_ABI_VERSION 16
 #define BIEAR_EINVAL (-1)
 
 /* ABI version (== BIEAR_ABI_VERSION of the library that was built). */
@@ -52,6 +52,13 @@ int biear_init(void);
  *   X       (rows, T, n_fft/2+1, 2) out.
  * Supported: n_fft == 1024; any fs, T >= 1, win >= 1, hop >= 1.
  */
+/* Both ears in ONE launch, frames in frame-major order (frame 0 of every row first): rows [0, rows_each) come from wavA,
+ * [rows_each, 2 rows_each) from wavB; X (2 rows_each, T, n_fft/2+1, 2).  ready (nullable, 2 rows_each T + 4 int32, 8-byte
+ * aligned, cleared by the caller / biear_adaptive_prepare; the trailing entries are the kernel's in-order work counter): entry [row][t] is set to 1, with release ordering, once X[row][t] is
+ * complete -- the hand-over BiearSeqParams.x_ready describes. */
+int biear_stft_fwd_pair(const float* wavA, const float* wavB, int64_t rows_each, int64_t nsamp, int64_t wav_row_stride,
+                        const float* win_fn, int fs, int T, int win, int hop, int n_fft, float* X, int32_t* ready,
+                        void* stream);
 int biear_stft_fwd(const float* wav, int64_t rows, int64_t nsamp, int64_t wav_row_stride,
                    const float* win_fn, int fs, int T, int win, int hop, int n_fft,
                    float* X, void* stream);
@@ -170,6 +177,13 @@ typedef struct BiearSeqParams {
     /* non-zero: biear_adaptive_prepare has already run on this block's workspace / H / flags (stream-ordered before
        the forward), so biear_adaptive_fwd / _bwd skip their own preparation launch */
     int32_t prepared;
+    /* optional streaming hand-over of the spectra: x_ready[(ear * B + clip) * T + t] != 0 <=> X[row][t] is complete
+       (E*B*T + 4 int32: the last four are the STFT's work counter, cleared together with the flags).
+       When non-NULL the preparation launch clears it, biear_stft_fwd_pair (frame-major order, running CONCURRENTLY on
+       another stream, typically on the SMs the persistent kernel leaves idle) sets the entries, and the forward kernel
+       waits for the entries of a frame before it reads that frame -- so the recurrence does not wait for the whole STFT.
+       The caller must still order every later reader of X behind the STFT's completion. */
+    int32_t* x_ready;
 } BiearSeqParams;
 
 /* 1 if the persistent recurrence kernels can take N bands and F bins (their weight slices, activations and spectrum
