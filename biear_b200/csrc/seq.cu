@@ -249,6 +249,25 @@ __device__ __forceinline__ void wait_spectra(const BiearSeqParams& p, long long 
     __syncthreads();
 }
 
+// The same split in two, for the steady state: the flag of the NEXT frame is read at the start of a frame (the L2 round
+// trip hides behind the band stage) and only re-polled, before the block barrier that follows the band stage anyway, if
+// it was not set yet.
+__device__ __forceinline__ int peek_spectra(const BiearSeqParams& p, long long grow0, int b0, int t) {
+    int v = 1;
+    if (p.x_ready && threadIdx.x < kRT && b0 + (int)threadIdx.x < p.B)
+        asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(p.x_ready + (grow0 + threadIdx.x) * p.T + t) : "memory");
+    return v;
+}
+__device__ __forceinline__ void confirm_spectra(const BiearSeqParams& p, long long grow0, int t, int v) {
+    if (v != 0) return;                                        // (only threads that peeked a 0 get here)
+    const int32_t* flag = p.x_ready + (grow0 + threadIdx.x) * p.T + t;
+    for (unsigned spin = 0; v == 0; ++spin) {
+        __nanosleep(64);
+        asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (spin > (1u << 24)) __trap();
+    }
+}
+
 // Spectra of this CTA's 4 rows for frame t -> shared {1, abs, re, im} tiles (zeros for padding rows / bins), in two
 // steps so that the HBM latency hides behind the controller phases: prefetch_spectra() issues 8-byte cp.async copies
 // of the raw complex bins straight into the {re, im} half of their tile slots; finish_spectra() (same thread -> same
@@ -407,6 +426,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                 __syncthreads();
             }   // otherwise frame t's tile was fetched behind frame t-1's controller phases and converted before its barrier #5
             PHASE_MARK(0, 1);    // spectra ready
+            const int next_ready = (!STRICT && t + 1 < T) ? peek_spectra(p, grow0, bb0, t + 1) : 1;
 
             // ---- band stage of frame t for this CTA's 4 rows (model_torch.py:340-346, 1050-1060) ---------------
             // The 4 x quads (row, 4-band quad) pairs are dealt round-robin to the 16 warps, widest quads first and
@@ -487,9 +507,9 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                 if (STRICT) __syncthreads();
                 continue;
             }
+            if (!STRICT) confirm_spectra(p, grow0, t + 1, next_ready);   // (ordered for everybody by the barrier below)
             __syncthreads();
             if (!STRICT) {   // the tile is free again: start fetching the next frame's spectra behind the controller phases
-                wait_spectra(p, grow0, bb0, t + 1);
                 prefetch_spectra(p, spec_s, L.tile, grow0, bb0, t + 1);
                 spec_t = t + 1;
             }
