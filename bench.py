@@ -258,6 +258,8 @@ def run_ours(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":   # NCCL prints its banner on stdout: keep stdout = the JSON line
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
     bind_to_gpu_numa_node(local)
