@@ -418,9 +418,13 @@ class BinauralAdaptiveGammatoneFB(nn.Module):
             for w in (wavL_1s, wavR_1s):
                 if w.requires_grad:
                     raise RuntimeError("biear_b200: gradients with respect to the waveform are not implemented")
+            # (only when the whole batch is resident at once: with several waves of clusters the first wave would wait
+            # for the frames of every row)
+            tiles = 2 * ((B + ops.tile_rows() - 1) // ops.tile_rows())
+            streamed = STREAM_SPECTRA and tiles <= ops.resident_clusters(fb.Nbands, fb.n_fft // 2 + 1, wavL_1s.device)
             prep = ops.adaptive_prepare(_controller_weights([self.fb_L, self.fb_R]), B, fb.timesteps, fb.Nbands,
-                                        self.training, stream=side, streamed_spectra=STREAM_SPECTRA)
-            if STREAM_SPECTRA:
+                                        self.training, stream=side, streamed_spectra=streamed)
+            if streamed:
                 with torch.cuda.stream(side):
                     x = ops.stft_pair(wavL_1s.float().contiguous(), wavR_1s.float().contiguous(), fb.win_fn, fb.fs,
                                       fb.timesteps, fb.win, fb.hop, fb.n_fft, ready=prep.x_ready)

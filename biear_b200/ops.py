@@ -404,6 +404,24 @@ def fused_supported(n_bands: int, n_bins: int) -> bool:
     return bool(_lib.load().biear_adaptive_supported(int(n_bands), int(n_bins)))
 
 
+_resident = {}
+
+
+def resident_clusters(n_bands: int, n_bins: int, device=None) -> int:
+    """How many clusters (tiles) of the persistent forward kernel fit on the device at once
+    (cudaOccupancyMaxActiveClusters; 33 on a B200).  Cached per (device, geometry)."""
+    idx = torch.cuda.current_device() if device is None or device.index is None else device.index
+    key = (idx, int(n_bands), int(n_bins))
+    if key not in _resident:
+        from ctypes import byref, c_int
+        f, b = c_int(0), c_int(0)
+        with torch.cuda.device(idx):
+            _lib.check(_lib.load().biear_adaptive_occupancy(int(n_bands), int(n_bins), byref(f), byref(b)),
+                       "biear_adaptive_occupancy")
+        _resident[key] = int(f.value)
+    return _resident[key]
+
+
 def tile_rows() -> int:
     """Rows per tile (R) of the "tile layout" tensors (G, T-1, tiles, D, R), see include/biear_b200.h."""
     return int(_lib.load().biear_adaptive_tile_rows())
