@@ -199,16 +199,32 @@ def make_loss(model, up):
     # non-trivial): mean(up * x) per feature, written as ONE dot product with the 1/numel folded into the fixed weights
     wts = {k: (v / v.numel()).reshape(-1) for k, v in up.items()}
 
+    branches = {}
+
     def loss_fn(wl, wr):
         # one call for everything the back-end consumes: log band energies (model_torch.py:1080-1083, fused into the
         # band stage), sub-band phases, Q, and the CC feature (forked stream)
         o = model.forward_features(wl, wr, want_phase=True, want_cc=True, want_logenergy=True)
-        lin = lambda k, x: torch.dot(wts[k], x.reshape(-1))
+        # The five feature terms are independent of each other (like the per-ear encoders of the real back-end): each
+        # runs on its own forked stream, so the few small kernels of a term -- and, in the backward, of its gradient --
+        # overlap with the other terms' instead of queueing behind them.
+        cur = torch.cuda.current_stream(wl.device)
+        terms = []
+        for key, x in (("gYL", o["logYL"]), ("gYR", o["logYR"]), ("gPL", o["phaseL"]), ("gPR", o["phaseR"]), ("gC", o["cc"])):
+            st = branches.setdefault(key, torch.cuda.Stream(device=wl.device, priority=-1))
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                terms.append(torch.dot(wts[key], x.reshape(-1)))
         # ... plus the reference's Q regularisers on (QL + QR) / 2 (train_biear.py:476-490): value and gradient from one
         # kernel (biear_q_regularizers)
-        reg = ops.q_regularizers(o["QL"], o["QR"], model.Q0, REG_Q_W, REG_SMOOTH_W)[0]
-        return torch.stack([lin("gYL", o["logYL"]), lin("gYR", o["logYR"]), lin("gPL", o["phaseL"]),
-                            lin("gPR", o["phaseR"]), lin("gC", o["cc"]), reg]).sum()
+        st = branches.setdefault("reg", torch.cuda.Stream(device=wl.device, priority=-1))
+        st.wait_stream(cur)
+        with torch.cuda.stream(st):
+            terms.append(ops.q_regularizers(o["QL"], o["QR"], model.Q0, REG_Q_W, REG_SMOOTH_W)[0])
+        for key, t in zip(("gYL", "gYR", "gPL", "gPR", "gC", "reg"), terms):
+            cur.wait_stream(branches[key])
+            t.record_stream(cur)
+        return torch.stack(terms).sum()
 
     return loss_fn, params
 
