@@ -265,19 +265,26 @@ __device__ __forceinline__ void wgrad_matrix_tc(const WgradPlan& pl, const Wgrad
         const float* bp = a.B + (long long)g * a.b_group + (long long)r * tile_w + half * 8;
         // register prefetch ring, kWtAhead slabs deep: a slab is little work, so the loads of several slabs must be in
         // flight at once to cover the L2 / HBM latency
-        constexpr int kWtAhead = 3;
+        constexpr int kWtAhead = 6;
         float4 xa[kWtAhead][2], xb[kWtAhead][2];
-        auto fetch = [&](long long q, float4 (&ra)[2], float4 (&rb)[2]) {
-            const long long cc = q / per;
-            const int sub = (int)(q % per) * kTcKB;
-            const bool live = cc < a.tile_chunks;
+        // Slabs are fetched strictly in order, so the producers carry running pointers instead of recomputing
+        // (chunk, offset) -> address per slab: 16-row tiles advance one operand chunk per slab, 32-row tiles alternate
+        // between the two halves of a chunk.
+        const float* pa = ap + (c0 / per) * a.a_chunk + (int)(c0 % per) * kTcKB;
+        const float* pb = bp + (c0 / per) * a.b_chunk + (int)(c0 % per) * kTcKB;
+        long long q_next = c0;                                   // slab the next fetch() loads
+        const long long q_end = a.tile_chunks * per;             // slabs that exist (the last split may run past it)
+        auto fetch = [&](long long, float4 (&ra)[2], float4 (&rb)[2]) {
+            const bool live = q_next < q_end;
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
-                ra[c] = (live && a_ok) ? __ldg(reinterpret_cast<const float4*>(ap + cc * a.a_chunk + sub) + c)
-                                       : make_float4(0.f, 0.f, 0.f, 0.f);
-                rb[c] = (live && b_ok) ? __ldg(reinterpret_cast<const float4*>(bp + cc * a.b_chunk + sub) + c)
-                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+                ra[c] = (live && a_ok) ? __ldg(reinterpret_cast<const float4*>(pa) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                rb[c] = (live && b_ok) ? __ldg(reinterpret_cast<const float4*>(pb) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+            const bool wrap = per == 1 || (q_next & 1);           // next slab starts a new operand chunk
+            pa += wrap ? a.a_chunk - (per - 1) * kTcKB : kTcKB;
+            pb += wrap ? a.b_chunk - (per - 1) * kTcKB : kTcKB;
+            ++q_next;
         };
         float bsum = 0.f;
 #pragma unroll
@@ -287,7 +294,7 @@ __device__ __forceinline__ void wgrad_matrix_tc(const WgradPlan& pl, const Wgrad
 #pragma unroll
             for (int u = 0; u < kWtAhead; ++u) {
                 const int i = i0 + u;
-                if (i >= n_slabs) break;
+                if (i >= n_slabs) continue;          // (no break: the ring index u must stay a compile-time constant)
                 const int s = i % kWtStages;
                 const uint32_t ph = (i / kWtStages) & 1;
                 mbar_wait(bar_empty + 8 * s, ph ^ 1);

@@ -11,7 +11,9 @@ mk = lambda d: torch.randn((G, K + tiles, d, R), generator=g).to(dev)
 GG, yc, hp, a1, d1, a2, d2, pre, v1, x1 = mk(512), mk(N), mk(H), mk(H), mk(H), mk(H), mk(H), mk(N), mk(H), mk(H)
 jobs = [(GG, 384, yc, N, K, True), (GG, 256, hp, H, K, True), (GG[:, :, 384:], 128, hp, H, K, True), (a1, H, hp[:, tiles:], H, K, True),
         (a2, H, d1, H, K, True), (pre, N, d2, H, K, True), (v1, H, x1, 0, K, True), (a2, H, x1, 0, K, True)]
-for variant in ("ffma", "tc"):
+import itertools
+for variant, jobs in itertools.chain((("ffma", jobs), ("tc", jobs), ("tc", jobs[:6]), ("tc", jobs[:1]), ("ffma", jobs[6:]))):
+    print(f"{len(jobs)} job(s):", end=" ")
     for _ in range(3):
         ops.ctrl_wgrad(jobs, variant=variant)
     gr = torch.cuda.CUDAGraph()
