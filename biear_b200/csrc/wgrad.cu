@@ -172,7 +172,9 @@ __device__ __forceinline__ void wgrad_diagonal(const WgradPlan& pl, const WgradJ
     if (f < a.Do) {
         const float* Ag = a.A + (long long)g * a.a_group + (long long)f * tile_w + half * per;
         const float* Bg = a.B + (long long)g * a.b_group + (long long)f * tile_w + half * per;
+#pragma unroll 4      // independent loads of several chunks in flight: the job is pure latency
         for (long long c = c0; c < c1; ++c) {
+#pragma unroll
             for (int q = 0; q < per; q += 4) {
                 const float4 x = __ldg(reinterpret_cast<const float4*>(Ag + c * a.a_chunk + q));
                 const float4 y = __ldg(reinterpret_cast<const float4*>(Bg + c * a.b_chunk + q));
