@@ -714,11 +714,14 @@ __device__ __forceinline__ void ln_silu_drop_bwd(const BiearSeqParams& p, unsign
                                                  const float* __restrict__ gamma_s, const float* __restrict__ beta_s,
                                                  int layer, int t, long long grow0, int rank,
                                                  const float (&xh)[kHid / (kSeqThreads / kR)], float rstd,
-                                                 float* gv_tile, float* ga_tile) {
+                                                 float (&dv_out)[kHid / (kSeqThreads / kR)],
+                                                 float (&da_out)[kHid / (kSeqThreads / kR)]) {
+    // dv_out / da_out: dL/d(LN output) and dL/d(LN input) of this thread's (row, 4 features); the caller stores the CTA's
+    // own slice to HBM (store_ln_grads) AFTER it has signalled the next cluster barrier, whose release would otherwise
+    // wait for those stores.
     constexpr int PARTS = kSeqThreads / kR, FPP = kHid / PARTS;
     const int row = threadIdx.x % kR, part = threadIdx.x / kR;
     const int f0 = part * FPP;
-    const bool mine = f0 / kU == rank;
     float dxh[FPP];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -734,7 +737,7 @@ __device__ __forceinline__ void ln_silu_drop_bwd(const BiearSeqParams& p, unsign
             const float sg = sigmoid_fast(y);
             const float d = buf_s[f * kR + row] * scv[j];
             const float dv = d * sg * (1.0f + y * (1.0f - sg));
-            if (mine) gv_tile[f * kR + row] = dv;
+            dv_out[i] = dv;
             dxh[i] = dv * gm;
             s1 += dxh[i];
             s2 = fmaf(dxh[i], xh[i], s2);
@@ -759,9 +762,21 @@ __device__ __forceinline__ void ln_silu_drop_bwd(const BiearSeqParams& p, unsign
         const int f = f0 + i;
         const float da = rstd * (dxh[i] - m1 - xh[i] * m2);
         buf_s[f * kR + row] = da;
-        if (mine) ga_tile[f * kR + row] = da;
+        da_out[i] = da;
     }
     __syncthreads();
+}
+
+__device__ __forceinline__ void store_ln_grads(int rank, const float (&dv)[kHid / (kSeqThreads / kR)],
+                                               const float (&da)[kHid / (kSeqThreads / kR)], float* gv_tile, float* ga_tile) {
+    constexpr int PARTS = kSeqThreads / kR, FPP = kHid / PARTS;
+    const int row = threadIdx.x % kR, f0 = (threadIdx.x / kR) * FPP;
+    if (f0 / kU != rank) return;
+#pragma unroll
+    for (int i = 0; i < FPP; ++i) {
+        gv_tile[(f0 + i) * kR + row] = dv[i];
+        ga_tile[(f0 + i) * kR + row] = da[i];
+    }
 }
 
 __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqParams p, const float* __restrict__ img) {
@@ -900,8 +915,10 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
         }
         cluster.sync();   // #2
         PHASE_MARK(1, 2);    // Linear 3 ^T
+        constexpr int kFPP = kHid / (kSeqThreads / kR);
+        float dv2[kFPP], da2[kFPP];
         ln_silu_drop_bwd(p, seed, bufa_s, stat_s, vec_s + VB_LN2G, vec_s + VB_LN2B, 1, t, (long long)g * p.B + b0, rank,
-                         ln2.xh, ln2.rstd, p.G_v2 + tb * kHid * kR, p.G_a2 + tb * kHid * kR);
+                         ln2.xh, ln2.rstd, dv2, da2);
         const LnSaved ln1 = load_ln_saved(p.xh1 + tb * kHid * kR, p.rstd + tb * 2 * kR, 0);   // used after #3
         PHASE_MARK(1, 3);    // LayerNorm 2 backward
         // ---- Linear 2 ^T --------------------------------------------------------------------------------------
@@ -913,10 +930,13 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
             reduce_ks1<kRT>(acc, red_s, ks, slot);
             if (ks == 0) broadcast_rows(cluster, bufb_s, ug, rg * kRT, acc);   // bufb aliases dpre: its reads ended before #2
         }
-        cluster.sync();   // #3
+        cluster.barrier_arrive();   // #3 signalled before the saved LayerNorm-2 gradients go out
+        store_ln_grads(rank, dv2, da2, p.G_v2 + tb * kHid * kR, p.G_a2 + tb * kHid * kR);
+        cluster.barrier_wait();   // #3
         PHASE_MARK(1, 4);    // Linear 2 ^T
+        float dv1[kFPP], da1[kFPP];
         ln_silu_drop_bwd(p, seed, bufb_s, stat_s, vec_s + VB_LN1G, vec_s + VB_LN1B, 0, t, (long long)g * p.B + b0, rank,
-                         ln1.xh, ln1.rstd, p.G_v1 + tb * kHid * kR, p.G_a1 + tb * kHid * kR);
+                         ln1.xh, ln1.rstd, dv1, da1);
         PHASE_MARK(1, 5);    // LayerNorm 1 backward
         // ---- Linear 1 ^T, GRU cell backward ------------------------------------------------------------------------
         float dh_direct[kRT] = {0.f, 0.f, 0.f, 0.f};
@@ -961,6 +981,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
                 broadcast_rows(cluster, gate_s, 3 * kHid + ug, rg * kRT, v3);
             }
             cluster.barrier_arrive();   // #4 signalled before the saved gradients go out
+            store_ln_grads(rank, dv1, da1, p.G_v1 + tb * kHid * kR, p.G_a1 + tb * kHid * kR);
             if (ks == 0) {
                 float* gg = p.GG + tb * 4 * kHid * kR + ug * kR + rg * kRT;
                 store4(gg, v0);
