@@ -38,6 +38,35 @@ def _zero_nonfinite(x):
     return torch.nan_to_num(x, nan=0.0, posinf=0.0, neginf=0.0)
 
 
+PARALLEL_BRANCHES = True    # independent sub-networks of the back-end (two encoders, eight sector heads) on forked streams
+_branch_streams = {}
+
+
+def _fork_join(fns, ref: torch.Tensor):
+    """Run independent closures on forked CUDA streams and join them on the current one.  Each branch is a few dozen
+    tiny kernels (the eight sector heads alone are ~200 launches forward); side by side -- also inside a captured CUDA
+    graph, where the forks become parallel branches, and in the backward, which autograd runs on the forward's streams --
+    they cost the depth of one branch instead of the sum.  Results (and dropout masks: the generator offset advances in
+    host order) are identical to running them one after the other.  CPU tensors: plain sequential calls."""
+    if not (PARALLEL_BRANCHES and ref.is_cuda and len(fns) > 1):
+        return [fn() for fn in fns]
+    dev = ref.device
+    cur = torch.cuda.current_stream(dev)
+    pool = _branch_streams.setdefault(dev.index if dev.index is not None else torch.cuda.current_device(), [])
+    while len(pool) < len(fns):
+        pool.append(torch.cuda.Stream(device=dev))
+    outs = []
+    for fn, st in zip(fns, pool):
+        st.wait_stream(cur)
+        with torch.cuda.stream(st):
+            outs.append(fn())
+    for o, st in zip(outs, pool):
+        cur.wait_stream(st)
+        for t in (o if isinstance(o, (tuple, list)) else (o,)):
+            t.record_stream(cur)
+    return outs
+
+
 class _PairEncoder(nn.Module):
     """LayerNorm -> GRU(in->hidden) -> GRU(hidden->latent) -> mean over frames (model_torch.py:828-867).
     Sub-classes define the interaural feature built from the left/right inputs."""
@@ -111,11 +140,12 @@ class _BackEnd(nn.Module):
         self.subheads = nn.ModuleList([SubHead(200, n_dist_class=n_dist_class) for _ in range(n_sectors)])
 
     def _backend(self, x1, x2, x3, ph_l, ph_r):
-        feats = [self.encoder_ild(x1, x2), self.encoder_ipd(ph_l, ph_r)]
+        branches = [lambda: self.encoder_ild(x1, x2), lambda: self.encoder_ipd(ph_l, ph_r)]
         if self.use_cc:
-            feats.append(self.cc_proj(x3))
+            branches.append(lambda: self.cc_proj(x3))
+        feats = _fork_join(branches, x1)
         body = self.body(torch.cat(feats, dim=-1))
-        outs = [head(body) for head in self.subheads]
+        outs = _fork_join([lambda h=head: h(body) for head in self.subheads], body)
         sound = torch.cat([o[0] for o in outs], dim=1)
         aoa = torch.cat([o[1] for o in outs], dim=1)
         dist = torch.stack([o[2] for o in outs], dim=1)
