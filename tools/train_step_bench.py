@@ -30,7 +30,7 @@ model = model.to(dev).train()
 fb_params = list(model.bifb.parameters()); be_params = [p for n, p in model.named_parameters() if not n.startswith("bifb.")]
 params = fb_params + be_params
 opt = torch.optim.Adam([{"params": fb_params, "lr": 5e-5}, {"params": be_params, "lr": 1e-4}], weight_decay=1e-5, eps=1e-7,
-                       capturable=True)
+                       capturable=True, fused=True)
 wl, wr = bench.synth_binaural(B, 1234 + rank)
 wl, wr = torch.from_numpy(wl).to(dev), torch.from_numpy(wr).to(dev)
 rs = np.random.RandomState(5)
