@@ -105,3 +105,42 @@ def test_no_cpu_fallback():
     # the reference's own error for the active model's finiteness check is kept by the drop-in namespace
     from biear_b200 import model_torch as mt
     assert mt.N_SECTORS == 8 and mt.N_DIST_CLASS == 5 and mt.DATA_DIM == 100
+
+
+def test_3xtf32_split_keeps_fp32_accuracy():
+    """The tensor-core kernels (band_fixed_tc.cu, wgrad_tc_kernel) feed TF32 operands split as x = hi + lo, hi = the top
+    19 bits (what tf32_hi() in csrc/tc_dev.cuh computes), lo = x - hi, and form hi*hi + lo*hi + hi*lo with fp32
+    accumulation.  Emulated here in numpy (lo additionally truncated to TF32, as the tensor core reads it): the result
+    stays within a few 1e-6 of the float64 dot product, where plain TF32 operands are off by ~1e-3 -- the reason the
+    split exists (parity contract 1e-4)."""
+    rs = np.random.RandomState(0)
+
+    def tf32(x):
+        return (x.astype(np.float32).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+
+    a = rs.standard_normal((64, 513)).astype(np.float32) * np.linspace(3.0, 0.2, 513, dtype=np.float32)
+    w = np.abs(rs.standard_normal((100, 513))).astype(np.float32)
+    w /= w.sum(1, keepdims=True)
+    ref = a.astype(np.float64) @ w.astype(np.float64).T
+    a_hi, w_hi = tf32(a), tf32(w)
+    a_lo, w_lo = tf32(a - a_hi), tf32(w - w_hi)
+    assert np.array_equal(a_hi + (a - a_hi), a)                       # the split is exact in fp32
+    split = (a_lo.astype(np.float64) @ w_hi.astype(np.float64).T + a_hi.astype(np.float64) @ w_lo.astype(np.float64).T
+             + a_hi.astype(np.float64) @ w_hi.astype(np.float64).T).astype(np.float32)
+    plain = (a_hi.astype(np.float64) @ w_hi.astype(np.float64).T).astype(np.float32)
+    scale = np.abs(ref).max()
+    assert np.abs(split - ref).max() / scale <= 2e-6
+    assert np.abs(plain - ref).max() / scale >= 1e-5                  # plain TF32 is far outside what the contract allows
+
+
+def test_umma_tile_layout_is_a_bijection():
+    """tc_tile_off() of csrc/tc_dev.cuh (K-major, no swizzle: core matrices of 8 rows x 16 bytes, chunk-major): every
+    (row, k) of a 128 x 16 tile maps to a distinct float slot of the 8 KB tile, 16-byte groups stay together."""
+    lbo, sbo = 16 * 128, 128
+    off = lambda r, kk: (kk >> 2) * (lbo // 4) + (r >> 3) * (sbo // 4) + (r & 7) * 4 + (kk & 3)
+    slots = {off(r, kk) for r in range(128) for kk in range(16)}
+    assert slots == set(range(128 * 16))
+    for r in range(128):
+        for c in range(4):
+            assert [off(r, 4 * c + i) for i in range(4)] == list(range(off(r, 4 * c), off(r, 4 * c) + 4))
+            assert off(r, 4 * c) % 4 == 0
