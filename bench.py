@@ -12,7 +12,10 @@ all-reduced over NCCL every step.
 
 Prints ONE JSON line (rank 0).  `value` is measured with the inputs resident in HBM, `e2e` through the
 same public call with pinned HOST buffers (H2D of both waveforms and D2H of the loss inside the timed region).
-`--impl reference` times the CPU restatement of the reference (oracle/) on the host cores instead.
+`--impl reference` times the reference's own code (oracle/_ref staging of model_torch.py / utils.py; the oracle port only
+if that staging is absent) on the host cores instead.  The line also carries `roofline` (HBM, as the contract asks, plus the
+compute-side bound under `roofline.compute`), `cpu_baseline`, and -- at N = 1 -- the sub-records `gpu_eager_reference`
+(the reference code in PyTorch eager on the same GPU), `fixed_q` (BASELINE config 3) and `full_step` (config 4).
 """
 import argparse
 import json
@@ -471,8 +474,19 @@ def run_ours(args):
                           "note": "whole step per GPU; the adaptive path is bound by the 19-step dependency chain "
                                   "and fp32/MUFU work, not HBM (SURVEY.md 8(d))"},
     }
+    import bench_extra
+    roof["compute"] = bench_extra.compute_roofline(model, dev_in, value / world, roof["us_per_launch"], NCU_SUMMARY)
+    if world == 1 and not args.no_extra:
+        # sub-records (1 GPU only; each bounded to a few seconds): the same-box competitor and BASELINE configs 3 / 4
+        for key, fn in (("gpu_eager_reference", lambda: bench_extra.gpu_eager_reference(B, steps=5, warmup=2, device=str(dev))),
+                        ("fixed_q", lambda: bench_extra.fixed_q(4096, device=str(dev))),
+                        ("full_step", lambda: bench_extra.full_step(B, steps=30, device=str(dev)))):
+            try:
+                out[key] = fn()
+            except Exception as e:  # noqa: BLE001  (a failing side measurement must not lose the main line)
+                out[key] = {"error": repr(e)[:300]}
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(sample_batch=16, budget_s=20.0)
+        out["cpu_baseline"] = bench_extra.reference_cpu(sample_batch=16, budget_s=20.0)
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
@@ -584,7 +598,8 @@ def cpu_step_factory(sample_batch):
     return step
 
 
-def cpu_baseline(sample_batch=16, budget_s=20.0, steps=None, warmup=1):
+def cpu_baseline_port(sample_batch=16, budget_s=20.0, steps=None, warmup=1):
+    """The oracle PORT timed on the host cores (only used when oracle/_ref -- the reference itself -- is not staged)."""
     try:     # every host thread this process may use (torchrun exports OMP_NUM_THREADS=1)
         torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
     except Exception:  # noqa: BLE001
@@ -600,7 +615,7 @@ def cpu_baseline(sample_batch=16, budget_s=20.0, steps=None, warmup=1):
         el = time.perf_counter() - t0
         if (steps is not None and n >= steps) or (steps is None and (el >= budget_s or n >= 50)):
             break
-    return {"value": sample_batch * n / el, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+    return {"value": sample_batch * n / el, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "steps": n,
             "sample": f"{n} steps of batch {sample_batch} (same clips/weights recipe), oracle/biear_oracle.py "
                       f"(torch CPU fp32 restatement of model_torch.py + utils.py CC), {el:.1f} s, "
                       f"os.cpu_count()={os.cpu_count()}",
@@ -608,21 +623,24 @@ def cpu_baseline(sample_batch=16, budget_s=20.0, steps=None, warmup=1):
 
 
 def run_reference(args):
+    """The reference arm: the reference's own CPU implementation of the path (oracle/_ref) on the box's host cores, all the
+    threads it can use, on our arm's config / metric / unit; each step a bounded sample (16 clips) of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import bench_extra
     sample = 16
-    warm = min(args.warmup, 2)
-    steps = max(1, min(args.steps, 20))
-    cb = cpu_baseline(sample_batch=sample, steps=steps, warmup=warm)
+    warm = max(3, min(args.warmup, 5))
+    steps = max(10, min(args.steps, 40))
+    cb = bench_extra.reference_cpu(sample_batch=sample, steps=steps, warmup=warm)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     out = {
-        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": world, "steps": steps,
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": world, "steps": cb.get("steps", steps),
         "warmup": warm, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"BiEAR active front-end fwd+bwd, adaptive Q (dual) + phase + CC, batch {args.batch} x 1 s "
                                f"binaural clips @16 kHz per GPU, conf/config.yaml settings, train mode",
-                   "note": f"CPU arm: each step is a bounded sample of {sample} clips of that workload, eval-mode dropout"},
+                   "note": f"CPU arm ({cb['kind']}): each step is a bounded sample of {sample} clips of that workload, train-mode dropout"},
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -638,6 +656,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="clips per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the gpu_eager_reference / fixed_q / full_step sub-records")
     ap.add_argument("--eager", action="store_true", help="issue every launch from Python instead of replaying CUDA graphs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -7,9 +7,11 @@ The wire format is the H5 layout written by create_h5_data/data_h5_save.py:72-81
 h5py is not available in this image, so a path is read as follows:
     <path>        if it exists and h5py imports     -> the real H5 file
     <path>.npz    (same datasets, numpy archive)     -> loaded with numpy
-    otherwise                                        -> a deterministic synthetic set (size BIEAR_SYNTH_CLIPS,
-                                                        default 256) generated from a hash of the path, so the
-                                                        reference's scripts run end to end without the corpora.
+    otherwise                                        -> FileNotFoundError / ImportError.  Only with the explicit opt-in
+                                                        BIEAR_ALLOW_SYNTHETIC=1 (tests, smoke runs of the reference's
+                                                        scripts without the corpora): a deterministic synthetic set (size
+                                                        BIEAR_SYNTH_CLIPS, default 256) generated from a hash of the
+                                                        path, announced with a loud warning.
 Datasets are fork-safe (plain numpy arrays) for DataLoader(num_workers=4).
 """
 import os
@@ -52,17 +54,28 @@ def _synthetic(path, n, passive):
 
 def load_arrays_from_h5(path, keys=("x1", "x2", "x3", "y"), passive=False):
     path = str(path)
+    if os.path.exists(path + ".npz"):          # numpy twin of the H5 wire format (written by biear_b200.precompute)
+        z = np.load(path + ".npz")
+        return {k: z[k] for k in keys}
+    problem = None
     if os.path.exists(path):
         try:
             import h5py
+        except ImportError as e:
+            problem = ImportError(f"{path} exists but h5py is not importable ({e}); install h5py or provide {path}.npz")
+        else:
             with h5py.File(path, "r") as f:
                 return {k: np.asarray(f[k]) for k in keys}
-        except ImportError:
-            pass
-    if os.path.exists(path + ".npz"):
-        z = np.load(path + ".npz")
-        return {k: z[k] for k in keys}
-    return _synthetic(path, int(os.environ.get("BIEAR_SYNTH_CLIPS", "256")), passive)
+    else:
+        problem = FileNotFoundError(f"dataset not found: {path} (nor {path}.npz)")
+    if os.environ.get("BIEAR_ALLOW_SYNTHETIC") == "1":
+        n = int(os.environ.get("BIEAR_SYNTH_CLIPS", "256"))
+        import warnings
+        msg = f"biear_b200.dropin.data: {problem}; BIEAR_ALLOW_SYNTHETIC=1 -> using {n} SYNTHETIC clips, metrics are meaningless"
+        warnings.warn(msg, stacklevel=2)
+        print("[WARNING] " + msg, flush=True)
+        return _synthetic(path, n, passive)
+    raise problem
 
 
 class DeepEarH5Dataset_Active(Dataset):

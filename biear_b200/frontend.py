@@ -27,7 +27,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+from . import ops, timing
 
 Q_MIN, Q_MAX = 0.05, 30.0
 
@@ -247,8 +247,9 @@ def _adaptive_chain(x: torch.Tensor, ears: int, ctrl_mods, fc, q0, dq_vec, dq_mo
         q_new = _next_q(torch.tanh(pre), q0g, dqg, dq_mode)
         # batch-global non-finite fallback of the reference, decided per controller, on the device
         ok = torch.isfinite(q_new).flatten(1).all(dim=1).view(G, 1, 1)
-        q = torch.where(ok, q_new, q0g.expand_as(q_new))
-        h = h * ok
+        # (built from Q0 / zeros directly: NaN * 0 is NaN, and the reference cuts the graph on the fallback branch)
+        q = torch.where(ok, torch.nan_to_num(q_new, nan=0.0, posinf=0.0, neginf=0.0), q0g.expand_as(q_new))
+        h = torch.where(ok, torch.nan_to_num(h, nan=0.0, posinf=0.0, neginf=0.0), torch.zeros_like(h))
         if shared:
             mem = 0.8 * mem + 0.2 * ycd
     y_all = torch.stack(ys, dim=1)
@@ -264,7 +265,8 @@ def _log_energy(y: torch.Tensor) -> torch.Tensor:
     return torch.clamp(torch.log(y + 1e-8), -12.0, 12.0)
 
 
-STREAM_SPECTRA = os.environ.get("BIEAR_STREAM_SPECTRA", "1") != "0"   # STFT next to the recurrence (flag hand-over)
+STREAM_SPECTRA = True     # STFT next to the recurrence (flag hand-over) whenever the co-residency conditions below hold
+STFT_PRODUCER_SMS = 16    # SMs that must remain free of recurrence CTAs for the streamed STFT producer
 FIXED_ENGINE = "gemm"   # "gemm": shared-weight dense contraction (csrc/band_fixed.cu); "item": per-item band kernel,
                         # bit-identical to the adaptive path at Q == Q0 (kept for that identity and as a cross-check)
 
@@ -393,6 +395,10 @@ class BinauralAdaptiveGammatoneFB(nn.Module):
         persistent recurrence kernels occupy 128 of the 148 SMs).  With want_logenergy the log band energies
         clamp(log(Y + 1e-8), +-12) (model_torch.py:1080-1083) come out of the band stage's epilogue as "logYL" / "logYR"
         and their gradient is folded into the backward kernel."""
+        with timing.span("frontend.forward", wavL_1s.shape[0] if wavL_1s.dim() == 2 else 0):
+            return self._forward_features(wavL_1s, wavR_1s, want_phase, want_cc, cc_max_lag_ms, want_logenergy)
+
+    def _forward_features(self, wavL_1s, wavR_1s, want_phase, want_cc, cc_max_lag_ms, want_logenergy):
         fb = self.fb_L
         if wavL_1s.shape != wavR_1s.shape:
             raise ValueError(f"wavL {tuple(wavL_1s.shape)} and wavR {tuple(wavR_1s.shape)} differ")
@@ -422,8 +428,16 @@ class BinauralAdaptiveGammatoneFB(nn.Module):
                     raise RuntimeError("biear_b200: gradients with respect to the waveform are not implemented")
             # (only when the whole batch is resident at once: with several waves of clusters the first wave would wait
             # for the frames of every row)
+            # Co-residency: the recurrence kernel spin-waits on flags the STFT kernel (another stream) publishes, so the
+            # STFT must be able to run NEXT TO it.  Required: every cluster of the recurrence is resident at once, and
+            # -- counted on the device's actual SM count, the 227 KB CTAs of the recurrence own their SM -- at least
+            # STFT_PRODUCER_SMS SMs stay free for the producer.  Anything else (small parts, MIG slices, very large
+            # batches) takes the STFT-first order.  The STFT is always LAUNCHED first and never waits for anything, so a
+            # serialising tool (ncu, compute-sanitizer) runs it to completion before the consumer starts.
             tiles = 2 * ((B + ops.tile_rows() - 1) // ops.tile_rows())
-            streamed = STREAM_SPECTRA and tiles <= ops.resident_clusters(fb.Nbands, fb.n_fft // 2 + 1, wavL_1s.device)
+            sms = torch.cuda.get_device_properties(wavL_1s.device).multi_processor_count
+            streamed = STREAM_SPECTRA and tiles <= ops.resident_clusters(fb.Nbands, fb.n_fft // 2 + 1, wavL_1s.device) \
+                and tiles * ops.CLUSTER_CTAS + STFT_PRODUCER_SMS <= sms
             prep = ops.adaptive_prepare(_controller_weights([self.fb_L, self.fb_R]), B, fb.timesteps, fb.Nbands,
                                         self.training, stream=side, streamed_spectra=streamed)
             if streamed:

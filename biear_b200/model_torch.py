@@ -184,14 +184,46 @@ class DeepEarActiveWaveform(_BackEnd):
         self._init_backend(use_cc, n_bands, latent_dim, n_sectors, n_dist_class)
         self.last_QL = self.last_QR = self.last_Q = None
 
+    # model_torch.py:1032-1037, 1071-1074 raise RuntimeError when YL / YR / QL / QR hold NaN / Inf -- four host
+    # synchronisations per forward there.  Here the four counts are ONE device-side reduction whose result travels to
+    # pinned host memory behind the step; the host looks at it when the NEXT forward starts (or on check_finite()), so
+    # the forward path has no host synchronisation and can be captured in a CUDA graph.
+    #   finite_check = "deferred" (default) | "sync" (the reference's immediate raise, one host sync) | "off"
+    finite_check = "deferred"
+    _FINITE_NAMES = ("YL", "YR", "QL", "QR")
+
+    def _raise_if_bad(self, counts):
+        for name, n in zip(self._FINITE_NAMES, counts):
+            if n:
+                raise RuntimeError(f"[NaN/Inf] {name} has {int(n)} non-finite values.")
+
+    def check_finite(self):
+        """Raise now if an earlier forward produced non-finite YL / YR / QL / QR (waits for that forward)."""
+        pend = getattr(self, "_finite_pending", None)
+        if pend is not None:
+            host, ev = pend
+            self._finite_pending = None
+            ev.synchronize()
+            self._raise_if_bad(host.tolist())
+
     def _assert_finite(self, tensors):
-        """model_torch.py:1032-1037, 1071-1074 with one device-side reduction instead of four host syncs."""
+        if self.finite_check == "off":
+            return
         bad = torch.stack([(~torch.isfinite(t)).sum() for _, t in tensors])
-        if bool(bad.any()):            # the only host read on the forward path
-            for (name, t), n in zip(tensors, bad.tolist()):
-                if n:
-                    raise RuntimeError(f"[NaN/Inf] {name} has {n} non-finite values. "
-                                       f"min={t.min().item()} max={t.max().item()}")
+        if torch.cuda.is_current_stream_capturing():
+            self.finite_flags = bad                       # static tensor of the graph: the owner of the graph may read it
+            return
+        if self.finite_check == "sync":
+            self._raise_if_bad(bad.tolist())
+            return
+        self.check_finite()                               # the previous forward's verdict (long finished: no stall)
+        host = getattr(self, "_finite_host", None)
+        if host is None:
+            host = self._finite_host = torch.zeros(len(tensors), dtype=torch.int64).pin_memory()
+        host.copy_(bad, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._finite_pending = (host, ev)
 
     def forward(self, wavL_1s, wavR_1s, x3=None):
         wavL_1s = wavL_1s.float()
@@ -199,9 +231,22 @@ class DeepEarActiveWaveform(_BackEnd):
         if hasattr(self.bifb, "forward_features"):
             o = self.bifb.forward_features(wavL_1s, wavR_1s, want_phase=True, want_logenergy=True)
             YL, YR, QL, QR, ph_l, ph_r = o["YL"], o["YR"], o["QL"], o["QR"], o["phaseL"], o["phaseR"]
-        else:   # a foreign bifb_class that only implements the reference's 6-tuple protocol
-            raise TypeError("bifb_class must provide forward_features(wavL, wavR, want_phase) "
-                            "(biear_b200 front-ends do); the reference's own classes run on its own model")
+        else:   # a foreign bifb_class that only implements the reference's 6-tuple protocol (model_torch.py:1069):
+            # log energies in PyTorch, sub-band phase from (X, Q) through the band kernel (one pass, all frames)
+            from . import ops
+            from .frontend import _log_energy
+            YL, YR, QL, QR, XL, XR = self.bifb(wavL_1s, wavR_1s)
+            fc = self.bifb.fc.to(YL.device)
+            df = float(self.bifb.f_fft[1] - self.bifb.f_fft[0])
+            phs = []
+            for X, Q in ((XL, QL), (XR, QR)):
+                xr = torch.view_as_real(X.contiguous())
+                T_ = xr.shape[1]
+                ph = torch.stack([ops.BandFrame.apply(Q[:, t], xr, t, fc, df, ops.DEFAULT_CUTOFF, True, "jacobian")[1]
+                                  for t in range(T_)], dim=1)
+                phs.append(ph)
+            ph_l, ph_r = phs
+            o = {"logYL": _log_energy(YL), "logYR": _log_energy(YR)}
         self._assert_finite((("YL", YL), ("YR", YR), ("QL", QL), ("QR", QR)))
         self.last_QL, self.last_QR, self.last_Q = QL, QR, 0.5 * (QL + QR)
         x1, x2 = o["logYL"], o["logYR"]          # clamp(log(Y + 1e-8), +-12), fused into the band stage (:1080-1083)

@@ -6,7 +6,6 @@ no fallback path.
 """
 from __future__ import annotations
 
-import os
 from ctypes import c_void_p
 from functools import lru_cache
 from typing import Optional, Tuple
@@ -14,7 +13,7 @@ from typing import Optional, Tuple
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, timing
 
 DEFAULT_CUTOFF = 6.0   # Gaussian support half-width in units of bw (1.5e-8 on Y, 4e-7 on dY/dQ)
 
@@ -159,8 +158,9 @@ def band_forward(xr: torch.Tensor, t: Optional[int], q: torch.Tensor, fc: torch.
     return y, ph, dy, dp
 
 
-FIXED_VARIANT = os.environ.get("BIEAR_FIXED_VARIANT", "tc")   # "tc": tcgen05 / TMEM 3xTF32 GEMM (csrc/band_fixed_tc.cu); "ffma": fp32 FFMA2 GEMM (csrc/band_fixed.cu).
-                       # Picked by measured throughput (profiles/): the tensor-core variant wins at every batch size.
+FIXED_VARIANT = "tc"   # the shipped path: tcgen05 / TMEM 3xTF32 GEMM (csrc/band_fixed_tc.cu), picked by measured throughput
+                       # (profiles/r1_other_configs.txt).  variant="ffma" (fp32 FFMA2 GEMM, csrc/band_fixed.cu) is a
+                       # test hook: the parity tests cross-check the two; nothing in the package selects it.
 
 
 def band_fixed_forward(xr: torch.Tensor, q: torch.Tensor, fc: torch.Tensor, df: float,
@@ -233,8 +233,8 @@ class BandFrame(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, xr, t, fc, df, cutoff, want_phase, mode):
         ctx.set_materialize_grads(False)
+        need_grad = ctx.needs_input_grad[0]      # (before contiguous(): inside forward() a copy never requires grad)
         q = q.contiguous()
-        need_grad = q.requires_grad
         jac = need_grad and mode == "jacobian"
         y, ph, dy, dp = band_forward(xr, t, q, fc, df, cutoff, want_phase, jac)
         ctx.mode = mode
@@ -422,12 +422,16 @@ def resident_clusters(n_bands: int, n_bins: int, device=None) -> int:
     return _resident[key]
 
 
+CLUSTER_CTAS = 4   # CTAs per cluster of the persistent recurrence kernels (kCS in csrc/seq_dev.cuh)
+
+
 def tile_rows() -> int:
     """Rows per tile (R) of the "tile layout" tensors (G, T-1, tiles, D, R), see include/biear_b200.h."""
     return int(_lib.load().biear_adaptive_tile_rows())
 
 
-WGRAD_VARIANT = os.environ.get("BIEAR_WGRAD_VARIANT", "tc")   # "tc": tcgen05 / TMEM 3xTF32 (wgrad_tc_kernel); "ffma": fp32 FFMA2
+WGRAD_VARIANT = "tc"   # the shipped path: tcgen05 / TMEM 3xTF32 (wgrad_tc_kernel); variant="ffma" is a test hook and the
+                       # shape fallback below
 
 
 def ctrl_wgrad(jobs, variant: Optional[str] = None):
@@ -643,6 +647,15 @@ class AdaptiveSequence(torch.autograd.Function):
             gLX = [None] * G
         if T < 2 or all(g is None for g in gY + gQ + gP + gLX):
             return none13 + (None,) * (G * len(WEIGHT_NAMES))
+        with timing.span("frontend.backward", B):
+            return AdaptiveSequence._backward(ctx, gY, gQ, gP, gLX)
+
+    @staticmethod
+    def _backward(ctx, gY, gQ, gP, gLX):
+        from ctypes import byref
+        xr, fc, q0, dq, weights, Y, Q, P, LX, D, dY, dP, sv, flags, work, H, _seed_dev, _x_ready = ctx.keep
+        G, B, T, N, Kin, tiles, TILE = ctx.dims
+        none13 = (None,) * 14
         dev = Y.device
         f32 = dict(dtype=torch.float32, device=dev)
         S = T - 1

@@ -65,3 +65,33 @@ def cfg_single(**kw):
 def loss_a(yl, yr, ql, qr, up):
     return (up["gYL"] * torch.log(yl + 1e-8)).sum() + (up["gYR"] * torch.log(yr + 1e-8)).sum() \
         + (up["gQL"] * ql).sum() + (up["gQR"] * qr).sum()
+
+
+def oracle_dual_chunked(wl, wr, w_l, w_r, up, cfg, dtype=torch.float32, chunk=32, want_phase=False):
+    """The oracle's dual front-end, forward + backward of loss A (+ optionally a phase term), run in row chunks (rows are
+    independent; the weight gradients are sums over rows, so they accumulate across chunks) to bound host memory at the
+    benchmark batch.  Returns ({YL,YR,QL,QR[,PL,PR]} numpy, {"L.<param>" / "R.<param>": grad numpy})."""
+    pl = orc.to_torch(w_l, dtype=dtype, requires_grad=True)
+    pr = orc.to_torch(w_r, dtype=dtype, requires_grad=True)
+    c = orc.constants(cfg, dtype)
+    outs = {k: [] for k in ("YL", "YR", "QL", "QR", "PL", "PR")}
+    B = wl.shape[0]
+    for lo in range(0, B, chunk):
+        sl = slice(lo, min(B, lo + chunk))
+        tl = torch.from_numpy(wl[sl]).to(dtype)
+        tr = torch.from_numpy(wr[sl]).to(dtype)
+        u = {k: torch.from_numpy(v[sl]).to(dtype) for k, v in up.items()}
+        yl, yr, ql, qr, xl, xr = orc.binaural_forward(tl, tr, pl, pr, cfg, c=c)
+        loss = loss_a(yl, yr, ql, qr, u)
+        if want_phase:
+            phl = orc.subband_phase(xl, ql, c["f_fft"], c["fc"])
+            phr = orc.subband_phase(xr, qr, c["f_fft"], c["fc"])
+            loss = loss + 1e-3 * ((u["gPL"] * phl).sum() + (u["gPR"] * phr).sum())
+            outs["PL"].append(phl.detach().numpy())
+            outs["PR"].append(phr.detach().numpy())
+        loss.backward()
+        for k, v in (("YL", yl), ("YR", yr), ("QL", ql), ("QR", qr)):
+            outs[k].append(v.detach().numpy())
+    res = {k: np.concatenate(v) for k, v in outs.items() if v}
+    grads = {f"{side}.{k}": p.grad.numpy() for side, prm in (("L", pl), ("R", pr)) for k, p in prm.items()}
+    return res, grads

@@ -185,6 +185,17 @@ def main():
     out["single.YL"], out["single.YR"], out["single.Q"] = yl.detach().numpy(), yr.detach().numpy(), q.detach().numpy()
     for name, prm in sc.named_parameters():
         out[f"single.gradA.{name}"] = sub(prm.grad.numpy())
+    # float64 twin of the same run: how far the reference's own fp32 result is from the truth (conditioning record)
+    sc64 = ref_model.BinauralAdaptiveGammatoneFB_SingleController(**CONFIG_SINGLE)
+    load_ctrl(sc64, w_s)
+    sc64 = sc64.double().eval()
+    yl, yr, q, _, _, _ = sc64(tl2.double(), tr2.double())
+    loss = (up["gYL"].double() * torch.log(yl + 1e-8)).sum() + (up["gYR"].double() * torch.log(yr + 1e-8)).sum() \
+        + (up["gQL"].double() * q).sum()
+    loss.backward()
+    out["single64.YL"], out["single64.Q"] = yl.detach().numpy(), q.detach().numpy()
+    for name, prm in sc64.named_parameters():
+        out[f"single64.gradA.{name}"] = sub(prm.grad.numpy())
 
     # ---- CC feature ---------------------------------------------------------------------------
     cw_l, cw_r = orc.synth_binaural(6, seed=77)

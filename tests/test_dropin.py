@@ -57,15 +57,26 @@ def test_dropin_modules_resolve():
             "w = ds[0]; assert [tuple(t.shape) for t in w] == [(16000,), (16000,), (100,), (56,)], w; "
             "assert abs(float(max(w[0].abs().max(), w[1].abs().max())) - 1.0) < 1e-6; print(len(ds))"
             ) % os.path.join(ROOT, "biear_b200", "dropin")
-    env = dict(os.environ, BIEAR_SYNTH_CLIPS="8")
+    env = dict(os.environ, BIEAR_SYNTH_CLIPS="8", BIEAR_ALLOW_SYNTHETIC="1")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd="/tmp")
     assert out.returncode == 0, out.stderr
-    assert out.stdout.strip() == "8"
+    assert out.stdout.strip().splitlines()[-1] == "8" and "SYNTHETIC" in out.stdout   # the loud warning comes first
+
+
+def test_data_shim_refuses_missing_datasets_by_default():
+    """A mistyped path (or an H5 file without h5py) must not silently train on synthetic data."""
+    code = ("import sys; sys.path.insert(0, %r); import data\n"
+            "try:\n    data.DeepEarH5Dataset_Active('/nonexistent/anechoic_val_active_wav.h5')\n"
+            "except FileNotFoundError as e:\n    print('refused')\n") % os.path.join(ROOT, "biear_b200", "dropin")
+    env = {k: v for k, v in os.environ.items() if k != "BIEAR_ALLOW_SYNTHETIC"}
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd="/tmp")
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.strip() == "refused"
 
 
 @pytest.mark.skipif(not os.path.exists(os.path.join(REF, "train_biear.py")), reason="reference tree not present")
 def test_reference_train_script_runs_unchanged_passive():
-    env = dict(os.environ, BIEAR_SYNTH_CLIPS="48", CUDA_VISIBLE_DEVICES="")
+    env = dict(os.environ, BIEAR_SYNTH_CLIPS="48", BIEAR_ALLOW_SYNTHETIC="1", CUDA_VISIBLE_DEVICES="")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "run_reference_script.py"),
                           os.path.join(REF, "train_biear.py"), "Active=false", "BATCH_SIZE=16"],
                          capture_output=True, text=True, env=env, timeout=600)

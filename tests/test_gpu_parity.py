@@ -73,7 +73,7 @@ def _phase_truth(wav, q64):
 def _weighted_phase_err(ph, truth, wgt):
     """max over entries of (wrap-aware phase error) * abs(Z)/Y: phase = atan2 of a cancelling complex sum Z, so an
     fp32 error dZ ~ eps*Y becomes dphi ~ dZ/abs(Z); weighting by abs(Z)/Y measures dZ/Y, which is what an fp32
-    implementation controls (tools/diag_phase2.py: 1.5e-7 for this kernel, 1.6e-7 for the reference formula)."""
+    implementation controls (profiles/r1_phase_conditioning.txt: 1.5e-7 for this kernel, 1.6e-7 for the reference formula)."""
     d = np.abs(np.asarray(ph, np.float64) - truth) % (2 * np.pi)
     return float(np.max(np.minimum(d, 2 * np.pi - d) * wgt))
 
@@ -609,8 +609,15 @@ def test_single_controller(bb, golden):
     assert_close(_np(q), golden["single.Q"], RTOL, "single Q")
     up = {k: torch.from_numpy(v).to(DEV) for k, v in upstream(2).items()}
     ((up["gYL"] * torch.log(yl + 1e-8)).sum() + (up["gYR"] * torch.log(yr + 1e-8)).sum() + (up["gQL"] * q).sum()).backward()
+    worst = 0.0
     for name, prm in m.named_parameters():
-        assert rel_err(sub(_np(prm.grad)), golden[f"single.gradA.{name}"]) <= 2 * RTOL, name
+        # the reference's own fp32 result is within 5e-7 of its float64 twin here (golden single64.*): the case is well
+        # conditioned and the plain 1e-4 contract applies
+        e = rel_err(sub(_np(prm.grad)), golden[f"single.gradA.{name}"])
+        worst = max(worst, e)
+        assert rel_err(golden[f"single.gradA.{name}"], golden[f"single64.gradA.{name}"]) <= 1e-5
+        assert e <= RTOL, (name, e)
+    print(f"[single controller] worst weight-gradient error vs reference {worst:.2e}")
 
 
 # ------------------------------------------------------------------------------------------------
