@@ -150,7 +150,7 @@ struct FwdSmem {   // offsets in floats
     __host__ __device__ int q() const { return stat() + 2 * kSeqThreads; }      // [128][4]: Q_t of this CTA's 4 rows
     __host__ __device__ int ystage() const { return q() + kHid * kRT; }         // [4][128]
     __host__ __device__ int spec() const { return ystage() + kRT * kHid; }      // [4][tile] float4
-    __host__ __device__ int misc() const { return spec() + kRT * tile * 4; }
+    __host__ __device__ int misc() const { return spec() + kRT * tile * 4; }   // 5 mbarriers (8 B each), 16-byte aligned
     __host__ __device__ int total() const { return misc() + 16; }
 };
 // vec area
@@ -342,6 +342,24 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
     const int quads = (N + 3) >> 2;
     int* any_flag = p.flags + S * p.G;
     const unsigned long long seed = p.seed_ptr ? *p.seed_ptr : p.seed;
+    // Hand-overs inside the cluster (fast pass): st.async + one mbarrier per phase type (seq_dev.cuh).  The strict pass
+    // exchanges its state through global memory and keeps the hardware cluster barrier.
+    const uint32_t bars = smem_u32(smem + L.misc());
+    auto bar_of = [&](int i) { return bars + 8u * (uint32_t)i; };          // i = 0..4: yc, h, a1, a2, Q
+    const uint32_t tx_bytes[5] = {(uint32_t)(N * kR * 4), (uint32_t)(kHid * kR * 4), (uint32_t)(kHid * kR * 4),
+                                  (uint32_t)(kHid * kR * 4), (uint32_t)(N * kRT * 4)};
+    if (!STRICT) {
+        if (tid == 0) {
+#pragma unroll
+            for (int i = 0; i < 5; ++i) mbar_init(bar_of(i), 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        cluster.sync();                                       // every CTA's barriers exist before anybody signals them
+    }
+    // hand-over i of step t is complete: fast pass = all bytes have landed here; strict pass = hardware cluster barrier
+    auto arm = [&](int i) {            // (fast pass) this CTA's expectation for the hand-over, by one thread
+        if (!STRICT && tid == 0) mbar_arrive_expect_tx(bar_of(i), tx_bytes[i]);
+    };
 
     if (STRICT) {
         if (!p.force_strict && *reinterpret_cast<volatile int*>(any_flag) == 0) return;   // uniform over the grid
@@ -449,6 +467,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                 const float q = own ? q_s[n_own * kRT + row_own] : 1.0f;
                 const BandParams bp_own = band_params(fc, q, p.df, p.cutoff, p.F, own);
                 BandSums keep = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                PHASE_MARK(0, 10);   // band stage: own-band parameters
                 for (int m = 0, pr = warp; pr < n_pairs; ++m, pr += kWarps) {
                     const int row = ((pr & 3) + (pr >> 4)) & 3;
                     const int src = (m << 2) + (lane >> 3);          // lane owning the band this lane helps with
@@ -459,7 +478,9 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                     bp.kc = __shfl_sync(0xffffffffu, bp_own.kc, src);
                     bp.k_lo = __shfl_sync(0xffffffffu, bp_own.k_lo, src);
                     bp.k_hi = __shfl_sync(0xffffffffu, bp_own.k_hi, src);
+                    PHASE_MARK(0, 11);   // band stage: per-pair parameter hand-out
                     const BandSums sums = band_accumulate(spec_s + row * L.tile, p.F, bp, lane);
+                    PHASE_MARK(0, 12);   // band stage: band_accumulate
                     const int from = (lane & 3) << 3;                // any lane of the group that holds my band's sums
                     const bool mine = (lane >> 2) == m;
                     float v;
@@ -471,6 +492,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                     v = __shfl_sync(0xffffffffu, sums.a2, from);  if (mine) keep.a2 = v;
                     v = __shfl_sync(0xffffffffu, sums.z2r, from); if (mine) keep.z2r = v;
                     v = __shfl_sync(0xffffffffu, sums.z2i, from); if (mine) keep.z2i = v;
+                    PHASE_MARK(0, 13);   // band stage: sums back to the owner lanes
                 }
                 if (own) {
                     const BandResult r = band_finish(keep);
@@ -500,6 +522,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                     p.dPdQ[own_e] = oK;
                 }
             };
+            PHASE_MARK(0, 14);   // band stage: epilogue (normalise, atan2, log1p, Jacobians)
             PHASE_MARK(0, 2);    // band stage (this warp)
             if (t == T - 1) {
                 // The reference runs the controller once more and discards the result (model_torch.py:361-380).
@@ -514,19 +537,26 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                 spec_t = t + 1;
             }
             const long long tb = tile_base(p, g, t, tiles, tile);
+            const uint32_t par = (uint32_t)t & 1u;     // every hand-over barrier completes exactly once per frame
             if (tid < N) {   // features of my 4 rows -> every CTA of the cluster (+ saved for dW_ih)
                 const float4 v = make_float4(ystage_s[tid], ystage_s[kHid + tid], ystage_s[2 * kHid + tid],
                                              ystage_s[3 * kHid + tid]);
+                if (STRICT) {
 #pragma unroll
-                for (int dst = 0; dst < kCS; ++dst)
-                    *reinterpret_cast<float4*>(cluster.map_shared_rank(yc_s, dst) + tid * kR + rank * kRT) = v;
+                    for (int dst = 0; dst < kCS; ++dst)
+                        *reinterpret_cast<float4*>(cluster.map_shared_rank(yc_s, dst) + tid * kR + rank * kRT) = v;
+                } else {
+                    bcast_f4_tx(yc_s + tid * kR + rank * kRT, v, bar_of(0));
+                }
             }
-            cluster.barrier_arrive();   // #1: my part of yc is delivered ...
+            if (STRICT) cluster.barrier_arrive();   // #1: my part of yc is delivered ...
+            arm(0);
             if (tid < N)
                 *reinterpret_cast<float4*>(p.yc + tb * N * kR + tid * kR + rank * kRT) =
                     make_float4(ystage_s[tid], ystage_s[kHid + tid], ystage_s[2 * kHid + tid], ystage_s[3 * kHid + tid]);
             store_band_outputs();
-            cluster.barrier_wait();     // ... and complete everywhere
+            if (STRICT) cluster.barrier_wait();     // ... and complete everywhere
+            else tx_wait(bar_of(0), par);
             PHASE_MARK(0, 3);    // band barrier + push + cluster barrier #1
 
             // ---- GRU cell (torch gate order r, z, n; n = tanh(i_n + r * (W_hn h + b_hn))) ----------------------
@@ -559,9 +589,11 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                         const float hp = h_zero ? 0.0f : hcur_s[ug * kR + rg * kRT + i];
                         hv[i] = (1.0f - vz[i]) * vn[i] + vz[i] * hp;
                     }
-                    broadcast_rows(cluster, hnext_s, ug, rg * kRT, hv);
+                    if (STRICT) broadcast_rows(cluster, hnext_s, ug, rg * kRT, hv);
+                    else broadcast_rows_tx(hnext_s, ug, rg * kRT, hv, bar_of(1));
                 }
-                cluster.barrier_arrive();   // #2 signalled before the saves go out (a later release covers them)
+                if (STRICT) cluster.barrier_arrive();   // #2 signalled before the saves go out (a later release covers them)
+                arm(1);
                 if (ks == 0) {
                     store4(h_tile(p, g, t, tiles, tile) + ug * kR + rg * kRT, hv);
                     float* gt = p.gates + tb * 4 * kHid * kR + ug * kR + rg * kRT;
@@ -571,7 +603,8 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                     store4(gt + 3 * kHid * kR, vh);
                 }
             }
-            cluster.barrier_wait();   // #2: h_t complete everywhere
+            if (STRICT) cluster.barrier_wait();   // #2: h_t complete everywhere
+            else tx_wait(bar_of(1), par);
             PHASE_MARK(0, 4);    // GRU
 
             // ---- Linear 1 -> LayerNorm -> SiLU -> Dropout ------------------------------------------------------
@@ -585,10 +618,16 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                     const float bb = vec_s[V_B1 + u];
 #pragma unroll
                     for (int i = 0; i < kRT; ++i) acc[i] += bb;
-                    broadcast_rows(cluster, a1_s, ug, rg * kRT, acc);
+                    if (STRICT) broadcast_rows(cluster, a1_s, ug, rg * kRT, acc);
+                    else broadcast_rows_tx(a1_s, ug, rg * kRT, acc, bar_of(2));
                 }
             }
-            cluster.sync();   // #3
+            if (STRICT) {
+                cluster.sync();   // #3
+            } else {
+                arm(2);
+                tx_wait(bar_of(2), par);
+            }
             PHASE_MARK(0, 5);    // Linear 1
             ln_silu_drop_fwd(p, seed, a1_s, stat_s, vec_s + V_LN1G, vec_s + V_LN1B, 0, t, (long long)g * p.B + b0, rank,
                              p.xh1 + tb * kHid * kR, p.d1 + tb * kHid * kR, p.rstd + tb * 2 * kR);
@@ -605,10 +644,17 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                     const float bb = vec_s[V_B2 + u];
 #pragma unroll
                     for (int i = 0; i < kRT; ++i) acc[i] += bb;
-                    broadcast_rows(cluster, a2_s, ug, rg * kRT, acc);   // a2 aliases yc: all yc reads ended before #2
+                    // a2 aliases yc: every CTA's yc reads (its GRU products) ended before it sent h_t, i.e. before #2
+                    if (STRICT) broadcast_rows(cluster, a2_s, ug, rg * kRT, acc);
+                    else broadcast_rows_tx(a2_s, ug, rg * kRT, acc, bar_of(3));
                 }
             }
-            cluster.sync();   // #4
+            if (STRICT) {
+                cluster.sync();   // #4
+            } else {
+                arm(3);
+                tx_wait(bar_of(3), par);
+            }
             PHASE_MARK(0, 7);    // Linear 2
             ln_silu_drop_fwd(p, seed, a2_s, stat_s, vec_s + V_LN2G, vec_s + V_LN2B, 1, t, (long long)g * p.B + b0, rank,
                              p.xh2 + tb * kHid * kR, p.d2 + tb * kHid * kR, p.rstd + tb * 2 * kR);
@@ -636,7 +682,12 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                         bad = bad || (b0 + rg * kRT + i < p.B && !finite_f(qu));
                     }
                     // Q_{t+1} of rows 4rg..4rg+3 goes to the CTA that runs their band stage
-                    store4(cluster.map_shared_rank(q_s, rg) + n * kRT, qv);
+                    if (STRICT) {
+                        store4(cluster.map_shared_rank(q_s, rg) + n * kRT, qv);
+                    } else {
+                        st_async_f4(cluster_addr(smem_u32(q_s + n * kRT), (uint32_t)rg), make_float4(qv[0], qv[1], qv[2], qv[3]),
+                                    cluster_addr(bar_of(4), (uint32_t)rg));
+                    }
                     if (bad) {   // NaN / Inf: the reference falls back for the whole batch of this ear
                         atomicOr(p.flags + t * p.G + g, 1);
                         atomicOr(any_flag, 1);
@@ -664,14 +715,21 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                     // completes, every thread of this CTA has converted its slots, so the band stage can start at once
                     finish_spectra(p, spec_s, L.tile, bb0);
                 }
-                cluster.barrier_arrive();   // #5
+                if (STRICT) cluster.barrier_arrive();   // #5
+                arm(4);
                 if (!STRICT) store_q();
             }
-            cluster.barrier_wait();   // #5: Q_{t+1} delivered; a2 / yc free for the next frame
+            if (STRICT) {
+                cluster.barrier_wait();   // #5: Q_{t+1} delivered; a2 / yc free for the next frame
+            } else {
+                tx_wait(bar_of(4), par);  // Q_{t+1} of my band-stage rows has landed ...
+                __syncthreads();          // ... and every thread of this CTA has converted its slots of the next spectrum tile
+            }
             PHASE_MARK(0, 9);    // Linear 3 + Q
             if (!STRICT) hsel ^= 1;   // strict: h_{t-1} is reloaded from global memory, the buffers keep their roles
         }
     }
+    if (!STRICT) cluster.sync();   // no CTA leaves (and frees its shared memory) while a peer could still be sending to it
 }
 
 // ==================================================================================================
@@ -688,7 +746,8 @@ struct BwdSmem {   // offsets in floats
     __host__ __device__ int red() const { return dpre() + kHid * kR; }             // (kKS - 1) x 8 x 128
     __host__ __device__ int stat() const { return red() + (kKS - 1) * 8 * 128; }   // 2 x kSeqThreads
     __host__ __device__ int pre() const { return stat() + 2 * kSeqThreads; }       // [3][kR][kU]: ext, jac, fac
-    __host__ __device__ int total() const { return pre() + 3 * kR * kU; }
+    __host__ __device__ int bars() const { return pre() + 3 * kR * kU; }           // 4 mbarriers (8 B each)
+    __host__ __device__ int total() const { return bars() + 16; }
 };
 constexpr int VB_LN1G = 0, VB_LN1B = 128, VB_LN2G = 256, VB_LN2B = 384, VB_Q0 = 512, VB_DQ = 640;   // < 1024
 
@@ -866,7 +925,21 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
         r.fac = (qu >= p.q_min && qu <= p.q_max) ? scale * (1.0f - w.delta * w.delta) : 0.f;
         return r;
     };
-    cluster.sync();                                  // vec_s ready (fetch_pre reads q0 / dq from it)
+    // Hand-overs inside the cluster: st.async + one mbarrier per phase type (seq_dev.cuh): 0 = dL/dpre, 1 = Linear 3^T
+    // output (bufa), 2 = Linear 2^T output (bufb), 3 = the four gate-gradient blocks.
+    const uint32_t bars = smem_u32(smem + L.bars());
+    auto bar_of = [&](int i) { return bars + 8u * (uint32_t)i; };
+    const uint32_t tx_bytes[4] = {(uint32_t)(N * kR * 4), (uint32_t)(kHid * kR * 4), (uint32_t)(kHid * kR * 4),
+                                  (uint32_t)(4 * kHid * kR * 4)};
+    auto arm = [&](int i) {
+        if (tid == 0) mbar_arrive_expect_tx(bar_of(i), tx_bytes[i]);
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mbar_init(bar_of(i), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cluster.sync();                                  // vec_s ready (fetch_pre reads q0 / dq from it); every CTA's barriers exist
     // dL/dpre of step t for (band n of this CTA's slice, rows 4rg..4rg+3), from the pre-fetched recurrence-independent
     // parts in pre_s and dL/dY_{t+1} through the controller (dyc, zero for the last step): broadcast to every CTA of the
     // cluster (the next Linear^T contracts over all bands) and saved for dW3.  Returns the values for the deferred store.
@@ -878,7 +951,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
             dp[i] = flagged_t ? 0.f
                               : (pre_s[r * kU + u] + dyc[i] * pre_s[kR * kU + r * kU + u]) * pre_s[2 * kR * kU + r * kU + u];
         }
-        broadcast_rows(cluster, dpre_s, rank * NU + u, rg * kRT, dp);
+        broadcast_rows_tx(dpre_s, rank * NU + u, rg * kRT, dp, bar_of(0));
     };
     {   // prologue: dL/dpre of the last step (nothing arrives through a later controller step)
         const Pre pf = finish_pre(issue_pre(S - 1));
@@ -892,7 +965,8 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
             push_dpre(S - 1, zero, dp);
             store4(p.G_pre + tile_base(p, g, S - 1, tiles, tile) * N * kR + (rank * NU + u) * kR + rg * kRT, dp);
         }
-        cluster.sync();
+        arm(0);
+        tx_wait(bar_of(0), 0);       // hand-over 0 completes once in the prologue, then once per step with t > 0
     }
 
     PHASE_INIT();
@@ -911,9 +985,11 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
             k_range(N, ks, k0, k1);
             dot_rows(acc, dpre_s + rg * kRT, img_s + bwd_img_w3c(N) + u, k0, k1);
             reduce_ks1<kRT>(acc, red_s, ks, slot);
-            if (ks == 0) broadcast_rows(cluster, bufa_s, ug, rg * kRT, acc);
+            if (ks == 0) broadcast_rows_tx(bufa_s, ug, rg * kRT, acc, bar_of(1));
         }
-        cluster.sync();   // #2
+        const uint32_t par = (uint32_t)(S - 1 - t) & 1u;      // hand-overs 1..3 complete exactly once per step
+        arm(1);
+        tx_wait(bar_of(1), par);   // #2
         PHASE_MARK(1, 2);    // Linear 3 ^T
         constexpr int kFPP = kHid / (kSeqThreads / kR);
         float dv2[kFPP], da2[kFPP];
@@ -928,11 +1004,12 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
             k_range(kHid, ks, k0, k1);
             dot_rows(acc, bufa_s + rg * kRT, img_s + bwd_img_w2c(N) + u, k0, k1);
             reduce_ks1<kRT>(acc, red_s, ks, slot);
-            if (ks == 0) broadcast_rows(cluster, bufb_s, ug, rg * kRT, acc);   // bufb aliases dpre: its reads ended before #2
+            // bufb aliases dpre: every CTA's dpre reads (its Linear 3^T products) ended before it sent its part of bufa
+            if (ks == 0) broadcast_rows_tx(bufb_s, ug, rg * kRT, acc, bar_of(2));
         }
-        cluster.barrier_arrive();   // #3 signalled before the saved LayerNorm-2 gradients go out
+        arm(2);
         store_ln_grads(rank, dv2, da2, p.G_v2 + tb * kHid * kR, p.G_a2 + tb * kHid * kR);
-        cluster.barrier_wait();   // #3
+        tx_wait(bar_of(2), par);   // #3
         PHASE_MARK(1, 4);    // Linear 2 ^T
         float dv1[kFPP], da1[kFPP];
         ln_silu_drop_bwd(p, seed, bufb_s, stat_s, vec_s + VB_LN1G, vec_s + VB_LN1B, 0, t, (long long)g * p.B + b0, rank,
@@ -975,12 +1052,13 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
                     v2[i] = dnp;                                         // dL/d (i_n pre-activation)
                     v3[i] = dnp * rr[i];                                 // dL/d (W_hn h + b_hn)
                 }
-                broadcast_rows(cluster, gate_s, 0 * kHid + ug, rg * kRT, v0);   // gate_s[0:128] aliases bufa: free since #3
-                broadcast_rows(cluster, gate_s, 1 * kHid + ug, rg * kRT, v1);
-                broadcast_rows(cluster, gate_s, 2 * kHid + ug, rg * kRT, v2);
-                broadcast_rows(cluster, gate_s, 3 * kHid + ug, rg * kRT, v3);
+                // gate_s[0:128] aliases bufa: every CTA's bufa reads (its Linear 2^T products) ended before it sent bufb
+                broadcast_rows_tx(gate_s, 0 * kHid + ug, rg * kRT, v0, bar_of(3));
+                broadcast_rows_tx(gate_s, 1 * kHid + ug, rg * kRT, v1, bar_of(3));
+                broadcast_rows_tx(gate_s, 2 * kHid + ug, rg * kRT, v2, bar_of(3));
+                broadcast_rows_tx(gate_s, 3 * kHid + ug, rg * kRT, v3, bar_of(3));
             }
-            cluster.barrier_arrive();   // #4 signalled before the saved gradients go out
+            arm(3);
             store_ln_grads(rank, dv1, da1, p.G_v1 + tb * kHid * kR, p.G_a1 + tb * kHid * kR);
             if (ks == 0) {
                 float* gg = p.GG + tb * 4 * kHid * kR + ug * kR + rg * kRT;
@@ -990,9 +1068,10 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
                 store4(gg + 3 * kHid * kR, v3);
             }
         }
-        cluster.barrier_wait();   // #4
+        tx_wait(bar_of(3), par);   // #4
         PHASE_MARK(1, 6);    // Linear 1 ^T + GRU cell backward
         const PreRaw pf_raw = issue_pre(t - 1);    // next step's recurrence-independent inputs: in flight during the products below
+        PHASE_MARK(1, 8);    // last phase: issue the next step's loads
         // ---- dL/dh_{t-1} = z * dh + W_hh^T [drp, dzp, dhn];  dL/dY_t = W_ih[:, :N]^T [drp, dzp, dnp] * d log1p --------
         {
             float acc[2 * kRT] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -1008,6 +1087,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
             dot_rows_pair(acc, acc + kRT, x, whhc, wihc, min(o0, 2 * kHid), min(o1, 2 * kHid));
             dot_rows(acc, x + kHid * kR, whhc, max(o0, 2 * kHid), max(o1, 2 * kHid));
             dot_rows(acc + kRT, x, wihc, max(o0, 2 * kHid), max(o1, 2 * kHid));
+            PHASE_MARK(1, 9);    // last phase: the K = 384 transposed products
             const bool mine = u < nu_c;
             const int n = rank * NU + u;
             float yv[kRT] = {0.f, 0.f, 0.f, 0.f};       // Y_t of this thread's 4 rows (for d log1p): fetched before the products
@@ -1025,7 +1105,9 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
                 pre_s[kR * kU + pre_r * kU + pre_u] = pf.jac;
                 pre_s[2 * kR * kU + pre_r * kU + pre_u] = pf.fac;
             }
+            PHASE_MARK(1, 10);   // last phase: Y_t loads + finish_pre (waits for the loads issued above)
             reduce_ks1<2 * kRT>(acc, red_s, ks, slot);   // (its barriers also order the pre_s writes before the reads below)
+            PHASE_MARK(1, 11);   // last phase: k-split reduction
             float dp[kRT] = {0.f, 0.f, 0.f, 0.f};
             const bool fin = ks == 0 && mine && t > 0;
             if (ks == 0) {
@@ -1038,12 +1120,14 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
                     push_dpre(t - 1, dy, dp);
                 }
             }
-            cluster.barrier_arrive();   // #5: dL/dpre of step t-1 is on its way everywhere; gate buffers free again
+            PHASE_MARK(1, 12);   // last phase: dh carry + dL/dpre assembly + push
+            if (t > 0) arm(0);          // #5: dL/dpre of step t-1 is on its way everywhere
             if (fin) store4(p.G_pre + tile_base(p, g, t - 1, tiles, tile) * N * kR + n * kR + rg * kRT, dp);
         }
-        cluster.barrier_wait();
+        if (t > 0) tx_wait(bar_of(0), (uint32_t)(S - t) & 1u);   // (prologue = completion 0, step t = completion S - t)
         PHASE_MARK(1, 7);    // W_hh^T / W_ih^T products
     }
+    cluster.sync();   // no CTA leaves (and frees its shared memory) while a peer could still be sending to it
 }
 
 // ==================================================================================================
@@ -1220,7 +1304,10 @@ extern "C" int biear_debug_phase_cycles(unsigned long long* out_host) {
 #ifdef BIEAR_PHASE_PROF
     using namespace biear;
     unsigned long long zero[2][16] = {};
+    unsigned long long zero_b[8] = {};
     if (int e = check_cuda(cudaMemcpyFromSymbol(out_host, g_phase_cycles, sizeof(zero)), "cudaMemcpyFromSymbol")) return e;
+    if (int e = check_cuda(cudaMemcpyFromSymbol(out_host + 32, g_band_prof, sizeof(zero_b)), "cudaMemcpyFromSymbol")) return e;
+    if (int e = check_cuda(cudaMemcpyToSymbol(g_band_prof, zero_b, sizeof(zero_b)), "cudaMemcpyToSymbol")) return e;
     return check_cuda(cudaMemcpyToSymbol(g_phase_cycles, zero, sizeof(zero)), "cudaMemcpyToSymbol");
 #else
     (void)out_host;

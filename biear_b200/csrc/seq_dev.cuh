@@ -26,6 +26,7 @@
 #include <cooperative_groups.h>
 
 #include "common.cuh"
+#include "tc_dev.cuh"
 
 namespace biear {
 namespace cg = cooperative_groups;
@@ -228,6 +229,59 @@ __device__ __forceinline__ void broadcast_rows(cg::cluster_group& cluster, float
     for (int dst = 0; dst < kCS; ++dst) {
         float* remote = cluster.map_shared_rank(buf_s, dst);
         *reinterpret_cast<float4*>(remote + feature * kR + row0) = val;
+    }
+}
+
+// ---- cluster exchange without the hardware cluster barrier ---------------------------------------------------------
+// Every hand-over between the CTAs of a cluster (activations of one phase going to the peers) is a set of st.async
+// stores: the store carries its own completion to an mbarrier in the DESTINATION CTA (complete_tx of its 16 bytes), so a
+// consumer only waits on a local mbarrier until all the bytes of the phase have landed.  Compared with
+// "DSMEM stores + barrier.cluster.arrive.release / wait.acquire" this removes, per hand-over, the release fence (which
+// also drains the thread's outstanding GLOBAL stores -- the saved state -- and showed up as `membar` stalls in ncu), the
+// ~500-cycle hardware barrier and its L1 invalidation.  One mbarrier per phase type, used once per step, parity = step & 1.
+// Ordering argument (why no all-CTA barrier is needed): a CTA can only run ahead of a peer by less than one phase type --
+// to send phase p of step s+1 it must have RECEIVED every peer's phase p-1 .. of step s+1 / phase last of step s, which
+// the peer sends only after it finished reading the buffers of the phases before (see seq.cu for the buffer-by-buffer list).
+__device__ __forceinline__ uint32_t cluster_addr(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+
+__device__ __forceinline__ void st_async_f4(uint32_t remote_addr, const float4 v, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(remote_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(remote_bar)
+                 : "memory");
+}
+
+// 16 bytes to the same shared-memory location of every CTA of the cluster, each signalling that CTA's mbarrier `bar`.
+__device__ __forceinline__ void bcast_f4_tx(const float* dst_s, const float4 v, uint32_t bar) {
+    const uint32_t a = smem_u32(dst_s);
+#pragma unroll
+    for (uint32_t dst = 0; dst < (uint32_t)kCS; ++dst) st_async_f4(cluster_addr(a, dst), v, cluster_addr(bar, dst));
+}
+
+// Write 4 row values of one feature into the [feature][kR] buffer of every CTA of the cluster (st.async form).
+__device__ __forceinline__ void broadcast_rows_tx(float* buf_s, int feature, int row0, const float v[kRT], uint32_t bar) {
+    bcast_f4_tx(buf_s + feature * kR + row0, make_float4(v[0], v[1], v[2], v[3]), bar);
+}
+
+// Wait for phase `parity` of a local mbarrier (all bytes of the hand-over have landed).  Bounded: a protocol bug must
+// end in a launch failure, never in a hung GPU.
+// (CTA-scope acquire, like every cluster kernel that waits on a local mbarrier for remote producers: the data and its
+// complete_tx arrive in this SM's own shared memory, which no cache sits in front of; a cluster-scope acquire would make
+// ptxas add an L1 invalidation -- CCTL.IVALL -- to every wait.)
+__device__ __forceinline__ void tx_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (unsigned spin = 0; !ok; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (spin > (1u << 22)) __trap();
     }
 }
 
