@@ -190,6 +190,7 @@ def build_frontend(device):
     with torch.no_grad():
         for fb in (m.fb_L, m.fb_R):   # default zero-init pins Q == Q0; make the controller actually act
             torch.nn.init.normal_(fb.q_out[-1].weight, std=0.02)
+    m.graph_replay = False      # the whole step is captured by GraphedStep below; no per-module graphs inside it
     return m.to(device).train()
 
 
@@ -291,8 +292,17 @@ def run_ours(args):
     loss_fn, params = make_loss(model, up)
     flat_numel = sum(p.numel() for p in params)
 
-    from biear_b200.dist import FlatGradAllReducer
+    from biear_b200.dist import FlatGradAllReducer, captured_average
+    host_reduce = dist is not None and (args.eager or args.host_allreduce)
     current = {"reducer": FlatGradAllReducer(params) if (dist is not None and args.eager) else None}
+    # Data-parallel gradient exchange: ONE flat-bucket NCCL all-reduce (sum, x 1/world) per step.  By default it is
+    # recorded INSIDE the step's CUDA graph, right behind the split-K reduction that produces the bucket, so a replay
+    # carries it and the host issues nothing per step (--host-allreduce: issue it from the host after each replay).
+    grad_sync = captured_average(world) if (dist is not None and not host_reduce) else None
+    if dist is not None:
+        warm = torch.zeros(flat_numel, device=dev)
+        dist.all_reduce(warm)                      # communicator set-up outside any capture
+        torch.cuda.synchronize()
 
     def allreduce_grads():
         if current["reducer"] is not None:
@@ -305,7 +315,13 @@ def run_ours(args):
         wl, wr = host[i % 2]
         sh = (i // 2) * 7
         dev_in.append((torch.from_numpy(np.roll(wl, sh, axis=1)).to(dev), torch.from_numpy(np.roll(wr, sh, axis=1)).to(dev)))
-    pinned = [(torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()) for a, b in host]
+    if args.e2e_f32:
+        pinned = [(torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()) for a, b in host]
+    else:   # end-to-end input = 16-bit PCM, the wire format of audio (the reference's harness expects int16-range input too,
+            # train_biear.py:463-467): half the host->device bytes; biear_pcm16_to_f32 converts on the copy stream
+        to_pcm = lambda x: torch.from_numpy(np.clip(np.round(x * 32767.0), -32768, 32767).astype(np.int16)).pin_memory()
+        pinned = [(to_pcm(a), to_pcm(b)) for a, b in host]
+    e2e_bytes_per_sample = 4 if args.e2e_f32 else 2
 
     # The step (forward + loss + backward) is captured once per resident batch as a CUDA graph (biear_b200.GraphedStep)
     # and replayed: ~60 launches per step issued from Python are host-bound, the replay is not.  --eager times the
@@ -324,16 +340,16 @@ def run_ours(args):
         graphs, pool = [], None
         for i in range(N_ROTATE):
             gs = GraphedStep(loss_fn, dev_in[i], params, warmup=2 if i == 0 else 1, pool=pool, copy_inputs=False,
-                             flat_grads=dist is not None)
+                             flat_grads=dist is not None, grad_sync=grad_sync)
             pool = gs.pool()
             graphs.append(gs)
         # end-to-end: two graphs with their own static inputs, so the H2D of step i+1 (copy stream) overlaps step i
         e2e_graphs = [GraphedStep(loss_fn, dev_in[0], params, warmup=1, pool=pool, copy_inputs=True,
-                                  flat_grads=dist is not None) for _ in range(2)]
+                                  flat_grads=dist is not None, grad_sync=grad_sync) for _ in range(2)]
         e2e_graph = e2e_graphs[0]
         copy_stream = torch.cuda.Stream(device=dev)
         launches_per_step = graphs[0].launches_per_replay
-        if dist is not None:   # every graph writes its gradients into its own flat bucket: all-reduce that, no copies
+        if host_reduce:        # every graph writes its gradients into its own flat bucket: all-reduce that, no copies
             for gs in graphs + e2e_graphs:
                 gs.reducer = FlatGradAllReducer(params, flat=gs.flat)
 
@@ -410,8 +426,11 @@ def run_ours(args):
             losses.append(float(host_loss[prev[0]]))
 
     def steps_eager_e2e(a, b):
+        from biear_b200 import ops
         wl = a.to(dev, non_blocking=True)
         wr = b.to(dev, non_blocking=True)
+        if wl.dtype == torch.int16:
+            wl, wr = ops.pcm16_to_f32(wl), ops.pcm16_to_f32(wr)
         for p in params:
             p.grad = None
         loss = loss_fn(wl, wr)
@@ -463,9 +482,13 @@ def run_ours(args):
                    "l2": f"inputs rotate over {N_ROTATE} resident batches "
                          f"({N_ROTATE * B * 2 * FS * 4 / 1e6:.0f} MB > 126 MB L2)",
                    "issue": "eager launches" if args.eager else "one CUDA graph per step (biear_b200.GraphedStep)",
-                   "allreduce_floats": flat_numel if world > 1 else 0},
-        "e2e": {"value": clips / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * B * FS * 4,
-                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "wall_ms_per_step": wall_e2e / args.steps},
+                   "allreduce_floats": flat_numel if world > 1 else 0,
+                   "allreduce": ("none (1 GPU)" if world == 1 else "NCCL, issued by the host after each replay" if host_reduce
+                                 else "NCCL, recorded inside the step's CUDA graph")},
+        "e2e": {"value": clips / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * B * FS * e2e_bytes_per_sample,
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "wall_ms_per_step": wall_e2e / args.steps,
+                "input": "float32 waveforms in pinned host memory" if args.e2e_f32 else
+                         "16-bit PCM waveforms in pinned host memory, converted to float32 on the device (biear_pcm16_to_f32)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roof,
@@ -658,6 +681,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the gpu_eager_reference / fixed_q / full_step sub-records")
     ap.add_argument("--eager", action="store_true", help="issue every launch from Python instead of replaying CUDA graphs")
+    ap.add_argument("--host-allreduce", action="store_true", help="issue the gradient all-reduce from the host after each replay")
+    ap.add_argument("--e2e-f32", action="store_true", help="end-to-end arm with float32 host waveforms instead of 16-bit PCM")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -165,6 +165,7 @@ def fixed_q(batch=4096, device="cuda:0", reps=None):
     import biear_b200
     dev = torch.device(device)
     fb = biear_b200.BinauralAdaptiveGammatoneFB(fixed_frontend_q=True).to(dev).eval()
+    fb.graph_replay = False     # captured explicitly below
     g = torch.Generator(device="cpu").manual_seed(batch)
     n_in = 4
     ins = [(torch.rand((batch, FS), generator=g) * 2 - 1).to(dev) for _ in range(n_in)]
@@ -224,6 +225,7 @@ def build_full_step(batch, dev, world=1, rank=0):
         for fb in (model.bifb.fb_L, model.bifb.fb_R):
             torch.nn.init.normal_(fb.q_out[-1].weight, std=0.02)
     model = model.to(dev).train()
+    model.bifb.graph_replay = False     # the whole step is captured as one graph below
     fb_params = list(model.bifb.parameters())
     be_params = [p for n, p in model.named_parameters() if not n.startswith("bifb.")]
     params = fb_params + be_params

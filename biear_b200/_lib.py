@@ -11,7 +11,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BIEAR_B200_LIB") or os.path.join(_HERE, "lib", "libbiear_b200.so")
-ABI_VERSION = 16
+ABI_VERSION = 17
 
 _p = c_void_p
 _i = c_int
@@ -60,6 +60,7 @@ SIGNATURES = {
     "biear_reset_launch_count": (None, []),
     "biear_init": (_i, []),
     "biear_stft_fwd": (_i, [_p, _l, _l, _l, _p, _i, _i, _i, _i, _i, _p, _p]),
+    "biear_pcm16_to_f32": (_i, [_p, _p, _l, _f, _p]),
     "biear_stft_fwd_pair": (_i, [_p, _p, _l, _l, _l, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
     "biear_band_fwd": (_i, [_p, _l, _p, _l, _p, _l, _i, _i, _f, _f, _p, _l, _p, _l, _p, _p, _l, _p]),
     "biear_band_bwd": (_i, [_p, _l, _p, _l, _p, _l, _i, _i, _f, _f, _p, _l, _p, _l, _p, _l, _i, _p]),

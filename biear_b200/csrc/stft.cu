@@ -235,3 +235,44 @@ extern "C" int biear_stft_fwd_pair(const float* wavA, const float* wavB, int64_t
     return stft_launch(wavA, wavB, rows_each, 2 * rows_each, nsamp, wav_row_stride, win_fn, fs, T, win, hop, n_fft, X, ready,
                        1, stream, "biear_stft_fwd_pair");
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// 16-bit PCM -> float32 (the end-to-end input path: clips travel host -> device as int16, half the bytes of float32)
+// ------------------------------------------------------------------------------------------------------------------
+namespace biear {
+__global__ void __launch_bounds__(256) pcm16_to_f32_kernel(const int16_t* __restrict__ in, float* __restrict__ out,
+                                                           long long n, float scale) {
+    // 8 samples per thread and step: one 128-bit load, two 128-bit stores; grid-stride
+    const long long n8 = n >> 3;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+        const int4 v = __ldg(reinterpret_cast<const int4*>(in) + i);
+        const int w[4] = {v.x, v.y, v.z, v.w};
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            f[2 * j] = (float)(short)(w[j] & 0xffff) * scale;
+            f[2 * j + 1] = (float)(short)(w[j] >> 16) * scale;
+        }
+        float4* o = reinterpret_cast<float4*>(out) + 2 * i;
+        o[0] = make_float4(f[0], f[1], f[2], f[3]);
+        o[1] = make_float4(f[4], f[5], f[6], f[7]);
+    }
+    for (long long i = (n8 << 3) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = (float)in[i] * scale;
+}
+}  // namespace biear
+
+extern "C" int biear_pcm16_to_f32(const int16_t* in, float* out, int64_t n, float scale, void* stream) {
+    using namespace biear;
+    BIEAR_REQUIRE(n >= 0, "biear_pcm16_to_f32: negative length");
+    if (n == 0) return 0;
+    BIEAR_REQUIRE(in && out, "biear_pcm16_to_f32: null pointer");
+    BIEAR_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                  "biear_pcm16_to_f32: buffers must be 16-byte aligned");
+    const long long blocks = (n / 8 + 255) / 256;
+    const int grid = (int)(blocks < 1 ? 1 : (blocks > (long long)kSmCountB200 * 8 ? (long long)kSmCountB200 * 8 : blocks));
+    pcm16_to_f32_kernel<<<grid, 256, 0, as_stream(stream)>>>(in, out, (long long)n, scale);
+    BIEAR_LAUNCH_CHECK("pcm16_to_f32_kernel");
+    return 0;
+}

@@ -69,3 +69,13 @@ class FlatGradAllReducer:
                 else:
                     p.grad.copy_(v)
         return self.flat
+
+
+def captured_average(world: int, group: Optional[dist.ProcessGroup] = None):
+    """grad_sync callback for GraphedStep(flat_grads=True, grad_sync=...): sum the flat gradient bucket over the ranks and
+    scale by 1 / world, both recorded inside the step's CUDA graph (NCCL collectives are capturable), so that the exchange
+    replays with the step -- behind the kernel that produces the bucket -- instead of being issued by the host per step."""
+    def sync(flat: torch.Tensor):
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.mul_(1.0 / world)
+    return sync

@@ -348,6 +348,10 @@ class AuralNetGammatoneFB(_FilterbankBase):
 # ------------------------------------------------------------------------------------------------
 # binaural filterbanks
 # ------------------------------------------------------------------------------------------------
+GRAPH_REPLAY_DEFAULT = True   # value of BinauralAdaptiveGammatoneFB.graph_replay at construction (tests that pin RNG
+                              # streams or count launches construct their modules with False)
+
+
 class _FeatureTuple(nn.Module):
     """forward_features as a tensors-in / tuple-of-tensors-out module (what torch.cuda.make_graphed_callables captures)."""
 
@@ -379,11 +383,21 @@ class _GraphCache:
         self.seen = {}
         self.graphed = {}
 
+    def __deepcopy__(self, memo):          # copies of a module start with an empty cache (graphs are not copyable)
+        return _GraphCache()
+
+    def __getstate__(self):                # ... and so do pickled ones
+        return {}
+
+    def __setstate__(self, state):
+        self.seen, self.graphed = {}, {}
+
     def lookup(self, bifb, wl, wr, flags):
         params = tuple(bifb.parameters())
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-        key = (wl.device.index, tuple(wl.shape), wl.dtype, wr.dtype, bifb.training, need_grad, flags, bifb.engine,
-               bifb.fixed_frontend_q, bifb.fb_L.freeze_Q if hasattr(bifb.fb_L, "freeze_Q") else None,
+        key = (wl.device.index, tuple(wl.shape), wl.dtype, wr.dtype, bifb.training, need_grad, flags,
+               getattr(bifb, "engine", None), bifb.fixed_frontend_q, getattr(bifb, "freeze_Q", None),
+               getattr(getattr(bifb, "fb_L", None), "freeze_Q", None), getattr(getattr(bifb, "fb_R", None), "freeze_Q", None),
                tuple((p.data_ptr(), p.requires_grad) for p in params))
         if wl.dtype != torch.float32 or wr.dtype != torch.float32 or wl.requires_grad or wr.requires_grad:
             return None
@@ -397,33 +411,100 @@ class _GraphCache:
             self.graphed[key] = entry
         fn, mod = entry
         outs = fn(wl.contiguous(), wr.contiguous())
+        if need_grad and timing.enabled:
+            node = next((o.grad_fn for o in outs if o.grad_fn is not None), None)
+            timing.time_backward_node("frontend.backward", wl.shape[0], node)
         return dict(zip(mod.keys, outs))
 
     @staticmethod
     def _capture(bifb, wl, wr, flags, need_grad):
         mod = _FeatureTuple(bifb, flags)
-        if need_grad:
-            fn = torch.cuda.make_graphed_callables(mod, (wl.detach().clone(), wr.detach().clone()), num_warmup_iters=1,
-                                                   allow_unused_input=True)
-            return fn, mod
-        # no-grad calls (evaluation): one forward graph over static input / output buffers
+        return _GraphedCall(mod, wl, wr, need_grad), mod
+
+
+class _GraphedCall:
+    """forward (and, in grad mode, backward) of a _FeatureTuple as CUDA graphs over static buffers, exposed as ONE autograd
+    node.  Same scheme as torch.cuda.make_graphed_callables, but captured with capture_error_mode="thread_local": the
+    reference's training loop runs a DataLoader pin-memory thread whose CUDA calls would invalidate a "global" capture."""
+
+    def __init__(self, mod, wl, wr, need_grad):
         dev = wl.device
-        s_wl, s_wr = wl.detach().clone(), wr.detach().clone()
+        self.s_in = (wl.detach().clone(), wr.detach().clone())
+        named = [(n, p) for n, p in mod.named_parameters() if p.requires_grad] if need_grad else []
+        self.params = [p for _, p in named]
+        self.need_grad = bool(self.params)
+        # The graphs are recorded against fresh leaf ALIASES of the parameters (same storage, so every replay reads the
+        # current weights): the parameters' own AccumulateGrad nodes may still be alive from an eager backward on another
+        # stream (e.g. the previous step's loss tensor keeps them), and routing a captured gradient into such a node would
+        # make that stream depend on the capturing one, which CUDA refuses.
+        alias = {n: p.detach().requires_grad_(True) for n, p in named}
+        aliases = list(alias.values())
+        run = (lambda: torch.func.functional_call(mod, alias, self.s_in)) if self.need_grad else (lambda: mod(*self.s_in))
+        grad_ctx = torch.enable_grad if self.need_grad else torch.no_grad
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side), torch.no_grad():
-            mod(s_wl, s_wr)
+        with torch.cuda.stream(side), grad_ctx():          # one more eager pass on the capture side (allocator warm-up)
+            outs = run()
+            if self.need_grad:
+                req = [o for o in outs if o.requires_grad]
+                torch.autograd.grad(req, aliases, [torch.zeros_like(o) for o in req], allow_unused=True)
         torch.cuda.current_stream(dev).wait_stream(side)
-        graph = torch.cuda.CUDAGraph()
-        with torch.no_grad(), torch.cuda.graph(graph):
-            outs = mod(s_wl, s_wr)
+        torch.cuda.synchronize(dev)
+        self.fwd = torch.cuda.CUDAGraph()
+        with grad_ctx(), torch.cuda.graph(self.fwd, capture_error_mode="thread_local"):
+            outs = run()
+        self.s_out = tuple(outs)
+        self.req_idx = [i for i, o in enumerate(outs) if o.requires_grad] if self.need_grad else []
+        if self.need_grad:
+            req = [outs[i] for i in self.req_idx]
+            self.s_gout = tuple(torch.zeros_like(o) for o in req)
+            self.bwd = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.bwd, pool=self.fwd.pool(), capture_error_mode="thread_local"):
+                gin = torch.autograd.grad(req, aliases, self.s_gout, allow_unused=True)
+            self.s_gin = tuple(gin)
+        call = self
 
-        def fn(a, b):
-            s_wl.copy_(a, non_blocking=True)
-            s_wr.copy_(b, non_blocking=True)
-            graph.replay()
-            return outs
-        return fn, mod
+        class _Node(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, a, b, *params):
+                call.s_in[0].copy_(a, non_blocking=True)
+                call.s_in[1].copy_(b, non_blocking=True)
+                call.fwd.replay()
+                outs_ = tuple(o.detach() for o in call.s_out)
+                ctx.mark_non_differentiable(*[o for i, o in enumerate(outs_) if i not in call.req_idx])
+                return outs_
+
+            @staticmethod
+            def backward(ctx, *grads):
+                for dst, i in zip(call.s_gout, call.req_idx):
+                    g = grads[i]
+                    if g is None:
+                        dst.zero_()
+                    elif g.data_ptr() != dst.data_ptr():
+                        dst.copy_(g, non_blocking=True)
+                call.bwd.replay()
+                # Fresh copies (autograd may adopt a returned tensor as .grad, and the static buffers are rewritten by the
+                # next step): ONE concatenating launch, handed out as views of that new buffer.
+                live = [g for g in call.s_gin if g is not None]
+                flat = torch.cat([g.reshape(-1) for g in live])
+                out, off = [], 0
+                for g in call.s_gin:
+                    if g is None:
+                        out.append(None)
+                    else:
+                        out.append(flat[off:off + g.numel()].view_as(g))
+                        off += g.numel()
+                return (None, None) + tuple(out)
+
+        self.node = _Node
+
+    def __call__(self, wl, wr):
+        if self.need_grad:
+            return self.node.apply(wl, wr, *self.params)
+        self.s_in[0].copy_(wl, non_blocking=True)
+        self.s_in[1].copy_(wr, non_blocking=True)
+        self.fwd.replay()
+        return self.s_out
 
 
 class BinauralAdaptiveGammatoneFB(nn.Module):
@@ -463,7 +544,7 @@ class BinauralAdaptiveGammatoneFB(nn.Module):
         # Transparent CUDA-graph replay of the front-end's forward and backward for callers that issue it eagerly (the
         # reference's train_biear.py / evaluate_biear.py): see _GraphCache.  Outputs then live in static buffers that the
         # next forward of the same shape / mode overwrites.  Set to False for plain eager launches.
-        self.graph_replay = True
+        self.graph_replay = GRAPH_REPLAY_DEFAULT
         self._graphs = _GraphCache()
         # "fused": the whole recurrence in one persistent cluster kernel per direction (csrc/seq.cu);
         # "fused-strict": only its batch-global-fallback replay pass (testing);
@@ -478,7 +559,8 @@ class BinauralAdaptiveGammatoneFB(nn.Module):
         persistent recurrence kernels occupy 128 of the 148 SMs).  With want_logenergy the log band energies
         clamp(log(Y + 1e-8), +-12) (model_torch.py:1080-1083) come out of the band stage's epilogue as "logYL" / "logYR"
         and their gradient is folded into the backward kernel."""
-        with timing.span("frontend.forward", wavL_1s.shape[0] if wavL_1s.dim() == 2 else 0):
+        mode = "train" if (self.training and torch.is_grad_enabled()) else "eval"
+        with timing.span(f"frontend.forward[{mode}]", wavL_1s.shape[0] if wavL_1s.dim() == 2 else 0):
             flags = (bool(want_phase), bool(want_cc), float(cc_max_lag_ms), bool(want_logenergy))
             if self.graph_replay and wavL_1s.is_cuda and wavL_1s.dim() == 2 and wavL_1s.shape == wavR_1s.shape \
                     and not torch.cuda.is_current_stream_capturing():
@@ -598,6 +680,8 @@ class BinauralAdaptiveGammatoneFB_SingleController(_FilterbankBase):
         self.freeze_Q = False
         self.band_mode = "jacobian"
         self.cutoff = ops.DEFAULT_CUTOFF
+        self.graph_replay = GRAPH_REPLAY_DEFAULT      # see _GraphCache
+        self._graphs = _GraphCache()
         if not self.fixed_frontend_q:
             self.q_rnn, self.q_out = _make_controller(4 * Nbands, Nbands)
             self.fb_L = self.fb_R = None
@@ -609,6 +693,17 @@ class BinauralAdaptiveGammatoneFB_SingleController(_FilterbankBase):
             self.fb_R = mk()
 
     def forward_features(self, wavL_1s, wavR_1s, want_phase: bool = True, want_logenergy: bool = False):
+        mode = "train" if (self.training and torch.is_grad_enabled()) else "eval"
+        with timing.span(f"frontend.forward[{mode}]", wavL_1s.shape[0] if wavL_1s.dim() == 2 else 0):
+            flags = (bool(want_phase), False, 3.0, bool(want_logenergy))
+            if self.graph_replay and wavL_1s.is_cuda and wavL_1s.dim() == 2 and wavL_1s.shape == wavR_1s.shape \
+                    and not torch.cuda.is_current_stream_capturing():
+                hit = self._graphs.lookup(self, wavL_1s, wavR_1s, flags)
+                if hit is not None:
+                    return hit
+            return self._forward_features(wavL_1s, wavR_1s, *flags)
+
+    def _forward_features(self, wavL_1s, wavR_1s, want_phase, want_cc, cc_max_lag_ms, want_logenergy):
         x = self._spectra([wavL_1s, wavR_1s])
         B = wavL_1s.shape[0]
         if self.fixed_frontend_q or self.freeze_Q:

@@ -32,8 +32,13 @@ class _null:
 class GraphedStep:
     def __init__(self, fn: Callable[..., torch.Tensor], example_inputs: Sequence[torch.Tensor],
                  params: Iterable[torch.nn.Parameter], warmup: int = 3, pool=None, copy_inputs: bool = True,
-                 flat_grads: bool = False):
+                 flat_grads: bool = False, grad_sync: Optional[Callable[[torch.Tensor], None]] = None):
+        """grad_sync (needs flat_grads): called on the flat gradient bucket INSIDE the capture, right after the backward --
+        e.g. an NCCL all-reduce + scaling for data-parallel training, which then replays as part of the step's graph
+        instead of being issued by the host after it."""
         self.params = [p for p in params if p.requires_grad]
+        self._pcm_stage = {}
+        assert grad_sync is None or flat_grads, "grad_sync works on the flat gradient bucket (flat_grads=True)"
         self.copy_inputs = copy_inputs
         self.static_inputs = [x.clone() for x in example_inputs] if copy_inputs else list(example_inputs)
         dev = self.static_inputs[0].device
@@ -53,7 +58,7 @@ class GraphedStep:
         from . import _lib
         n0 = _lib.launch_count()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph, pool=pool, stream=side):
+        with torch.cuda.graph(self.graph, pool=pool, stream=side, capture_error_mode="thread_local"):
             self.loss = fn(*self.static_inputs)
             grads = torch.autograd.grad(self.loss, self.params, allow_unused=True)
             if flat_grads:
@@ -66,6 +71,8 @@ class GraphedStep:
                     views.append(self.flat[off:off + p.numel()].view_as(p))
                     off += p.numel()
                 grads = views
+                if grad_sync is not None:
+                    grad_sync(self.flat)
         self.launches_per_replay = _lib.launch_count() - n0   # kernels of libbiear_b200.so recorded in the graph
         self.loss = self.loss.detach()
         self.grads = list(grads)                      # static tensors (graph pool) rewritten by every replay
@@ -80,8 +87,17 @@ class GraphedStep:
         the H2D transfer of the next step overlaps this step's replay; returns an event to wait on before replay()."""
         ctx = torch.cuda.stream(stream) if stream is not None else _null()
         with ctx:
-            for dst, src in zip(self.static_inputs, inputs):
-                dst.copy_(src, non_blocking=True)
+            for i, (dst, src) in enumerate(zip(self.static_inputs, inputs)):
+                if src.dtype == torch.int16 and dst.dtype == torch.float32:
+                    # 16-bit PCM wire format: half the host->device bytes; converted next to the copy (biear_pcm16_to_f32)
+                    from . import ops
+                    stage = self._pcm_stage.get(i)
+                    if stage is None:
+                        stage = self._pcm_stage[i] = torch.empty(dst.shape, dtype=torch.int16, device=dst.device)
+                    stage.copy_(src, non_blocking=True)
+                    ops.pcm16_to_f32(stage, dst)
+                else:
+                    dst.copy_(src, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record()
         return ev

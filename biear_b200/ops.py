@@ -87,6 +87,23 @@ def stft(wav, win_fn: torch.Tensor, fs: int, timesteps: int, win: int, hop: int,
     return torch.view_as_complex(xr)
 
 
+def pcm16_to_f32(pcm: torch.Tensor, out: Optional[torch.Tensor] = None, scale: float = 1.0 / 32768.0) -> torch.Tensor:
+    """int16 PCM (any shape, CUDA, contiguous) -> float32 waveform pcm * scale, on the current stream (biear_pcm16_to_f32).
+    The reference's harness divides int16-range input by 32768 itself (train_biear.py:463-467)."""
+    _need_cuda(pcm, "pcm", torch.int16)
+    dev = pcm.device
+    if out is None:
+        out = torch.empty(pcm.shape, dtype=torch.float32, device=dev)
+    else:
+        _need_cuda(out, "out")
+        if out.shape != pcm.shape:
+            raise ValueError(f"out {tuple(out.shape)} and pcm {tuple(pcm.shape)} differ")
+    with torch.cuda.device(dev):
+        lib = _prepare(dev)
+        _lib.check(lib.biear_pcm16_to_f32(_ptr(pcm), _ptr(out), pcm.numel(), float(scale), _stream(dev)), "biear_pcm16_to_f32")
+    return out
+
+
 def stft_pair(wav_a: torch.Tensor, wav_b: torch.Tensor, win_fn: torch.Tensor, fs: int, timesteps: int, win: int, hop: int,
               n_fft: int, ready: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Both ears in one launch, frame-major work order: X (2B, T, F) complex64 (rows of wav_a first).  `ready` ((2B*T + 4,)

@@ -29,11 +29,30 @@ def span(name: str, batch: int = 0):
         _spans.setdefault(name, []).append((time.perf_counter() - t0, e0, e1, batch))
 
 
+def time_backward_node(name: str, batch: int, node):
+    """Record a span around the execution of one autograd node (the graphed front-end's backward replay)."""
+    if not enabled or node is None:
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t = [0.0]
+
+    def pre(grad_outputs):
+        t[0] = time.perf_counter()
+        e0.record()
+
+    def post(grad_inputs, grad_outputs):
+        e1.record()
+        _spans.setdefault(name, []).append((time.perf_counter() - t[0], e0, e1, batch))
+
+    node.register_prehook(pre)
+    node.register_hook(post)
+
+
 def reset():
     _spans.clear()
 
 
-def summary(skip: int = 2):
+def summary(skip: int = 4):
     """name -> {calls, batch (mode), device_ms, host_ms}: means over the calls after the first `skip` (warm-up) of the most
     frequent batch size."""
     torch.cuda.synchronize()
@@ -41,7 +60,7 @@ def summary(skip: int = 2):
     for name, rows in _spans.items():
         sizes = [r[3] for r in rows]
         mode = max(set(sizes), key=sizes.count) if sizes else 0
-        sel = [r for r in rows if r[3] == mode][skip:] or rows
+        sel = [r for r in rows if r[3] == mode][skip:] or rows      # (the first calls: lazy set-up and graph capture)
         out[name] = {"calls": len(rows), "batch": mode,
                      "device_ms": sum(r[1].elapsed_time(r[2]) for r in sel) / len(sel),
                      "host_ms": 1e3 * sum(r[0] for r in sel) / len(sel)}
@@ -53,8 +72,8 @@ def report(prefix: str = "[biear_b200 timing]"):
     for name, d in s.items():
         print(f"{prefix} {name}: {d['calls']} calls, batch {d['batch']}: {d['device_ms']:.3f} ms device, "
               f"{d['host_ms']:.3f} ms host per call", flush=True)
-    if "frontend.forward" in s and "frontend.backward" in s:
-        f, b = s["frontend.forward"], s["frontend.backward"]
+    if "frontend.forward[train]" in s and "frontend.backward" in s:
+        f, b = s["frontend.forward[train]"], s["frontend.backward"]
         print(f"{prefix} front-end per training step (forward + backward): {f['device_ms'] + b['device_ms']:.3f} ms device, "
               f"{f['host_ms'] + b['host_ms']:.3f} ms host", flush=True)
     return s

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BIEAR_ABI_VERSION 16
+#define BIEAR_ABI_VERSION 17
 #define BIEAR_EINVAL (-1)
 
 /* ABI version (== BIEAR_ABI_VERSION of the library that was built). */
@@ -52,6 +52,14 @@ int biear_init(void);
  *   X       (rows, T, n_fft/2+1, 2) out.
  * Supported: n_fft == 1024; any fs, T >= 1, win >= 1, hop >= 1.
  */
+/*
+ * 16-bit PCM waveform -> float32 in [-1, 1): out[i] = in[i] * scale (scale = 1/32768 is the reference harness's own
+ * convention for int16-range input, train_biear.py:463-467).  Lets the host hand clips over in the audio wire format --
+ * half the host->device bytes of float32 -- with the conversion on the device, next to the copy.
+ *   in (n) int16, out (n) float32, both device pointers; any n >= 0.
+ */
+int biear_pcm16_to_f32(const int16_t* in, float* out, int64_t n, float scale, void* stream);
+
 /* Both ears in ONE launch, frames in frame-major order (frame 0 of every row first): rows [0, rows_each) come from wavA,
  * [rows_each, 2 rows_each) from wavB; X (2 rows_each, T, n_fft/2+1, 2).  ready (nullable, 2 rows_each T + 4 int32, 8-byte
  * aligned, cleared by the caller / biear_adaptive_prepare; the trailing entries are the kernel's in-order work counter): entry [row][t] is set to 1, with release ordering, once X[row][t] is

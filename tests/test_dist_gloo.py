@@ -11,7 +11,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from biear_b200 import model_torch as mt
-from biear_b200.dist import FlatGradAllReducer, shard_bounds
+from biear_b200.dist import FlatGradAllReducer, captured_average, shard_bounds
 
 
 def _free_port():
@@ -47,6 +47,10 @@ def _worker(rank, world, port, n, out_dir):
     assert red.numel == 1288468                         # fixed-Q / passive parameter count
     if rank == 0:
         np.save(os.path.join(out_dir, "flat.npy"), flat.numpy())
+    # the capturable form (what GraphedStep records into the step's graph) gives the plain average of the buckets
+    mine = torch.full((5,), float(rank + 1))
+    captured_average(world)(mine)
+    assert torch.allclose(mine, torch.full((5,), sum(range(1, world + 1)) / world))
     # every rank must hold the same reduced gradients
     chk = torch.tensor([float(flat.double().sum())], dtype=torch.float64)
     both = [torch.zeros_like(chk) for _ in range(world)]

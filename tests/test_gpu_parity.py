@@ -838,3 +838,52 @@ def test_streamed_spectra_replays_with_changing_inputs_full_size(bb):
         assert float(loss) == eager[k][0], (k, float(loss), eager[k][0])
         for p, ge in zip(params, eager[k][1]):
             assert torch.equal(p.grad, ge)
+
+
+def test_transparent_graph_replay_matches_eager(bb):
+    """BinauralAdaptiveGammatoneFB.graph_replay: the third call with an unchanged (shape, mode) key captures forward and
+    backward as CUDA graphs and later calls replay them -- same bits as the eager launches (eval mode), for changing
+    inputs, in grad and in no-grad mode; in train mode every replay draws new dropout masks."""
+    B = 24
+    wl, wr = orc.synth_binaural(B * 4, seed=321)
+    rs = np.random.RandomState(4)
+    up = torch.from_numpy(rs.standard_normal((B, 19, 100)).astype(np.float32)).to(DEV)
+    held = {}
+
+    def run(m, i, grad=True):
+        tl = torch.from_numpy(wl[i * B:(i + 1) * B]).to(DEV)
+        tr = torch.from_numpy(wr[i * B:(i + 1) * B]).to(DEV)
+        for p in m.parameters():
+            p.grad = None
+        with torch.enable_grad() if grad else torch.no_grad():
+            o = m.forward_features(tl, tr, want_phase=True, want_logenergy=True)
+            if grad:
+                loss = (up * o["logYL"]).sum() + (up * o["QR"]).sum() + 1e-2 * (up * o["phaseR"]).sum()
+                loss.backward()
+                held[id(m)] = loss      # like a training loop's `loss` variable: keeps the step's autograd nodes (and the
+                                        # parameters' AccumulateGrad nodes, created on THIS stream) alive into the next call
+        res = {k: o[k].detach().clone() for k in ("YL", "YR", "QL", "QR", "phaseL", "logYR", "XL")}
+        g = {n: p.grad.clone() for n, p in m.named_parameters()} if grad else {}
+        return res, g
+
+    m_e, _, _ = _dual(bb, 1, (11, 12), CONFIG_YAML, 0.05)
+    m_g, _, _ = _dual(bb, 1, (11, 12), CONFIG_YAML, 0.05)
+    m_g.graph_replay = True
+    for i in (0, 1, 2, 3, 1):                       # calls 0, 1 eager; call 2 captures; 3, 1 replay with other inputs
+        (re, ge), (rg, gg) = run(m_e, i), run(m_g, i)
+        for k in re:
+            assert torch.equal(re[k], rg[k]), (i, k)
+        for k in ge:
+            assert torch.equal(ge[k], gg[k]), (i, k)
+    assert len(m_g._graphs.graphed) == 1 and not m_e._graphs.graphed
+    for i in (0, 1, 2, 3):                          # the no-grad key gets its own (forward-only) graph
+        re, _ = run(m_e, i, grad=False)
+        rg, _ = run(m_g, i, grad=False)
+        for k in re:
+            assert torch.equal(re[k], rg[k]), (i, k)
+    assert len(m_g._graphs.graphed) == 2
+    m_g.train()
+    outs = [run(m_g, 0)[0]["QL"] for _ in range(5)]
+    assert len(m_g._graphs.graphed) == 3
+    assert not torch.equal(outs[3], outs[4])        # replays 4 and 5: fresh dropout masks
+    assert all(torch.isfinite(o).all() for o in outs)

@@ -43,7 +43,7 @@ def test_reference_train_and_evaluate_scripts_run_unchanged_active(tmp_path):
     train_log = (tmp_path / "r2_train_biear_unchanged.log").read_text()
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:] + train_log[-3000:]
     assert "Training finished." in train_log and "Test metrics:" in train_log
-    assert "[biear_b200 timing] frontend.forward" in train_log and "frontend.backward" in train_log   # the CUDA path ran
+    assert "[biear_b200 timing] frontend.forward[train]" in train_log and "frontend.backward" in train_log   # the CUDA path ran
     ev = tmp_path / "r2_evaluate_biear_unchanged.log"
     if "skipping it" in out.stdout:
         pytest.skip("evaluate_biear.py's hard-coded absolute paths cannot be created here")

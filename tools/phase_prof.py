@@ -30,7 +30,7 @@ torch.cuda.synchronize()
 _lib.check(lib.biear_debug_phase_cycles(buf), "phase cycles")
 names = [["loop head", "spectra ready (wait + convert)", "band stage (rest)", "band barrier + push + hand-over #1", "GRU + #2",
           "Linear 1 + #3", "LayerNorm 1", "Linear 2 + #4", "LayerNorm 2", "Linear 3 + Q + #5",
-          "band: own-band parameters", "band: per-pair parameter hand-out", "band: band_accumulate", "band: sums back to owners",
+          "band: own-band parameters", "band: loop control", "band: band_accumulate", "band: sums back to owners",
           "band: epilogue"],
          ["loop head", "dL/dpre + push + #1", "Linear 3^T + #2", "LayerNorm 2 bwd", "Linear 2^T + #3", "LayerNorm 1 bwd",
           "Linear 1^T + GRU bwd + #4", "last phase: wait for hand-over #5", "last: issue next step's loads",

@@ -1,7 +1,7 @@
 """Run the reference's train_biear.py and then evaluate_biear.py BYTE-UNCHANGED, in ACTIVE mode, against biear_b200's
 drop-in modules on a GPU.
 
-    python tools/run_reference_pipeline.py [--clips 2048] [--batch 256] [--log-dir gpurun_out]
+    python tools/run_reference_pipeline.py [--clips 6144] [--batch 256] [--log-dir gpurun_out]
 
 What it does (nothing of the reference is modified; its files come from /root/reference or, on the GPU box, from the
 byte-identical staging in oracle/_ref -- sha256 checked against the manifest):
@@ -80,7 +80,7 @@ def run_script(script, log, env, *overrides):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--clips", type=int, default=2048)
+    ap.add_argument("--clips", type=int, default=6144)
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--log-dir", default=os.path.join(ROOT, "gpurun_out"))
     ap.add_argument("--skip-evaluate", action="store_true")
