@@ -293,11 +293,12 @@ def run_ours(args):
     flat_numel = sum(p.numel() for p in params)
 
     from biear_b200.dist import FlatGradAllReducer, captured_average
-    host_reduce = dist is not None and (args.eager or args.host_allreduce)
+    host_reduce = dist is not None and (args.eager or not args.graph_allreduce)
     current = {"reducer": FlatGradAllReducer(params) if (dist is not None and args.eager) else None}
-    # Data-parallel gradient exchange: ONE flat-bucket NCCL all-reduce (sum, x 1/world) per step.  By default it is
-    # recorded INSIDE the step's CUDA graph, right behind the split-K reduction that produces the bucket, so a replay
-    # carries it and the host issues nothing per step (--host-allreduce: issue it from the host after each replay).
+    # Data-parallel gradient exchange: ONE flat-bucket NCCL all-reduce (sum, x 1/world) per step, issued by the host right
+    # after the step's graph replay (the bucket is written by the graph itself: no copies).  --graph-allreduce records it
+    # INSIDE the step's CUDA graph instead; measured at 2 GPUs that is slower (0.885 vs 0.866 ms per step: NCCL's
+    # graph-captured launch costs more than the two host-issued launches it saves), so it is not the default.
     grad_sync = captured_average(world) if (dist is not None and not host_reduce) else None
     if dist is not None:
         warm = torch.zeros(flat_numel, device=dev)
@@ -466,6 +467,11 @@ def run_ours(args):
     ms, ms_e2e = float(times[0]), float(times[1])
     if rank != 0:
         if dist is not None:
+            if not args.eager:
+                del graphs, e2e_graphs, steps_res
+                import gc
+                gc.collect()
+                torch.cuda.synchronize()
             dist.destroy_process_group()
         return
     clips = B * world * args.steps
@@ -510,19 +516,24 @@ def run_ours(args):
                 out[key] = {"error": repr(e)[:300]}
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = bench_extra.reference_cpu(sample_batch=16, budget_s=20.0)
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
     if dist is not None:
+        if not args.eager:          # graphs that recorded NCCL work must be gone before the communicator is
+            del graphs, e2e_graphs, steps_res
+            import gc
+            gc.collect()
+            torch.cuda.synchronize()
         dist.destroy_process_group()
 
 
-NCU_SUMMARY = os.path.join(ROOT, "profiles", "r1_ncu_summary.json")
+NCU_SUMMARY = os.path.join(ROOT, "profiles", "r2_ncu_summary.json")
 # floats the forward recurrence saves per (row, step) for the backward: H 128 + gates 512 + LN in/out 4 x 128 + log1p(Y)
 # 100 + rstd 2
 SAVED_PER_ROW_STEP = 128 + 512 + 4 * 128 + NBANDS + 2
 
 
 def kernel_roofline(model, dev_in, dev, B):
-    """The dominant kernel alone: seq_fwd_kernel, the persistent forward recurrence (band stage + controller, all 19
+    """The dominant kernel alone: seq_fwd2_kernel, the persistent forward recurrence (band stage + controller, all 19
     frames, both ears), timed with CUDA events around graph replays of just the recurrence call on spectra of rotating
     input batches.  The call's two tiny companion launches (weight packing, ~5 us, and the early-exit replay check,
     ~3 us) are inside the window: < 2 % of it.  `traffic` comes from the committed ncu capture of the same kernel."""
@@ -574,12 +585,12 @@ def kernel_roofline(model, dev_in, dev, B):
     try:
         with open(NCU_SUMMARY) as f:
             k = json.load(f)["kernels"]
-        name = next(n for n in k if n.startswith("seq_fwd_kernel") and k[n]["duration_us"] > 50)
+        name = next(n for n in k if n.startswith("seq_fwd2_kernel") and k[n]["duration_us"] > 50)
         if B == 256:                       # the capture was taken at the benchmark batch
-            traffic, traffic_src = k[name]["dram_bytes"], "profiles/r1_ncu_summary.json (dram__bytes_read+write per launch)"
+            traffic, traffic_src = k[name]["dram_bytes"], "profiles/r2_ncu_summary.json (dram__bytes_read+write per launch)"
     except Exception:
         pass
-    return {"kernel": "seq_fwd_kernel (persistent forward recurrence: band stage + Q controller, 19 frames, both ears)",
+    return {"kernel": "seq_fwd2_kernel (persistent forward recurrence: band stage + Q controller, 19 frames, both ears)",
             "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
             "traffic_source": traffic_src, "us_per_launch": us, "algorithmic_bytes_per_launch": alg,
             "peak_source": peak_src,
@@ -681,7 +692,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the gpu_eager_reference / fixed_q / full_step sub-records")
     ap.add_argument("--eager", action="store_true", help="issue every launch from Python instead of replaying CUDA graphs")
-    ap.add_argument("--host-allreduce", action="store_true", help="issue the gradient all-reduce from the host after each replay")
+    ap.add_argument("--graph-allreduce", action="store_true", help="record the gradient all-reduce inside the step's CUDA graph")
     ap.add_argument("--e2e-f32", action="store_true", help="end-to-end arm with float32 host waveforms instead of 16-bit PCM")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -353,15 +353,17 @@ def compute_roofline(model, dev_in, value_per_gpu, fwd_us, ncu_summary_path):
     try:
         with open(ncu_summary_path) as f:
             k = json.load(f)["kernels"]
-        for short, prefix in (("seq_fwd", "seq_fwd_kernel"), ("seq_bwd", "seq_bwd_kernel")):
+        for short, prefix in (("seq_fwd", "seq_fwd2_kernel"), ("seq_bwd", "seq_bwd_kernel")):
             name = next(n for n in k if n.startswith(prefix) and k[n]["duration_us"] > 50)
             d = k[name]
             rec = {"issue_slot_pct": d.get("issue_active_pct"), "warp_instructions": d.get("warp_instructions"),
                    "duration_us_under_ncu": d.get("duration_us")}
-            for key in ("pipe_fma_pct", "pipe_fmaheavy_pct", "pipe_alu_pct", "pipe_xu_pct", "pipe_lsu_pct",
-                        "inst_pipe_fma", "inst_pipe_xu", "sm_busy_pct"):
-                if key in d:
+            for key in ("pipe_fma_cycles_pct", "pipe_fma_inst_pct", "pipe_alu_pct", "pipe_xu_pct", "pipe_lsu_pct",
+                        "smem_wavefronts_pct"):
+                if d.get(key) is not None:
                     rec[key] = d[key]
+            if d.get("pipe_fma_cycles_pct") is not None:     # the fp32 roofline fraction of the kernel: share of the
+                rec["fma_pipe_frac"] = d["pipe_fma_cycles_pct"] / 100.0      # cycles in which the FMA pipe is busy
             out[short] = rec
         out["ncu_source"] = os.path.relpath(ncu_summary_path, ROOT)
     except Exception as e:  # noqa: BLE001

@@ -249,25 +249,6 @@ __device__ __forceinline__ void wait_spectra(const BiearSeqParams& p, long long 
     __syncthreads();
 }
 
-// The same split in two, for the steady state: the flag of the NEXT frame is read at the start of a frame (the L2 round
-// trip hides behind the band stage) and only re-polled, before the block barrier that follows the band stage anyway, if
-// it was not set yet.
-__device__ __forceinline__ int peek_spectra(const BiearSeqParams& p, long long grow0, int b0, int t) {
-    int v = 1;
-    if (p.x_ready && threadIdx.x < kRT && b0 + (int)threadIdx.x < p.B)
-        asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(p.x_ready + (grow0 + threadIdx.x) * p.T + t) : "memory");
-    return v;
-}
-__device__ __forceinline__ void confirm_spectra(const BiearSeqParams& p, long long grow0, int t, int v) {
-    if (v != 0) return;                                        // (only threads that peeked a 0 get here)
-    const int32_t* flag = p.x_ready + (grow0 + threadIdx.x) * p.T + t;
-    for (unsigned spin = 0; v == 0; ++spin) {
-        __nanosleep(64);
-        asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-        if (spin > (1u << 24)) __trap();
-    }
-}
-
 // Spectra of this CTA's 4 rows for frame t -> shared {1, abs, re, im} tiles (zeros for padding rows / bins), in two
 // steps so that the HBM latency hides behind the controller phases: prefetch_spectra() issues 8-byte cp.async copies
 // of the raw complex bins straight into the {re, im} half of their tile slots; finish_spectra() (same thread -> same
@@ -303,12 +284,11 @@ __device__ __forceinline__ void finish_spectra(const BiearSeqParams& p, float4* 
     }
 }
 
-// STRICT == false: one cluster per tile, state carried in shared memory (the fast path).
-// STRICT == true : ONE cluster walks all tiles frame by frame with the state going through global memory, which
-//                  makes the reference's batch-global non-finite fallback exact; it exits at once unless the fast
-//                  path recorded a non-finite Q (or p.force_strict).
-template <bool STRICT>
-__global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqParams p, const float* __restrict__ img) {
+// The STRICT pass: ONE cluster walks all tiles frame by frame, one chain of 16 rows, with the state going through global
+// memory and hardware cluster barriers between the phases -- which makes the reference's batch-global non-finite
+// fallback (model_torch.py:378-380) exact.  It exits at once unless the fast pass (seq_fwd2_kernel below) recorded a
+// non-finite Q (or p.force_strict).  Same arithmetic per row as the fast pass.
+__global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_strict_kernel(const BiearSeqParams p, const float* __restrict__ img) {
     extern __shared__ __align__(16) float smem[];
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
@@ -342,36 +322,14 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
     const int quads = (N + 3) >> 2;
     int* any_flag = p.flags + S * p.G;
     const unsigned long long seed = p.seed_ptr ? *p.seed_ptr : p.seed;
-    // Hand-overs inside the cluster (fast pass): st.async + one mbarrier per phase type (seq_dev.cuh).  The strict pass
-    // exchanges its state through global memory and keeps the hardware cluster barrier.
-    const uint32_t bars = smem_u32(smem + L.misc());
-    auto bar_of = [&](int i) { return bars + 8u * (uint32_t)i; };          // i = 0..4: yc, h, a1, a2, Q
-    const uint32_t tx_bytes[5] = {(uint32_t)(N * kR * 4), (uint32_t)(kHid * kR * 4), (uint32_t)(kHid * kR * 4),
-                                  (uint32_t)(kHid * kR * 4), (uint32_t)(N * kRT * 4)};
-    if (!STRICT) {
-        if (tid == 0) {
-#pragma unroll
-            for (int i = 0; i < 5; ++i) mbar_init(bar_of(i), 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        cluster.sync();                                       // every CTA's barriers exist before anybody signals them
-    }
-    // hand-over i of step t is complete: fast pass = all bytes have landed here; strict pass = hardware cluster barrier
-    auto arm = [&](int i) {            // (fast pass) this CTA's expectation for the hand-over, by one thread
-        if (!STRICT && tid == 0) mbar_arrive_expect_tx(bar_of(i), tx_bytes[i]);
-    };
-
-    if (STRICT) {
-        if (!p.force_strict && *reinterpret_cast<volatile int*>(any_flag) == 0) return;   // uniform over the grid
-        cluster.sync();                                       // everyone has read the old any-flag
-        for (int i = rank * kSeqThreads + tid; i < S * p.G; i += kCS * kSeqThreads) p.flags[i] = 0;
-        __threadfence();
-        cluster.sync();
-    }
-    PHASE_INIT();
-    const int tl_begin = STRICT ? 0 : (int)(blockIdx.x / kCS);
-    const int tl_end = STRICT ? n_tiles : tl_begin + 1;
-    int cur_g = -1, spec_t = -1, hsel = 0;
+    if (!p.force_strict && *reinterpret_cast<volatile int*>(any_flag) == 0) return;   // uniform over the grid
+    cluster.sync();                                       // everyone has read the old any-flag
+    for (int i = rank * kSeqThreads + tid; i < S * p.G; i += kCS * kSeqThreads) p.flags[i] = 0;
+    __threadfence();
+    cluster.sync();
+    const int tl_begin = 0, tl_end = n_tiles;
+    int cur_g = -1;
+    constexpr int hsel = 0;        // h_{t-1} is reloaded from global memory every frame: the two buffers keep their roles
 
     for (int t = 0; t < T; ++t) {
         for (int tl = tl_begin; tl < tl_end; ++tl) {
@@ -413,7 +371,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
             }
             // ---- state of this (tile, frame) ---------------------------------------------------------------
             bool fallback_prev = false;                       // Q_t was replaced by Q0 and h_{t-1} dropped
-            if (STRICT && t > 0) fallback_prev = __ldcg(p.flags + (t - 1) * p.G + g) != 0;
+            if (t > 0) fallback_prev = __ldcg(p.flags + (t - 1) * p.G + g) != 0;
             const bool use_q0 = (t == 0) || fallback_prev;
             const bool h_zero = use_q0;
             float* hcur_s = hbuf_s + hsel * kHid * kR;
@@ -424,7 +382,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                     q_s[n * kRT + i] = vec_s[V_Q0 + n];
                     if (bb0 + i < p.B) p.Q[((grow0 + i) * T + t) * N + n] = vec_s[V_Q0 + n];
                 }
-            } else if (STRICT) {
+            } else {
                 for (int idx = tid; idx < kRT * N; idx += kSeqThreads) {
                     const int i = idx / N, n = idx - i * N;
                     q_s[n * kRT + i] = (bb0 + i < p.B) ? __ldcg(p.Q + ((grow0 + i) * T + t) * N + n) : vec_s[V_Q0 + n];
@@ -432,19 +390,16 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                 const float4* hsrc = reinterpret_cast<const float4*>(h_tile(p, g, t - 1, tiles, tile));
                 for (int i = tid; i < kHid * kR / 4; i += kSeqThreads) reinterpret_cast<float4*>(hcur_s)[i] = __ldcg(hsrc + i);
             }
-            if (STRICT && fallback_prev && rank == 0) {   // h_{t-1} was dropped: it must not feed dW_hh either
+            if (fallback_prev && rank == 0) {   // h_{t-1} was dropped: it must not feed dW_hh either
                 float4* hdst = reinterpret_cast<float4*>(h_tile(p, g, t - 1, tiles, tile));
                 for (int i = tid; i < kHid * kR / 4; i += kSeqThreads) hdst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            PHASE_MARK(0, 0);    // loop head / weight load
-            if (STRICT || spec_t != t) {   // first frame / strict pass: fetch and convert now (also orders the q_s fill)
-                wait_spectra(p, grow0, bb0, t);
-                prefetch_spectra(p, spec_s, L.tile, grow0, bb0, t);
-                finish_spectra(p, spec_s, L.tile, bb0);
-                __syncthreads();
-            }   // otherwise frame t's tile was fetched behind frame t-1's controller phases and converted before its barrier #5
-            PHASE_MARK(0, 1);    // spectra ready
-            const int next_ready = (!STRICT && t + 1 < T) ? peek_spectra(p, grow0, bb0, t + 1) : 1;
+            // spectra of this CTA's rows for frame t (the STFT has long finished when this pass runs; the wait is a no-op
+            // then, but the hand-over protocol allows a caller to stream them here too)
+            wait_spectra(p, grow0, bb0, t);
+            prefetch_spectra(p, spec_s, L.tile, grow0, bb0, t);
+            finish_spectra(p, spec_s, L.tile, bb0);
+            __syncthreads();
 
             // ---- band stage of frame t for this CTA's 4 rows (model_torch.py:340-346, 1050-1060) ---------------
             // The 4 x quads (row, 4-band quad) pairs are dealt round-robin to the 16 warps, widest quads first and
@@ -467,7 +422,6 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                 const float q = own ? q_s[n_own * kRT + row_own] : 1.0f;
                 const BandParams bp_own = band_params(fc, q, p.df, p.cutoff, p.F, own);
                 BandSums keep = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                PHASE_MARK(0, 10);   // band stage: own-band parameters
                 for (int m = 0, pr = warp; pr < n_pairs; ++m, pr += kWarps) {
                     const int row = ((pr & 3) + (pr >> 4)) & 3;
                     const int src = (m << 2) + (lane >> 3);          // lane owning the band this lane helps with
@@ -478,9 +432,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                     bp.kc = __shfl_sync(0xffffffffu, bp_own.kc, src);
                     bp.k_lo = __shfl_sync(0xffffffffu, bp_own.k_lo, src);
                     bp.k_hi = __shfl_sync(0xffffffffu, bp_own.k_hi, src);
-                    PHASE_MARK(0, 11);   // band stage: per-pair parameter hand-out
                     const BandSums sums = band_accumulate(spec_s + row * L.tile, p.F, bp, lane);
-                    PHASE_MARK(0, 12);   // band stage: band_accumulate
                     const int from = (lane & 3) << 3;                // any lane of the group that holds my band's sums
                     const bool mine = (lane >> 2) == m;
                     float v;
@@ -492,7 +444,6 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                     v = __shfl_sync(0xffffffffu, sums.a2, from);  if (mine) keep.a2 = v;
                     v = __shfl_sync(0xffffffffu, sums.z2r, from); if (mine) keep.z2r = v;
                     v = __shfl_sync(0xffffffffu, sums.z2i, from); if (mine) keep.z2i = v;
-                    PHASE_MARK(0, 13);   // band stage: sums back to the owner lanes
                 }
                 if (own) {
                     const BandResult r = band_finish(keep);
@@ -522,42 +473,27 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                     p.dPdQ[own_e] = oK;
                 }
             };
-            PHASE_MARK(0, 14);   // band stage: epilogue (normalise, atan2, log1p, Jacobians)
-            PHASE_MARK(0, 2);    // band stage (this warp)
             if (t == T - 1) {
                 // The reference runs the controller once more and discards the result (model_torch.py:361-380).
                 store_band_outputs();
-                if (STRICT) __syncthreads();
+                __syncthreads();
                 continue;
             }
-            if (!STRICT) confirm_spectra(p, grow0, t + 1, next_ready);   // (ordered for everybody by the barrier below)
             __syncthreads();
-            if (!STRICT) {   // the tile is free again: start fetching the next frame's spectra behind the controller phases
-                prefetch_spectra(p, spec_s, L.tile, grow0, bb0, t + 1);
-                spec_t = t + 1;
-            }
             const long long tb = tile_base(p, g, t, tiles, tile);
-            const uint32_t par = (uint32_t)t & 1u;     // every hand-over barrier completes exactly once per frame
             if (tid < N) {   // features of my 4 rows -> every CTA of the cluster (+ saved for dW_ih)
                 const float4 v = make_float4(ystage_s[tid], ystage_s[kHid + tid], ystage_s[2 * kHid + tid],
                                              ystage_s[3 * kHid + tid]);
-                if (STRICT) {
 #pragma unroll
-                    for (int dst = 0; dst < kCS; ++dst)
-                        *reinterpret_cast<float4*>(cluster.map_shared_rank(yc_s, dst) + tid * kR + rank * kRT) = v;
-                } else {
-                    bcast_f4_tx(yc_s + tid * kR + rank * kRT, v, bar_of(0));
-                }
+                for (int dst = 0; dst < kCS; ++dst)
+                    *reinterpret_cast<float4*>(cluster.map_shared_rank(yc_s, dst) + tid * kR + rank * kRT) = v;
             }
-            if (STRICT) cluster.barrier_arrive();   // #1: my part of yc is delivered ...
-            arm(0);
+            cluster.barrier_arrive();   // #1: my part of yc is delivered ...
             if (tid < N)
                 *reinterpret_cast<float4*>(p.yc + tb * N * kR + tid * kR + rank * kRT) =
                     make_float4(ystage_s[tid], ystage_s[kHid + tid], ystage_s[2 * kHid + tid], ystage_s[3 * kHid + tid]);
             store_band_outputs();
-            if (STRICT) cluster.barrier_wait();     // ... and complete everywhere
-            else tx_wait(bar_of(0), par);
-            PHASE_MARK(0, 3);    // band barrier + push + cluster barrier #1
+            cluster.barrier_wait();     // ... and complete everywhere
 
             // ---- GRU cell (torch gate order r, z, n; n = tanh(i_n + r * (W_hn h + b_hn))) ----------------------
             {
@@ -589,11 +525,9 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                         const float hp = h_zero ? 0.0f : hcur_s[ug * kR + rg * kRT + i];
                         hv[i] = (1.0f - vz[i]) * vn[i] + vz[i] * hp;
                     }
-                    if (STRICT) broadcast_rows(cluster, hnext_s, ug, rg * kRT, hv);
-                    else broadcast_rows_tx(hnext_s, ug, rg * kRT, hv, bar_of(1));
+                    broadcast_rows(cluster, hnext_s, ug, rg * kRT, hv);
                 }
-                if (STRICT) cluster.barrier_arrive();   // #2 signalled before the saves go out (a later release covers them)
-                arm(1);
+                cluster.barrier_arrive();   // #2 signalled before the saves go out (a later release covers them)
                 if (ks == 0) {
                     store4(h_tile(p, g, t, tiles, tile) + ug * kR + rg * kRT, hv);
                     float* gt = p.gates + tb * 4 * kHid * kR + ug * kR + rg * kRT;
@@ -603,9 +537,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                     store4(gt + 3 * kHid * kR, vh);
                 }
             }
-            if (STRICT) cluster.barrier_wait();   // #2: h_t complete everywhere
-            else tx_wait(bar_of(1), par);
-            PHASE_MARK(0, 4);    // GRU
+            cluster.barrier_wait();   // #2: h_t complete everywhere
 
             // ---- Linear 1 -> LayerNorm -> SiLU -> Dropout ------------------------------------------------------
             {
@@ -618,21 +550,12 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                     const float bb = vec_s[V_B1 + u];
 #pragma unroll
                     for (int i = 0; i < kRT; ++i) acc[i] += bb;
-                    if (STRICT) broadcast_rows(cluster, a1_s, ug, rg * kRT, acc);
-                    else broadcast_rows_tx(a1_s, ug, rg * kRT, acc, bar_of(2));
+                    broadcast_rows(cluster, a1_s, ug, rg * kRT, acc);
                 }
             }
-            if (STRICT) {
-                cluster.sync();   // #3
-            } else {
-                arm(2);
-                tx_wait(bar_of(2), par);
-            }
-            PHASE_MARK(0, 5);    // Linear 1
+            cluster.sync();   // #3
             ln_silu_drop_fwd(p, seed, a1_s, stat_s, vec_s + V_LN1G, vec_s + V_LN1B, 0, t, (long long)g * p.B + b0, rank,
                              p.xh1 + tb * kHid * kR, p.d1 + tb * kHid * kR, p.rstd + tb * 2 * kR);
-
-            PHASE_MARK(0, 6);    // LayerNorm 1
             // ---- Linear 2 -> LayerNorm -> SiLU -> Dropout ------------------------------------------------------
             {
                 float acc[kRT] = {0.f, 0.f, 0.f, 0.f};
@@ -645,21 +568,12 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
 #pragma unroll
                     for (int i = 0; i < kRT; ++i) acc[i] += bb;
                     // a2 aliases yc: every CTA's yc reads (its GRU products) ended before it sent h_t, i.e. before #2
-                    if (STRICT) broadcast_rows(cluster, a2_s, ug, rg * kRT, acc);
-                    else broadcast_rows_tx(a2_s, ug, rg * kRT, acc, bar_of(3));
+                    broadcast_rows(cluster, a2_s, ug, rg * kRT, acc);   // a2 aliases yc: all yc reads ended before #2
                 }
             }
-            if (STRICT) {
-                cluster.sync();   // #4
-            } else {
-                arm(3);
-                tx_wait(bar_of(3), par);
-            }
-            PHASE_MARK(0, 7);    // Linear 2
+            cluster.sync();   // #4
             ln_silu_drop_fwd(p, seed, a2_s, stat_s, vec_s + V_LN2G, vec_s + V_LN2B, 1, t, (long long)g * p.B + b0, rank,
                              p.xh2 + tb * kHid * kR, p.d2 + tb * kHid * kR, p.rstd + tb * 2 * kR);
-
-            PHASE_MARK(0, 8);    // LayerNorm 2
             // ---- Linear 3 -> tanh -> Q_{t+1} (model_torch.py:367-380) -------------------------------------------
             {
                 float acc[kRT] = {0.f, 0.f, 0.f, 0.f};
@@ -682,12 +596,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                         bad = bad || (b0 + rg * kRT + i < p.B && !finite_f(qu));
                     }
                     // Q_{t+1} of rows 4rg..4rg+3 goes to the CTA that runs their band stage
-                    if (STRICT) {
-                        store4(cluster.map_shared_rank(q_s, rg) + n * kRT, qv);
-                    } else {
-                        st_async_f4(cluster_addr(smem_u32(q_s + n * kRT), (uint32_t)rg), make_float4(qv[0], qv[1], qv[2], qv[3]),
-                                    cluster_addr(bar_of(4), (uint32_t)rg));
-                    }
+                    store4(cluster.map_shared_rank(q_s, rg) + n * kRT, qv);
                     if (bad) {   // NaN / Inf: the reference falls back for the whole batch of this ear
                         atomicOr(p.flags + t * p.G + g, 1);
                         atomicOr(any_flag, 1);
@@ -705,31 +614,543 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd_kernel(const BiearSeqP
                         }
                     }
                 };
-                // Fast pass: signal the barrier first, the row-major outputs are nobody's input inside the cluster.
-                // Strict pass: Q / flags / H are read back from global memory by other CTAs, so they must precede it.
-                if (STRICT) {
-                    store_q();
-                    __threadfence();
-                } else {
-                    // finish the next frame's spectrum tile (cp.async data has long arrived) BEFORE signalling: once #5
-                    // completes, every thread of this CTA has converted its slots, so the band stage can start at once
-                    finish_spectra(p, spec_s, L.tile, bb0);
-                }
-                if (STRICT) cluster.barrier_arrive();   // #5
-                arm(4);
-                if (!STRICT) store_q();
+                // Q / flags / H are read back from global memory by other CTAs in the next frame: they precede the barrier
+                store_q();
+                __threadfence();
+                cluster.barrier_arrive();   // #5
             }
-            if (STRICT) {
-                cluster.barrier_wait();   // #5: Q_{t+1} delivered; a2 / yc free for the next frame
-            } else {
-                tx_wait(bar_of(4), par);  // Q_{t+1} of my band-stage rows has landed ...
-                __syncthreads();          // ... and every thread of this CTA has converted its slots of the next spectrum tile
-            }
-            PHASE_MARK(0, 9);    // Linear 3 + Q
-            if (!STRICT) hsel ^= 1;   // strict: h_{t-1} is reloaded from global memory, the buffers keep their roles
+            cluster.barrier_wait();   // #5: Q_{t+1} delivered; a2 / yc free for the next frame
         }
     }
-    if (!STRICT) cluster.sync();   // no CTA leaves (and frees its shared memory) while a peer could still be sending to it
+}
+
+// ==================================================================================================
+// forward, fast pass: TWO independent chains per CTA
+// ==================================================================================================
+// The tile of 16 rows is split into two half-tiles of 8 rows; warps 0-7 of every CTA of the cluster carry half-tile 0
+// through the recurrence, warps 8-15 half-tile 1, each with its own activation buffers, named block barrier and hand-over
+// mbarriers, sharing only the (read-only) weight image.  The two chains drift apart on their own, so the FMA-bound band
+// stage of one half overlaps the latency-bound controller phases of the other: every chain keeps the serial latency of
+// its phases, but the throughput-bound parts of a phase (the band loop, the shared-memory traffic of the dot products)
+// now serve 8 rows instead of 16.  Same arithmetic per row as the single-chain kernel (which remains as the strict pass).
+constexpr int kCh = 2;                         // chains per CTA
+constexpr int kCT = kSeqThreads / kCh;         // 256 threads per chain
+constexpr int kRC = kR / kCh;                  // 8 rows of the tile per chain
+constexpr int kRB = kRC / kCS;                 // 2 band-stage rows per CTA and chain
+constexpr int kRGC = kRC / kRT;                // 2 row groups of 4 rows in the GEMM phases
+constexpr int kSlotsC = kRGC * kU;             // 64 (row group, unit) slots per k-split
+constexpr int kWarpsC = kCT / 32;              // 8 warps per chain
+static_assert(kKS * kSlotsC == kCT && kRB * kCS == kRC, "chain thread layout");
+
+struct Fwd2Smem {   // offsets in floats
+    int N, tile;
+    __host__ __device__ Fwd2Smem(int N_, int F) : N(N_), tile(spec_tile_len(F)) {}
+    __host__ __device__ int vec() const { return fwd_img_floats(N); }           // behind the (shared) weight image
+    __host__ __device__ int chain0() const { return vec() + 1088; }
+    // per chain:
+    __host__ __device__ int c_yc() const { return 0; }                           // [128][kRC]; aliased by a2
+    __host__ __device__ int c_a1() const { return kHid * kRC; }                  // directly behind yc
+    __host__ __device__ int c_h() const { return 2 * kHid * kRC; }               // x 2 (ping-pong)
+    __host__ __device__ int c_stat() const { return 4 * kHid * kRC; }            // 2 * kCT
+    __host__ __device__ int c_q() const { return c_stat() + 2 * kCT; }           // [128][kRB]
+    __host__ __device__ int c_ystage() const { return c_q() + kHid * kRB; }      // [kRB][128]
+    __host__ __device__ int c_spec() const { return c_ystage() + kRB * kHid; }   // [kRB][tile] float4
+    __host__ __device__ int c_bars() const { return c_spec() + kRB * tile * 4; } // 5 mbarriers
+    __host__ __device__ int c_total() const { return c_bars() + 16; }
+    __host__ __device__ int total() const { return chain0() + kCh * c_total(); }
+};
+
+__device__ __forceinline__ void chain_sync(int chain) {      // block barrier of one chain (named barrier 1 + chain)
+    asm volatile("bar.sync %0, %1;" ::"r"(chain + 1), "n"(kCT) : "memory");
+}
+// Band-stage token between the two chains (named barriers 3 and 4, one chain arrives, the other waits): the band stages of
+// the two half-tiles strictly alternate -- chain 0, chain 1, chain 0, ... -- so that each one has the FMA pipe to itself
+// while the other chain is in its (latency-bound) controller phases.  Left alone the two chains stay in lockstep: they do
+// the same work, and a phase offset between them neither grows nor shrinks.
+__device__ __forceinline__ void token_pass(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(kSeqThreads) : "memory"); }
+__device__ __forceinline__ void token_take(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kSeqThreads) : "memory"); }
+constexpr int kTokenToChain0 = 3, kTokenToChain1 = 4;
+
+// k-split sums of a chain (see reduce_ks / reduce_ks1): 64 slots, the chain's named barrier
+template <int NACC>
+__device__ __forceinline__ void reduce_ks_c(float* acc, float* red_s, int ks, int slot, int chain) {
+    chain_sync(chain);
+    if (ks >= 2) {
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) red_s[((ks - 2) * NACC + i) * kSlotsC + slot] = acc[i];
+    }
+    chain_sync(chain);
+    if (ks < 2) {
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) acc[i] += red_s[(ks * NACC + i) * kSlotsC + slot];
+    }
+    chain_sync(chain);
+    if (ks == 1) {
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) red_s[i * kSlotsC + slot] = acc[i];
+    }
+    chain_sync(chain);
+    if (ks == 0) {
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) acc[i] += red_s[i * kSlotsC + slot];
+    }
+}
+
+template <int NACC>
+__device__ __forceinline__ void reduce_ks1_c(float* acc, float* red_s, int ks, int slot, int chain) {
+    chain_sync(chain);
+    if (ks > 0) {
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) red_s[((ks - 1) * NACC + i) * kSlotsC + slot] = acc[i];
+    }
+    chain_sync(chain);
+    if (ks == 0) {
+#pragma unroll
+        for (int k = 0; k < kKS - 1; ++k)
+#pragma unroll
+            for (int i = 0; i < NACC; ++i) acc[i] += red_s[(k * NACC + i) * kSlotsC + slot];
+    }
+}
+
+// LayerNorm + SiLU + Dropout over the full rows of one chain in buf_s ([feature][kRC], in place), redundantly in every CTA;
+// the threads whose features are the CTA's own slice save them (tile layout, row offset row_off inside the 16-row tile).
+__device__ __forceinline__ void ln_silu_drop_fwd_c(const BiearSeqParams& p, unsigned long long seed, float* buf_s, float* stat_s,
+                                                   const float* __restrict__ gamma_s, const float* __restrict__ beta_s,
+                                                   int layer, int t, long long grow0, int rank, int chain, int tid,
+                                                   float* xh_tile, float* d_tile, float* rstd_tile, int row_off) {
+    constexpr int PARTS = kCT / kRC, FPP = kHid / PARTS;             // 32 parts of 4 features
+    static_assert(kRC == 8 && FPP == 4, "lanes l, l^8, l^16, l^24 of a warp hold four parts of one row");
+    const int row = tid % kRC, part = tid / kRC;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int f0 = part * FPP;
+    const float pivot = buf_s[row];
+    float v[FPP];
+    float s = 0.f, ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < FPP; ++i) {
+        v[i] = buf_s[(f0 + i) * kRC + row] - pivot;
+        s += v[i];
+        ss = fmaf(v[i], v[i], ss);
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 8);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 8);
+    s += __shfl_xor_sync(0xffffffffu, s, 16);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 16);
+    float2* stat2 = reinterpret_cast<float2*>(stat_s);               // [row][kWarpsC + 1] float2
+    if (lane < kRC) stat2[row * (kWarpsC + 1) + warp] = make_float2(s, ss);
+    chain_sync(chain);
+    float S = 0.f, SS = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarpsC; ++w) {
+        const float2 q = stat2[row * (kWarpsC + 1) + w];
+        S += q.x;
+        SS += q.y;
+    }
+    const float mean = S * (1.0f / kHid);
+    const float var = fmaxf(fmaf(-mean, mean, SS * (1.0f / kHid)), 0.0f) * kHid;
+#pragma unroll
+    for (int i = 0; i < FPP; ++i) v[i] -= mean;
+    const float rstd = rsqrtf(var * (1.0f / kHid) + kLnEps);
+    const bool mine = f0 / kU == rank;
+    if (rank == 0 && part == 0) rstd_tile[layer * kR + row_off + row] = rstd;
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (p.training) sc = dropout_scale4(seed, t, layer, grow0 + row, f0 >> 2);
+    const float scv[4] = {sc.x, sc.y, sc.z, sc.w};
+#pragma unroll
+    for (int i = 0; i < FPP; ++i) {
+        const int f = f0 + i;
+        const float xh = v[i] * rstd;
+        const float y = fmaf(xh, gamma_s[f], beta_s[f]);
+        const float o = (y * sigmoid_fast(y)) * scv[i];
+        buf_s[f * kRC + row] = o;
+        if (mine) {
+            xh_tile[f * kR + row_off + row] = xh;
+            d_tile[f * kR + row_off + row] = o;
+        }
+    }
+    chain_sync(chain);
+}
+
+__global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd2_kernel(const BiearSeqParams p, const float* __restrict__ img) {
+    extern __shared__ __align__(16) float smem[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int N = p.N, T = p.T, S = p.T - 1;
+    const int tiles = (p.B + kR - 1) / kR;
+    const int NU = bands_per_cta(N);
+    const Fwd2Smem L(N, p.F);
+    float* img_s = smem;
+    float* vec_s = smem + L.vec();
+    const int chain = (int)threadIdx.x / kCT, tid = (int)threadIdx.x % kCT, lane = tid & 31, warp = tid >> 5;
+    float* cs = smem + L.chain0() + chain * L.c_total();
+    float* yc_s = cs + L.c_yc();
+    float* a2_s = yc_s;
+    float* a1_s = cs + L.c_a1();
+    float* hbuf_s = cs + L.c_h();
+    float* stat_s = cs + L.c_stat();
+    float* q_s = cs + L.c_q();
+    float* ystage_s = cs + L.c_ystage();
+    float4* spec_s = reinterpret_cast<float4*>(cs + L.c_spec());
+    // reduction scratch in activation buffers that are idle at that point of the frame (as in seq_fwd_strict_kernel)
+    float* red_gru_s = yc_s;      // yc | a1: 2 x 16 x 64 floats
+    float* red_l1_s = yc_s;
+    float* red_l23_s = a1_s;
+    static_assert(2 * 16 * kSlotsC <= 2 * kHid * kRC && (kKS - 1) * kRT * kSlotsC <= kHid * kRC, "reduction scratch fits");
+    const int ks = tid >> 6, slot = tid & (kSlotsC - 1), rg = slot / kU, u = slot % kU;
+    const int ug = rank * kU + u;
+    const int nu_c = max(0, min(NU, N - rank * NU));
+    const int quads = (N + 3) >> 2;
+    int* any_flag = p.flags + S * p.G;
+    const unsigned long long seed = p.seed_ptr ? *p.seed_ptr : p.seed;
+    const int tl = (int)(blockIdx.x / kCS);
+    const int g = tl / tiles, tile = tl % tiles;
+    const int row_off = chain * kRC;                               // this chain's rows inside the 16-row tile
+    const int b0 = tile * kR + row_off;                            // clip index of the chain's first row
+    const long long crow0 = (long long)g * p.B + b0;               // global row of the chain's first row
+    const long long grow0 = crow0 + rank * kRB;                    // ... of this CTA's first band-stage row
+    const int bb0 = b0 + rank * kRB;
+
+    const uint32_t bars = smem_u32(cs + L.c_bars());
+    auto bar_of = [&](int i) { return bars + 8u * (uint32_t)i; };  // i = 0..4: yc, h, a1, a2, Q
+    const uint32_t tx_bytes[5] = {(uint32_t)(N * kRC * 4), (uint32_t)(kHid * kRC * 4), (uint32_t)(kHid * kRC * 4),
+                                  (uint32_t)(kHid * kRC * 4), (uint32_t)(N * kRB * 4)};
+    auto arm = [&](int i) {
+        if (tid == 0) mbar_arrive_expect_tx(bar_of(i), tx_bytes[i]);
+    };
+
+    // ---- set-up by the whole CTA: weight image, constants, barriers -----------------------------------------------
+    copy_f4(reinterpret_cast<float4*>(img_s),
+            reinterpret_cast<const float4*>(img + (long long)(g * kCS + rank) * fwd_img_floats(N)), fwd_img_floats(N) / 4);
+    for (int i = threadIdx.x; i < kHid; i += kSeqThreads) {
+        vec_s[V_LN1G + i] = ctrl_ptr(p.ln1_g, g)[i];
+        vec_s[V_LN1B + i] = ctrl_ptr(p.ln1_b, g)[i];
+        vec_s[V_LN2G + i] = ctrl_ptr(p.ln2_g, g)[i];
+        vec_s[V_LN2B + i] = ctrl_ptr(p.ln2_b, g)[i];
+        vec_s[V_FC + i] = i < N ? p.fc[i] : 1.0f;
+        vec_s[V_Q0 + i] = i < N ? p.q0[i] : 1.0f;
+    }
+    if (threadIdx.x < kU) {
+        const int i = threadIdx.x;
+        const float* b_ih = ctrl_ptr(p.b_ih, g);
+        const float* b_hh = ctrl_ptr(p.b_hh, g);
+        const int o = rank * kU + i;
+        vec_s[V_BR + i] = b_ih[o] + b_hh[o];
+        vec_s[V_BZ + i] = b_ih[kHid + o] + b_hh[kHid + o];
+        vec_s[V_BIN + i] = b_ih[2 * kHid + o];
+        vec_s[V_BHN + i] = b_hh[2 * kHid + o];
+        vec_s[V_B1 + i] = ctrl_ptr(p.b1, g)[o];
+        vec_s[V_B2 + i] = ctrl_ptr(p.b2, g)[o];
+        const int n = rank * NU + i;
+        const bool own = i < NU && n < N;
+        vec_s[V_B3 + i] = own ? ctrl_ptr(p.b3, g)[n] : 0.f;
+        vec_s[V_Q0S + i] = own ? p.q0[n] : 1.f;
+        vec_s[V_DQS + i] = own ? p.dq[n] : 0.f;
+    }
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) mbar_init(bar_of(i), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    cluster.sync();                                           // every CTA's barriers exist before anybody signals them
+    PHASE_INIT();
+    int spec_t = -1, hsel = 0;
+
+    // spectra of this chain's kRB rows for frame t -> {1, abs, re, im} tiles (cp.async now, conversion later)
+    auto prefetch = [&](int t) {
+#pragma unroll
+        for (int i = 0; i < kRB; ++i) {
+            const float2* src = reinterpret_cast<const float2*>(p.X) + ((grow0 + i) * p.T + t) * p.F;
+            const bool row_ok = bb0 + i < p.B;
+            for (int k = tid; k < L.tile; k += kCT) {
+                float4* slot4 = spec_s + i * L.tile + k;
+                if (row_ok && k < p.F) {
+                    const unsigned dst = (unsigned)__cvta_generic_to_shared(&slot4->z);
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src + k) : "memory");
+                } else {
+                    *slot4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto finish = [&]() {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < kRB; ++i) {
+            if (bb0 + i >= p.B) continue;
+            for (int k = tid; k < p.F; k += kCT) {
+                float4* slot4 = spec_s + i * L.tile + k;
+                *slot4 = spec_entry(make_float2(slot4->z, slot4->w));
+            }
+        }
+    };
+    // streamed hand-over of the spectra (x_ready): flag of (row, frame), polled by one thread per band-stage row
+    auto flag_of = [&](int t) { return p.x_ready + (grow0 + tid) * p.T + t; };
+    auto poll = [&](int t, int v) {
+        for (unsigned spin = 0; v == 0; ++spin) {
+            asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(flag_of(t)) : "memory");
+            if (v != 0) break;
+            if (spin > (1u << 24)) __trap();
+            __nanosleep(64);
+        }
+    };
+
+    for (int t = 0; t < T; ++t) {
+        float* hcur_s = hbuf_s + hsel * kHid * kRC;
+        float* hnext_s = hbuf_s + (hsel ^ 1) * kHid * kRC;
+        const bool h_zero = t == 0;
+        if (t == 0) {
+            for (int idx = tid; idx < kRB * N; idx += kCT) {
+                const int i = idx / N, n = idx - i * N;
+                q_s[n * kRB + i] = vec_s[V_Q0 + n];
+                if (bb0 + i < p.B) p.Q[((grow0 + i) * T + t) * N + n] = vec_s[V_Q0 + n];
+            }
+        }
+        PHASE_MARK(0, 0);    // loop head
+        if (spec_t != t) {   // first frame: fetch and convert now (also orders the q_s fill)
+            if (p.x_ready && tid < kRB && bb0 + tid < p.B) poll(t, 0);
+            chain_sync(chain);
+            prefetch(t);
+            finish();
+            chain_sync(chain);
+        }
+        PHASE_MARK(0, 1);    // spectra ready
+        int next_ready = 1;
+        if (p.x_ready && t + 1 < T && tid < kRB && bb0 + tid < p.B)
+            asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(next_ready) : "l"(flag_of(t + 1)) : "memory");
+
+        // ---- band stage of frame t for this chain's kRB rows of this CTA ------------------------------------------
+        // The kRB x quads (row, quad) pairs are dealt round-robin to the chain's 8 warps, widest quads first; lane l OWNS
+        // band (l & 3) of the warp's (l >> 2)-th pair (parameters once, epilogue once per warp).
+        // (token: chain 0 goes first in every frame, chain 1 follows it, chain 0's next frame follows chain 1)
+        if (chain == 0) {
+            if (t > 0) token_take(kTokenToChain0);
+        } else {
+            token_take(kTokenToChain1);
+        }
+        bool own_store = false;
+        long long own_e = 0;
+        float oY = 0.f, oJ = 0.f, oP = 0.f, oK = 0.f;
+        {
+            const int n_pairs = kRB * quads;
+            const int p_own = warp + kWarpsC * (lane >> 2);
+            const int row_own = p_own & (kRB - 1);
+            const int n_own = ((quads - 1 - (p_own / kRB)) << 2) + (lane & 3);
+            const bool own = p_own < n_pairs && n_own < N;
+            const float fc = own ? vec_s[V_FC + n_own] : 1.0f;
+            const float q = own ? q_s[n_own * kRB + row_own] : 1.0f;
+            const BandParams bp_own = band_params(fc, q, p.df, p.cutoff, p.F, own);
+            BandSums keep = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int m = 0, pr = warp; pr < n_pairs; ++m, pr += kWarpsC) {
+                const int row = pr & (kRB - 1);
+                const int src = (m << 2) + (lane >> 3);          // lane owning the band this lane helps with
+                BandParams bp;
+                bp.bw = 0.f;
+                bp.a = __shfl_sync(0xffffffffu, bp_own.a, src);
+                bp.b = __shfl_sync(0xffffffffu, bp_own.b, src);
+                bp.kc = __shfl_sync(0xffffffffu, bp_own.kc, src);
+                bp.k_lo = __shfl_sync(0xffffffffu, bp_own.k_lo, src);
+                bp.k_hi = __shfl_sync(0xffffffffu, bp_own.k_hi, src);
+                const BandSums sums = band_accumulate(spec_s + row * L.tile, p.F, bp, lane);
+                const int from = (lane & 3) << 3;                // any lane of the group that holds my band's sums
+                const bool mine = (lane >> 2) == m;
+                float v;
+                v = __shfl_sync(0xffffffffu, sums.S, from);   if (mine) keep.S = v;
+                v = __shfl_sync(0xffffffffu, sums.Y, from);   if (mine) keep.Y = v;
+                v = __shfl_sync(0xffffffffu, sums.Zr, from);  if (mine) keep.Zr = v;
+                v = __shfl_sync(0xffffffffu, sums.Zi, from);  if (mine) keep.Zi = v;
+                v = __shfl_sync(0xffffffffu, sums.m2, from);  if (mine) keep.m2 = v;
+                v = __shfl_sync(0xffffffffu, sums.a2, from);  if (mine) keep.a2 = v;
+                v = __shfl_sync(0xffffffffu, sums.z2r, from); if (mine) keep.z2r = v;
+                v = __shfl_sync(0xffffffffu, sums.z2i, from); if (mine) keep.z2i = v;
+            }
+            if (own) {
+                const BandResult r = band_finish(keep);
+                ystage_s[row_own * kHid + n_own] = log1pf(fmaxf(r.Y, 0.0f));
+                own_store = bb0 + row_own < p.B;
+                own_e = ((grow0 + row_own) * T + t) * N + n_own;
+                const float qe = q + 1e-8f;
+                const float kappa = -fc / (qe * qe * bp_own.bw);
+                oY = r.Y;
+                oJ = kappa * (r.a2 - r.Yraw * r.m2);
+                if (p.phase) {
+                    oP = atan2f(r.Zi, r.Zr);
+                    const float mag2 = r.Zr * r.Zr + r.Zi * r.Zi;
+                    oK = mag2 > 0.0f ? kappa * (r.Zr * r.z2i - r.Zi * r.z2r) / mag2 : 0.0f;
+                }
+            }
+        }
+        auto store_band_outputs = [&]() {
+            if (!own_store) return;
+            p.Y[own_e] = oY;
+            p.dYdQ[own_e] = oJ;
+            if (p.logY) p.logY[own_e] = fminf(fmaxf(logf(oY + 1e-8f), -12.0f), 12.0f);
+            if (p.phase) {
+                p.phase[own_e] = oP;
+                p.dPdQ[own_e] = oK;
+            }
+        };
+        PHASE_MARK(0, 2);    // band stage (this warp)
+        if (chain == 0) token_pass(kTokenToChain1);
+        else if (t + 1 < T) token_pass(kTokenToChain0);
+        if (t == T - 1) {
+            // The reference runs the controller once more and discards the result (model_torch.py:361-380).
+            store_band_outputs();
+            continue;
+        }
+        if (p.x_ready && tid < kRB && bb0 + tid < p.B) poll(t + 1, next_ready);   // (ordered for the chain by the barrier below)
+        chain_sync(chain);
+        prefetch(t + 1);     // the tile is free again: the next frame's spectra travel behind the controller phases
+        spec_t = t + 1;
+        const long long tb = tile_base(p, g, t, tiles, tile);
+        const uint32_t par = (uint32_t)t & 1u;
+        if (tid < N) {   // features of my kRB rows -> every CTA of the cluster (+ saved for dW_ih)
+            const float2 v = make_float2(ystage_s[tid], ystage_s[kHid + tid]);
+            const uint32_t a = smem_u32(yc_s + tid * kRC + rank * kRB);
+#pragma unroll
+            for (uint32_t dst = 0; dst < (uint32_t)kCS; ++dst)
+                st_async_f2(cluster_addr(a, dst), v, cluster_addr(bar_of(0), dst));
+            *reinterpret_cast<float2*>(p.yc + tb * N * kR + tid * kR + row_off + rank * kRB) = v;
+        }
+        arm(0);
+        store_band_outputs();
+        tx_wait(bar_of(0), par);
+        PHASE_MARK(0, 3);    // band barrier + push + hand-over #1
+
+        // ---- GRU cell --------------------------------------------------------------------------------------------
+        {
+            float ar[kRT] = {0.f, 0.f, 0.f, 0.f}, az[kRT] = {0.f, 0.f, 0.f, 0.f};
+            float ain[kRT] = {0.f, 0.f, 0.f, 0.f}, ahn[kRT] = {0.f, 0.f, 0.f, 0.f};
+            int k0, k1;
+            k_range(N, ks, k0, k1);
+            dot_rows3<kRC>(ar, az, ain, yc_s + rg * kRT, img_s + fwd_img_wih(N) + u, k0, k1);
+            k_range(kHid, ks, k0, k1);
+            if (!h_zero) dot_rows3<kRC>(ar, az, ahn, hcur_s + rg * kRT, img_s + fwd_img_whh(N) + u, k0, k1);
+            float acc[16];
+#pragma unroll
+            for (int i = 0; i < kRT; ++i) {
+                acc[i] = ar[i];
+                acc[4 + i] = az[i];
+                acc[8 + i] = ain[i];
+                acc[12 + i] = ahn[i];
+            }
+            reduce_ks_c<16>(acc, red_gru_s, ks, slot, chain);
+            if (ks == 0) {
+                float hv[kRT], vr[kRT], vz[kRT], vn[kRT], vh[kRT];
+                const float br = vec_s[V_BR + u], bz = vec_s[V_BZ + u], bin = vec_s[V_BIN + u], bhn = vec_s[V_BHN + u];
+#pragma unroll
+                for (int i = 0; i < kRT; ++i) {
+                    vr[i] = sigmoid_fast(acc[i] + br);
+                    vz[i] = sigmoid_fast(acc[4 + i] + bz);
+                    vh[i] = acc[12 + i] + bhn;
+                    vn[i] = tanhf(acc[8 + i] + bin + vr[i] * vh[i]);
+                    const float hp = h_zero ? 0.0f : hcur_s[ug * kRC + rg * kRT + i];
+                    hv[i] = (1.0f - vz[i]) * vn[i] + vz[i] * hp;
+                }
+                bcast_f4_tx(hnext_s + ug * kRC + rg * kRT, make_float4(hv[0], hv[1], hv[2], hv[3]), bar_of(1));
+                store4(h_tile(p, g, t, tiles, tile) + ug * kR + row_off + rg * kRT, hv);
+                float* gt = p.gates + tb * 4 * kHid * kR + ug * kR + row_off + rg * kRT;
+                store4(gt, vr);
+                store4(gt + kHid * kR, vz);
+                store4(gt + 2 * kHid * kR, vn);
+                store4(gt + 3 * kHid * kR, vh);
+            }
+            arm(1);
+        }
+        tx_wait(bar_of(1), par);
+        PHASE_MARK(0, 4);    // GRU
+
+        // ---- Linear 1 -> LayerNorm -> SiLU -> Dropout --------------------------------------------------------------
+        {
+            float acc[kRT] = {0.f, 0.f, 0.f, 0.f};
+            int k0, k1;
+            k_range(kHid, ks, k0, k1);
+            dot_rows<kRC>(acc, hnext_s + rg * kRT, img_s + fwd_img_w1(N) + u, k0, k1);
+            reduce_ks1_c<kRT>(acc, red_l1_s, ks, slot, chain);
+            if (ks == 0) {
+                const float bb = vec_s[V_B1 + u];
+                bcast_f4_tx(a1_s + ug * kRC + rg * kRT, make_float4(acc[0] + bb, acc[1] + bb, acc[2] + bb, acc[3] + bb), bar_of(2));
+            }
+            arm(2);
+        }
+        tx_wait(bar_of(2), par);
+        PHASE_MARK(0, 5);    // Linear 1
+        ln_silu_drop_fwd_c(p, seed, a1_s, stat_s, vec_s + V_LN1G, vec_s + V_LN1B, 0, t, crow0, rank, chain, tid,
+                           p.xh1 + tb * kHid * kR, p.d1 + tb * kHid * kR, p.rstd + tb * 2 * kR, row_off);
+        PHASE_MARK(0, 6);    // LayerNorm 1
+
+        // ---- Linear 2 -> LayerNorm -> SiLU -> Dropout --------------------------------------------------------------
+        {
+            float acc[kRT] = {0.f, 0.f, 0.f, 0.f};
+            int k0, k1;
+            k_range(kHid, ks, k0, k1);
+            dot_rows<kRC>(acc, a1_s + rg * kRT, img_s + fwd_img_w2(N) + u, k0, k1);
+            reduce_ks1_c<kRT>(acc, red_l23_s, ks, slot, chain);
+            if (ks == 0) {
+                const float bb = vec_s[V_B2 + u];
+                // a2 aliases yc: every CTA's yc reads (its GRU products) ended before it sent h_t
+                bcast_f4_tx(a2_s + ug * kRC + rg * kRT, make_float4(acc[0] + bb, acc[1] + bb, acc[2] + bb, acc[3] + bb), bar_of(3));
+            }
+            arm(3);
+        }
+        tx_wait(bar_of(3), par);
+        PHASE_MARK(0, 7);    // Linear 2
+        ln_silu_drop_fwd_c(p, seed, a2_s, stat_s, vec_s + V_LN2G, vec_s + V_LN2B, 1, t, crow0, rank, chain, tid,
+                           p.xh2 + tb * kHid * kR, p.d2 + tb * kHid * kR, p.rstd + tb * 2 * kR, row_off);
+        PHASE_MARK(0, 8);    // LayerNorm 2
+
+        // ---- Linear 3 -> tanh -> Q_{t+1} (model_torch.py:367-380) ---------------------------------------------------
+        {
+            float acc[kRT] = {0.f, 0.f, 0.f, 0.f};
+            const bool mine = u < nu_c;
+            int k0, k1;
+            k_range(kHid, ks, k0, k1);
+            if (mine) dot_rows<kRC>(acc, a2_s + rg * kRT, img_s + fwd_img_w3(N) + u, k0, k1);
+            reduce_ks1_c<kRT>(acc, red_l23_s, ks, slot, chain);
+            const bool fin = ks == 0 && mine;
+            const int n = rank * NU + u;
+            float qv[kRT] = {0.f, 0.f, 0.f, 0.f}, dv[kRT] = {0.f, 0.f, 0.f, 0.f};
+            if (fin) {
+                const float bb = vec_s[V_B3 + u], q0 = vec_s[V_Q0S + u], dq = vec_s[V_DQS + u];
+                bool bad = false;
+#pragma unroll
+                for (int i = 0; i < kRT; ++i) {
+                    dv[i] = tanhf(acc[i] + bb);
+                    const float qu = p.relative ? q0 * (1.0f + dq * dv[i]) : fmaf(dq, dv[i], q0);
+                    qv[i] = fminf(fmaxf(qu, p.q_min), p.q_max);
+                    bad = bad || (b0 + rg * kRT + i < p.B && !finite_f(qu));
+                }
+                // Q_{t+1} of chain rows 4 rg + {0,1} goes to CTA 2 rg, of rows 4 rg + {2,3} to CTA 2 rg + 1 (their band stage)
+                const uint32_t a = smem_u32(q_s + n * kRB);
+                st_async_f2(cluster_addr(a, 2u * rg), make_float2(qv[0], qv[1]), cluster_addr(bar_of(4), 2u * rg));
+                st_async_f2(cluster_addr(a, 2u * rg + 1u), make_float2(qv[2], qv[3]), cluster_addr(bar_of(4), 2u * rg + 1u));
+                if (bad) {   // NaN / Inf: the reference falls back for the whole batch of this ear -> strict replay pass
+                    atomicOr(p.flags + t * p.G + g, 1);
+                    atomicOr(any_flag, 1);
+                }
+            }
+            finish();        // the next frame's spectrum tile (its cp.async data has long arrived)
+            arm(4);
+            if (fin) {
+#pragma unroll
+                for (int i = 0; i < kRT; ++i) {
+                    const int b = b0 + rg * kRT + i;
+                    if (b < p.B) {
+                        const long long e = (((long long)g * p.B + b) * T + (t + 1)) * N + n;
+                        p.Q[e] = qv[i];
+                        p.delta[e] = dv[i];
+                    }
+                }
+            }
+        }
+        tx_wait(bar_of(4), par);   // Q_{t+1} of my band-stage rows has landed ...
+        chain_sync(chain);         // ... and every thread of the chain has converted its slots of the next spectrum tile
+        PHASE_MARK(0, 9);    // Linear 3 + Q
+        hsel ^= 1;
+    }
+    __syncthreads();
+    cluster.sync();   // no CTA leaves (and frees its shared memory) while a peer could still be sending to it
 }
 
 // ==================================================================================================
@@ -1206,7 +1627,8 @@ extern "C" int biear_adaptive_supported(int N, int F) {
     using namespace biear;
     if (N < 1 || N > kHid || F < 2) return 0;
     const size_t limit = 227 * 1024;
-    return sizeof(float) * (size_t)FwdSmem(N, F).total() <= limit && sizeof(float) * (size_t)BwdSmem(N).total() <= limit;
+    return sizeof(float) * (size_t)FwdSmem(N, F).total() <= limit && sizeof(float) * (size_t)Fwd2Smem(N, F).total() <= limit &&
+           sizeof(float) * (size_t)BwdSmem(N).total() <= limit;
 }
 
 extern "C" int64_t biear_adaptive_workspace_floats(int G, int N) {
@@ -1245,10 +1667,13 @@ extern "C" int biear_adaptive_fwd(const BiearSeqParams* p, void* stream) {
     const int tiles = (p->B + kR - 1) / kR;
     if (!p->prepared)
         if (int e = launch_prepare(p, 1, st)) return e;
-    if (!p->force_strict)
-        if (int e = launch_cluster(seq_fwd_kernel<false>, "seq_fwd_kernel", p->G * tiles, smem, st, *p, p->workspace)) return e;
+    if (!p->force_strict) {   // fast pass: two chains of 8 rows per cluster
+        const size_t smem2 = sizeof(float) * (size_t)Fwd2Smem(p->N, p->F).total();
+        BIEAR_REQUIRE(smem2 <= 227 * 1024, "biear_adaptive_fwd: N=%d F=%d needs %zu B of shared memory", p->N, p->F, smem2);
+        if (int e = launch_cluster(seq_fwd2_kernel, "seq_fwd2_kernel", p->G * tiles, smem2, st, *p, p->workspace)) return e;
+    }
     // replay with batch-global fallback semantics; returns immediately unless a non-finite Q was recorded
-    return launch_cluster(seq_fwd_kernel<true>, "seq_fwd_kernel<strict>", 1, smem, st, *p, p->workspace);
+    return launch_cluster(seq_fwd_strict_kernel, "seq_fwd_strict_kernel", 1, smem, st, *p, p->workspace);
 }
 
 extern "C" int biear_adaptive_bwd(const BiearSeqParams* p, void* stream) {
@@ -1269,7 +1694,7 @@ extern "C" int biear_adaptive_bwd(const BiearSeqParams* p, void* stream) {
 extern "C" int biear_adaptive_occupancy(int N, int F, int* fwd_clusters, int* bwd_clusters) {
     using namespace biear;
     BIEAR_REQUIRE(N >= 1 && N <= kHid && F >= 2 && fwd_clusters && bwd_clusters, "biear_adaptive_occupancy: bad arguments");
-    const size_t smem_f = sizeof(float) * (size_t)FwdSmem(N, F).total();
+    const size_t smem_f = sizeof(float) * (size_t)Fwd2Smem(N, F).total();
     const size_t smem_b = sizeof(float) * (size_t)BwdSmem(N).total();
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1286,8 +1711,8 @@ extern "C" int biear_adaptive_occupancy(int N, int F, int* fwd_clusters, int* bw
         int n = 0;
         cudaError_t e;
         if (pass == 0) {
-            e = cudaFuncSetAttribute(seq_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
-            if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, seq_fwd_kernel<false>, &cfg);
+            e = cudaFuncSetAttribute(seq_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, seq_fwd2_kernel, &cfg);
         } else {
             e = cudaFuncSetAttribute(seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
             if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, seq_bwd_kernel, &cfg);

@@ -108,6 +108,7 @@ __device__ __forceinline__ void copy_f4(float4* __restrict__ dst, const float4* 
 
 // acc[i] += sum_{k in [k0,k1)} x_s[k*kR + i] * w_s[k*kU]     (x_s / w_s already offset to the thread's rows / unit)
 // The 4 rows are two packed fp32x2 FMAs (FFMA2, sm_100): same rounding as four scalar FMAs, half the issue slots.
+template <int RS = kR>
 __device__ __forceinline__ void dot_rows(float acc[kRT], const float* __restrict__ x_s, const float* __restrict__ w_s,
                                          int k0, int k1) {
 #ifdef BIEAR_SKIP_DOTS   // timing experiment only: what the phases cost without their contractions
@@ -116,7 +117,7 @@ __device__ __forceinline__ void dot_rows(float acc[kRT], const float* __restrict
     float2 lo = make_float2(acc[0], acc[1]), hi = make_float2(acc[2], acc[3]);
 #pragma unroll 8
     for (int k = k0; k < k1; ++k) {
-        const float4 x = *reinterpret_cast<const float4*>(x_s + k * kR);
+        const float4 x = *reinterpret_cast<const float4*>(x_s + k * RS);
         const float wk = w_s[k * kU];
         const float2 w2 = make_float2(wk, wk);
         lo = __ffma2_rn(w2, make_float2(x.x, x.y), lo);
@@ -127,6 +128,7 @@ __device__ __forceinline__ void dot_rows(float acc[kRT], const float* __restrict
 
 // Two contractions that share the activations (rows k of x_s) but not the weights:
 //   accA[i] += sum_k x_s[k*kR+i] * wa_s[k*kU],   accB[i] += sum_k x_s[k*kR+i] * wb_s[k*kU]        (one x load per k)
+template <int RS = kR>
 __device__ __forceinline__ void dot_rows_pair(float accA[kRT], float accB[kRT], const float* __restrict__ x_s,
                                               const float* __restrict__ wa_s, const float* __restrict__ wb_s, int k0, int k1) {
 #ifdef BIEAR_SKIP_DOTS
@@ -136,7 +138,7 @@ __device__ __forceinline__ void dot_rows_pair(float accA[kRT], float accB[kRT], 
     float2 bl = make_float2(accB[0], accB[1]), bh = make_float2(accB[2], accB[3]);
 #pragma unroll 8
     for (int k = k0; k < k1; ++k) {
-        const float4 x = *reinterpret_cast<const float4*>(x_s + k * kR);
+        const float4 x = *reinterpret_cast<const float4*>(x_s + k * RS);
         const float2 xl = make_float2(x.x, x.y), xh = make_float2(x.z, x.w);
         const float wa = wa_s[k * kU], wb = wb_s[k * kU];
         const float2 pa = make_float2(wa, wa), pb = make_float2(wb, wb);
@@ -148,6 +150,7 @@ __device__ __forceinline__ void dot_rows_pair(float accA[kRT], float accB[kRT], 
 }
 
 // Three gate rows at once: the weights of one k are [gate][kU] (w3_s already offset to the thread's unit).
+template <int RS = kR>
 __device__ __forceinline__ void dot_rows3(float a0[kRT], float a1[kRT], float a2[kRT], const float* __restrict__ x_s,
                                           const float* __restrict__ w3_s, int k0, int k1) {
 #ifdef BIEAR_SKIP_DOTS
@@ -158,7 +161,7 @@ __device__ __forceinline__ void dot_rows3(float a0[kRT], float a1[kRT], float a2
     float2 l2 = make_float2(a2[0], a2[1]), h2 = make_float2(a2[2], a2[3]);
 #pragma unroll 4
     for (int k = k0; k < k1; ++k) {
-        const float4 x = *reinterpret_cast<const float4*>(x_s + k * kR);
+        const float4 x = *reinterpret_cast<const float4*>(x_s + k * RS);
         const float2 xl = make_float2(x.x, x.y), xh = make_float2(x.z, x.w);
         const float w0 = w3_s[k * 3 * kU], w1 = w3_s[k * 3 * kU + kU], w2 = w3_s[k * 3 * kU + 2 * kU];
         const float2 p0 = make_float2(w0, w0), p1 = make_float2(w1, w1), p2 = make_float2(w2, w2);
@@ -251,6 +254,12 @@ __device__ __forceinline__ uint32_t cluster_addr(uint32_t saddr, uint32_t rank) 
 __device__ __forceinline__ void st_async_f4(uint32_t remote_addr, const float4 v, uint32_t remote_bar) {
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
                  ::"r"(remote_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(remote_bar)
+                 : "memory");
+}
+
+__device__ __forceinline__ void st_async_f2(uint32_t remote_addr, const float2 v, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
+                 ::"r"(remote_addr), "f"(v.x), "f"(v.y), "r"(remote_bar)
                  : "memory");
 }
 

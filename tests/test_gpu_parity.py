@@ -401,9 +401,10 @@ def test_fused_multi_tile_batches_match_chain_engine(bb):
                 assert_close(res[engine][0][k], v, 2e-5, f"B={batch} {engine} {k}")
             for k, v in res["chain"][1].items():
                 assert rel_err(res[engine][1][k], v) <= RTOL, (batch, engine, k, rel_err(res[engine][1][k], v))
-        # the fast pass and the strict replay pass run the same arithmetic: identical bits
+        # the fast pass (two chains of 8 rows) and the strict replay pass (one chain of 16 rows) run the same arithmetic up
+        # to the order of the LayerNorm partial sums: equal to rounding
         for k in ("YL", "QL", "QR"):
-            np.testing.assert_array_equal(res["fused"][0][k], res["fused-strict"][0][k])
+            assert_close(res["fused"][0][k], res["fused-strict"][0][k], 1e-5, f"B={batch} fast vs strict {k}")
 
 
 def test_nonfinite_q_fallback_is_batch_global(bb):

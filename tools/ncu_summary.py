@@ -27,7 +27,9 @@ for r in rows[2:]:
 summary = {}
 lines = []
 for name, rs in groups.items():
-    med = lambda f: statistics.median([x for x in (f(r) for r in rs) if x is not None])
+    def med(f):
+        xs = [x for x in (f(r) for r in rs) if x is not None]
+        return statistics.median(xs) if xs else None
     d = {
         "launches_captured": len(rs),
         "duration_us": med(lambda r: scaled(r, "gpu__time_duration.sum")) * 1e6,
@@ -38,6 +40,15 @@ for name, rs in groups.items():
         "registers_per_thread": med(lambda r: num(r, "launch__registers_per_thread")),
         "grid": rs[0][col["launch__grid_size"]], "block": rs[0][col["launch__block_size"]],
         "smem_bank_conflicts": med(lambda r: num(r, "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum")),
+        # pipe utilisation (per cent of the peak sustained rate while the SM is active)
+        "pipe_fma_inst_pct": med(lambda r: num(r, "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active")),
+        "pipe_fma_cycles_pct": med(lambda r: num(r, "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active")),
+        "pipe_alu_pct": med(lambda r: num(r, "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active")),
+        "pipe_xu_pct": med(lambda r: num(r, "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active")),
+        "pipe_lsu_pct": med(lambda r: num(r, "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active")),
+        "smem_wavefronts_pct": med(lambda r: num(r, "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed")),
+        "sm_cycles_active_avg": med(lambda r: num(r, "sm__cycles_active.avg")),
+        "sm_cycles_elapsed_max": med(lambda r: num(r, "sm__cycles_elapsed.max")),
     }
     d["dram_bytes"] = d["dram_read_bytes"] + d["dram_write_bytes"]
     d["dram_gbs"] = d["dram_bytes"] / (d["duration_us"] * 1e-6) / 1e9
@@ -47,7 +58,8 @@ for name, rs in groups.items():
     summary[name] = d
     lines.append(f"{name:28s} n={d['launches_captured']:2d} {d['duration_us']:9.1f} us  grid {d['grid']:>5s} x {d['block']:>4s}  "
                  f"regs {int(d['registers_per_thread']):3d}  DRAM {d['dram_bytes'] / 1e6:8.2f} MB ({d['dram_gbs']:7.1f} GB/s)  "
-                 f"issue {d['issue_active_pct']:5.1f}%  stalls " + ", ".join(f"{k} {v}" for k, v in d["top_stalls_per_issue"].items()))
+                 f"issue {d['issue_active_pct']:5.1f}%  fma-pipe {d['pipe_fma_cycles_pct'] or 0:5.1f}%  xu {d['pipe_xu_pct'] or 0:4.1f}%  "
+                 f"smem-wavefronts {d['smem_wavefronts_pct'] or 0:5.1f}%  stalls " + ", ".join(f"{k} {v}" for k, v in d["top_stalls_per_issue"].items()))
 json.dump({"source": rep.split("/")[-1], "note": "ncu --set full --clock-control none; per-launch medians; cold-cache, serialised",
            "kernels": summary}, open(out + ".json", "w"), indent=1)
 open(out + ".txt", "w").write("\n".join(lines) + "\n")

@@ -28,20 +28,16 @@ for _ in range(reps):
     step(wl, wr)
 torch.cuda.synchronize()
 _lib.check(lib.biear_debug_phase_cycles(buf), "phase cycles")
-names = [["loop head", "spectra ready (wait + convert)", "band stage (rest)", "band barrier + push + hand-over #1", "GRU + #2",
-          "Linear 1 + #3", "LayerNorm 1", "Linear 2 + #4", "LayerNorm 2", "Linear 3 + Q + #5",
-          "band: own-band parameters", "band: loop control", "band: band_accumulate", "band: sums back to owners",
-          "band: epilogue"],
+names = [["loop head", "spectra ready (wait + convert)", "band stage (incl. waiting for the band token)",
+          "chain barrier + push + hand-over #1", "GRU + #2", "Linear 1 + #3", "LayerNorm 1", "Linear 2 + #4", "LayerNorm 2",
+          "Linear 3 + Q + #5"],
          ["loop head", "dL/dpre + push + #1", "Linear 3^T + #2", "LayerNorm 2 bwd", "Linear 2^T + #3", "LayerNorm 1 bwd",
           "Linear 1^T + GRU bwd + #4", "last phase: wait for hand-over #5", "last: issue next step's loads",
           "last: K = 384 transposed products", "last: Y loads + finish_pre", "last: k-split reduction", "last: dh + dL/dpre push"]]
-for k, title in enumerate(("seq_fwd_kernel", "seq_bwd_kernel")):
+for k, title in enumerate(("seq_fwd2_kernel (chain 0 of block 0)", "seq_bwd_kernel")):
     vals = [buf[k * 16 + i] / reps for i in range(len(names[k]))]
     tot = sum(vals)
     print(f"{title}: {tot:.0f} cycles per launch (block 0) = {tot / 1.965e3:.0f} us at 1965 MHz")
     for n, v in zip(names[k], vals):
         print(f"   {n:36s} {v:10.0f} cyc  {100 * v / tot:5.1f}%  {v / 1.965e3 / (19 if k == 0 else 18):6.2f} us/frame")
 
-b = [buf[32 + i] / reps for i in range(8)]
-print(f"inside band_accumulate (warp 0 of block 0, per launch): window + parameter shuffles {b[0]:.0f} cyc, bin loop {b[1]:.0f} cyc "
-      f"({b[4]:.0f} iterations of 32 bins x 4 bands), transposing reduction {b[2]:.0f} cyc")
