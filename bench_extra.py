@@ -24,7 +24,7 @@ FS, T, NBANDS, NBINS = 16000, 19, 100, 513
 CONFIG_YAML = dict(deltaQ_base=1.0, deltaQ_low_factor=0.3, deltaQ_high_factor=5.0, deltaQ_mode="relative")
 REG_Q_W = REG_SMOOTH_W = 1e-3
 UNIT = "audio-s/s"
-A_FIXED = 128000 + 15200 * 2 + 15200 * 2 + 400     # wav in; Y L/R, phase L/R, CC out (bytes per clip)
+A_FIXED = 128000 + 15200 + 15200 + 400     # SURVEY 8(d) A_fixed = 158 800 B per clip: both ears' waveforms in; Y, phase (both ears each), CC out
 
 
 def _peaks():

@@ -8,7 +8,7 @@ import numpy as np, torch
 import biear_b200
 from biear_b200 import ops, precompute
 dev = torch.device("cuda", 0)
-A_FIXED = 128000 + 15200 * 2 + 15200 * 2 + 400         # wav in; logY L/R, phase L/R, CC out (bytes per clip)
+A_FIXED = 128000 + 15200 + 15200 + 400         # both ears' wav in; Y, phase (both ears each), CC out (bytes per clip)
 peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"] \
     if os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")) else 6650.0
 fb = biear_b200.BinauralAdaptiveGammatoneFB(fixed_frontend_q=True).to(dev).eval()
