@@ -11,7 +11,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BIEAR_B200_LIB") or os.path.join(_HERE, "lib", "libbiear_b200.so")
-ABI_VERSION = 17
+ABI_VERSION = 18
 
 _p = c_void_p
 _i = c_int
@@ -77,6 +77,8 @@ SIGNATURES = {
     "biear_adaptive_occupancy": (_i, [_i, _i, POINTER(c_int), POINTER(c_int)]),
     "biear_adaptive_tile_rows": (_i, []),
     "biear_adaptive_supported": (_i, [_i, _i]),
+    "biear_single_supported": (_i, [_i, _i]),
+    "biear_single_workspace_floats": (_l, [_i]),
     "biear_wgrad_scratch_floats": (_l, [POINTER(WgradJob), _i, _i, _i]),
     "biear_ctrl_wgrad": (_i, [POINTER(WgradJob), _i, _i, _i, _p, _p]),
     "biear_wgrad_scratch_floats_tc": (_l, [POINTER(WgradJob), _i, _i, _i]),

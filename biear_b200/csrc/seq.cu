@@ -1164,10 +1164,10 @@ struct BwdSmem {   // offsets in floats
     __host__ __device__ int bufa() const { return vec() + 1024; }                  // [128][32]; first quarter of gate
     __host__ __device__ int gate() const { return bufa(); }                        // [4*128][32]: drp, dzp, dnp, dhn
     __host__ __device__ int dpre() const { return gate() + 4 * kHid * kR; }        // [128][32]; aliased by bufb
-    __host__ __device__ int red() const { return dpre() + kHid * kR; }             // (kKS - 1) x 8 x 128
-    __host__ __device__ int stat() const { return red() + (kKS - 1) * 8 * 128; }   // 2 x kSeqThreads
-    __host__ __device__ int pre() const { return stat() + 2 * kSeqThreads; }       // [3][kR][kU]: ext, jac, fac
-    __host__ __device__ int bars() const { return pre() + 3 * kR * kU; }           // 4 mbarriers (8 B each)
+    __host__ __device__ int red() const { return dpre() + kHid * kR; }             // (kKS - 1) x 12 x 128
+    __host__ __device__ int stat() const { return red() + (kKS - 1) * 12 * 128; }  // 2 x kSeqThreads
+    __host__ __device__ int pre() const { return stat() + 2 * kSeqThreads; }       // [4][kR][kU]: ext, jac, fac, jac of the right ear
+    __host__ __device__ int bars() const { return pre() + 4 * kR * kU; }           // 4 mbarriers (8 B each)
     __host__ __device__ int total() const { return bars() + 16; }
 };
 constexpr int VB_LN1G = 0, VB_LN1B = 128, VB_LN2G = 256, VB_LN2B = 384, VB_Q0 = 512, VB_DQ = 640;   // < 1024
@@ -1259,7 +1259,13 @@ __device__ __forceinline__ void store_ln_grads(int rank, const float (&dv)[kHid 
     }
 }
 
-__global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqParams p, const float* __restrict__ img) {
+// SINGLE: the single-controller front-end (model_torch.py:695-776; forward in seq_single.cu): one controller, both ears'
+// band outputs feed it and its one Q drives both ears' band stages, so dL/dQ sums the two ears' closed-form terms and the
+// transposed GRU input product has two column slices (current features of the left and of the right ear; the memory inputs
+// are detached).  Those two slices do not fit in shared memory next to the rest: they are read from L2 (wihc_lr).
+template <bool SINGLE>
+__global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqParams p, const float* __restrict__ img,
+                                                                 const float* __restrict__ wihc_lr) {
     extern __shared__ __align__(16) float smem[];
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
@@ -1287,8 +1293,14 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
     const int bb0 = b0 + rank * kRT;
     const unsigned long long seed = p.seed_ptr ? *p.seed_ptr : p.seed;
 
-    copy_f4(reinterpret_cast<float4*>(img_s),
-            reinterpret_cast<const float4*>(img + (long long)(g * kCS + rank) * bwd_img_floats(N)), bwd_img_floats(N) / 4);
+    if (SINGLE)
+        copy_f4(reinterpret_cast<float4*>(img_s),
+                reinterpret_cast<const float4*>(img + (long long)rank * single_bwd_res_floats(N)), single_bwd_res_floats(N) / 4);
+    else
+        copy_f4(reinterpret_cast<float4*>(img_s),
+                reinterpret_cast<const float4*>(img + (long long)(g * kCS + rank) * bwd_img_floats(N)), bwd_img_floats(N) / 4);
+    const float* wl_g = SINGLE ? wihc_lr + (long long)rank * 2 * 3 * kHid * kU : nullptr;   // W_ih[:, n] (left ear's features)
+    const float* wr_g = SINGLE ? wl_g + 3 * kHid * kU : nullptr;                             // W_ih[:, 2N + n] (right ear's)
     for (int i = tid; i < kHid; i += kSeqThreads) {
         vec_s[VB_LN1G + i] = ctrl_ptr(p.ln1_g, g)[i];
         vec_s[VB_LN1B + i] = ctrl_ptr(p.ln1_b, g)[i];
@@ -1301,50 +1313,80 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
     static_assert(kRT * kHid <= kSeqThreads, "one (row, band) element of the dL/dpre assembly per thread");
     // Part of dL/dpre_{t} that does not depend on the recurrence, for the element (row i, band n) this thread assembles:
     //   ext = gY dY/dQ + gphase dphase/dQ + gQ,  jac = dY/dQ,  fac = d clamp/dQ * dQ/ddelta * d tanh  (all at frame t+1)
-    const float *gY_g = ctrl_ptr(p.gY, g), *gP_g = ctrl_ptr(p.gP, g), *gQ_g = ctrl_ptr(p.gQ, g), *gLogY_g = ctrl_ptr(p.gLogY, g);
-    struct Pre { float ext, jac, fac; };
-    struct PreRaw { float gy, jac, gp, dp, gq, delta, y, glx; bool live; };
+    // (SINGLE: index e of gY / gP / gLogY is the EAR, and the row-major (E*B,T,N) tensors hold ear e at row offset e*B)
+    constexpr int NE = SINGLE ? 2 : 1;
+    const float* gY_e[NE];
+    const float* gP_e[NE];
+    const float* gLX_e[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        gY_e[e] = SINGLE ? (e ? p.gY[1] : p.gY[0]) : ctrl_ptr(p.gY, g);
+        gP_e[e] = SINGLE ? (e ? p.gP[1] : p.gP[0]) : ctrl_ptr(p.gP, g);
+        gLX_e[e] = SINGLE ? (e ? p.gLogY[1] : p.gLogY[0]) : ctrl_ptr(p.gLogY, g);
+    }
+    const float* gQ_g = ctrl_ptr(p.gQ, g);
+    struct Pre { float ext, jac, fac, jac2; };
+    struct PreRaw { float gy[NE], jac[NE], gp[NE], dp[NE], y[NE], glx[NE], gq, delta; bool live; };
     // issue_pre: only the global loads (so that they are in flight during whatever comes next);
     // finish_pre: the arithmetic, called when the values are needed.
     static_assert(kR * kU == kSeqThreads, "one (tile row, band of the CTA's slice) element per thread");
     const int pre_r = tid / kU, pre_u = tid % kU;                 // element this thread fetches: row pre_r, band rank*NU + pre_u
     auto issue_pre = [&](int t) {
-        PreRaw r = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, false};
+        PreRaw r;
+#pragma unroll
+        for (int e = 0; e < NE; ++e) r.gy[e] = r.jac[e] = r.gp[e] = r.dp[e] = r.y[e] = r.glx[e] = 0.f;
+        r.gq = r.delta = 0.f;
+        r.live = false;
         if (t < 0 || pre_u >= nu_c || b0 + pre_r >= p.B) return r;
-        const long long el = (((long long)(b0 + pre_r) * T) + (t + 1)) * N + rank * NU + pre_u;   // within this ear's tensors
-        const long long e = el + (long long)g * p.B * T * N;                                        // within the (E*B,T,N) ones
+        const long long el = (((long long)(b0 + pre_r) * T) + (t + 1)) * N + rank * NU + pre_u;   // within one ear's / controller's tensors
         r.live = true;
-        r.jac = __ldg(p.dYdQ + e);
-        if (gY_g) r.gy = __ldg(gY_g + el);
-        if (gLogY_g) {
-            r.y = __ldg(p.Y + e);
-            r.glx = __ldg(gLogY_g + el);
-        }
-        if (gP_g) {
-            r.gp = __ldg(gP_g + el);
-            r.dp = __ldg(p.dPdQ + e);
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            const long long ee = el + (long long)(SINGLE ? e : g) * p.B * T * N;                    // within the (E*B,T,N) ones
+            r.jac[e] = __ldg(p.dYdQ + ee);
+            if (gY_e[e]) r.gy[e] = __ldg(gY_e[e] + el);
+            if (gLX_e[e]) {
+                r.y[e] = __ldg(p.Y + ee);
+                r.glx[e] = __ldg(gLX_e[e] + el);
+            }
+            if (gP_e[e]) {
+                r.gp[e] = __ldg(gP_e[e] + el);
+                r.dp[e] = __ldg(p.dPdQ + ee);
+            }
         }
         if (gQ_g) r.gq = __ldg(gQ_g + el);
-        r.delta = __ldg(p.delta + e);
+        r.delta = __ldg(p.delta + el + (long long)g * p.B * T * N);
         return r;
     };
     auto finish_pre = [&](const PreRaw& w) {
-        Pre r = {0.f, 0.f, 0.f};
+        Pre r = {0.f, 0.f, 0.f, 0.f};
         if (!w.live) return r;
         const int n = rank * NU + pre_u;
-        float gy = w.gy;
-        if (gLogY_g) {   // d clamp(log(Y + 1e-8), +-12) / dY, as autograd derives it (model_torch.py:1080-1083)
-            const float ye = w.y + 1e-8f;
-            const float lx = logf(ye);
-            if (lx >= -12.0f && lx <= 12.0f) gy += w.glx / ye;
+        float ext = w.gq;
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            float gy = w.gy[e];
+            if (gLX_e[e]) {   // d clamp(log(Y + 1e-8), +-12) / dY, as autograd derives it (model_torch.py:1080-1083)
+                const float ye = w.y[e] + 1e-8f;
+                const float lx = logf(ye);
+                if (lx >= -12.0f && lx <= 12.0f) gy += w.glx[e] / ye;
+            }
+            ext += fmaf(w.gp[e], w.dp[e], gy * w.jac[e]);
         }
-        r.jac = w.jac;
-        r.ext = fmaf(w.gp, w.dp, gy * w.jac) + w.gq;
+        r.jac = w.jac[0];
+        r.jac2 = w.jac[NE - 1];
+        r.ext = ext;
         const float q0 = vec_s[VB_Q0 + n], dq = vec_s[VB_DQ + n];
         const float qu = p.relative ? q0 * (1.0f + dq * w.delta) : fmaf(dq, w.delta, q0);
         const float scale = p.relative ? q0 * dq : dq;
         r.fac = (qu >= p.q_min && qu <= p.q_max) ? scale * (1.0f - w.delta * w.delta) : 0.f;
         return r;
+    };
+    auto publish_pre = [&](const Pre& pf) {
+        pre_s[pre_r * kU + pre_u] = pf.ext;
+        pre_s[kR * kU + pre_r * kU + pre_u] = pf.jac;
+        pre_s[2 * kR * kU + pre_r * kU + pre_u] = pf.fac;
+        if (SINGLE) pre_s[3 * kR * kU + pre_r * kU + pre_u] = pf.jac2;
     };
     // Hand-overs inside the cluster: st.async + one mbarrier per phase type (seq_dev.cuh): 0 = dL/dpre, 1 = Linear 3^T
     // output (bufa), 2 = Linear 2^T output (bufb), 3 = the four gate-gradient blocks.
@@ -1364,26 +1406,25 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
     // dL/dpre of step t for (band n of this CTA's slice, rows 4rg..4rg+3), from the pre-fetched recurrence-independent
     // parts in pre_s and dL/dY_{t+1} through the controller (dyc, zero for the last step): broadcast to every CTA of the
     // cluster (the next Linear^T contracts over all bands) and saved for dW3.  Returns the values for the deferred store.
-    auto push_dpre = [&](int t, const float dyc[kRT], float (&dp)[kRT]) {
+    // (SINGLE: dyc2 = dL/dY_{t+1} of the right ear through the controller, paired with the right ear's dY/dQ)
+    auto push_dpre = [&](int t, const float dyc[kRT], const float dyc2[kRT], float (&dp)[kRT]) {
         const bool flagged_t = p.flags[t * p.G + g] != 0;           // Q_{t+1} was replaced by Q0: no gradient through it
 #pragma unroll
         for (int i = 0; i < kRT; ++i) {
             const int r = rg * kRT + i;
-            dp[i] = flagged_t ? 0.f
-                              : (pre_s[r * kU + u] + dyc[i] * pre_s[kR * kU + r * kU + u]) * pre_s[2 * kR * kU + r * kU + u];
+            float v = pre_s[r * kU + u] + dyc[i] * pre_s[kR * kU + r * kU + u];
+            if (SINGLE) v = fmaf(dyc2[i], pre_s[3 * kR * kU + r * kU + u], v);
+            dp[i] = flagged_t ? 0.f : v * pre_s[2 * kR * kU + r * kU + u];
         }
         broadcast_rows_tx(dpre_s, rank * NU + u, rg * kRT, dp, bar_of(0));
     };
     {   // prologue: dL/dpre of the last step (nothing arrives through a later controller step)
-        const Pre pf = finish_pre(issue_pre(S - 1));
-        pre_s[pre_r * kU + pre_u] = pf.ext;
-        pre_s[kR * kU + pre_r * kU + pre_u] = pf.jac;
-        pre_s[2 * kR * kU + pre_r * kU + pre_u] = pf.fac;
+        publish_pre(finish_pre(issue_pre(S - 1)));
         __syncthreads();
         if (ks == 0 && u < nu_c) {
             const float zero[kRT] = {0.f, 0.f, 0.f, 0.f};
             float dp[kRT];
-            push_dpre(S - 1, zero, dp);
+            push_dpre(S - 1, zero, zero, dp);
             store4(p.G_pre + tile_base(p, g, S - 1, tiles, tile) * N * kR + (rank * NU + u) * kR + rg * kRT, dp);
         }
         arm(0);
@@ -1495,39 +1536,64 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
         PHASE_MARK(1, 8);    // last phase: issue the next step's loads
         // ---- dL/dh_{t-1} = z * dh + W_hh^T [drp, dzp, dhn];  dL/dY_t = W_ih[:, :N]^T [drp, dzp, dnp] * d log1p --------
         {
-            float acc[2 * kRT] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            constexpr int NA = SINGLE ? 3 : 2;         // dh, dL/dc (left | only ear)[, dL/dc right ear]
+            float acc[NA * kRT];
+#pragma unroll
+            for (int i = 0; i < NA * kRT; ++i) acc[i] = 0.f;
             const float* x = gate_s + rg * kRT;
             const float* whhc = img_s + bwd_img_whhc(N) + u;
-            const float* wihc = img_s + bwd_img_wihc(N) + u;
             // rows o of W_hh: [0,128) r gate, [128,256) z gate, [256,384) n gate (pairs with dhn = gate block 3, i.e.
             // gate_s rows o + 128); rows o of W_ih pair with gate_s rows o (drp, dzp, dnp)
             int o0, o1;
             k_range(3 * kHid, ks, o0, o1);
-            // o < 256: both products read gate_s row o (one load); o >= 256: W_hh pairs with row o + 128, W_ih with row o.
-            // (Bands beyond the CTA's slice have zero W_ih columns in the image: computing them is harmless.)
-            dot_rows_pair(acc, acc + kRT, x, whhc, wihc, min(o0, 2 * kHid), min(o1, 2 * kHid));
-            dot_rows(acc, x + kHid * kR, whhc, max(o0, 2 * kHid), max(o1, 2 * kHid));
-            dot_rows(acc + kRT, x, wihc, max(o0, 2 * kHid), max(o1, 2 * kHid));
+            if (SINGLE) {
+                // the two W_ih column slices come from L2 (coalesced over u, 16 loads in flight per thread)
+                const float* wl = wl_g + u;
+                const float* wr = wr_g + u;
+                float2 hl = make_float2(0.f, 0.f), hh = make_float2(0.f, 0.f), ll = hl, lh = hl, rl = hl, rh = hl;
+#ifdef BIEAR_SKIP_DOTS
+                o1 = o0;
+#endif
+#pragma unroll 8
+                for (int o = o0; o < o1; ++o) {
+                    const float wlv = __ldg(wl + o * kU), wrv = __ldg(wr + o * kU), whv = whhc[o * kU];
+                    const float4 xg = *reinterpret_cast<const float4*>(x + o * kR);
+                    const float4 xh = o < 2 * kHid ? xg : *reinterpret_cast<const float4*>(x + (o + kHid) * kR);
+                    const float2 pl = make_float2(wlv, wlv), pr = make_float2(wrv, wrv), ph = make_float2(whv, whv);
+                    ll = __ffma2_rn(pl, make_float2(xg.x, xg.y), ll); lh = __ffma2_rn(pl, make_float2(xg.z, xg.w), lh);
+                    rl = __ffma2_rn(pr, make_float2(xg.x, xg.y), rl); rh = __ffma2_rn(pr, make_float2(xg.z, xg.w), rh);
+                    hl = __ffma2_rn(ph, make_float2(xh.x, xh.y), hl); hh = __ffma2_rn(ph, make_float2(xh.z, xh.w), hh);
+                }
+                acc[0] = hl.x; acc[1] = hl.y; acc[2] = hh.x; acc[3] = hh.y;
+                acc[4] = ll.x; acc[5] = ll.y; acc[6] = lh.x; acc[7] = lh.y;
+                acc[NA * kRT - 4] = rl.x; acc[NA * kRT - 3] = rl.y; acc[NA * kRT - 2] = rh.x; acc[NA * kRT - 1] = rh.y;
+            } else {
+                const float* wihc = img_s + bwd_img_wihc(N) + u;
+                // o < 256: both products read gate_s row o (one load); o >= 256: W_hh pairs with row o + 128, W_ih with row o.
+                // (Bands beyond the CTA's slice have zero W_ih columns in the image: computing them is harmless.)
+                dot_rows_pair(acc, acc + kRT, x, whhc, wihc, min(o0, 2 * kHid), min(o1, 2 * kHid));
+                dot_rows(acc, x + kHid * kR, whhc, max(o0, 2 * kHid), max(o1, 2 * kHid));
+                dot_rows(acc + kRT, x, wihc, max(o0, 2 * kHid), max(o1, 2 * kHid));
+            }
             PHASE_MARK(1, 9);    // last phase: the K = 384 transposed products
             const bool mine = u < nu_c;
             const int n = rank * NU + u;
             float yv[kRT] = {0.f, 0.f, 0.f, 0.f};       // Y_t of this thread's 4 rows (for d log1p): fetched before the products
+            float yv2[kRT] = {0.f, 0.f, 0.f, 0.f};      // (SINGLE: the right ear's)
             if (ks == 0 && mine) {
 #pragma unroll
                 for (int i = 0; i < kRT; ++i) {
                     const int b = b0 + rg * kRT + i;
-                    if (b < p.B) yv[i] = __ldg(p.Y + (((long long)g * p.B + b) * T + t) * N + n);
+                    if (b < p.B) {
+                        yv[i] = __ldg(p.Y + (((long long)g * p.B + b) * T + t) * N + n);
+                        if (SINGLE) yv2[i] = __ldg(p.Y + (((long long)p.B + b) * T + t) * N + n);
+                    }
                 }
             }
             // the recurrence-independent parts of the NEXT step's dL/dpre (step t-1) have arrived: publish them CTA-wide
-            if (t > 0) {
-                const Pre pf = finish_pre(pf_raw);
-                pre_s[pre_r * kU + pre_u] = pf.ext;
-                pre_s[kR * kU + pre_r * kU + pre_u] = pf.jac;
-                pre_s[2 * kR * kU + pre_r * kU + pre_u] = pf.fac;
-            }
+            if (t > 0) publish_pre(finish_pre(pf_raw));
             PHASE_MARK(1, 10);   // last phase: Y_t loads + finish_pre (waits for the loads issued above)
-            reduce_ks1<2 * kRT>(acc, red_s, ks, slot);   // (its barriers also order the pre_s writes before the reads below)
+            reduce_ks1<NA * kRT>(acc, red_s, ks, slot);   // (its barriers also order the pre_s writes before the reads below)
             PHASE_MARK(1, 11);   // last phase: k-split reduction
             float dp[kRT] = {0.f, 0.f, 0.f, 0.f};
             const bool fin = ks == 0 && mine && t > 0;
@@ -1535,10 +1601,13 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_bwd_kernel(const BiearSeqP
 #pragma unroll
                 for (int i = 0; i < kRT; ++i) dh_carry[i] = acc[i] + dh_direct[i];
                 if (fin) {   // dL/dY_t through the controller (d log1p), straight into dL/dpre of step t-1: no exchange needed
-                    float dy[kRT];
+                    float dy[kRT], dy2[kRT];
 #pragma unroll
-                    for (int i = 0; i < kRT; ++i) dy[i] = yv[i] >= 0.0f ? acc[kRT + i] / (1.0f + yv[i]) : 0.0f;
-                    push_dpre(t - 1, dy, dp);
+                    for (int i = 0; i < kRT; ++i) {
+                        dy[i] = yv[i] >= 0.0f ? acc[kRT + i] / (1.0f + yv[i]) : 0.0f;
+                        dy2[i] = SINGLE ? (yv2[i] >= 0.0f ? acc[(NA - 1) * kRT + i] / (1.0f + yv2[i]) : 0.0f) : 0.0f;
+                    }
+                    push_dpre(t - 1, dy, dy2, dp);
                 }
             }
             PHASE_MARK(1, 12);   // last phase: dh carry + dL/dpre assembly + push
@@ -1558,9 +1627,11 @@ static int validate_seq(const BiearSeqParams* p, const char* who, bool backward)
     BIEAR_REQUIRE(p != nullptr, "%s: null parameter block", who);
     BIEAR_REQUIRE(p->G >= 1 && p->B >= 1 && p->T >= 1 && p->N >= 1 && p->N <= kHid && p->F >= 2,
                   "%s: bad geometry G=%d B=%d T=%d N=%d F=%d", who, p->G, p->B, p->T, p->N, p->F);
-    BIEAR_REQUIRE(p->E == p->G && p->Kin == 2 * p->N,
-                  "%s: only the dual front-end (one controller per ear, Kin = 2N) is fused; got E=%d G=%d Kin=%d",
-                  who, p->E, p->G, p->Kin);
+    const bool single = p->G == 1 && p->E == 2;
+    BIEAR_REQUIRE((p->E == p->G && p->Kin == 2 * p->N) || (single && p->Kin == 4 * p->N),
+                  "%s: fused are the dual front-end (one controller per ear, E == G, Kin = 2N) and the single-controller one "
+                  "(G = 1, E = 2, Kin = 4N); got E=%d G=%d Kin=%d N=%d", who, p->E, p->G, p->Kin, p->N);
+    BIEAR_REQUIRE(!single || !p->x_ready, "%s: the single-controller kernel does not take streamed spectra (x_ready)", who);
     BIEAR_REQUIRE(p->G <= BIEAR_MAX_CTRL, "%s: at most %d controllers per call, got %d", who, BIEAR_MAX_CTRL, p->G);
     BIEAR_REQUIRE(p->fc && p->q0 && p->dq, "%s: null constant pointer", who);
     for (int g = 0; g < p->G; ++g)
@@ -1582,9 +1653,9 @@ static int validate_seq(const BiearSeqParams* p, const char* who, bool backward)
     return 0;
 }
 
-template <typename Kern>
+template <typename Kern, typename... Extra>
 static int launch_cluster(Kern kern, const char* name, int clusters, size_t smem, cudaStream_t st,
-                          const BiearSeqParams& p, const float* img) {
+                          const BiearSeqParams& p, const float* img, Extra... extra) {
     // the opt-in is per device and sticky; remember the largest size set so that steady-state launches (and launches
     // recorded into a CUDA graph) make no attribute call
     static std::mutex mu;
@@ -1613,7 +1684,7 @@ static int launch_cluster(Kern kern, const char* name, int clusters, size_t smem
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    e = check_cuda(cudaLaunchKernelEx(&cfg, kern, p, img), name);
+    e = check_cuda(cudaLaunchKernelEx(&cfg, kern, p, img, extra...), name);
     if (e) return e;
     count_launch();
     return 0;
@@ -1629,6 +1700,19 @@ extern "C" int biear_adaptive_supported(int N, int F) {
     const size_t limit = 227 * 1024;
     return sizeof(float) * (size_t)FwdSmem(N, F).total() <= limit && sizeof(float) * (size_t)Fwd2Smem(N, F).total() <= limit &&
            sizeof(float) * (size_t)BwdSmem(N).total() <= limit;
+}
+
+extern "C" int biear_single_supported(int N, int F) {
+    using namespace biear;
+    if (N < 1 || N > kHid || F < 2) return 0;
+    const size_t limit = 227 * 1024;
+    return single_fwd_smem_bytes(N, F) <= limit && sizeof(float) * (size_t)BwdSmem(N).total() <= limit;
+}
+
+extern "C" int64_t biear_single_workspace_floats(int N) {
+    using namespace biear;
+    if (N < 1 || N > kHid) return 0;
+    return (int64_t)single_workspace_floats(N);
 }
 
 extern "C" int64_t biear_adaptive_workspace_floats(int G, int N) {
@@ -1648,13 +1732,15 @@ static int launch_prepare(const BiearSeqParams* p, int want, cudaStream_t st) {
 extern "C" int biear_adaptive_prepare(const BiearSeqParams* p, void* stream) {
     using namespace biear;
     BIEAR_REQUIRE(p != nullptr, "biear_adaptive_prepare: null parameter block");
+    const bool single = p->G == 1 && p->E == 2 && p->Kin == 4 * p->N;
     BIEAR_REQUIRE(p->G >= 1 && p->G <= BIEAR_MAX_CTRL && p->B >= 1 && p->T >= 1 && p->N >= 1 && p->N <= kHid &&
-                      p->Kin == 2 * p->N,
+                      (single || p->Kin == 2 * p->N),
                   "biear_adaptive_prepare: bad geometry G=%d B=%d T=%d N=%d Kin=%d", p->G, p->B, p->T, p->N, p->Kin);
     for (int g = 0; g < p->G; ++g)
         BIEAR_REQUIRE(p->w_ih[g] && p->w_hh[g] && p->w1[g] && p->w2[g] && p->w3[g],
                       "biear_adaptive_prepare: null weight pointer of controller %d", g);
     BIEAR_REQUIRE(p->workspace && p->H && p->flags, "biear_adaptive_prepare: null workspace / H / flags");
+    if (single) return launch_single_prepare(p, 3, as_stream(stream));
     return launch_prepare(p, 3, as_stream(stream));
 }
 
@@ -1662,6 +1748,11 @@ extern "C" int biear_adaptive_fwd(const BiearSeqParams* p, void* stream) {
     using namespace biear;
     if (int e = validate_seq(p, "biear_adaptive_fwd", false)) return e;
     cudaStream_t st = as_stream(stream);
+    if (p->G == 1 && p->E == 2) {   // single controller (seq_single.cu)
+        if (!p->prepared)
+            if (int e = launch_single_prepare(p, 1, st)) return e;
+        return launch_single_fwd(p, st);
+    }
     const size_t smem = sizeof(float) * (size_t)FwdSmem(p->N, p->F).total();
     BIEAR_REQUIRE(smem <= 227 * 1024, "biear_adaptive_fwd: N=%d F=%d needs %zu B of shared memory", p->N, p->F, smem);
     const int tiles = (p->B + kR - 1) / kR;
@@ -1684,10 +1775,17 @@ extern "C" int biear_adaptive_bwd(const BiearSeqParams* p, void* stream) {
     const size_t smem = sizeof(float) * (size_t)BwdSmem(p->N).total();
     BIEAR_REQUIRE(smem <= 227 * 1024, "biear_adaptive_bwd: N=%d needs %zu B of shared memory", p->N, smem);
     const int tiles = (p->B + kR - 1) / kR;
+    if (p->G == 1 && p->E == 2) {   // single controller
+        if (!p->prepared)
+            if (int e = launch_single_prepare(p, 2, st)) return e;
+        return launch_cluster(seq_bwd_kernel<true>, "seq_bwd_kernel<single>", tiles, smem, st, *p,
+                              (const float*)(p->workspace + single_off_bres(p->N)),
+                              (const float*)(p->workspace + single_off_bstr(p->N)));
+    }
     if (!p->prepared)
         if (int e = launch_prepare(p, 2, st)) return e;
-    return launch_cluster(seq_bwd_kernel, "seq_bwd_kernel", p->G * tiles, smem, st, *p,
-                          p->workspace + bwd_images_offset(p->G, p->N));
+    return launch_cluster(seq_bwd_kernel<false>, "seq_bwd_kernel", p->G * tiles, smem, st, *p,
+                          (const float*)(p->workspace + bwd_images_offset(p->G, p->N)), (const float*)nullptr);
 }
 
 // Diagnostics: how many clusters of the persistent kernels can be resident at once on the current device.
@@ -1714,8 +1812,8 @@ extern "C" int biear_adaptive_occupancy(int N, int F, int* fwd_clusters, int* bw
             e = cudaFuncSetAttribute(seq_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
             if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, seq_fwd2_kernel, &cfg);
         } else {
-            e = cudaFuncSetAttribute(seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
-            if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, seq_bwd_kernel, &cfg);
+            e = cudaFuncSetAttribute(seq_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, seq_bwd_kernel<false>, &cfg);
         }
         if (int rc = check_cuda(e, "cudaOccupancyMaxActiveClusters")) return rc;
         *(pass ? bwd_clusters : fwd_clusters) = n;

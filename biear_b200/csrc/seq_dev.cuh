@@ -67,6 +67,26 @@ __host__ __device__ constexpr int bwd_img_whhc(int N) { return bwd_img_w1c(N) + 
 __host__ __device__ constexpr int bwd_img_wihc(int N) { return bwd_img_whhc(N) + 3 * kHid * kU; }
 __host__ __device__ constexpr int bwd_img_floats(int N) { return bwd_img_wihc(N) + 3 * kHid * kU; }
 
+// ---- single-controller variant (seq_single.cu; model_torch.py:579-776): GRU(4N -> 128), one Q for both ears ------------
+// Workspace: [kCS forward resident images: whh3 | w1 | w2 | w3, skewed columns][kCS streamed W_ih images [Kp][3][32],
+// input order cL | cR | mL | mR][kCS backward resident images: w3c | w2c | w1c | whhc][kCS streamed W_ih^T column images:
+// wihcL | wihcR, [384][32] each].
+__host__ __device__ constexpr int single_kp(int N) { return (4 * N + 7) & ~7; }              // controller input width, padded
+__host__ __device__ constexpr int single_chunk_rows(int N) {                                   // k-rows per W_ih ring stage
+    const int m = single_kp(N) / 8;
+    return 8 * (m % 5 == 0 ? 5 : (m % 4 == 0 ? 4 : (m % 3 == 0 ? 3 : (m % 2 == 0 ? 2 : 1))));
+}
+__host__ __device__ constexpr int single_fwd_res_floats() { return kHid * 3 * kU + 3 * kHid * kU; }
+__host__ __device__ constexpr int single_bwd_res_floats(int N) { return bwd_img_wihc(N); }
+__host__ __device__ constexpr long long single_off_fres() { return 0; }
+__host__ __device__ constexpr long long single_off_fstr(int) { return (long long)kCS * single_fwd_res_floats(); }
+__host__ __device__ constexpr long long single_off_bres(int N) { return single_off_fstr(N) + (long long)kCS * single_kp(N) * 3 * kU; }
+__host__ __device__ constexpr long long single_off_bstr(int N) { return single_off_bres(N) + (long long)kCS * single_bwd_res_floats(N); }
+__host__ __device__ constexpr long long single_workspace_floats(int N) { return single_off_bstr(N) + (long long)kCS * 2 * 3 * kHid * kU; }
+size_t single_fwd_smem_bytes(int N, int F);
+int launch_single_prepare(const BiearSeqParams* p, int want, cudaStream_t st);
+int launch_single_fwd(const BiearSeqParams* p, cudaStream_t st);
+
 // ---- Philox4x32-10 (counter-based RNG for the dropout masks; regenerated in the backward, not stored) ------
 __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
     const unsigned int M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;

@@ -209,13 +209,17 @@ def _adaptive_chain(x: torch.Tensor, ears: int, ctrl_mods, fc, q0, dq_vec, dq_mo
     N = fc.numel()
     xr = torch.view_as_real(x)
     if engine in ("fused", "fused-strict"):
-        if shared or G != ears or not ops.fused_supported(N, Fbins):
-            raise NotImplementedError("the fused recurrence covers the dual front-end with at most 128 bands")
+        single = shared and G == 1 and ears == 2
+        if not (single or (not shared and G == ears)) or not \
+                (ops.single_supported(N, Fbins) if single else ops.fused_supported(N, Fbins)):
+            raise NotImplementedError("the fused recurrence covers the dual and the single-controller front-end with at "
+                                      "most 128 bands")
         w = _controller_weights(ctrl_mods)
         # CPU generator: no device sync.  (Under CUDA-graph capture the kernels read a device-side seed instead.)
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if training else 0
         res = ops.adaptive_sequence(xr, fc, q0, dq_vec, w, dq_mode == "relative", training, want_phase, cutoff,
-                                    df, seed, strict=(engine == "fused-strict"), want_logy=want_logy, prep=prep)
+                                    df, seed, strict=(engine == "fused-strict"), want_logy=want_logy, prep=prep,
+                                    ears=ears)
         return res if want_logy else res + (None,)
     stack = _ControllerStack(ctrl_mods)
     q0g = q0.view(1, 1, N)
@@ -682,6 +686,7 @@ class BinauralAdaptiveGammatoneFB_SingleController(_FilterbankBase):
         self.cutoff = ops.DEFAULT_CUTOFF
         self.graph_replay = GRAPH_REPLAY_DEFAULT      # see _GraphCache
         self._graphs = _GraphCache()
+        self.engine = "fused"                         # "chain": per-frame launches + PyTorch controller (cross-check)
         if not self.fixed_frontend_q:
             self.q_rnn, self.q_out = _make_controller(4 * Nbands, Nbands)
             self.fb_L = self.fb_R = None
@@ -711,15 +716,18 @@ class BinauralAdaptiveGammatoneFB_SingleController(_FilterbankBase):
             y, ph = _fixed_bands(x, self.fc, qf, self.df, want_phase, self.cutoff)
             q = qf.view(1, 1, -1).expand(B, self.timesteps, -1)
             y, ph = [y[:B], y[B:]], ([ph[:B], ph[B:]] if ph is not None else None)
+            lx = None
         else:
-            y, q, ph, _ = _adaptive_chain(x, 2, [self], self.fc, self.Q0, self.deltaQ_vec, self.deltaQ_mode, self.df,
-                                          self.training, True, want_phase, self.band_mode, self.cutoff)
+            engine = self.engine if ops.single_supported(self.Nbands, self.n_fft // 2 + 1) else "chain"
+            y, q, ph, lx = _adaptive_chain(x, 2, [self], self.fc, self.Q0, self.deltaQ_vec, self.deltaQ_mode, self.df,
+                                           self.training, True, want_phase, self.band_mode, self.cutoff, engine,
+                                           want_logy=want_logenergy)
             q = q[0]
         out = {"YL": y[0], "YR": y[1], "QL": q, "QR": q, "XL": x[:B], "XR": x[B:]}
         if want_phase:
             out["phaseL"], out["phaseR"] = ph
         if want_logenergy:
-            out["logYL"], out["logYR"] = _log_energy(y[0]), _log_energy(y[1])
+            out["logYL"], out["logYR"] = lx if lx is not None else (_log_energy(y[0]), _log_energy(y[1]))
         return out
 
     def forward(self, wavL_1s, wavR_1s):

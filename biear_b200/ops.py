@@ -421,6 +421,11 @@ def fused_supported(n_bands: int, n_bins: int) -> bool:
     return bool(_lib.load().biear_adaptive_supported(int(n_bands), int(n_bins)))
 
 
+def single_supported(n_bands: int, n_bins: int) -> bool:
+    """The same for the single-controller variant (csrc/seq_single.cu)."""
+    return bool(_lib.load().biear_single_supported(int(n_bands), int(n_bins)))
+
+
 _resident = {}
 
 
@@ -510,7 +515,7 @@ class PreparedSequence:
 
 
 def adaptive_prepare(weights, B: int, T: int, N: int, training: bool, stream: Optional[torch.cuda.Stream] = None,
-                     launch: bool = True, streamed_spectra: bool = False):
+                     launch: bool = True, streamed_spectra: bool = False, ears: Optional[int] = None):
     """Run the spectra-independent part of a recurrence step (weight-image packing for the forward AND the backward
     kernel, H[:, 0] = 0, flags = 0, dropout-seed snapshot) as one launch, on `stream` if given: the front-end issues
     it on a forked stream so that it overlaps the STFT.  Pass the result to adaptive_sequence(prep=...).
@@ -520,6 +525,9 @@ def adaptive_prepare(weights, B: int, T: int, N: int, training: bool, stream: Op
     the path a C caller that never calls biear_adaptive_prepare takes (testing).
     weights: dict name -> list of the G controllers' tensors."""
     G = len(weights[WEIGHT_NAMES[0]])
+    E = G if ears is None else int(ears)          # ears == 2 with one controller: the single-controller front-end
+    single = (G == 1 and E == 2)
+    assert E == G or single
     ws = [w.detach() for k in WEIGHT_NAMES for w in weights[k]]
     dev = ws[0].device
     for i, w in enumerate(ws):
@@ -539,11 +547,13 @@ def adaptive_prepare(weights, B: int, T: int, N: int, training: bool, stream: Op
             # h_t lives at step index t+1 of H; H[:, 0] = 0 is "h_{-1}", so H[:, :S] are the GRU's previous states
             out.H = torch.empty((G, S + 1, tiles, HID, TILE), **f32)
             out.flags = torch.empty((S * G + 1,), dtype=torch.int32, device=dev)
-            out.work = torch.empty(int(lib.biear_adaptive_workspace_floats(G, N)), **f32)
+            out.work = torch.empty(int(lib.biear_single_workspace_floats(N) if single
+                                       else lib.biear_adaptive_workspace_floats(G, N)), **f32)
             out.seed_dev = _captured_seed(dev) if (training and torch.cuda.is_current_stream_capturing()) else None
-            out.x_ready = torch.empty((G * B * T + 4,), dtype=torch.int32, device=dev) if (streamed_spectra and launch) else None
+            out.x_ready = torch.empty((G * B * T + 4,), dtype=torch.int32, device=dev) \
+                if (streamed_spectra and launch and not single) else None
             prm = _lib.SeqParams()
-            prm.G, prm.E, prm.B, prm.T, prm.N, prm.F, prm.Kin = G, G, B, T, N, 2, ws[0].shape[1]
+            prm.G, prm.E, prm.B, prm.T, prm.N, prm.F, prm.Kin = G, E, B, T, N, 2, ws[0].shape[1]
             _fill(prm, workspace=out.work, H=out.H, flags=out.flags, x_ready=out.x_ready)
             for i, name in enumerate(WEIGHT_NAMES):
                 arr = getattr(prm, name)
@@ -560,7 +570,7 @@ def adaptive_prepare(weights, B: int, T: int, N: int, training: bool, stream: Op
             out.event = torch.cuda.Event()
             out.event.record(run)
     out.stream = run
-    out.key = (G, B, T, N, tuple(w.data_ptr() for w in ws))
+    out.key = (G, E, B, T, N, tuple(w.data_ptr() for w in ws))
     return out
 
 
@@ -581,25 +591,25 @@ class AdaptiveSequence(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, xr, fc, q0, dq, relative, training, want_phase, cutoff, df, seed, strict, want_logy, G, prep, *weights):
+    def forward(ctx, xr, fc, q0, dq, relative, training, want_phase, cutoff, df, seed, strict, want_logy, G, E, prep, *weights):
         ctx.set_materialize_grads(False)
         _need_cuda(xr, "X")
         dev = xr.device
         rows, T, F, _ = xr.shape
         N = fc.numel()
-        assert len(weights) == G * len(WEIGHT_NAMES) and 1 <= G <= _lib.MAX_CTRL
-        B = rows // G
+        assert len(weights) == G * len(WEIGHT_NAMES) and 1 <= G <= _lib.MAX_CTRL and (E == G or (G == 1 and E == 2))
+        B = rows // E
         weights = tuple(w.detach().contiguous() for w in weights)
         for i, w in enumerate(weights):
             _need_cuda(w, WEIGHT_NAMES[i // G])
         Kin = weights[0].shape[1]
-        need_grad = any(ctx.needs_input_grad[14:])
+        need_grad = any(ctx.needs_input_grad[15:])
         f32 = dict(dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             lib = _prepare(dev)
             Y = torch.empty((rows, T, N), **f32)
-            Q = torch.empty((rows, T, N), **f32)
-            D = torch.empty((rows, T, N), **f32)
+            Q = torch.empty((G * B, T, N), **f32)
+            D = torch.empty((G * B, T, N), **f32)
             P = torch.empty((rows, T, N), **f32) if want_phase else None
             LX = torch.empty((rows, T, N), **f32) if want_logy else None
             dY = torch.empty((rows, T, N), **f32)
@@ -609,8 +619,8 @@ class AdaptiveSequence(torch.autograd.Function):
             tiles = (B + TILE - 1) // TILE
             wdict = {name: list(weights[i * G:(i + 1) * G]) for i, name in enumerate(WEIGHT_NAMES)}
             if prep is None:
-                prep = adaptive_prepare(wdict, B, T, N, training)
-            elif prep.key != (G, B, T, N, tuple(w.data_ptr() for w in weights)):
+                prep = adaptive_prepare(wdict, B, T, N, training, ears=E)
+            elif prep.key != (G, E, B, T, N, tuple(w.data_ptr() for w in weights)):
                 raise ValueError("biear_b200: adaptive_prepare was called for another geometry / other weights")
             cur = torch.cuda.current_stream(dev)
             if prep.stream != cur:                       # prepared on a forked stream: join it here
@@ -620,9 +630,10 @@ class AdaptiveSequence(torch.autograd.Function):
                         t_.record_stream(cur)
             H, flags, work, seed_dev = prep.H, prep.flags, prep.work, prep.seed_dev
             sv = {k: torch.empty((G, S, tiles, d, TILE), **f32) for k, d in
-                  (("gates", 4 * HID), ("xh1", HID), ("d1", HID), ("xh2", HID), ("d2", HID), ("rstd", 2), ("yc", N))}
+                  (("gates", 4 * HID), ("xh1", HID), ("d1", HID), ("xh2", HID), ("d2", HID), ("rstd", 2),
+                   ("yc", N if E == G else 4 * N))}       # single controller: the whole 4N-wide controller input
             prm = _lib.SeqParams()
-            prm.G, prm.E, prm.B, prm.T, prm.N, prm.F, prm.Kin = G, G, B, T, N, F, Kin
+            prm.G, prm.E, prm.B, prm.T, prm.N, prm.F, prm.Kin = G, E, B, T, N, F, Kin
             prm.relative, prm.training, prm.seed, prm.force_strict = int(relative), int(training), int(seed), int(strict)
             prm.prepared = int(prep.launched)
             prm.df, prm.cutoff, prm.q_min, prm.q_max = float(df), float(cutoff), 0.05, 30.0
@@ -640,10 +651,10 @@ class AdaptiveSequence(torch.autograd.Function):
         ctx.keep = (xr, fc, q0, dq, weights, Y, Q, P, LX, D, dY, dP, sv, flags, work, H, seed_dev, prep.x_ready)
         ctx.has_phase = P is not None
         ctx.has_logy = LX is not None
-        ctx.dims = (G, B, T, N, Kin, tiles, TILE)
+        ctx.dims = (G, E, B, T, N, Kin, tiles, TILE)
         empty = Y.new_empty(0)
-        ears = lambda t: tuple(t[e * B:(e + 1) * B] for e in range(G)) if t is not None else tuple(empty for _ in range(G))
-        outs = ears(Y) + ears(Q) + ears(P) + ears(LX)
+        ears = lambda t, k=E: tuple(t[e * B:(e + 1) * B] for e in range(k)) if t is not None else tuple(empty for _ in range(k))
+        outs = ears(Y) + ears(Q, G) + ears(P) + ears(LX)
         nd = [o for o in outs if o.numel() == 0]
         if not need_grad:
             nd = list(outs)
@@ -655,13 +666,14 @@ class AdaptiveSequence(torch.autograd.Function):
     def backward(ctx, *grads):
         from ctypes import byref
         xr, fc, q0, dq, weights, Y, Q, P, LX, D, dY, dP, sv, flags, work, H, _seed_dev, _x_ready = ctx.keep
-        G, B, T, N, Kin, tiles, TILE = ctx.dims
-        none13 = (None,) * 14
-        gY, gQ, gP, gLX = (list(grads[i * G:(i + 1) * G]) for i in range(4))
+        G, E, B, T, N, Kin, tiles, TILE = ctx.dims
+        none13 = (None,) * 15
+        gY, gQ, gP, gLX = grads[:E], grads[E:E + G], grads[E + G:2 * E + G], grads[2 * E + G:3 * E + G]
+        gY, gQ, gP, gLX = list(gY), list(gQ), list(gP), list(gLX)
         if not ctx.has_phase:
-            gP = [None] * G
+            gP = [None] * E
         if not ctx.has_logy:
-            gLX = [None] * G
+            gLX = [None] * E
         if T < 2 or all(g is None for g in gY + gQ + gP + gLX):
             return none13 + (None,) * (G * len(WEIGHT_NAMES))
         with timing.span("frontend.backward", B):
@@ -671,8 +683,8 @@ class AdaptiveSequence(torch.autograd.Function):
     def _backward(ctx, gY, gQ, gP, gLX):
         from ctypes import byref
         xr, fc, q0, dq, weights, Y, Q, P, LX, D, dY, dP, sv, flags, work, H, _seed_dev, _x_ready = ctx.keep
-        G, B, T, N, Kin, tiles, TILE = ctx.dims
-        none13 = (None,) * 14
+        G, E, B, T, N, Kin, tiles, TILE = ctx.dims
+        none13 = (None,) * 15
         dev = Y.device
         f32 = dict(dtype=torch.float32, device=dev)
         S = T - 1
@@ -687,7 +699,7 @@ class AdaptiveSequence(torch.autograd.Function):
             for name, lst in (("gY", gY), ("gQ", gQ), ("gP", gP), ("gLogY", gLX)):
                 arr = getattr(prm, name)
                 for g in range(_lib.MAX_CTRL):
-                    arr[g] = lst[g].data_ptr() if (g < G and lst[g] is not None) else None
+                    arr[g] = lst[g].data_ptr() if (g < len(lst) and lst[g] is not None) else None
             _lib.check(lib.biear_adaptive_bwd(byref(prm), _stream(dev)), "biear_adaptive_bwd")
             for name in ("gY", "gQ", "gP", "gLogY"):
                 arr = getattr(prm, name)
@@ -703,10 +715,15 @@ class AdaptiveSequence(torch.autograd.Function):
             d_w_hh = torch.empty((G, 3 * HID, HID), **f32)
             d_b_hh = torch.empty((G, 3 * HID), **f32)
             fold = Kin == 2 * N                   # feat = [yc, 0.2 yc.detach()]: dW_ih[:, N:] = 0.2 dW_ih[:, :N]
-            d_w_ih = torch.empty((G, 3 * HID, Kin), **f32) if fold else None
-            ih_out = (d_w_ih[:, :, :N], None, d_w_ih[:, :, N:], 0.2) if fold else ()
+            d_w_ih = torch.empty((G, 3 * HID, Kin), **f32)
+            ih_out = (d_w_ih[:, :, :N], None, d_w_ih[:, :, N:], 0.2) if fold else (d_w_ih[:, :, :N],)
+            yc_t = fl(sv["yc"])
+            if not fold:   # single controller: weight_ih is (384, 4N) over [cL, mL, cR, mR]; one job per N-wide column block
+                assert Kin == 4 * N and yc_t.shape[2] == 4 * N
+                ctrl_wgrad([(GG, 3 * HID, yc_t[:, :, j * N:(j + 1) * N], N, K, False, d_w_ih[:, :, j * N:(j + 1) * N])
+                            for j in range(1, 4)])
             (a, d_b_ih), _, _, (d_w1, d_b1), (d_w2, d_b2), (d_w3, d_b3), (d_g1, d_be1), (d_g2, d_be2) = ctrl_wgrad([
-                (GG, 3 * HID, fl(sv["yc"]), N, K, True) + ih_out,                                 # dL/dW_ih (both halves), b_ih
+                (GG, 3 * HID, yc_t[:, :, :N], N, K, True) + ih_out,                               # dL/dW_ih (both halves), b_ih
                 (GG, 2 * HID, h_prev, HID, K, True, d_w_hh[:, :2 * HID], d_b_hh[:, :2 * HID]),     # r, z rows of W_hh / b_hh
                 (GG[:, :, 3 * HID:], HID, h_prev, HID, K, True, d_w_hh[:, 2 * HID:], d_b_hh[:, 2 * HID:]),   # n rows: dL/d(W_hn h + b_hn)
                 (fl(wk["G_a1"]), HID, h_cur, HID, K, True),
@@ -722,15 +739,18 @@ class AdaptiveSequence(torch.autograd.Function):
 
 def adaptive_sequence(xr, fc, q0, dq, weights, relative: bool, training: bool, want_phase: bool,
                       cutoff: float, df: float, seed: int = 0, strict: bool = False, want_logy: bool = False,
-                      prep: Optional[PreparedSequence] = None):
+                      prep: Optional[PreparedSequence] = None, ears: Optional[int] = None):
     """weights: dict name -> list of the G controllers' tensors (WEIGHT_NAMES).  Returns Y, Q, phase|None[, logY], each a
     LIST with one (B,T,N) tensor per ear / controller.
+    ears=2 with ONE controller selects the single-controller front-end (model_torch.py:695-776): x holds both ears,
+    Y / phase / logY come back per ear, Q once.
     strict=True skips the fast pass and runs the batch-global-fallback replay pass only (testing).
     prep: result of adaptive_prepare (same weights / geometry) issued earlier, typically on a forked stream."""
     G = len(weights[WEIGHT_NAMES[0]])
+    E = G if ears is None else int(ears)
     outs = AdaptiveSequence.apply(xr, fc, q0, dq, relative, training, want_phase, cutoff, df, seed, strict,
-                                  want_logy, G, prep, *[w for k in WEIGHT_NAMES for w in weights[k]])
-    y, q, ph, lx = (list(outs[i * G:(i + 1) * G]) for i in range(4))
+                                  want_logy, G, E, prep, *[w for k in WEIGHT_NAMES for w in weights[k]])
+    y, q, ph, lx = list(outs[:E]), list(outs[E:E + G]), list(outs[E + G:2 * E + G]), list(outs[2 * E + G:3 * E + G])
     if want_logy:
         return y, q, (ph if want_phase else None), lx
     return y, q, (ph if want_phase else None)

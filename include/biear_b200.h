@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BIEAR_ABI_VERSION 17
+#define BIEAR_ABI_VERSION 18
 #define BIEAR_EINVAL (-1)
 
 /* ABI version (== BIEAR_ABI_VERSION of the library that was built). */
@@ -197,6 +197,14 @@ typedef struct BiearSeqParams {
 /* 1 if the persistent recurrence kernels can take N bands and F bins (their weight slices, activations and spectrum
  * tiles must fit the 227 KB of shared memory of an SM), else 0: callers fall back to per-frame launches. */
 int biear_adaptive_supported(int N, int F);
+/* The SINGLE-controller front-end (BinauralAdaptiveGammatoneFB_SingleController, model_torch.py:579-776) goes through the
+ * same entry points with G = 1, E = 2, Kin = 4N: one controller (GRU(4N -> 128) + MLP) whose input is
+ * [log1p YL, memL, log1p YR, memR] and whose one Q per clip drives both ears' band stages.  Differences of the block:
+ *   Q, delta (B,T,N); Y, phase, dYdQ, dPdQ, logY (2B,T,N) ear-major; gY / gP / gLogY indexed by EAR, gQ[0] only;
+ *   `yc` saves the whole controller input, tile layout with D = 4N in weight_ih's column order; x_ready must be NULL;
+ *   workspace = biear_single_workspace_floats(N) floats. */
+int biear_single_supported(int N, int F);
+int64_t biear_single_workspace_floats(int N);
 /* Rows per tile (R) of the tile-layout tensors. */
 int biear_adaptive_tile_rows(void);
 /* Floats of scratch the calls below need in BiearSeqParams.workspace. */
