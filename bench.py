@@ -509,7 +509,8 @@ def run_ours(args):
         # sub-records (1 GPU only; each bounded to a few seconds): the same-box competitor and BASELINE configs 3 / 4
         for key, fn in (("gpu_eager_reference", lambda: bench_extra.gpu_eager_reference(B, steps=5, warmup=2, device=str(dev))),
                         ("fixed_q", lambda: bench_extra.fixed_q(4096, device=str(dev))),
-                        ("full_step", lambda: bench_extra.full_step(B, steps=30, device=str(dev)))):
+                        ("full_step", lambda: bench_extra.full_step(B, steps=30, device=str(dev))),
+                        ("variants", lambda: bench_extra.variants(B, device=str(dev)))):
             try:
                 out[key] = fn()
             except Exception as e:  # noqa: BLE001  (a failing side measurement must not lose the main line)

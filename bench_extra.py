@@ -6,6 +6,7 @@
   gpu_eager_reference(...)  the same reference code on the same B200 in PyTorch eager (the real same-box competitor)
   fixed_q(...)              BASELINE config 3: fixed-Q front-end + phase + CC, forward only, with its own HBM roofline
   full_step(...)            BASELINE config 4: full active training step (front-end + back-end + losses + clips + Adam)
+  variants(...)             BASELINE config 5: single controller, band-count / lag sweeps, 10 s clips, AuralNet filterbank
   compute_roofline(...)     what actually bounds the adaptive path: issue slots / FMA pipe / MUFU / SURVEY 8(d) ceilings
 """
 import json
@@ -307,6 +308,93 @@ def full_step(batch=256, steps=30, device="cuda:0"):
                        "backward as one CUDA graph, clips + Adam as a second; resident inputs"}
     del full, step, model
     torch.cuda.empty_cache()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE config 5: the other front-end variants (single controller, band-count / lag sweeps, 10 s clips, AuralNet FB)
+# ------------------------------------------------------------------------------------------------
+def _time_calls(fn, warmup=4, reps=20):
+    for _ in range(warmup):          # (the drop-in's transparent CUDA-graph replay records itself on the third call)
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def variants(batch=256, device="cuda:0"):
+    """Throughput of the variants BASELINE.json config 5 names, each fwd+bwd in train mode at `batch` clips through the
+    module's own API (forward_features + autograd, transparent graph replay on), random-init controllers with a non-zero
+    last layer.  Values in audio-s/s (1 clip = 1 s x 2 ears)."""
+    import biear_b200
+    from biear_b200 import ops
+    dev = torch.device(device)
+    g = torch.Generator(device="cpu").manual_seed(99)
+    out = {"batch": batch, "unit": UNIT,
+           "workload": "fwd+bwd (Y, phase, log-energy features; loss = fixed random functionals), train mode, resident inputs, "
+                       "module API with transparent CUDA-graph replay"}
+
+    def frontend_case(mod, n_bands, b):
+        mod = mod.to(dev).train()
+        with torch.no_grad():
+            for name, prm in mod.named_parameters():
+                if name.endswith("q_out.8.weight"):
+                    torch.nn.init.normal_(prm, std=0.02)
+        wl = (torch.rand((b, FS), generator=g) * 2 - 1).to(dev)
+        wr = (torch.rand((b, FS), generator=g) * 2 - 1).to(dev)
+        ups = [torch.randn((b, T, n_bands), generator=g).to(dev) for _ in range(4)]
+        has_grad = any(p.requires_grad for p in mod.parameters())
+
+        def call():
+            with torch.set_grad_enabled(has_grad):
+                o = mod.forward_features(wl, wr, want_phase=True, want_logenergy=True)
+                if has_grad:
+                    for p_ in mod.parameters():
+                        p_.grad = None
+                    ((ups[0] * o["logYL"]).sum() + (ups[1] * o["logYR"]).sum() + (ups[2] * o["phaseL"]).sum()
+                     + (ups[3] * o["phaseR"]).sum()).backward()
+        ms = _time_calls(call)
+        del mod
+        return {"ms_per_step": ms, "value": b / (ms * 1e-3)}
+
+    single_kw = dict(deltaQ_base=2.0, deltaQ_low_factor=0.5, deltaQ_high_factor=5.0, deltaQ_mode="absolute")   # config_single_ctrl.yaml
+    cases = [("single_controller", lambda: frontend_case(biear_b200.BinauralAdaptiveGammatoneFB_SingleController(**single_kw), NBANDS, batch))]
+    for nb in (32, 64, 128):
+        cases.append((f"dual_bands_{nb}", lambda nb=nb: frontend_case(
+            biear_b200.BinauralAdaptiveGammatoneFB(Nbands=nb, alpha=0.0, **CONFIG_YAML), nb, batch)))
+        cases.append((f"single_controller_bands_{nb}", lambda nb=nb: frontend_case(
+            biear_b200.BinauralAdaptiveGammatoneFB_SingleController(Nbands=nb, **single_kw), nb, batch)))
+    # 10 s clips = 10 x 1 s segments folded into the batch (the reference itself truncates to the first second, SURVEY section 4)
+    cases.append(("dual_10s_clips", lambda: frontend_case(biear_b200.BinauralAdaptiveGammatoneFB(alpha=0.0, **CONFIG_YAML), NBANDS, 10 * batch)))
+    for key, fn in cases:
+        try:
+            out[key] = fn()
+        except Exception as e:  # noqa: BLE001
+            out[key] = {"error": repr(e)[:200]}
+        torch.cuda.empty_cache()
+    # AuralNet filterbank (fixed Q0, GEMM form; model_torch.py:70-195), forward only, both ears
+    try:
+        fb = biear_b200.AuralNetGammatoneFB().to(dev).eval()
+        wav = (torch.rand((2 * batch, FS), generator=g) * 2 - 1).to(dev)
+        with torch.no_grad():
+            ms = _time_calls(lambda: fb(wav))
+        out["auralnet_fb_forward"] = {"ms_per_step": ms, "value": batch / (ms * 1e-3)}
+    except Exception as e:  # noqa: BLE001
+        out["auralnet_fb_forward"] = {"error": repr(e)[:200]}
+    # CC lag-range sweep (utils.py:390-420), num_lags == Nbands == 100
+    wl = (torch.rand((batch, FS), generator=g) * 2 - 1).to(dev)
+    wr = (torch.rand((batch, FS), generator=g) * 2 - 1).to(dev)
+    for ms_lag in (1.0, 3.0, 5.0):
+        try:
+            ms = _time_calls(lambda: ops.cc_feature(wl, wr, max_lag_ms=ms_lag))
+            out[f"cc_max_lag_{ms_lag:g}ms"] = {"ms_per_step": ms, "value": batch / (ms * 1e-3)}
+        except Exception as e:  # noqa: BLE001
+            out[f"cc_max_lag_{ms_lag:g}ms"] = {"error": repr(e)[:200]}
     return out
 
 

@@ -74,6 +74,7 @@ SIGNATURES = {
     "biear_adaptive_bwd": (_i, [POINTER(SeqParams), _p]),
     "biear_adaptive_workspace_floats": (_l, [_i, _i]),
     "biear_debug_phase_cycles": (_i, [_p]),
+    "biear_debug_phase_cycles_single": (_i, [_p]),
     "biear_adaptive_occupancy": (_i, [_i, _i, POINTER(c_int), POINTER(c_int)]),
     "biear_adaptive_tile_rows": (_i, []),
     "biear_adaptive_supported": (_i, [_i, _i]),

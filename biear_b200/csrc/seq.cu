@@ -1837,3 +1837,6 @@ extern "C" int biear_debug_phase_cycles(unsigned long long* out_host) {
     return biear::fail_invalid("biear_debug_phase_cycles: library built without BIEAR_PHASE_PROF");
 #endif
 }
+
+// The same for the single-controller forward kernel (16 counters), see csrc/seq_single.cu.
+extern "C" int biear_debug_phase_cycles_single(unsigned long long* out_host) { return biear::debug_phase_cycles_single(out_host); }

@@ -86,6 +86,7 @@ __host__ __device__ constexpr long long single_workspace_floats(int N) { return 
 size_t single_fwd_smem_bytes(int N, int F);
 int launch_single_prepare(const BiearSeqParams* p, int want, cudaStream_t st);
 int launch_single_fwd(const BiearSeqParams* p, cudaStream_t st);
+int debug_phase_cycles_single(unsigned long long* out_host);
 
 // ---- Philox4x32-10 (counter-based RNG for the dropout masks; regenerated in the backward, not stored) ------
 __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {

@@ -29,6 +29,23 @@
 namespace biear {
 namespace sc {
 
+// Optional per-phase cycle accounting (diagnostic builds: -DBIEAR_PHASE_PROF, `make prof`), see seq.cu.
+#ifdef BIEAR_PHASE_PROF
+__device__ unsigned long long g_phase_cycles1[16];
+#define PHASE1_INIT() long long _ph_last = clock64()
+#define PHASE1_MARK(i)                                                 \
+    do {                                                               \
+        if (blockIdx.x == 0 && threadIdx.x == 0) {                     \
+            const long long _now = clock64();                          \
+            g_phase_cycles1[i] += (unsigned long long)(_now - _ph_last); \
+            _ph_last = _now;                                           \
+        }                                                              \
+    } while (0)
+#else
+#define PHASE1_INIT() do {} while (0)
+#define PHASE1_MARK(i) do {} while (0)
+#endif
+
 constexpr int kRows = 8;                 // clips per cluster
 constexpr int kRG = kRows / kRT;         // 2 row groups of 4 clips
 constexpr int kKL = 8;                   // k-splits = adjacent lanes
@@ -338,6 +355,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq1_fwd_kernel(const BiearSeq
     int hsel = 0;
     int spec_key = -1;                                        // (frame * n_half + half) whose spectra sit in spec_s
 
+    PHASE1_INIT();
     const int half_begin = STRICT ? 0 : (int)(blockIdx.x / kCS), half_end = STRICT ? n_half : half_begin + 1;
     for (int t = 0; t < T; ++t) {
         for (int hf = half_begin; hf < half_end; ++hf) {
@@ -374,6 +392,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq1_fwd_kernel(const BiearSeq
                 }
             };
 
+            PHASE1_MARK(0);   // loop tail / head
             // ---- state of this (frame, half-tile) ----------------------------------------------------------------
             bool h_zero = t == 0;
             float* hcur_s = hbuf_s + hsel * kHid * kRows;
@@ -435,6 +454,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq1_fwd_kernel(const BiearSeq
                 spec_key = want_key;
             }
             __syncthreads();
+            PHASE1_MARK(1);   // state + spectra ready
 
             // ---- band stage of frame t for this CTA's 4 items (model_torch.py:729-737, 1050-1060) ---------------------
             // The kItems x quads (item, 4-band quad) pairs are dealt round-robin to the 16 warps, widest quads first and
@@ -506,6 +526,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq1_fwd_kernel(const BiearSeq
                 continue;
             }
             __syncthreads();
+            PHASE1_MARK(2);   // band stage
             if (!STRICT) {           // the tile is free again: the next frame's spectra travel behind the controller phases
                 prefetch(t + 1);
                 spec_key = (t + 1) * n_half + hf;
@@ -522,6 +543,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq1_fwd_kernel(const BiearSeq
             }
             arm(0);
             tx_wait(bar_of(0), par);
+            PHASE1_MARK(3);   // prefetch issue + push + hand-over #1
             // saved controller input (torch column order cL | mL | cR | mR, tile layout): ranks 0 / 1 save cL / cR here,
             // ranks 2 / 3 save mL / mR where the memory is advanced
             float* in_tile = p.yc + tb * (4 * N * kR);
@@ -618,6 +640,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq1_fwd_kernel(const BiearSeq
                 arm(1);
             }
             tx_wait(bar_of(1), par);
+            PHASE1_MARK(4);   // GRU + #2
             // ---- carried memory: Y_mem <- 0.8 Y_mem + 0.2 Y_ctrl.detach() (model_torch.py:770-771); every warp of every
             // CTA has finished its GRU products (its h values are part of hand-over 1), so the buffer may change now.
             // Ranks 2 / 3 save the OLD memory (this step's controller input) on the way.
@@ -647,8 +670,10 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq1_fwd_kernel(const BiearSeq
                 arm(2);
             }
             tx_wait(bar_of(2), par);
+            PHASE1_MARK(5);   // memory update + Linear 1 + #3
             ln_silu_drop(p, seed, a1_s, stat_s, vec_s + V_LN1G, vec_s + V_LN1B, 0, t, (long long)b0, rank,
                          p.xh1 + tb * kHid * kR, p.d1 + tb * kHid * kR, p.rstd + tb * 2 * kR, row_off);
+            PHASE1_MARK(6);   // LayerNorm 1
             // ---- Linear 2 -> LayerNorm -> SiLU -> Dropout ------------------------------------------------------------------
             {
                 float2 lo[1] = {make_float2(0.f, 0.f)}, hi[1] = {make_float2(0.f, 0.f)};
@@ -662,8 +687,10 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq1_fwd_kernel(const BiearSeq
                 arm(3);
             }
             tx_wait(bar_of(3), par);
+            PHASE1_MARK(7);   // Linear 2 + #4
             ln_silu_drop(p, seed, a2_s, stat_s, vec_s + V_LN2G, vec_s + V_LN2B, 1, t, (long long)b0, rank,
                          p.xh2 + tb * kHid * kR, p.d2 + tb * kHid * kR, p.rstd + tb * 2 * kR, row_off);
+            PHASE1_MARK(8);   // LayerNorm 2
             // ---- Linear 3 -> tanh -> Q_{t+1} (model_torch.py:757-768) ---------------------------------------------------------
             {
                 float2 lo[1] = {make_float2(0.f, 0.f)}, hi[1] = {make_float2(0.f, 0.f)};
@@ -704,6 +731,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq1_fwd_kernel(const BiearSeq
                 arm(4);
             }
             tx_wait(bar_of(4), par);   // Q_{t+1} of my band-stage clips has landed ...
+            PHASE1_MARK(9);   // Linear 3 + Q + #5
             ++iter;
             if (STRICT) {
                 __threadfence();       // Q / H / saved inputs / flags are read back from global memory in the next frame
@@ -752,6 +780,17 @@ int launch_single_prepare(const BiearSeqParams* p, int want, cudaStream_t st) {
     sc::prepare_single_kernel<<<dim3(4 * kCS + 1, 16), 256, 0, st>>>(*p, p->workspace, want);
     BIEAR_LAUNCH_CHECK("prepare_single_kernel");
     return 0;
+}
+
+int debug_phase_cycles_single(unsigned long long* out_host) {
+#ifdef BIEAR_PHASE_PROF
+    unsigned long long zero[16] = {};
+    if (int e = check_cuda(cudaMemcpyFromSymbol(out_host, sc::g_phase_cycles1, sizeof(zero)), "cudaMemcpyFromSymbol")) return e;
+    return check_cuda(cudaMemcpyToSymbol(sc::g_phase_cycles1, zero, sizeof(zero)), "cudaMemcpyToSymbol");
+#else
+    (void)out_host;
+    return fail_invalid("biear_debug_phase_cycles_single: library built without BIEAR_PHASE_PROF");
+#endif
 }
 
 int launch_single_fwd(const BiearSeqParams* p, cudaStream_t st) {

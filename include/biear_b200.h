@@ -223,6 +223,8 @@ int biear_adaptive_occupancy(int N, int F, int* fwd_clusters, int* bwd_clusters)
 /* Diagnostic builds only (-DBIEAR_PHASE_PROF, `make -C biear_b200/csrc prof`): per-phase clock64() totals of block 0 of
  * the forward [0][*] and backward [1][*] recurrence kernels, copied to out_host[2*16 + 8] (the last 8: inside the band stage) and cleared. */
 int biear_debug_phase_cycles(unsigned long long* out_host);
+/* ... and of the single-controller forward kernel (csrc/seq_single.cu): out_host[16]. */
+int biear_debug_phase_cycles_single(unsigned long long* out_host);
 
 /* Whole forward recurrence in ONE persistent cluster kernel (plus a weight-packing launch and a conditional
  * replay launch that exits immediately unless a non-finite Q was produced): each cluster of 4 CTAs carries R rows
