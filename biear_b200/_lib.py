@@ -11,7 +11,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BIEAR_B200_LIB") or os.path.join(_HERE, "lib", "libbiear_b200.so")
-ABI_VERSION = 18
+ABI_VERSION = 19
 
 _p = c_void_p
 _i = c_int
@@ -50,6 +50,15 @@ class WgradJob(Structure):
                 ("dW2", c_void_p), ("scale2", c_float)]
 
 
+class HeadsParams(Structure):
+    """struct BiearHeadsParams of include/biear_b200.h."""
+    _fields_ = [("B", c_int32), ("S", c_int32), ("D", c_int32), ("C", c_int32), ("training", c_int32),
+                ("seed", c_uint64), ("seed_ptr", c_void_p), ("body", c_void_p), ("wptr", c_void_p),
+                ("sound", c_void_p), ("aoa", c_void_p), ("dist", c_void_p),
+                ("g_sound", c_void_p), ("g_aoa", c_void_p), ("g_dist", c_void_p),
+                ("d_body_part", c_void_p), ("dw_part", c_void_p), ("d_body", c_void_p), ("dw", c_void_p)]
+
+
 WGRAD_MAX_JOBS = 8
 
 # name -> (restype, argtypes); mirrors include/biear_b200.h one to one
@@ -84,6 +93,11 @@ SIGNATURES = {
     "biear_ctrl_wgrad": (_i, [POINTER(WgradJob), _i, _i, _i, _p, _p]),
     "biear_wgrad_scratch_floats_tc": (_l, [POINTER(WgradJob), _i, _i, _i]),
     "biear_ctrl_wgrad_tc": (_i, [POINTER(WgradJob), _i, _i, _i, _p, _p]),
+    "biear_heads_tile_rows": (_i, []),
+    "biear_heads_tensors_per_head": (_i, []),
+    "biear_heads_flat_floats": (_l, [_i, _i]),
+    "biear_heads_fwd": (_i, [POINTER(HeadsParams), _p]),
+    "biear_heads_bwd": (_i, [POINTER(HeadsParams), _p]),
     "biear_q_regularizers_workspace_floats": (_l, []),
     "biear_q_regularizers": (_i, [_p, _p, _p, _l, _i, _f, _f, _p, _p, _p, _p]),
 }

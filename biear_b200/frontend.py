@@ -25,7 +25,6 @@ from typing import List, Optional, Tuple
 import numpy as np
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import ops, timing
 
@@ -125,53 +124,6 @@ def _make_controller(in_features: int, Nbands: int):
     return q_rnn, q_out
 
 
-class _ControllerStack:
-    """Weights of G structurally identical controllers stacked along a leading group axis, so that the
-    per-ear chains of the dual front-end run as one batched chain (autograd un-stacks the gradients)."""
-
-    def __init__(self, mods):
-        st = lambda f: torch.stack([f(m) for m in mods])
-        self.w_ih = st(lambda m: m.q_rnn.weight_ih_l0).transpose(1, 2)   # (G, in, 384)
-        self.w_hh = st(lambda m: m.q_rnn.weight_hh_l0).transpose(1, 2)   # (G, 128, 384)
-        self.b_ih = st(lambda m: m.q_rnn.bias_ih_l0).unsqueeze(1)        # (G, 1, 384)
-        self.b_hh = st(lambda m: m.q_rnn.bias_hh_l0).unsqueeze(1)
-        self.lin = []
-        for i in (0, 4, 8):
-            self.lin.append((st(lambda m: m.q_out[i].weight).transpose(1, 2),
-                             st(lambda m: m.q_out[i].bias).unsqueeze(1)))
-        self.ln = []
-        for i in (1, 5):
-            self.ln.append((st(lambda m: m.q_out[i].weight).unsqueeze(1), st(lambda m: m.q_out[i].bias).unsqueeze(1),
-                            mods[0].q_out[i].eps))
-        self.p_drop = mods[0].q_out[3].p
-        self.hid = mods[0].q_rnn.hidden_size
-
-    def step(self, feat: torch.Tensor, h: Optional[torch.Tensor], training: bool):
-        """feat (G,B,in), h (G,B,128) or None -> (pre-tanh output (G,B,N), new h).  torch.nn.GRU gate
-        order (r, z, n) and n = tanh(i_n + r * (W_hn h + b_hn)); q_out as model_torch.py:257-267."""
-        gi = torch.baddbmm(self.b_ih, feat, self.w_ih)
-        if h is None:
-            gh = self.b_hh.expand(-1, feat.shape[1], -1)
-        else:
-            gh = torch.baddbmm(self.b_hh, h, self.w_hh)
-        i_r, i_z, i_n = gi.split(self.hid, dim=-1)
-        h_r, h_z, h_n = gh.split(self.hid, dim=-1)
-        r = torch.sigmoid(i_r + h_r)
-        z = torch.sigmoid(i_z + h_z)
-        n = torch.tanh(i_n + r * h_n)
-        h_new = (1.0 - z) * n if h is None else (1.0 - z) * n + z * h
-        a = h_new
-        for k in range(2):
-            w, b = self.lin[k]
-            g, beta, eps = self.ln[k]
-            a = torch.baddbmm(b, a, w)
-            a = F.layer_norm(a, (a.shape[-1],), None, None, eps) * g + beta
-            a = F.silu(a)
-            a = F.dropout(a, self.p_drop, training)
-        w, b = self.lin[2]
-        return torch.baddbmm(b, a, w), h_new
-
-
 def _next_q(delta, q0, dq, mode):
     if mode == "relative":
         q = q0 * (1.0 + dq * delta)
@@ -192,8 +144,11 @@ def _controller_weights(ctrl_mods):
             "w3": st(lambda m: m.q_out[8].weight), "b3": st(lambda m: m.q_out[8].bias)}
 
 
+CHAIN_ENGINE = None   # test hook: tests/chain_engine.py installs the per-frame band kernel + PyTorch controller cross-check here
+
+
 def _adaptive_chain(x: torch.Tensor, ears: int, ctrl_mods, fc, q0, dq_vec, dq_mode, df, training,
-                    shared: bool, want_phase: bool, band_mode: str, cutoff: float, engine: str = "chain",
+                    shared: bool, want_phase: bool, band_mode: str, cutoff: float, engine: str = "fused",
                     want_logy: bool = False, prep=None):
     """The 19-step Q recurrence for `ears` ears of B clips.
 
@@ -212,8 +167,9 @@ def _adaptive_chain(x: torch.Tensor, ears: int, ctrl_mods, fc, q0, dq_vec, dq_mo
         single = shared and G == 1 and ears == 2
         if not (single or (not shared and G == ears)) or not \
                 (ops.single_supported(N, Fbins) if single else ops.fused_supported(N, Fbins)):
-            raise NotImplementedError("the fused recurrence covers the dual and the single-controller front-end with at "
-                                      "most 128 bands")
+            raise NotImplementedError(f"biear_b200: the fused recurrence kernels cover the dual and the single-controller "
+                                      f"front-end with at most 128 bands and spectra that fit the shared memory of an SM; "
+                                      f"got Nbands={N}, {Fbins} bins (there is no PyTorch fallback)")
         w = _controller_weights(ctrl_mods)
         # CPU generator: no device sync.  (Under CUDA-graph capture the kernels read a device-side seed instead.)
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if training else 0
@@ -221,47 +177,11 @@ def _adaptive_chain(x: torch.Tensor, ears: int, ctrl_mods, fc, q0, dq_vec, dq_mo
                                     df, seed, strict=(engine == "fused-strict"), want_logy=want_logy, prep=prep,
                                     ears=ears)
         return res if want_logy else res + (None,)
-    stack = _ControllerStack(ctrl_mods)
-    q0g = q0.view(1, 1, N)
-    dqg = dq_vec.view(1, 1, N)
-    q = q0.view(1, 1, N).expand(G, B, N)
-    h = None
-    mem = None
-    ys, qs, phs = [], [], []
-    for t in range(T):
-        q_rows = (q.expand(ears, B, N) if shared else q).reshape(rows, N)
-        y, ph = ops.BandFrame.apply(q_rows, xr, t, fc, df, cutoff, want_phase, band_mode)
-        ys.append(y)
-        qs.append(q.reshape(G * B, N))
-        if want_phase:
-            phs.append(ph)
-        if t == T - 1:
-            # The reference runs the controller once more and discards the result (model_torch.py:361-380);
-            # that step only consumes dropout RNG and receives zero gradient, so it is skipped.
-            break
-        yc = torch.log1p(torch.clamp(y, min=0.0)).view(ears, B, N)
-        ycd = yc.detach()
-        if shared:
-            if mem is None:
-                mem = torch.zeros_like(ycd)
-            feat = torch.cat([yc[0], mem[0], yc[1], mem[1]], dim=-1).unsqueeze(0)      # (1,B,4N)
-        else:
-            feat = torch.cat([yc, 0.2 * ycd], dim=-1)                                  # (G,B,2N)
-        pre, h = stack.step(feat, h, training)
-        q_new = _next_q(torch.tanh(pre), q0g, dqg, dq_mode)
-        # batch-global non-finite fallback of the reference, decided per controller, on the device
-        ok = torch.isfinite(q_new).flatten(1).all(dim=1).view(G, 1, 1)
-        # (built from Q0 / zeros directly: NaN * 0 is NaN, and the reference cuts the graph on the fallback branch)
-        q = torch.where(ok, torch.nan_to_num(q_new, nan=0.0, posinf=0.0, neginf=0.0), q0g.expand_as(q_new))
-        h = torch.where(ok, torch.nan_to_num(h, nan=0.0, posinf=0.0, neginf=0.0), torch.zeros_like(h))
-        if shared:
-            mem = 0.8 * mem + 0.2 * ycd
-    y_all = torch.stack(ys, dim=1)
-    q_all = torch.stack(qs, dim=1)
-    ph_all = torch.stack(phs, dim=1) if want_phase else None
-    lx_all = _log_energy(y_all) if want_logy else None
-    split = lambda t, k: [t[i * B:(i + 1) * B] for i in range(k)] if t is not None else None
-    return split(y_all, ears), split(q_all, G), split(ph_all, ears), split(lx_all, ears)
+    if engine == "chain" and CHAIN_ENGINE is not None:
+        return CHAIN_ENGINE(x, ears, ctrl_mods, fc, q0, dq_vec, dq_mode, df, training, shared, want_phase, band_mode, cutoff,
+                            want_logy)
+    raise NotImplementedError(f"biear_b200: engine {engine!r} is not available (the per-frame cross-check engine lives in "
+                              "tests/chain_engine.py); the product path is the fused recurrence")
 
 
 def _log_energy(y: torch.Tensor) -> torch.Tensor:
@@ -314,7 +234,7 @@ class FramewiseAdaptiveGammatoneFB(_FilterbankBase):
             return y, self.Q0.view(1, 1, -1).expand(x.shape[0], self.timesteps, -1), x
         y, q, _, _ = _adaptive_chain(x, 1, [self], self.fc, self.Q0, self.deltaQ_vec, self.deltaQ_mode, self.df,
                                      self.training, False, False, self.band_mode, self.cutoff,
-                                     self.engine if ops.fused_supported(self.Nbands, self.n_fft // 2 + 1) else "chain")
+                                     self.engine)
         return y[0], q[0], x
 
 
@@ -552,7 +472,7 @@ class BinauralAdaptiveGammatoneFB(nn.Module):
         self._graphs = _GraphCache()
         # "fused": the whole recurrence in one persistent cluster kernel per direction (csrc/seq.cu);
         # "fused-strict": only its batch-global-fallback replay pass (testing);
-        # "chain": per-frame band kernel + batched torch controller (kept as a cross-check)
+        # ("chain": the per-frame cross-check engine of tests/chain_engine.py, when the tests have installed it)
         self.engine = "fused"
 
     def forward_features(self, wavL_1s: torch.Tensor, wavR_1s: torch.Tensor, want_phase: bool = True,
@@ -642,7 +562,7 @@ class BinauralAdaptiveGammatoneFB(nn.Module):
         else:
             if self.fb_L.freeze_Q != self.fb_R.freeze_Q:
                 raise NotImplementedError("freeze_Q on one ear only")
-            engine = self.engine if ops.fused_supported(fb.Nbands, fb.n_fft // 2 + 1) else "chain"
+            engine = self.engine
             y, q, ph, lx = _adaptive_chain(x, 2, [self.fb_L, self.fb_R], fb.fc, fb.Q0, fb.deltaQ_vec, fb.deltaQ_mode,
                                            fb.df, self.training, False, want_phase, fb.band_mode, fb.cutoff, engine,
                                            want_logy=want_logenergy, prep=prep if engine == self.engine else None)
@@ -686,7 +606,7 @@ class BinauralAdaptiveGammatoneFB_SingleController(_FilterbankBase):
         self.cutoff = ops.DEFAULT_CUTOFF
         self.graph_replay = GRAPH_REPLAY_DEFAULT      # see _GraphCache
         self._graphs = _GraphCache()
-        self.engine = "fused"                         # "chain": per-frame launches + PyTorch controller (cross-check)
+        self.engine = "fused"                         # ("chain": the cross-check engine of tests/chain_engine.py)
         if not self.fixed_frontend_q:
             self.q_rnn, self.q_out = _make_controller(4 * Nbands, Nbands)
             self.fb_L = self.fb_R = None
@@ -718,7 +638,7 @@ class BinauralAdaptiveGammatoneFB_SingleController(_FilterbankBase):
             y, ph = [y[:B], y[B:]], ([ph[:B], ph[B:]] if ph is not None else None)
             lx = None
         else:
-            engine = self.engine if ops.single_supported(self.Nbands, self.n_fft // 2 + 1) else "chain"
+            engine = self.engine
             y, q, ph, lx = _adaptive_chain(x, 2, [self], self.fc, self.Q0, self.deltaQ_vec, self.deltaQ_mode, self.df,
                                            self.training, True, want_phase, self.band_mode, self.cutoff, engine,
                                            want_logy=want_logenergy)

@@ -23,6 +23,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+from . import ops
 from .frontend import (AuralNetGammatoneFB, BinauralAdaptiveGammatoneFB,  # noqa: F401  (re-exported)
                        BinauralAdaptiveGammatoneFB_SingleController, FramewiseAdaptiveGammatoneFB,
                        FramewiseFixedGammatoneFB, erb_hz, erb_rate, erb_spaced_fc_and_q, inv_erb_rate,
@@ -138,6 +139,7 @@ class _BackEnd(nn.Module):
             self.cc_proj = nn.Linear(data_dim, latent_dim)
         self.body = _body(2 * latent_dim + (latent_dim if use_cc else 0))
         self.subheads = nn.ModuleList([SubHead(200, n_dist_class=n_dist_class) for _ in range(n_sectors)])
+        self.native_heads = True      # False: the torch.nn modules (the cross-check; what CPU tensors always take)
 
     def _backend(self, x1, x2, x3, ph_l, ph_r):
         branches = [lambda: self.encoder_ild(x1, x2), lambda: self.encoder_ipd(ph_l, ph_r)]
@@ -145,7 +147,11 @@ class _BackEnd(nn.Module):
             branches.append(lambda: self.cc_proj(x3))
         feats = _fork_join(branches, x1)
         body = self.body(torch.cat(feats, dim=-1))
-        outs = _fork_join([lambda h=head: h(body) for head in self.subheads], body)
+        if body.is_cuda and self.native_heads and body.dtype == torch.float32 and body.shape[1] % 4 == 0 \
+                and body.shape[1] <= 200:
+            # all sector heads in one launch forward, one backward (csrc/heads.cu)
+            return ops.sector_heads(body, list(self.subheads), self.training)
+        outs = _fork_join([lambda h=head: h(body) for head in self.subheads], body)     # host tensors: torch.nn
         sound = torch.cat([o[0] for o in outs], dim=1)
         aoa = torch.cat([o[1] for o in outs], dim=1)
         dist = torch.stack([o[2] for o in outs], dim=1)

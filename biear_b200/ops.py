@@ -754,3 +754,108 @@ def adaptive_sequence(xr, fc, q0, dq, weights, relative: bool, training: bool, w
     if want_logy:
         return y, q, (ph if want_phase else None), lx
     return y, q, (ph if want_phase else None)
+
+
+# ------------------------------------------------------------------------------------------------
+# back-end: the per-sector heads (csrc/heads.cu)
+# ------------------------------------------------------------------------------------------------
+HEAD_TENSOR_NAMES = ("shared.0.weight", "shared.0.bias") + tuple(
+    f"{b}.{i}.{w}" for b in ("sound", "aoa", "dist") for i in (0, 2, 4) for w in ("weight", "bias"))
+_head_tables = {}   # (device index, data_ptrs) -> int64 device tensor of parameter pointers
+
+
+def _head_table(params, dev) -> torch.Tensor:
+    """Device table of the heads' parameter pointers (rebuilt only when a parameter's storage moves)."""
+    ptrs = tuple(p.data_ptr() for p in params)
+    key = (dev.index, ptrs)
+    tab = _head_tables.get(key)
+    if tab is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("biear_b200: run the model once eagerly (warm-up) before capturing it in a CUDA graph")
+        if len(_head_tables) > 16:
+            _head_tables.clear()
+        tab = torch.tensor(ptrs, dtype=torch.int64).to(dev)
+        _head_tables[key] = tab
+    return tab
+
+
+class SectorHeads(torch.autograd.Function):
+    """All sector heads (model_torch.py:869-906 and the loop at :941-955 / :1096-1110) as one forward and one backward
+    launch.  Inputs: body (B,D), then the S * 20 head parameters in state-dict order (the nn.Linear parameters
+    themselves).  Outputs: sound logits (B,S), aoa in (0,1) (B,S), distance logits (B,S,C)."""
+
+    @staticmethod
+    def forward(ctx, body, S, C, training, seed, *params):
+        _need_cuda(body, "body")
+        dev = body.device
+        body = body.contiguous()
+        B, D = body.shape
+        with torch.cuda.device(dev):
+            lib = _prepare(dev)
+            per = int(lib.biear_heads_tensors_per_head())
+            assert len(params) == S * per
+            ps = tuple(p.detach() for p in params)
+            for p_ in ps:
+                _need_cuda(p_, "head parameter")
+                assert p_.is_contiguous()
+            table = _head_table(ps, dev)
+            f32 = dict(dtype=torch.float32, device=dev)
+            sound, aoa, dist = torch.empty((B, S), **f32), torch.empty((B, S), **f32), torch.empty((B, S, C), **f32)
+            seed_dev = _captured_seed(dev) if (training and torch.cuda.is_current_stream_capturing()) else None
+            prm = _lib.HeadsParams()
+            prm.B, prm.S, prm.D, prm.C, prm.training, prm.seed = B, S, D, C, int(training), int(seed)
+            _fill(prm, seed_ptr=seed_dev, body=body, wptr=table, sound=sound, aoa=aoa, dist=dist)
+            from ctypes import byref
+            _lib.check(lib.biear_heads_fwd(byref(prm), _stream(dev)), "biear_heads_fwd")
+        ctx.prm = prm
+        ctx.keep = (body, ps, table, seed_dev, sound, aoa, dist)
+        ctx.shapes = [tuple(p_.shape) for p_ in ps]
+        return sound, aoa, dist
+
+    @staticmethod
+    def backward(ctx, g_sound, g_aoa, g_dist):
+        from ctypes import byref
+        body, ps, table, seed_dev, sound, aoa, dist = ctx.keep
+        dev = body.device
+        B, D = body.shape
+        prm = ctx.prm
+        S, C = prm.S, prm.C
+        cont = lambda g: g.contiguous() if g is not None else None
+        g_sound, g_aoa, g_dist = cont(g_sound), cont(g_aoa), cont(g_dist)
+        with torch.cuda.device(dev):
+            lib = _prepare(dev)
+            flat = int(lib.biear_heads_flat_floats(D, C))
+            tiles = (B + int(lib.biear_heads_tile_rows()) - 1) // int(lib.biear_heads_tile_rows())
+            f32 = dict(dtype=torch.float32, device=dev)
+            d_body_part, dw_part = torch.empty((S, B, D), **f32), torch.empty((tiles, S, flat), **f32)
+            d_body, dw = torch.empty((B, D), **f32), torch.empty((S, flat), **f32)
+            _fill(prm, g_sound=g_sound, g_aoa=g_aoa, g_dist=g_dist, d_body_part=d_body_part, dw_part=dw_part,
+                  d_body=d_body, dw=dw)
+            _lib.check(lib.biear_heads_bwd(byref(prm), _stream(dev)), "biear_heads_bwd")
+            _fill(prm, g_sound=None, g_aoa=None, g_dist=None, d_body_part=None, dw_part=None, d_body=None, dw=None)
+        grads = []
+        per = len(ctx.shapes) // S
+        for s_ in range(S):
+            off = 0
+            for j in range(per):
+                shp = ctx.shapes[s_ * per + j]
+                n = 1
+                for d_ in shp:
+                    n *= d_
+                grads.append(dw[s_, off:off + n].view(shp))
+                off += n
+            assert off == flat
+        return (d_body, None, None, None, None) + tuple(grads)
+
+
+def sector_heads(body: torch.Tensor, head_modules, training: bool):
+    """head_modules: the S SubHead modules (shared / sound / aoa / dist as in model_torch.py:869-906)."""
+    params = []
+    for h in head_modules:
+        sd = dict(h.named_parameters())
+        params += [sd[k] for k in HEAD_TENSOR_NAMES]
+    S = len(head_modules)
+    C = head_modules[0].dist[4].out_features
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if training else 0
+    return SectorHeads.apply(body, S, C, bool(training), seed, *params)
+

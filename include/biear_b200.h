@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BIEAR_ABI_VERSION 18
+#define BIEAR_ABI_VERSION 19
 #define BIEAR_EINVAL (-1)
 
 /* ABI version (== BIEAR_ABI_VERSION of the library that was built). */
@@ -298,6 +298,38 @@ int biear_cc_fwd(const float* wavL, const float* wavR, int64_t B, int64_t nsamp,
 int64_t biear_q_regularizers_workspace_floats(void);
 int biear_q_regularizers(const float* QA, const float* QB, const float* Q0, int64_t rows, int N, float w_reg,
                          float w_smooth, float* out, float* gQ, float* workspace, void* stream);
+
+/*
+ * The per-sector heads of the back-end, all S heads in ONE forward and ONE backward launch (+ two
+ * fixed-order reductions).  Replaces SubHead.forward and the loop over self.subheads, model_torch.py:869-906, 941-955,
+ * 1096-1110 (80 small GEMMs and ~100 element-wise launches forward, three times that backward):
+ *   h = Dropout_0.2(ReLU(Linear(D,100)(body)));  three branches Linear(100,50)-ReLU-Linear(50,10)-ReLU-Linear(10,k):
+ *   sound (k = 1, logit), aoa (k = 1, sigmoid applied), dist (k = C, logits).
+ * wptr: DEVICE array of S * biear_heads_tensors_per_head() (= 20) pointers to the heads' parameters in state-dict order
+ *   (shared.0.weight, shared.0.bias, sound.0.weight, sound.0.bias, sound.2.*, sound.4.*, aoa.*, dist.*), torch (out, in)
+ *   layout -- the nn.Linear parameters themselves, no packing copy.
+ * Outputs sound (B,S), aoa (B,S), dist (B,S,C).  Dropout: Philox keyed by (seed | *seed_ptr, head, row, unit quad),
+ *   regenerated by the backward (which recomputes the forward of its tile: no activations are saved).
+ * Backward: g_sound / g_aoa (B,S), g_dist (B,S,C), each nullable -> d_body (B,D) and dw (S, biear_heads_flat_floats(D,C))
+ *   = every head's parameter gradients concatenated in state-dict order; scratch d_body_part (S,B,D) and
+ *   dw_part (ceil(B / biear_heads_tile_rows()), S, flat).  Deterministic (no atomics).
+ */
+typedef struct BiearHeadsParams {
+    int32_t B, S, D, C;              /* clips, sectors, body width (multiple of 4, <= 200), distance classes (<= 8) */
+    int32_t training;                /* dropout on */
+    uint64_t seed;
+    const uint64_t* seed_ptr;        /* optional device seed (overrides `seed`; for captured graphs) */
+    const float* body;               /* (B, D) */
+    const float* const* wptr;        /* device table of parameter pointers, see above */
+    float *sound, *aoa, *dist;
+    const float *g_sound, *g_aoa, *g_dist;
+    float *d_body_part, *dw_part, *d_body, *dw;
+} BiearHeadsParams;
+int biear_heads_tile_rows(void);
+int biear_heads_tensors_per_head(void);
+int64_t biear_heads_flat_floats(int D, int C);
+int biear_heads_fwd(const BiearHeadsParams* p, void* stream);
+int biear_heads_bwd(const BiearHeadsParams* p, void* stream);
 
 #ifdef __cplusplus
 }

@@ -27,3 +27,6 @@ def _eager_frontend_by_default(monkeypatch):
     except Exception:  # noqa: BLE001
         return
     monkeypatch.setattr(fe, "GRAPH_REPLAY_DEFAULT", False)
+    # `module.engine = "chain"` selects the per-frame cross-check engine (test infrastructure, tests/chain_engine.py)
+    from tests import chain_engine
+    monkeypatch.setattr(fe, "CHAIN_ENGINE", chain_engine.run)

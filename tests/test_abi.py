@@ -38,10 +38,13 @@ def test_ctypes_structs_match_the_header(tmp_path):
     probe = tmp_path / "probe.c"
     fields_seq = ["G", "seed", "df", "fc", "w_ih", "b3", "X", "Q", "delta", "gates", "H", "flags", "gY", "GG", "workspace", "seed_ptr", "gLogY", "prepared"]
     fields_job = ["A", "Do", "Bm", "Di", "chunks", "dW", "db", "dw_group_stride", "db_group_stride", "dW2", "scale2"]
+    fields_heads = ["B", "C", "training", "seed", "seed_ptr", "body", "wptr", "dist", "g_sound", "d_body_part", "dw"]
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){",
              'printf("%zu %zu\\n", sizeof(BiearSeqParams), sizeof(BiearWgradJob));']
     lines += [f'printf("%zu\\n", offsetof(BiearSeqParams, {f}));' for f in fields_seq]
     lines += [f'printf("%zu\\n", offsetof(BiearWgradJob, {f}));' for f in fields_job]
+    lines += ['printf("%zu\\n", sizeof(BiearHeadsParams));']
+    lines += [f'printf("%zu\\n", offsetof(BiearHeadsParams, {f}));' for f in fields_heads]
     lines += ["return 0;}"]
     probe.write_text("\n".join(lines))
     exe = tmp_path / "probe"
@@ -50,6 +53,7 @@ def test_ctypes_structs_match_the_header(tmp_path):
     assert [int(out[0]), int(out[1])] == [ctypes.sizeof(_lib.SeqParams), ctypes.sizeof(_lib.WgradJob)]
     offs = [int(x) for x in out[2:]]
     want = [getattr(_lib.SeqParams, f).offset for f in fields_seq] + [getattr(_lib.WgradJob, f).offset for f in fields_job]
+    want += [ctypes.sizeof(_lib.HeadsParams)] + [getattr(_lib.HeadsParams, f).offset for f in fields_heads]
     assert offs == want
 
 

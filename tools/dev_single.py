@@ -7,6 +7,8 @@ import torch
 import biear_b200 as bb
 from oracle import biear_oracle as orc
 from tests.common import CONFIG_SINGLE
+from tests import chain_engine
+chain_engine.install()
 
 DEV = "cuda:0"
 kw = dict(deltaQ_base=CONFIG_SINGLE["deltaq_base"], deltaQ_low_factor=CONFIG_SINGLE["deltaq_low"],
