@@ -60,66 +60,121 @@ struct Smem {   // offsets in floats
 };
 
 // torch-layout W (out, in) -> dst[k * pitch + o]  (coalesced global reads; conflict-free stores for an odd pitch)
+// (128-bit loads, 8 in flight per thread: the copy is bound by the latency of its loads -- 32 KB in flight per CTA)
 __device__ __forceinline__ void load_wT(float* __restrict__ dst, const float* __restrict__ W, int out, int in, int pitch) {
-    for (int idx = threadIdx.x; idx < out * in; idx += kThreads) {
+    const int n = out * in;
+    if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0) {
+        const float4* W4 = reinterpret_cast<const float4*>(W);
+        const int n4 = n >> 2;
+        for (int base = threadIdx.x; base < n4; base += 8 * kThreads) {
+            float4 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int i4 = base + j * kThreads;
+                v[j] = i4 < n4 ? __ldg(W4 + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int i4 = base + j * kThreads;
+                if (i4 < n4) {
+                    const float e[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+                    int o = (4 * i4) / in, k = 4 * i4 - o * in;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        dst[k * pitch + o] = e[c];
+                        if (++k == in) { k = 0; ++o; }
+                    }
+                }
+            }
+        }
+        return;
+    }
+    for (int idx = threadIdx.x; idx < n; idx += kThreads) {
         const int o = idx / in, k = idx - o * in;
         dst[k * pitch + o] = __ldg(W + idx);
     }
 }
 
 // out_s[o][r] = act(b[o] + sum_k in_s[k][r] * WT_s[k * pitch + o])  for o < outN and the tile's 32 rows.
-// thread = (o = tid % 128, row half = tid / 128); outN <= 128.  ACT: 0 none, 1 ReLU.
+// thread = (unit pair = tid % 64 -> units 2p, 2p + 1; row group = tid / 64 -> 8 rows): a 2 x 8 register tile, so that per k
+// the warp spends 10 shared-memory cycles (two 128-bit broadcast loads of x, two weights) on 16 FMAs -- with one unit per
+// thread the products are bound by the shared-memory pipe, not by the FMA pipe.  outN <= 128.  ACT: 0 none, 1 ReLU.
 template <int ACT>
 __device__ __forceinline__ void dense(const float* __restrict__ in_s, const float* __restrict__ wT_s, int pitch,
                                       const float* __restrict__ b_s, float* __restrict__ out_s, int K, int outN) {
-    const int o = threadIdx.x & 127, rh = threadIdx.x >> 7;
-    if (o < outN) {
-        float acc[16];
-        const float bb = b_s[o];
+    const int o0 = (threadIdx.x & 63) * 2, rg = threadIdx.x >> 6;
+    if (o0 < outN) {
+        const bool two = o0 + 1 < outN;
+        const int o1 = two ? o0 + 1 : o0;
+        float2 a0[4], a1[4];      // 8 rows as 4 packed pairs per unit
+        const float b0 = b_s[o0], b1 = b_s[o1];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) acc[i] = bb;
-        const float* xin = in_s + rh * 16;
-#pragma unroll 2
+        for (int i = 0; i < 4; ++i) {
+            a0[i] = make_float2(b0, b0);
+            a1[i] = make_float2(b1, b1);
+        }
+        const float* xin = in_s + rg * 8;
+#pragma unroll 4
         for (int k = 0; k < K; ++k) {
-            const float w = wT_s[k * pitch + o];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float4 x = *reinterpret_cast<const float4*>(xin + k * kHP + 4 * q);
-                acc[4 * q] = fmaf(w, x.x, acc[4 * q]);
-                acc[4 * q + 1] = fmaf(w, x.y, acc[4 * q + 1]);
-                acc[4 * q + 2] = fmaf(w, x.z, acc[4 * q + 2]);
-                acc[4 * q + 3] = fmaf(w, x.w, acc[4 * q + 3]);
-            }
+            const float w0 = wT_s[k * pitch + o0], w1 = wT_s[k * pitch + o1];
+            const float2 p0 = make_float2(w0, w0), p1 = make_float2(w1, w1);
+            const float4 xa = *reinterpret_cast<const float4*>(xin + k * kHP);
+            const float4 xb = *reinterpret_cast<const float4*>(xin + k * kHP + 4);
+            const float2 x0 = make_float2(xa.x, xa.y), x1 = make_float2(xa.z, xa.w), x2 = make_float2(xb.x, xb.y), x3 = make_float2(xb.z, xb.w);
+            a0[0] = __ffma2_rn(p0, x0, a0[0]); a0[1] = __ffma2_rn(p0, x1, a0[1]);
+            a0[2] = __ffma2_rn(p0, x2, a0[2]); a0[3] = __ffma2_rn(p0, x3, a0[3]);
+            a1[0] = __ffma2_rn(p1, x0, a1[0]); a1[1] = __ffma2_rn(p1, x1, a1[1]);
+            a1[2] = __ffma2_rn(p1, x2, a1[2]); a1[3] = __ffma2_rn(p1, x3, a1[3]);
         }
 #pragma unroll
-        for (int i = 0; i < 16; ++i) out_s[o * kHP + rh * 16 + i] = ACT == 1 ? fmaxf(acc[i], 0.0f) : acc[i];
+        for (int i = 0; i < 4; ++i) {
+            out_s[o0 * kHP + rg * 8 + 2 * i] = ACT == 1 ? fmaxf(a0[i].x, 0.0f) : a0[i].x;
+            out_s[o0 * kHP + rg * 8 + 2 * i + 1] = ACT == 1 ? fmaxf(a0[i].y, 0.0f) : a0[i].y;
+            if (two) {
+                out_s[o1 * kHP + rg * 8 + 2 * i] = ACT == 1 ? fmaxf(a1[i].x, 0.0f) : a1[i].x;
+                out_s[o1 * kHP + rg * 8 + 2 * i + 1] = ACT == 1 ? fmaxf(a1[i].y, 0.0f) : a1[i].y;
+            }
+        }
     }
 }
 
-// Transposed product: din_s[k][r] (+)= sum_o dout_s[o][r] * WT_s[k * pitch + o]  for k < K.  thread = (k = tid % 128 (+128), row half)
+// Transposed product: din_s[k][r] (+)= sum_o dout_s[o][r] * WT_s[k * pitch + o]  for k < K.
+// thread = (k pair: k0 = tid % 64 (+ 128 j), k0 + 64; row group of 8 rows): the same 2 x 8 register tile.
 template <bool ACCUM>
 __device__ __forceinline__ void dense_t(const float* __restrict__ dout_s, const float* __restrict__ wT_s, int pitch,
                                         float* __restrict__ din_s, int K, int outN) {
-    const int rh = threadIdx.x >> 7;
-    for (int k = threadIdx.x & 127; k < K; k += 128) {
-        float acc[16];
+    const int rg = threadIdx.x >> 6;
+    for (int k0 = threadIdx.x & 63; k0 < K; k0 += 128) {
+        const bool two = k0 + 64 < K;
+        const int k1 = two ? k0 + 64 : k0;
+        float2 a0[4], a1[4];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) acc[i] = ACCUM ? din_s[k * kHP + rh * 16 + i] : 0.0f;
-        const float* d = dout_s + rh * 16;
-#pragma unroll 2
+        for (int i = 0; i < 4; ++i) {
+            a0[i] = ACCUM ? make_float2(din_s[k0 * kHP + rg * 8 + 2 * i], din_s[k0 * kHP + rg * 8 + 2 * i + 1]) : make_float2(0.f, 0.f);
+            a1[i] = ACCUM ? make_float2(din_s[k1 * kHP + rg * 8 + 2 * i], din_s[k1 * kHP + rg * 8 + 2 * i + 1]) : make_float2(0.f, 0.f);
+        }
+        const float* d = dout_s + rg * 8;
+#pragma unroll 4
         for (int o = 0; o < outN; ++o) {
-            const float w = wT_s[k * pitch + o];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float4 x = *reinterpret_cast<const float4*>(d + o * kHP + 4 * q);
-                acc[4 * q] = fmaf(w, x.x, acc[4 * q]);
-                acc[4 * q + 1] = fmaf(w, x.y, acc[4 * q + 1]);
-                acc[4 * q + 2] = fmaf(w, x.z, acc[4 * q + 2]);
-                acc[4 * q + 3] = fmaf(w, x.w, acc[4 * q + 3]);
-            }
+            const float w0 = wT_s[k0 * pitch + o], w1 = wT_s[k1 * pitch + o];
+            const float2 p0 = make_float2(w0, w0), p1 = make_float2(w1, w1);
+            const float4 xa = *reinterpret_cast<const float4*>(d + o * kHP);
+            const float4 xb = *reinterpret_cast<const float4*>(d + o * kHP + 4);
+            const float2 x0 = make_float2(xa.x, xa.y), x1 = make_float2(xa.z, xa.w), x2 = make_float2(xb.x, xb.y), x3 = make_float2(xb.z, xb.w);
+            a0[0] = __ffma2_rn(p0, x0, a0[0]); a0[1] = __ffma2_rn(p0, x1, a0[1]);
+            a0[2] = __ffma2_rn(p0, x2, a0[2]); a0[3] = __ffma2_rn(p0, x3, a0[3]);
+            a1[0] = __ffma2_rn(p1, x0, a1[0]); a1[1] = __ffma2_rn(p1, x1, a1[1]);
+            a1[2] = __ffma2_rn(p1, x2, a1[2]); a1[3] = __ffma2_rn(p1, x3, a1[3]);
         }
 #pragma unroll
-        for (int i = 0; i < 16; ++i) din_s[k * kHP + rh * 16 + i] = acc[i];
+        for (int i = 0; i < 4; ++i) {
+            din_s[k0 * kHP + rg * 8 + 2 * i] = a0[i].x;
+            din_s[k0 * kHP + rg * 8 + 2 * i + 1] = a0[i].y;
+            if (two) {
+                din_s[k1 * kHP + rg * 8 + 2 * i] = a1[i].x;
+                din_s[k1 * kHP + rg * 8 + 2 * i + 1] = a1[i].y;
+            }
+        }
     }
 }
 
@@ -171,9 +226,28 @@ __device__ __forceinline__ void shared_layer(const BiearHeadsParams& p, const fl
     float* hs_s = smem + L.hs();
     float* b_s = smem + L.bias();
     const int D = p.D;
-    for (int idx = threadIdx.x; idx < kRows * D; idx += kThreads) {     // coalesced over the features of a row
-        const int r = idx / D, k = idx - r * D;
-        x_s[k * kHP + r] = r0 + r < p.B ? __ldg(p.body + (long long)(r0 + r) * D + k) : 0.0f;
+    {   // body tile, 128-bit loads (D % 4 == 0), 8 in flight per thread
+        const int D4 = D >> 2, n4 = kRows * D4;
+        const float4* b4 = reinterpret_cast<const float4*>(p.body + (long long)r0 * D);
+        for (int base = threadIdx.x; base < n4; base += 8 * kThreads) {
+            float4 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int i4 = base + j * kThreads, r = i4 / D4;
+                v[j] = (i4 < n4 && r0 + r < p.B) ? __ldg(b4 + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int i4 = base + j * kThreads;
+                if (i4 < n4) {
+                    const int r = i4 / D4, k = 4 * (i4 - r * D4);
+                    x_s[k * kHP + r] = v[j].x;
+                    x_s[(k + 1) * kHP + r] = v[j].y;
+                    x_s[(k + 2) * kHP + r] = v[j].z;
+                    x_s[(k + 3) * kHP + r] = v[j].w;
+                }
+            }
+        }
     }
     load_wT(ws_s, wp[0], kH1, D, odd(kH1));
     for (int i = threadIdx.x; i < kH1; i += kThreads) b_s[i] = __ldg(wp[1] + i);
