@@ -461,6 +461,15 @@ def run_ours(args):
     # ---- dominant kernel alone, for the roofline line ----------------------------------------------
     roof = kernel_roofline(model, dev_in, dev, B)
 
+    # BASELINE config 4 at N > 1 (every rank takes part: its all-reduce is the 1 634 780-float bucket of the whole model)
+    full_multi = None
+    if dist is not None and not args.no_extra and not args.eager:
+        import bench_extra
+        try:
+            full_multi = bench_extra.full_step(B, steps=30, device=str(dev), world=world, rank=rank, dist=dist)
+        except Exception as e:  # noqa: BLE001
+            full_multi = {"error": repr(e)[:300]}
+
     times = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -515,6 +524,8 @@ def run_ours(args):
                 out[key] = fn()
             except Exception as e:  # noqa: BLE001  (a failing side measurement must not lose the main line)
                 out[key] = {"error": repr(e)[:300]}
+    if full_multi is not None:
+        out["full_step"] = full_multi
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = bench_extra.reference_cpu(sample_batch=16, budget_s=20.0)
     print(json.dumps(out), flush=True)

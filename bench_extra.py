@@ -288,12 +288,16 @@ def build_full_step(batch, dev, world=1, rank=0):
     return full, step, model, sum(p.numel() for p in params)
 
 
-def full_step(batch=256, steps=30, device="cuda:0"):
+def full_step(batch=256, steps=30, device="cuda:0", world=1, rank=0, dist=None):
+    """world > 1: every rank calls this (batch clips each); the gradients of the whole model (one flat bucket of 1 634 780
+    floats, written by the step's graph) are all-reduced over NCCL between the backward and the clips; time = max over ranks."""
     dev = torch.device(device)
-    full, step, model, numel = build_full_step(batch, dev)
+    full, step, model, numel = build_full_step(batch, dev, world=world, rank=rank)
     for _ in range(3):
         full()
     torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
@@ -301,12 +305,21 @@ def full_step(batch=256, steps=30, device="cuda:0"):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
-    out = {"value": batch / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "batch": batch,
-           "loss": float(loss), "launches_of_ours_per_step": step.launches_per_replay, "parameters": numel,
-           "workload": "BASELINE config 4 on 1 GPU: full active training step (front-end + ILD/IPD encoders + body + 8 heads, "
-                       "the reference's losses + Q regularisers, two global-norm clips, Adam with two groups), forward + "
-                       "backward as one CUDA graph, clips + Adam as a second; resident inputs"}
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    out = {"value": batch * world / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "batch_per_gpu": batch,
+           "n_gpus": world, "loss": float(loss), "launches_of_ours_per_step": step.launches_per_replay, "parameters": numel,
+           "allreduce_floats": numel if world > 1 else 0,
+           "workload": f"BASELINE config 4 on {world} GPU(s): full active training step (front-end + ILD/IPD encoders + body "
+                       "+ 8 native sector heads, the reference's losses + Q regularisers, "
+                       + ("NCCL all-reduce of the whole model's gradient bucket, " if world > 1 else "")
+                       + "two global-norm clips, Adam with two groups), forward + backward as one CUDA graph, clips + Adam "
+                       "as a second; resident inputs"}
     del full, step, model
+    import gc
+    gc.collect()
     torch.cuda.empty_cache()
     return out
 

@@ -59,8 +59,11 @@ class FlatGradAllReducer:
         if world > 1:
             if weight is not None:
                 self.flat.mul_(weight)
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-            if weight is None:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            elif dist.get_backend(self.group) == "nccl":
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)    # the 1 / world scaling rides in the collective
+            else:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
                 self.flat.mul_(1.0 / world)
         if not self.aliased:
             for p, v in zip(self.params, self.views):
@@ -76,6 +79,9 @@ def captured_average(world: int, group: Optional[dist.ProcessGroup] = None):
     scale by 1 / world, both recorded inside the step's CUDA graph (NCCL collectives are capturable), so that the exchange
     replays with the step -- behind the kernel that produces the bucket -- instead of being issued by the host per step."""
     def sync(flat: torch.Tensor):
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-        flat.mul_(1.0 / world)
+        if dist.get_backend(group) == "nccl":
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
+        else:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+            flat.mul_(1.0 / world)
     return sync

@@ -1,7 +1,11 @@
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_heads.py -x -q > gpurun_out/r2n_pytest_heads.log 2>&1; tail -3 gpurun_out/r2n_pytest_heads.log
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:heads --csv --log-file gpurun_out/r2n_heads_launches.csv python -m pytest tests/test_gpu_heads.py -x -q -k "256" > /dev/null 2>&1
-python tools/launch_summary.py gpurun_out/r2n_heads_launches.csv 10
-timeout 600 python tools/train_step_bench.py 256 30 2>&1 | tail -1
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 200 --warmup 10 > gpurun_out/r2p_bench_2gpu.json 2> gpurun_out/r2p_bench_2gpu.err; echo "rc=$?"
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r2p_bench_2gpu.json').read().strip().splitlines()[-1])
+print("value", d['value'], "ms", d['ms_per_step'], "e2e", d['e2e']['value'], d['e2e']['ms_per_step'])
+print(d.get('full_step'))
+PY
+tail -3 gpurun_out/r2p_bench_2gpu.err
