@@ -1,8 +1,7 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-BIEAR_B200_LIB=$PWD/biear_b200/lib/libbiear_b200_prev.so timeout 600 ncu --set full --clock-control none -k regex:seq_fwd2 -c 2 -o gpurun_out/r2t_prev python tools/run_once.py 256 2 > /dev/null 2>&1
-timeout 600 ncu --set full --clock-control none -k regex:seq_fwd2 -c 2 -o gpurun_out/r2t_new python tools/run_once.py 256 2 > /dev/null 2>&1
-for v in prev new; do
-python tools/ncu_summary.py gpurun_out/r2t_$v.ncu-rep gpurun_out/r2t_ncu_$v > /dev/null 2>&1; cat gpurun_out/r2t_ncu_$v.txt | head -12
+for flag in "" "--graph-allreduce"; do
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 8 --steps 300 --warmup 10 --no-extra $flag 2>/dev/null | python -c "
+import sys,json
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$flag', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], d['e2e']['ms_per_step'], d['config']['allreduce'])"
 done
-rm -f gpurun_out/r2t_prev.ncu-rep
