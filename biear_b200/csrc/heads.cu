@@ -14,6 +14,10 @@
 // regenerates the dropout mask from the Philox key.  Weight gradients: thread = input feature, its 32 rows in registers,
 // one dot product per output unit, written as per-(tile, head) partials that a fixed-order second pass sums
 // (deterministic, no atomics); dL/dbody likewise as per-head partials.
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "common.cuh"
 #include "seq_dev.cuh"   // philox4x32_10
 
@@ -402,7 +406,17 @@ static int validate(const BiearHeadsParams* p, const char* who) {
 template <typename Kern>
 static int set_smem(Kern kern, size_t smem, const char* name) {
     BIEAR_REQUIRE(smem <= 227 * 1024, "%s needs %zu B of shared memory", name, smem);
-    return check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name);
+    // per device and sticky: only the first launch (or a larger geometry) makes the attribute call
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> configured;
+    int dev = 0;
+    if (int e = check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& have = configured[{dev, reinterpret_cast<const void*>(kern)}];
+    if (have >= smem) return 0;
+    if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name)) return e;
+    have = smem;
+    return 0;
 }
 
 }  // namespace hd

@@ -23,6 +23,10 @@
 //
 // STRICT = true is the replay pass with the reference's batch-global fallback semantics (one cluster walks all half-tiles
 // frame by frame, state through global memory); it exits at once unless the fast pass recorded a non-finite Q.
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "band_dev.cuh"
 #include "seq_dev.cuh"
 
@@ -752,8 +756,22 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq1_fwd_kernel(const BiearSeq
 
 template <typename Kern>
 static int launch(Kern kern, const char* name, int clusters, size_t smem, cudaStream_t st, const BiearSeqParams& p) {
-    int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name);
+    // the shared-memory opt-in is per device and sticky: remember the largest size set, so that steady-state launches (and
+    // launches recorded into a CUDA graph) make no attribute call
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> configured;
+    int dev = 0;
+    int e = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
     if (e) return e;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        size_t& have = configured[{dev, reinterpret_cast<const void*>(kern)}];
+        if (have < smem) {
+            e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name);
+            if (e) return e;
+            have = smem;
+        }
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(clusters * kCS));
     cfg.blockDim = dim3(kSeqThreads);
