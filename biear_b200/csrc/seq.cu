@@ -714,9 +714,10 @@ __device__ __forceinline__ void reduce_ks1_c(float* acc, float* red_s, int ks, i
 
 // LayerNorm + SiLU + Dropout over the full rows of one chain in buf_s ([feature][kRC], in place), redundantly in every CTA;
 // the threads whose features are the CTA's own slice save them (tile layout, row offset row_off inside the 16-row tile).
-__device__ __forceinline__ void ln_silu_drop_fwd_c(const BiearSeqParams& p, unsigned long long seed, float* buf_s, float* stat_s,
+// `sc`: the keep-mask scales of this thread's 4 features (drawn by the caller while it waits for hand-over #1).
+__device__ __forceinline__ void ln_silu_drop_fwd_c(const float4 sc, float* buf_s, float* stat_s,
                                                    const float* __restrict__ gamma_s, const float* __restrict__ beta_s,
-                                                   int layer, int t, long long grow0, int rank, int chain, int tid,
+                                                   int layer, int rank, int chain, int tid,
                                                    float* xh_tile, float* d_tile, float* rstd_tile, int row_off) {
     constexpr int PARTS = kCT / kRC, FPP = kHid / PARTS;             // 32 parts of 4 features
     static_assert(kRC == 8 && FPP == 4, "lanes l, l^8, l^16, l^24 of a warp hold four parts of one row");
@@ -753,8 +754,6 @@ __device__ __forceinline__ void ln_silu_drop_fwd_c(const BiearSeqParams& p, unsi
     const float rstd = rsqrtf(var * (1.0f / kHid) + kLnEps);
     const bool mine = f0 / kU == rank;
     if (rank == 0 && part == 0) rstd_tile[layer * kR + row_off + row] = rstd;
-    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
-    if (p.training) sc = dropout_scale4(seed, t, layer, grow0 + row, f0 >> 2);
     const float scv[4] = {sc.x, sc.y, sc.z, sc.w};
 #pragma unroll
     for (int i = 0; i < FPP; ++i) {
@@ -921,8 +920,10 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd2_kernel(const BiearSeq
             asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(next_ready) : "l"(flag_of(t + 1)) : "memory");
 
         // ---- band stage of frame t for this chain's kRB rows of this CTA ------------------------------------------
-        // The kRB x quads (row, quad) pairs are dealt round-robin to the chain's 8 warps, widest quads first; lane l OWNS
-        // band (l & 3) of the warp's (l >> 2)-th pair (parameters once, epilogue once per warp).
+        // The kRB x quads (row, quad) pairs are dealt to the chain's 8 warps widest quads first, in SNAKE order (round m goes
+        // warp 0..7 for even m, 7..0 for odd m): with the window widths growing monotonically with the band index a plain
+        // round-robin gives the first warps 11 % more bins than the average, the snake 4 %.  Lane l OWNS band (l & 3) of
+        // the warp's (l >> 2)-th pair (parameters once, epilogue once per warp).
         // (token: chain 0 goes first in every frame, chain 1 follows it, chain 0's next frame follows chain 1)
         if (chain == 0) {
             if (t > 0) token_take(kTokenToChain0);
@@ -934,7 +935,8 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd2_kernel(const BiearSeq
         float oY = 0.f, oJ = 0.f, oP = 0.f, oK = 0.f;
         {
             const int n_pairs = kRB * quads;
-            const int p_own = warp + kWarpsC * (lane >> 2);
+            const int m_own = lane >> 2;
+            const int p_own = kWarpsC * m_own + ((m_own & 1) ? kWarpsC - 1 - warp : warp);
             const int row_own = p_own & (kRB - 1);
             const int n_own = ((quads - 1 - (p_own / kRB)) << 2) + (lane & 3);
             const bool own = p_own < n_pairs && n_own < N;
@@ -942,7 +944,9 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd2_kernel(const BiearSeq
             const float q = own ? q_s[n_own * kRB + row_own] : 1.0f;
             const BandParams bp_own = band_params(fc, q, p.df, p.cutoff, p.F, own);
             BandSums keep = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            for (int m = 0, pr = warp; pr < n_pairs; ++m, pr += kWarpsC) {
+            for (int m = 0; m * kWarpsC < n_pairs; ++m) {
+                const int pr = kWarpsC * m + ((m & 1) ? kWarpsC - 1 - warp : warp);
+                if (pr >= n_pairs) break;                          // (warp-uniform)
                 const int row = pr & (kRB - 1);
                 const int src = (m << 2) + (lane >> 3);          // lane owning the band this lane helps with
                 BandParams bp;
@@ -1015,6 +1019,13 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd2_kernel(const BiearSeq
         }
         arm(0);
         store_band_outputs();
+        // the two dropout masks of this frame (Philox, ~120 instructions) are drawn here, while hand-over #1 is in flight,
+        // instead of inside the LayerNorm phases of the serial chain
+        float4 drop1 = make_float4(1.f, 1.f, 1.f, 1.f), drop2 = drop1;
+        if (p.training) {
+            drop1 = dropout_scale4(seed, t, 0, crow0 + (tid % kRC), tid / kRC);
+            drop2 = dropout_scale4(seed, t, 1, crow0 + (tid % kRC), tid / kRC);
+        }
         tx_wait(bar_of(0), par);
         PHASE_MARK(0, 3);    // band barrier + push + hand-over #1
 
@@ -1076,7 +1087,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd2_kernel(const BiearSeq
         }
         tx_wait(bar_of(2), par);
         PHASE_MARK(0, 5);    // Linear 1
-        ln_silu_drop_fwd_c(p, seed, a1_s, stat_s, vec_s + V_LN1G, vec_s + V_LN1B, 0, t, crow0, rank, chain, tid,
+        ln_silu_drop_fwd_c(drop1, a1_s, stat_s, vec_s + V_LN1G, vec_s + V_LN1B, 0, rank, chain, tid,
                            p.xh1 + tb * kHid * kR, p.d1 + tb * kHid * kR, p.rstd + tb * 2 * kR, row_off);
         PHASE_MARK(0, 6);    // LayerNorm 1
 
@@ -1096,7 +1107,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_fwd2_kernel(const BiearSeq
         }
         tx_wait(bar_of(3), par);
         PHASE_MARK(0, 7);    // Linear 2
-        ln_silu_drop_fwd_c(p, seed, a2_s, stat_s, vec_s + V_LN2G, vec_s + V_LN2B, 1, t, crow0, rank, chain, tid,
+        ln_silu_drop_fwd_c(drop2, a2_s, stat_s, vec_s + V_LN2G, vec_s + V_LN2B, 1, rank, chain, tid,
                            p.xh2 + tb * kHid * kR, p.d2 + tb * kHid * kR, p.rstd + tb * 2 * kR, row_off);
         PHASE_MARK(0, 8);    // LayerNorm 2
 
