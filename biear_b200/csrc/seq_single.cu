@@ -461,14 +461,16 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq1_fwd_kernel(const BiearSeq
             PHASE1_MARK(1);   // state + spectra ready
 
             // ---- band stage of frame t for this CTA's 4 items (model_torch.py:729-737, 1050-1060) ---------------------
-            // The kItems x quads (item, 4-band quad) pairs are dealt round-robin to the 16 warps, widest quads first and
-            // items rotating; lane l OWNS band (l & 3) of the warp's (l >> 2)-th pair (parameters once, epilogue once).
+            // The kItems x quads (item, 4-band quad) pairs are dealt to the 16 warps widest quads first in snake order (round
+            // m goes warp 0..15 for even m, 15..0 for odd m: evens out the bins per warp), items rotating; lane l OWNS band
+            // (l & 3) of the warp's (l >> 2)-th pair (parameters once, epilogue once).
             bool own_store = false;
             long long own_e = 0;
             float oY = 0.f, oJ = 0.f, oP = 0.f, oK = 0.f;
             {
                 const int n_pairs = kItems * quads;
-                const int p_own = warp + kWarps * (lane >> 2);
+                const int m_own = lane >> 2;
+                const int p_own = kWarps * m_own + ((m_own & 1) ? kWarps - 1 - warp : warp);
                 const int item_own = ((p_own & 3) + (p_own >> 4)) & 3;
                 const int n_own = ((quads - 1 - (p_own >> 2)) << 2) + (lane & 3);
                 const bool own = p_own < n_pairs && n_own < N;
@@ -476,7 +478,9 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq1_fwd_kernel(const BiearSeq
                 const float q = own ? q_s[n_own * kClipsB + (item_own & 1)] : 1.0f;
                 const BandParams bp_own = band_params(fc, q, p.df, p.cutoff, p.F, own);
                 BandSums keep = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                for (int m = 0, pr = warp; pr < n_pairs; ++m, pr += kWarps) {
+                for (int m = 0; m * kWarps < n_pairs; ++m) {
+                    const int pr = kWarps * m + ((m & 1) ? kWarps - 1 - warp : warp);
+                    if (pr >= n_pairs) break;                        // (warp-uniform)
                     const int item = ((pr & 3) + (pr >> 4)) & 3;
                     const int src = (m << 2) + (lane >> 3);          // lane owning the band this lane helps with
                     BandParams bp;
