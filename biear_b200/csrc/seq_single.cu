@@ -72,7 +72,7 @@ struct Smem {   // offsets in floats
     __host__ __device__ Smem(int N_, int F) : N(N_), Kp(single_kp(N_)), CK(single_chunk_rows(N_)), tile(spec_tile_len(F)) {}
     __host__ __device__ int img() const { return 0; }                           // resident: whh3, w1, w2, w3 (skewed)
     __host__ __device__ int vec() const { return single_fwd_res_floats(); }
-    __host__ __device__ int in() const { return vec() + 1088; }                 // [kRG][Kp][4]: cL | cR | mL | mR (+ zero pad)
+    __host__ __device__ int in() const { return vec() + 1088; }                 // [kRG][Kp][4]: mL | mR | cL | cR (+ zero pad)
     __host__ __device__ int h() const { return in() + Kp * kRows; }             // 2 x [kRG][128][4]
     __host__ __device__ int a1() const { return h() + 2 * kHid * kRows; }
     __host__ __device__ int a2() const { return a1() + kHid * kRows; }
@@ -90,13 +90,14 @@ __device__ __forceinline__ int skew_col(int u, int k) { return (u + 4 * (k & 7))
 
 // ---- weight images -------------------------------------------------------------------------------------------------------
 // forward, resident part of CTA rank c:  whh3 [k<128][gate<3][32], w1 | w2 | w3 [k<128][32], columns skewed
-// forward, streamed part:                wih3 [k<Kp][gate<3][32] with the input order cL | cR | mL | mR (torch: cL mL cR mR)
+// forward, streamed part:                wih3 [k<Kp][gate<3][32] with the input order mL | mR | cL | cR (torch: cL mL cR mR):
+//                                        the memory half first -- it does not depend on the current frame's band stage
 // backward, resident part:               w3c [n<N][32] | w2c | w1c [o<128][32] | whhc [o<384][32]   (as seq_dev.cuh)
 // backward, streamed part:               wihcL [o<384][32] | wihcR [o<384][32]: columns n and 2N + n of W_ih (the memory
 //                                        inputs are detached: no gradient flows through their columns)
 __device__ __forceinline__ int torch_col(int k, int N) {   // my input order -> torch column of weight_ih
-    const int part = k / N, n = k - part * N;
-    const int tpart = part == 1 ? 2 : (part == 2 ? 1 : part);
+    const int part = k / N, n = k - part * N;          // kernel order: mL, mR, cL, cR
+    const int tpart = part == 0 ? 1 : (part == 1 ? 3 : (part == 2 ? 0 : 2));
     return tpart * N + n;
 }
 
@@ -447,7 +448,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq1_fwd_kernel(const BiearSeq
                         m = make_float4(__fadd_rn(__fmul_rn(0.8f, mo.x), __fmul_rn(0.2f, c.x)), __fadd_rn(__fmul_rn(0.8f, mo.y), __fmul_rn(0.2f, c.y)),
                                         __fadd_rn(__fmul_rn(0.8f, mo.z), __fmul_rn(0.2f, c.z)), __fadd_rn(__fmul_rn(0.8f, mo.w), __fmul_rn(0.2f, c.w)));
                     }
-                    *reinterpret_cast<float4*>(in_s + (g2 * Kp + 2 * N + k2) * kRT) = m;
+                    *reinterpret_cast<float4*>(in_s + (g2 * Kp + k2) * kRT) = m;
                 }
             }
             const int want_key = t * n_half + hf;
@@ -544,31 +545,22 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq1_fwd_kernel(const BiearSeq
             if (tid < 2 * N) {   // current features of my 2 clips, both ears -> every CTA of the cluster
                 const int ear = tid / N, n = tid - ear * N;
                 const float2 v = make_float2(ystage_s[(ear * 2) * kHid + n], ystage_s[(ear * 2 + 1) * kHid + n]);
-                const uint32_t a = smem_u32(in_s + ((rank >> 1) * Kp + ear * N + n) * kRT + (rank & 1) * kClipsB);
+                const uint32_t a = smem_u32(in_s + ((rank >> 1) * Kp + 2 * N + ear * N + n) * kRT + (rank & 1) * kClipsB);
 #pragma unroll
                 for (uint32_t dst = 0; dst < (uint32_t)kCS; ++dst)
                     st_async_f2(cluster_addr(a, dst), v, cluster_addr(bar_of(0), dst));
             }
             arm(0);
-            tx_wait(bar_of(0), par);
-            PHASE1_MARK(3);   // prefetch issue + push + hand-over #1
-            // saved controller input (torch column order cL | mL | cR | mR, tile layout): ranks 0 / 1 save cL / cR here,
-            // ranks 2 / 3 save mL / mR where the memory is advanced
-            float* in_tile = p.yc + tb * (4 * N * kR);
-            if (rank < 2 && tid < N * kRG) {
-                const int n = tid >> 1, g2 = tid & 1;
-                const float4 v = *reinterpret_cast<const float4*>(in_s + (g2 * Kp + rank * N + n) * kRT);
-                *reinterpret_cast<float4*>(in_tile + (rank * 2 * N + n) * kR + row_off + g2 * kRT) = v;
-            }
-
-            // ---- GRU cell (torch gate order r, z, n; n = tanh(i_n + r * (W_hn h + b_hn))) ---------------------------------
-            {
-                float2 lo[4], hi[4];       // r, z, i_n, h_n
+            // ---- GRU cell, part A: everything that does not depend on this frame's band stage -- the memory half of the
+            // input product (the first n_pre chunks of the W_ih ring) and the recurrent product -- runs while hand-over #1
+            // (the current features of the cluster's 8 clips) is in flight.
+            float2 lo[4], hi[4];       // r, z, i_n, h_n
 #pragma unroll
-                for (int g = 0; g < 4; ++g) lo[g] = hi[g] = make_float2(0.f, 0.f);
-                const float* x_rg = in_s + rg * Kp * kRT;
+            for (int g = 0; g < 4; ++g) lo[g] = hi[g] = make_float2(0.f, 0.f);
+            const float* x_rg = in_s + rg * Kp * kRT;
+            auto ring_chunks = [&](int c_begin, int c_end) {
                 const int kper = CK / kKL;
-                for (int c = 0; c < n_chunks; ++c, ++gchunk) {
+                for (int c = c_begin; c < c_end; ++c, ++gchunk) {
                     const int s = (int)(gchunk % kStages);
                     if (tid == 0 && gchunk >= 1) {   // refill the slot of the previous chunk (everybody has long left it)
                         const unsigned gp = gchunk - 1;
@@ -592,20 +584,38 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq1_fwd_kernel(const BiearSeq
                     __syncwarp();
                     if (lane == 0) mbar_arrive(empty_of(s));
                 }
-                if (!h_zero) {
-                    const float* hx = hcur_s + rg * kHid * kRT;
-                    const float* w = whh_s + ucol;
+            };
+            const int n_pre = (2 * N) % CK == 0 ? (2 * N) / CK : 0;     // chunks that hold memory inputs only
+            ring_chunks(0, n_pre);
+            if (!h_zero) {
+                const float* hx = hcur_s + rg * kHid * kRT;
+                const float* w = whh_s + ucol;
 #pragma unroll 4
-                    for (int k = ks; k < kHid; k += kKL) {
-                        const float4 xv = *reinterpret_cast<const float4*>(hx + k * kRT);
-                        const float2 xl = make_float2(xv.x, xv.y), xh = make_float2(xv.z, xv.w);
-                        const float w0 = w[(k * 3) * kU], w1v = w[(k * 3 + 1) * kU], w2v = w[(k * 3 + 2) * kU];
-                        const float2 p0 = make_float2(w0, w0), p1 = make_float2(w1v, w1v), p2 = make_float2(w2v, w2v);
-                        lo[0] = __ffma2_rn(p0, xl, lo[0]); hi[0] = __ffma2_rn(p0, xh, hi[0]);
-                        lo[1] = __ffma2_rn(p1, xl, lo[1]); hi[1] = __ffma2_rn(p1, xh, hi[1]);
-                        lo[3] = __ffma2_rn(p2, xl, lo[3]); hi[3] = __ffma2_rn(p2, xh, hi[3]);
-                    }
+                for (int k = ks; k < kHid; k += kKL) {
+                    const float4 xv = *reinterpret_cast<const float4*>(hx + k * kRT);
+                    const float2 xl = make_float2(xv.x, xv.y), xh = make_float2(xv.z, xv.w);
+                    const float w0 = w[(k * 3) * kU], w1v = w[(k * 3 + 1) * kU], w2v = w[(k * 3 + 2) * kU];
+                    const float2 p0 = make_float2(w0, w0), p1 = make_float2(w1v, w1v), p2 = make_float2(w2v, w2v);
+                    lo[0] = __ffma2_rn(p0, xl, lo[0]); hi[0] = __ffma2_rn(p0, xh, hi[0]);
+                    lo[1] = __ffma2_rn(p1, xl, lo[1]); hi[1] = __ffma2_rn(p1, xh, hi[1]);
+                    lo[3] = __ffma2_rn(p2, xl, lo[3]); hi[3] = __ffma2_rn(p2, xh, hi[3]);
                 }
+            }
+            tx_wait(bar_of(0), par);
+            PHASE1_MARK(3);   // prefetch issue + push + GRU part A + hand-over #1
+            // saved controller input (torch column order cL | mL | cR | mR, tile layout): ranks 0 / 1 save cL / cR here,
+            // ranks 2 / 3 save mL / mR where the memory is advanced
+            float* in_tile = p.yc + tb * (4 * N * kR);
+            if (rank < 2 && tid < N * kRG) {
+                const int n = tid >> 1, g2 = tid & 1;
+                const float4 v = *reinterpret_cast<const float4*>(in_s + (g2 * Kp + 2 * N + rank * N + n) * kRT);
+                *reinterpret_cast<float4*>(in_tile + (rank * 2 * N + n) * kR + row_off + g2 * kRT) = v;
+            }
+
+            // ---- GRU cell, part B: the current-feature half of the input product, then the cell (torch gate order r, z, n;
+            // n = tanh(i_n + r * (W_hn h + b_hn))) ------------------------------------------------------------------------
+            {
+                ring_chunks(n_pre, n_chunks);
                 float acc[4][kRT];
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
@@ -654,8 +664,8 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq1_fwd_kernel(const BiearSeq
             // Ranks 2 / 3 save the OLD memory (this step's controller input) on the way.
             for (int idx = tid; idx < 2 * N * kRG; idx += kSeqThreads) {
                 const int k2 = idx >> 1, g2 = idx & 1;
-                float4* mp = reinterpret_cast<float4*>(in_s + (g2 * Kp + 2 * N + k2) * kRT);
-                const float4 c = *reinterpret_cast<const float4*>(in_s + (g2 * Kp + k2) * kRT);
+                float4* mp = reinterpret_cast<float4*>(in_s + (g2 * Kp + k2) * kRT);
+                const float4 c = *reinterpret_cast<const float4*>(in_s + (g2 * Kp + 2 * N + k2) * kRT);
                 const float4 m = *mp;
                 const int ear = k2 >= N ? 1 : 0;
                 if (rank == 2 + ear)

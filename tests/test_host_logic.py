@@ -43,9 +43,9 @@ def test_heads_reject_bad_geometry_and_cpu_tensors():
 
 
 def _torch_col(k, n):
-    """csrc/seq_single.cu torch_col: kernel input order cL | cR | mL | mR -> column of weight_ih (cL | mL | cR | mR)."""
+    """csrc/seq_single.cu torch_col: kernel input order mL | mR | cL | cR -> column of weight_ih (cL | mL | cR | mR)."""
     part, b = divmod(k, n)
-    return {0: 0, 1: 2, 2: 1, 3: 3}[part] * n + b
+    return {0: 1, 1: 3, 2: 0, 3: 2}[part] * n + b
 
 
 @pytest.mark.parametrize("n", [100, 32, 64, 128, 7])
@@ -54,8 +54,10 @@ def test_single_controller_image_geometry(n):
     # input permutation: a bijection of the 4N columns that sends the kernel's block order to torch's
     cols = [_torch_col(k, n) for k in range(4 * n)]
     assert sorted(cols) == list(range(4 * n))
-    assert cols[:n] == list(range(n)) and cols[n:2 * n] == list(range(2 * n, 3 * n))          # cL, cR
-    assert cols[2 * n:3 * n] == list(range(n, 2 * n)) and cols[3 * n:] == list(range(3 * n, 4 * n))   # mL, mR
+    assert cols[:n] == list(range(n, 2 * n)) and cols[n:2 * n] == list(range(3 * n, 4 * n))   # mL, mR (first: they do not
+    assert cols[2 * n:3 * n] == list(range(n)) and cols[3 * n:] == list(range(2 * n, 3 * n))   # depend on the frame); cL, cR
+    src = open(_lib.os.path.join(_lib.os.path.dirname(_lib.__file__), "csrc", "seq_single.cu")).read()
+    assert "part == 0 ? 1 : (part == 1 ? 3 : (part == 2 ? 0 : 2))" in src
     # bank skew of the weight images: for every k the 32 unit columns are permuted, and the 32 lanes of a warp
     # (4 units x 8 k-splits, k = j*8 + ks) hit 32 distinct banks
     for k in range(16):
