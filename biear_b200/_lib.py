@@ -11,7 +11,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BIEAR_B200_LIB") or os.path.join(_HERE, "lib", "libbiear_b200.so")
-ABI_VERSION = 19
+ABI_VERSION = 20
 
 _p = c_void_p
 _i = c_int
@@ -59,6 +59,13 @@ class HeadsParams(Structure):
                 ("d_body_part", c_void_p), ("dw_part", c_void_p), ("d_body", c_void_p), ("dw", c_void_p)]
 
 
+class GruParams(Structure):
+    """struct BiearGruParams of include/biear_b200.h."""
+    _fields_ = [("B", c_int32), ("T", c_int32), ("H", c_int32), ("I", c_int32), ("gi", c_void_p), ("w_hh", c_void_p),
+                ("b_hh", c_void_p), ("h_seq", c_void_p), ("h_prev", c_void_p), ("gates", c_void_p), ("dh_seq", c_void_p), ("dgi", c_void_p),
+                ("dgh", c_void_p), ("workspace", c_void_p)]
+
+
 WGRAD_MAX_JOBS = 8
 
 # name -> (restype, argtypes); mirrors include/biear_b200.h one to one
@@ -98,6 +105,10 @@ SIGNATURES = {
     "biear_heads_flat_floats": (_l, [_i, _i]),
     "biear_heads_fwd": (_i, [POINTER(HeadsParams), _p]),
     "biear_heads_bwd": (_i, [POINTER(HeadsParams), _p]),
+    "biear_gru_supported": (_i, [_i]),
+    "biear_gru_workspace_floats": (_l, [_i]),
+    "biear_gru_fwd": (_i, [POINTER(GruParams), _p]),
+    "biear_gru_bwd": (_i, [POINTER(GruParams), _p]),
     "biear_q_regularizers_workspace_floats": (_l, []),
     "biear_q_regularizers": (_i, [_p, _p, _p, _l, _i, _f, _f, _p, _p, _p, _p]),
 }

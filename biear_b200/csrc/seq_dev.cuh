@@ -195,6 +195,42 @@ __device__ __forceinline__ void dot_rows3(float a0[kRT], float a1[kRT], float a2
     a2[0] = l2.x; a2[1] = l2.y; a2[2] = h2.x; a2[3] = h2.y;
 }
 
+// Generic-pitch forms for the GRU layer kernels (gru.cu): activations [k][16 rows] (x_s offset to the thread's 4 rows),
+// weights [k][3 gates][pitch] resp. [o][pitch] (w_s offset to the thread's unit).
+__device__ __forceinline__ void dot_rows3x(float a0[kRT], float a1[kRT], float a2[kRT], const float* __restrict__ x_s,
+                                           const float* __restrict__ w_s, int pitch, int k0, int k1) {
+    float2 l0 = make_float2(a0[0], a0[1]), h0 = make_float2(a0[2], a0[3]);
+    float2 l1 = make_float2(a1[0], a1[1]), h1 = make_float2(a1[2], a1[3]);
+    float2 l2 = make_float2(a2[0], a2[1]), h2 = make_float2(a2[2], a2[3]);
+#pragma unroll 4
+    for (int k = k0; k < k1; ++k) {
+        const float4 x = *reinterpret_cast<const float4*>(x_s + k * kR);
+        const float2 xl = make_float2(x.x, x.y), xh = make_float2(x.z, x.w);
+        const float w0 = w_s[(k * 3) * pitch], w1 = w_s[(k * 3 + 1) * pitch], w2 = w_s[(k * 3 + 2) * pitch];
+        const float2 p0 = make_float2(w0, w0), p1 = make_float2(w1, w1), p2 = make_float2(w2, w2);
+        l0 = __ffma2_rn(p0, xl, l0); h0 = __ffma2_rn(p0, xh, h0);
+        l1 = __ffma2_rn(p1, xl, l1); h1 = __ffma2_rn(p1, xh, h1);
+        l2 = __ffma2_rn(p2, xl, l2); h2 = __ffma2_rn(p2, xh, h2);
+    }
+    a0[0] = l0.x; a0[1] = l0.y; a0[2] = h0.x; a0[3] = h0.y;
+    a1[0] = l1.x; a1[1] = l1.y; a1[2] = h1.x; a1[3] = h1.y;
+    a2[0] = l2.x; a2[1] = l2.y; a2[2] = h2.x; a2[3] = h2.y;
+}
+
+__device__ __forceinline__ void dot_rows_p(float acc[kRT], const float* __restrict__ x_s, const float* __restrict__ w_s,
+                                           int pitch, int k0, int k1) {
+    float2 lo = make_float2(acc[0], acc[1]), hi = make_float2(acc[2], acc[3]);
+#pragma unroll 8
+    for (int k = k0; k < k1; ++k) {
+        const float4 x = *reinterpret_cast<const float4*>(x_s + k * kR);
+        const float wk = w_s[k * pitch];
+        const float2 w2 = make_float2(wk, wk);
+        lo = __ffma2_rn(w2, make_float2(x.x, x.y), lo);
+        hi = __ffma2_rn(w2, make_float2(x.z, x.w), hi);
+    }
+    acc[0] = lo.x; acc[1] = lo.y; acc[2] = hi.x; acc[3] = hi.y;
+}
+
 // [k0, k1) of k-split ks over a contraction of length K
 __device__ __forceinline__ void k_range(int K, int ks, int& k0, int& k1) {
     k0 = (K * ks) / kKS;

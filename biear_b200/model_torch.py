@@ -8,10 +8,12 @@ front-end executing on the sm_100a kernels of this package.
 What is native and what is plain PyTorch:
   * the binaural front-end (``bifb``) -- STFT, Gaussian band stage, Q controllers, sub-band phase, and their
     backward -- is this package's CUDA path (frontend.py / ops.py / csrc);
-  * the back-end (ILD/IPD GRU encoders, body MLP, 8 sub-heads; model_torch.py:828-960, 1088-1110) is generic
-    cuDNN/cuBLAS work and is kept as ordinary ``torch.nn`` modules with the reference's module tree, so that
-    state-dict keys, default initialisation order (same parameters under the same seed) and the optimiser's
-    parameter groups are identical.
+  * the back-end (ILD/IPD GRU encoders, body MLP, 8 sub-heads; model_torch.py:828-960, 1088-1110) keeps the
+    reference's ``torch.nn`` module tree, so that state-dict keys, default initialisation order (same parameters
+    under the same seed) and the optimiser's parameter groups are identical; on CUDA tensors the two GRU layers of
+    each encoder run their recurrences through csrc/gru.cu (one launch per layer and direction) and the eight sector
+    heads through csrc/heads.cu (one launch forward, one backward); the body MLP, the input projections and the
+    weight-gradient products are plain library GEMMs.
 
 The one structural change in ``DeepEarActiveWaveform.forward``: the sub-band phase comes out of the same band
 pass that produces Y (``bifb.forward_features``) instead of a second W(Q) rebuild from (X, Q)
@@ -78,12 +80,21 @@ class _PairEncoder(nn.Module):
         self.gru1 = nn.GRU(input_dim, hidden_dim, batch_first=True)
         self.gru2 = nn.GRU(hidden_dim, latent_dim, batch_first=True)
 
+    native_gru = True         # False: torch.nn.GRU on the GPU too (the cross-check; what CPU tensors always take)
+
     def interaural(self, xL, xR):
         raise NotImplementedError
 
+    def _layer(self, gru, x):
+        # each layer's 19-step recurrence as one launch forward and one backward (csrc/gru.cu) instead of the library's
+        # per-step GEMM + cell kernels; same parameters, same results to fp32 rounding
+        if x.is_cuda and self.native_gru and x.dtype == torch.float32 and ops.gru_supported(gru.hidden_size):
+            return ops.gru_layer(x, gru)
+        return gru(x)[0]
+
     def forward(self, xL, xR):
-        seq, _ = self.gru1(self.in_norm(self.interaural(xL, xR)))
-        seq, _ = self.gru2(seq)
+        seq = self._layer(self.gru1, self.in_norm(self.interaural(xL, xR)))
+        seq = self._layer(self.gru2, seq)
         return _zero_nonfinite(seq.mean(dim=1))
 
 

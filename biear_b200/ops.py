@@ -859,3 +859,75 @@ def sector_heads(body: torch.Tensor, head_modules, training: bool):
     seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if training else 0
     return SectorHeads.apply(body, S, C, bool(training), seed, *params)
 
+
+
+# ------------------------------------------------------------------------------------------------
+# back-end: the recurrence of one GRU layer (csrc/gru.cu)
+# ------------------------------------------------------------------------------------------------
+@lru_cache(maxsize=None)
+def gru_supported(hidden: int) -> bool:
+    """Can the persistent GRU-layer kernels take this hidden width (shared-memory budget, H % 4 == 0)?"""
+    return bool(_lib.load().biear_gru_supported(int(hidden)))
+
+
+class GruLayer(torch.autograd.Function):
+    """One ``nn.GRU`` layer (batch_first, h_0 = 0; model_torch.py:834-835, 842-843) with the 19-step recurrence as ONE
+    launch forward and ONE backward instead of the library's per-step GEMM + cell kernels.  The input projection and the
+    weight gradients are plain GEMMs over all frames at once (library calls).  Inputs: x (B,T,I) and the layer's own
+    parameters (weight_ih_l0, weight_hh_l0, bias_ih_l0, bias_hh_l0); output: the hidden sequence (B,T,H)."""
+
+    @staticmethod
+    def forward(ctx, x, w_ih, w_hh, b_ih, b_hh):
+        from ctypes import byref
+        _need_cuda(x, "x")
+        dev = x.device
+        B, T, I = x.shape
+        H = w_hh.shape[1]
+        w_ih, w_hh, b_ih, b_hh = (p.detach() for p in (w_ih, w_hh, b_ih, b_hh))
+        for p_ in (w_ih, w_hh, b_ih, b_hh):
+            _need_cuda(p_, "GRU parameter")
+        assert w_ih.shape == (3 * H, I) and w_hh.shape == (3 * H, H)
+        with torch.cuda.device(dev):
+            lib = _prepare(dev)
+            f32 = dict(dtype=torch.float32, device=dev)
+            gi = torch.addmm(b_ih, x.reshape(B * T, I), w_ih.t())                   # (B*T, 3H)
+            h_seq, h_prev = torch.empty((B, T, H), **f32), torch.empty((B, T, H), **f32)
+            gates = torch.empty((B, T, 4, H), **f32)
+            ws = torch.empty(int(lib.biear_gru_workspace_floats(H)), **f32)
+            prm = _lib.GruParams()
+            prm.B, prm.T, prm.H, prm.I = B, T, H, I
+            _fill(prm, gi=gi, w_hh=w_hh, b_hh=b_hh, h_seq=h_seq, h_prev=h_prev, gates=gates, workspace=ws)
+            _lib.check(lib.biear_gru_fwd(byref(prm), _stream(dev)), "biear_gru_fwd")
+        ctx.prm = prm
+        ctx.keep = (x, w_ih, w_hh, h_prev, gates, ws)       # what the backward reads (the output itself is not among it)
+        return h_seq
+
+    @staticmethod
+    def backward(ctx, g_seq):
+        from ctypes import byref
+        x, w_ih, w_hh, h_prev, gates, ws = ctx.keep
+        dev = x.device
+        B, T, I = x.shape
+        H = w_hh.shape[1]
+        prm = ctx.prm
+        g_seq = g_seq.contiguous()
+        with torch.cuda.device(dev):
+            lib = _prepare(dev)
+            f32 = dict(dtype=torch.float32, device=dev)
+            dgi, dgh = torch.empty((B * T, 3 * H), **f32), torch.empty((B * T, 3 * H), **f32)
+            _fill(prm, dh_seq=g_seq, dgi=dgi, dgh=dgh)
+            _lib.check(lib.biear_gru_bwd(byref(prm), _stream(dev)), "biear_gru_bwd")
+            _fill(prm, dh_seq=None, dgi=None, dgh=None)
+            need = ctx.needs_input_grad
+            dx = (dgi @ w_ih).view(B, T, I) if need[0] else None
+            dw_ih = dgi.t() @ x.reshape(B * T, I) if need[1] else None
+            dw_hh = dgh.t() @ h_prev.view(B * T, H) if need[2] else None
+            db_ih = dgi.sum(0) if need[3] else None
+            db_hh = dgh.sum(0) if need[4] else None
+        return dx, dw_ih, dw_hh, db_ih, db_hh
+
+
+def gru_layer(x: torch.Tensor, gru: "torch.nn.GRU") -> torch.Tensor:
+    """Hidden sequence of a one-layer, unidirectional, batch_first ``nn.GRU`` with zero initial state."""
+    assert gru.num_layers == 1 and not gru.bidirectional and gru.batch_first and gru.bias
+    return GruLayer.apply(x.contiguous(), gru.weight_ih_l0, gru.weight_hh_l0, gru.bias_ih_l0, gru.bias_hh_l0)

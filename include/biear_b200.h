@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BIEAR_ABI_VERSION 19
+#define BIEAR_ABI_VERSION 20
 #define BIEAR_EINVAL (-1)
 
 /* ABI version (== BIEAR_ABI_VERSION of the library that was built). */
@@ -330,6 +330,33 @@ int biear_heads_tensors_per_head(void);
 int64_t biear_heads_flat_floats(int D, int C);
 int biear_heads_fwd(const BiearHeadsParams* p, void* stream);
 int biear_heads_bwd(const BiearHeadsParams* p, void* stream);
+
+/*
+ * The recurrence of ONE GRU layer (torch.nn.GRU semantics, gate order r, z, n; h_{-1} = 0) as a persistent cluster kernel,
+ * forward and backward.  Used for the wide first layer of the back-end's ILD / IPD encoders (model_torch.py:828-867:
+ * nn.GRU(100 -> 200) over the 19 frames), which the library runs as 19 x (GEMM + cell kernel) per direction.
+ * The input projection and everything that is a plain GEMM stays with the caller (a library GEMM each):
+ *   forward : gi (B,T,3H) = x W_ih^T + b_ih in  ->  h_seq (B,T,H), h_prev (B,T,H) = h_seq shifted by one step (h_prev[:,0] = 0),
+ *             gates (B,T,4,H) = r, z, n, W_hn h + b_hn out
+ *   backward: dh_seq (B,T,H) = dL/dh_t from the consumer of the sequence in  ->  dgi, dgh (B,T,3H) out, from which
+ *             dx = dgi W_ih, dW_ih = dgi^T x, db_ih = sum dgi, dW_hh = dgh^T h_prev, db_hh = sum dgh.
+ * workspace: biear_gru_workspace_floats(H) floats (weight images, packed by biear_gru_fwd; must stay untouched until
+ * biear_gru_bwd of the same step has run).  H % 4 == 0 and the
+ * shared-memory budget (H <= 216): ask biear_gru_supported(H).
+ */
+typedef struct BiearGruParams {
+    int32_t B, T, H, I;              /* rows, steps, hidden units, input width (informational) */
+    const float* gi;
+    const float *w_hh, *b_hh;        /* (3H, H), (3H): the nn.GRU parameters themselves */
+    float *h_seq, *h_prev, *gates;
+    const float* dh_seq;
+    float *dgi, *dgh;
+    float* workspace;
+} BiearGruParams;
+int biear_gru_supported(int H);
+int64_t biear_gru_workspace_floats(int H);
+int biear_gru_fwd(const BiearGruParams* p, void* stream);
+int biear_gru_bwd(const BiearGruParams* p, void* stream);
 
 #ifdef __cplusplus
 }

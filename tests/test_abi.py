@@ -45,6 +45,9 @@ def test_ctypes_structs_match_the_header(tmp_path):
     lines += [f'printf("%zu\\n", offsetof(BiearWgradJob, {f}));' for f in fields_job]
     lines += ['printf("%zu\\n", sizeof(BiearHeadsParams));']
     lines += [f'printf("%zu\\n", offsetof(BiearHeadsParams, {f}));' for f in fields_heads]
+    fields_gru = ["B", "I", "gi", "w_hh", "b_hh", "h_seq", "h_prev", "gates", "dh_seq", "dgi", "dgh", "workspace"]
+    lines += ['printf("%zu\\n", sizeof(BiearGruParams));']
+    lines += [f'printf("%zu\\n", offsetof(BiearGruParams, {f}));' for f in fields_gru]
     lines += ["return 0;}"]
     probe.write_text("\n".join(lines))
     exe = tmp_path / "probe"
@@ -54,6 +57,7 @@ def test_ctypes_structs_match_the_header(tmp_path):
     offs = [int(x) for x in out[2:]]
     want = [getattr(_lib.SeqParams, f).offset for f in fields_seq] + [getattr(_lib.WgradJob, f).offset for f in fields_job]
     want += [ctypes.sizeof(_lib.HeadsParams)] + [getattr(_lib.HeadsParams, f).offset for f in fields_heads]
+    want += [ctypes.sizeof(_lib.GruParams)] + [getattr(_lib.GruParams, f).offset for f in fields_gru]
     assert offs == want
 
 
@@ -74,6 +78,15 @@ def test_argument_validation_needs_no_gpu():
     assert lib.biear_adaptive_supported(129, 513) == 0
     assert lib.biear_adaptive_tile_rows() in (16, 32)
     assert lib.biear_adaptive_workspace_floats(2, 100) > 0
+    assert lib.biear_gru_supported(200) == 1 and lib.biear_gru_supported(100) == 1                          # the two encoder layers
+    assert lib.biear_gru_supported(216) == 1 and lib.biear_gru_supported(220) == 0
+    assert lib.biear_gru_supported(202) == 0 and lib.biear_gru_supported(260) == 0 and lib.biear_gru_workspace_floats(202) == -1
+    assert lib.biear_gru_workspace_floats(200) == 4 * 2 * 600 * 52
+    gp = _lib.GruParams()
+    gp.B, gp.T, gp.H, gp.I = 4, 19, 202, 100
+    assert lib.biear_gru_fwd(ctypes.byref(gp), None) == -1 and b"bad geometry" in lib.biear_last_error()
+    gp.H = 200
+    assert lib.biear_gru_fwd(ctypes.byref(gp), None) == -1 and b"null pointer" in lib.biear_last_error()
     job = (_lib.WgradJob * 1)()
     assert lib.biear_wgrad_scratch_floats(job, 1, 2, 16) == -1                                              # null operands
     assert lib.biear_wgrad_scratch_floats(job, 9, 2, 16) == -1                                              # too many jobs

@@ -4,8 +4,8 @@ the two global-norm clips (:523-525) and Adam with the two parameter groups (:61
 (forward + backward) followed by clip + optimizer.step, batch 256 per GPU.  With torchrun the gradients are all-reduced
 (one flat bucket) before the clips.  Prints ms/step and audio-s/s.
 
-The back-end is plain PyTorch/cuDNN on purpose (out of scope of the hot path): this tool shows what
-the front-end costs inside the whole step."""
+Back-end: the GRU recurrences (csrc/gru.cu) and the sector heads (csrc/heads.cu) are this package's kernels, the body MLP
+and the input / weight-gradient products library GEMMs.  argv: [batch] [steps] [libgru]"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, torch.nn.functional as F
@@ -21,6 +21,8 @@ if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 50
+if len(sys.argv) > 3 and sys.argv[3] == "libgru":      # A/B: the encoders' GRU layers through torch.nn.GRU (cuDNN)
+    mt._PairEncoder.native_gru = False
 torch.manual_seed(0)
 model = mt.build_model_active(use_cc=True, fb_alpha=0.0, **bench.CONFIG_YAML)
 with torch.no_grad():
