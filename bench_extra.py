@@ -312,8 +312,8 @@ def full_step(batch=256, steps=30, device="cuda:0", world=1, rank=0, dist=None):
     out = {"value": batch * world / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "batch_per_gpu": batch,
            "n_gpus": world, "loss": float(loss), "launches_of_ours_per_step": step.launches_per_replay, "parameters": numel,
            "allreduce_floats": numel if world > 1 else 0,
-           "workload": f"BASELINE config 4 on {world} GPU(s): full active training step (front-end + ILD/IPD encoders + body "
-                       "+ 8 native sector heads, the reference's losses + Q regularisers, "
+           "workload": f"BASELINE config 4 on {world} GPU(s): full active training step (front-end + ILD/IPD encoders with "
+                       "native GRU recurrences + body + 8 native sector heads, the reference's losses + Q regularisers, "
                        + ("NCCL all-reduce of the whole model's gradient bucket, " if world > 1 else "")
                        + "two global-norm clips, Adam with two groups), forward + backward as one CUDA graph, clips + Adam "
                        "as a second; resident inputs"}

@@ -870,6 +870,19 @@ def gru_supported(hidden: int) -> bool:
     return bool(_lib.load().biear_gru_supported(int(hidden)))
 
 
+_gru_sides = {}   # (device index, id of the stream the layer runs on) -> two side streams for its parameter gradients
+
+
+def _gru_side_streams(dev, cur):
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), cur.cuda_stream)
+    st = _gru_sides.get(key)
+    if st is None:
+        if len(_gru_sides) > 64:
+            _gru_sides.clear()
+        st = _gru_sides[key] = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+    return st
+
+
 class GruLayer(torch.autograd.Function):
     """One ``nn.GRU`` layer (batch_first, h_0 = 0; model_torch.py:834-835, 842-843) with the 19-step recurrence as ONE
     launch forward and ONE backward instead of the library's per-step GEMM + cell kernels.  The input projection and the
@@ -899,13 +912,13 @@ class GruLayer(torch.autograd.Function):
             _fill(prm, gi=gi, w_hh=w_hh, b_hh=b_hh, h_seq=h_seq, h_prev=h_prev, gates=gates, workspace=ws)
             _lib.check(lib.biear_gru_fwd(byref(prm), _stream(dev)), "biear_gru_fwd")
         ctx.prm = prm
-        ctx.keep = (x, w_ih, w_hh, h_prev, gates, ws)       # what the backward reads (the output itself is not among it)
+        ctx.keep = (x, w_ih, w_hh, h_prev, gates)           # what the backward reads (the output itself is not among it)
         return h_seq
 
     @staticmethod
     def backward(ctx, g_seq):
         from ctypes import byref
-        x, w_ih, w_hh, h_prev, gates, ws = ctx.keep
+        x, w_ih, w_hh, h_prev, gates = ctx.keep
         dev = x.device
         B, T, I = x.shape
         H = w_hh.shape[1]
@@ -919,11 +932,35 @@ class GruLayer(torch.autograd.Function):
             _lib.check(lib.biear_gru_bwd(byref(prm), _stream(dev)), "biear_gru_bwd")
             _fill(prm, dh_seq=None, dgi=None, dgh=None)
             need = ctx.needs_input_grad
+            # dL/dx continues the chain on this stream; the four parameter gradients (two GEMMs with a 4864-long
+            # contraction and few output tiles, two column sums) run beside it on two side streams -- inside a captured
+            # step they become parallel branches of the graph -- and are joined before the node returns.
+            cur = torch.cuda.current_stream(dev)
+            sides = _gru_side_streams(dev, cur)
+            dw_ih = torch.empty((3 * H, I), **f32) if need[1] else None
+            db_ih = torch.empty((3 * H,), **f32) if need[3] else None
+            dw_hh = torch.empty((3 * H, H), **f32) if need[2] else None
+            db_hh = torch.empty((3 * H,), **f32) if need[4] else None
+            used = []
+            if need[1] or need[3]:
+                sides[0].wait_stream(cur)
+                with torch.cuda.stream(sides[0]):
+                    if need[1]:
+                        torch.mm(dgi.t(), x.reshape(B * T, I), out=dw_ih)
+                    if need[3]:
+                        torch.sum(dgi, dim=0, out=db_ih)
+                used.append(sides[0])
+            if need[2] or need[4]:
+                sides[1].wait_stream(cur)
+                with torch.cuda.stream(sides[1]):
+                    if need[2]:
+                        torch.mm(dgh.t(), h_prev.view(B * T, H), out=dw_hh)
+                    if need[4]:
+                        torch.sum(dgh, dim=0, out=db_hh)
+                used.append(sides[1])
             dx = (dgi @ w_ih).view(B, T, I) if need[0] else None
-            dw_ih = dgi.t() @ x.reshape(B * T, I) if need[1] else None
-            dw_hh = dgh.t() @ h_prev.view(B * T, H) if need[2] else None
-            db_ih = dgi.sum(0) if need[3] else None
-            db_hh = dgh.sum(0) if need[4] else None
+            for st in used:
+                cur.wait_stream(st)
         return dx, dw_ih, dw_hh, db_ih, db_hh
 
 

@@ -340,9 +340,9 @@ int biear_heads_bwd(const BiearHeadsParams* p, void* stream);
  *             gates (B,T,4,H) = r, z, n, W_hn h + b_hn out
  *   backward: dh_seq (B,T,H) = dL/dh_t from the consumer of the sequence in  ->  dgi, dgh (B,T,3H) out, from which
  *             dx = dgi W_ih, dW_ih = dgi^T x, db_ih = sum dgi, dW_hh = dgh^T h_prev, db_hh = sum dgh.
- * workspace: biear_gru_workspace_floats(H) floats (weight images, packed by biear_gru_fwd; must stay untouched until
- * biear_gru_bwd of the same step has run).  H % 4 == 0 and the
- * shared-memory budget (H <= 216): ask biear_gru_supported(H).
+ * workspace: biear_gru_workspace_floats(H) floats (the forward's weight images, packed by biear_gru_fwd itself; the backward
+ * reads w_hh directly, so w_hh must be unchanged between the two calls of a step).  H % 4 == 0 and the shared-memory
+ * budget (H <= 232): ask biear_gru_supported(H).
  */
 typedef struct BiearGruParams {
     int32_t B, T, H, I;              /* rows, steps, hidden units, input width (informational) */

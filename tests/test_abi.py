@@ -79,9 +79,9 @@ def test_argument_validation_needs_no_gpu():
     assert lib.biear_adaptive_tile_rows() in (16, 32)
     assert lib.biear_adaptive_workspace_floats(2, 100) > 0
     assert lib.biear_gru_supported(200) == 1 and lib.biear_gru_supported(100) == 1                          # the two encoder layers
-    assert lib.biear_gru_supported(216) == 1 and lib.biear_gru_supported(220) == 0
+    assert lib.biear_gru_supported(232) == 1 and lib.biear_gru_supported(236) == 0        # shared-memory budget
     assert lib.biear_gru_supported(202) == 0 and lib.biear_gru_supported(260) == 0 and lib.biear_gru_workspace_floats(202) == -1
-    assert lib.biear_gru_workspace_floats(200) == 4 * 2 * 600 * 52
+    assert lib.biear_gru_workspace_floats(200) == 4 * 600 * 52
     gp = _lib.GruParams()
     gp.B, gp.T, gp.H, gp.I = 4, 19, 202, 100
     assert lib.biear_gru_fwd(ctypes.byref(gp), None) == -1 and b"bad geometry" in lib.biear_last_error()
