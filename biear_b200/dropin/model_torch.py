@@ -11,7 +11,8 @@ if _ROOT not in sys.path:
 
 from biear_b200.model_torch import *  # noqa: F401,F403,E402
 from biear_b200.model_torch import (DATA_DIM, LATENT_DIM, N_DIST_CLASS, N_SECTORS, build_model,  # noqa: F401,E402
-                                    build_model_active, build_model_active_single_controller)
+                                    build_model_active, build_model_active_single_controller,
+                                    build_model_auralnet_active)
 
 # BIEAR_TIMING=1: report at exit how much device / host time the front-end took per call (the reference's scripts have no
 # timers of their own; used by tools/run_reference_pipeline.py for the unchanged-script runs)

@@ -255,15 +255,23 @@ class FramewiseFixedGammatoneFB(_FilterbankBase):
 
 
 class AuralNetGammatoneFB(_FilterbankBase):
-    """model_torch.py:70-195: fixed-Q filterbank in batched form; forward(wav) -> Y (B,T,N) only."""
+    """model_torch.py:70-195: fixed-Q filterbank in batched form; forward(wav) -> Y (B,T,N) only.  Constructor arguments
+    in the reference's order and names (``n_bands``, not ``Nbands``: model_torch.py:89-98)."""
 
-    def __init__(self, fs=16000, timesteps=19, n_fft=1024, Nbands=100, fmin=50.0, fmax=None, hop_ratio=1.0):
+    def __init__(self, fs: int = 16000, n_bands: int = 100, fmin: float = 50.0, fmax: float = None, timesteps: int = 19,
+                 hop_ratio: float = 1.0, n_fft: int = 1024):
         super().__init__()
-        self._init_geometry(fs, timesteps, n_fft, Nbands, fmin, fmax, hop_ratio)
+        if int(timesteps) <= 0:
+            raise ValueError(f"[AuralNetGammatoneFB] timesteps must be > 0, got {timesteps}")
+        self._init_geometry(fs, int(timesteps), n_fft, n_bands, fmin, fmax, float(hop_ratio))
+        self.n_bands = n_bands
+        self.hop_ratio = float(hop_ratio)
         self.Q_min, self.Q_max = Q_MIN, Q_MAX
         self.cutoff = ops.DEFAULT_CUTOFF
 
     def forward(self, wav_1s: torch.Tensor):
+        if wav_1s.dim() != 2:
+            raise ValueError(f"[AuralNetGammatoneFB] Expected wav_1s (B,N), got {wav_1s.shape}")
         x = self._spectra([wav_1s])
         y, _ = _fixed_bands(x, self.fc, torch.clamp(self.Q0, self.Q_min, self.Q_max), self.df, False, self.cutoff)
         return y

@@ -22,6 +22,8 @@ pass that produces Y (``bifb.forward_features``) instead of a second W(Q) rebuil
 """
 from __future__ import annotations
 
+import math
+
 import torch
 import torch.nn as nn
 
@@ -157,7 +159,9 @@ class _BackEnd(nn.Module):
         if self.use_cc:
             branches.append(lambda: self.cc_proj(x3))
         feats = _fork_join(branches, x1)
-        body = self.body(torch.cat(feats, dim=-1))
+        return self._heads(self.body(torch.cat(feats, dim=-1)))
+
+    def _heads(self, body):
         if body.is_cuda and self.native_heads and body.dtype == torch.float32 and body.shape[1] % 4 == 0 \
                 and body.shape[1] <= 200:
             # all sector heads in one launch forward, one backward (csrc/heads.cu)
@@ -274,6 +278,70 @@ class DeepEarActiveWaveform(_BackEnd):
         return self._backend(x1, x2, x3, ph_l, ph_r)
 
 
+def _sinusoidal_positions(T: int, d_model: int, device) -> torch.Tensor:
+    """(T, d_model) transformer position table, sin on even / cos on odd features (model_torch.py:56-67)."""
+    pos = torch.arange(T, dtype=torch.float32, device=device).unsqueeze(1)
+    freq = torch.exp(torch.arange(0, d_model, 2, dtype=torch.float32, device=device) * (-math.log(10000.0) / max(d_model, 1)))
+    table = torch.zeros(T, d_model, dtype=torch.float32, device=device)
+    table[:, 0::2] = torch.sin(pos * freq)
+    table[:, 1::2] = torch.cos(pos * freq)
+    return table
+
+
+class AuralNetAttentionBlock(nn.Module):
+    """Linear(d_in -> d_model) + sinusoidal positions + 2 pre-norm transformer encoder layers (4 heads, GELU, FFN 4 x
+    d_model, dropout 0.1): (B,T,d_in) -> (B,T,d_model) (model_torch.py:779-823).  Library modules: the comparison model is
+    not on the hot path."""
+
+    def __init__(self, d_in: int = 64, d_model: int = 128, n_heads: int = 4, n_layers: int = 2, dropout: float = 0.1):
+        super().__init__()
+        self.d_model = d_model
+        self.proj = nn.Linear(d_in, d_model)
+        layer = nn.TransformerEncoderLayer(d_model=d_model, nhead=n_heads, dim_feedforward=4 * d_model, dropout=dropout,
+                                           activation="gelu", batch_first=True, norm_first=True)
+        self.encoder = nn.TransformerEncoder(layer, num_layers=n_layers)
+
+    def forward(self, x):
+        h = self.proj(x)
+        return self.encoder(h + _sinusoidal_positions(x.shape[1], self.d_model, x.device).unsqueeze(0))
+
+
+class AuralNetActiveWaveform(_BackEnd):
+    """The AuralNet-style comparison model (model_torch.py:1113-1247): same inputs / outputs / heads as the active model,
+    fixed filterbank per ear + attention aggregation instead of the adaptive front-end and the GRU encoders.  The two
+    filterbanks run on this package's kernels (STFT + the tcgen05 fixed-Q band GEMM), the sector heads on csrc/heads.cu;
+    the attention blocks and the body are torch.nn (library) modules with the reference's module tree."""
+
+    def __init__(self, fs: int = 16000, use_cc: bool = True, n_bands: int = DATA_DIM, timesteps: int = 19,
+                 hop_ratio: float = 1.0, n_fft: int = 1024, d_model: int = 128, n_sectors: int = N_SECTORS,
+                 n_dist_class: int = N_DIST_CLASS):
+        super().__init__()
+        self.use_cc = use_cc
+        self.fb_L = AuralNetGammatoneFB(fs=fs, n_bands=n_bands, timesteps=timesteps, hop_ratio=hop_ratio, n_fft=n_fft)
+        self.fb_R = AuralNetGammatoneFB(fs=fs, n_bands=n_bands, timesteps=timesteps, hop_ratio=hop_ratio, n_fft=n_fft)
+        self.bifb = None                       # (the scripts' front / back parameter split finds nothing: :1147-1149)
+        self.attn_L = AuralNetAttentionBlock(d_in=n_bands, d_model=d_model)
+        self.attn_R = AuralNetAttentionBlock(d_in=n_bands, d_model=d_model)
+        self.attn_diff = AuralNetAttentionBlock(d_in=n_bands, d_model=d_model)
+        self.cc_proj = nn.Linear(DATA_DIM, d_model) if use_cc else None
+        self.body = _body(3 * d_model + (d_model if use_cc else 0))
+        self.subheads = nn.ModuleList([SubHead(200, n_dist_class=n_dist_class) for _ in range(n_sectors)])
+        self.native_heads = True
+        self.last_Q = None                     # no adaptive Q here: the training loop's Q regularisers see None
+
+    def forward(self, wavL_1s, wavR_1s, x3=None):
+        wl = torch.clamp(wavL_1s.float(), -1.0, 1.0)
+        wr = torch.clamp(wavR_1s.float(), -1.0, 1.0)
+        xl = torch.clamp(torch.log(self.fb_L(wl) + 1e-8), -12.0, 12.0)
+        xr = torch.clamp(torch.log(self.fb_R(wr) + 1e-8), -12.0, 12.0)
+        feats = [self.attn_L(xl).mean(dim=1), self.attn_R(xr).mean(dim=1), self.attn_diff(xl - xr).mean(dim=1)]
+        if self.use_cc:
+            if x3 is None:
+                x3 = torch.zeros(wl.size(0), DATA_DIM, device=wl.device)
+            feats.append(self.cc_proj(x3.float()))
+        return self._heads(self.body(torch.cat(feats, dim=-1)))
+
+
 def build_model(use_cc: bool = True, data_dim: int = DATA_DIM, latent_dim: int = LATENT_DIM,
                 n_sectors: int = N_SECTORS, n_dist_class: int = N_DIST_CLASS) -> nn.Module:
     """model_torch.py:1252-1265."""
@@ -308,3 +376,11 @@ def build_model_active_single_controller(use_cc=True, fs=16000, timesteps=19, n_
     return _build_active(BinauralAdaptiveGammatoneFB_SingleController, use_cc, fs, timesteps, n_fft, data_dim,
                          latent_dim, n_sectors, n_dist_class, fb_alpha, fixed_frontend_q, deltaQ_base,
                          deltaQ_low_factor, deltaQ_high_factor, deltaQ_mode)
+
+
+def build_model_auralnet_active(use_cc: bool = True, fs: int = 16000, n_bands: int = DATA_DIM, timesteps: int = 19,
+                                hop_ratio: float = 1.0, n_fft: int = 1024, d_model: int = 128,
+                                n_sectors: int = N_SECTORS, n_dist_class: int = N_DIST_CLASS) -> nn.Module:
+    """model_torch.py:1337-1367 (the AuralNet-style comparison model)."""
+    return AuralNetActiveWaveform(fs=fs, use_cc=use_cc, n_bands=n_bands, timesteps=timesteps, hop_ratio=hop_ratio,
+                                  n_fft=n_fft, d_model=d_model, n_sectors=n_sectors, n_dist_class=n_dist_class)

@@ -21,6 +21,7 @@ BUILDS = {
     "active_single": ("build_model_active_single_controller", dict(deltaQ_base=2.0, deltaQ_low_factor=0.5,
                                                                    deltaQ_high_factor=5)),
     "passive": ("build_model", dict(use_cc=True)),
+    "active_auralnet": ("build_model_auralnet_active", dict(use_cc=True)),
 }
 
 

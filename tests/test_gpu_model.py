@@ -102,3 +102,41 @@ def test_precompute_wire_format_against_oracle():
     assert float(np.max(np.minimum(d, 2 * np.pi - d) * wgt)) <= 1e-6
     act = precompute.precompute(wl, wr, y, fmt="active", chunk=4)
     assert act["x1"].shape == (7, 16000) and np.array_equal(act["x3"], out["x3"]) and np.array_equal(act["x1"], wl)
+
+
+def test_auralnet_comparison_model_against_reference():
+    """build_model_auralnet_active (model_torch.py:1113-1247, 1337-1367) through the drop-in namespace: same default
+    initialisation under the seed, outputs and gradients against the unmodified reference's vectors
+    (tests/golden/make_auralnet_golden.py).  The two filterbanks run on the STFT + fixed-Q band kernels, the heads on
+    csrc/heads.cu."""
+    from biear_b200 import _lib, model_torch as mt
+    from tests.golden.make_auralnet_golden import GRAD_KEYS as A_KEYS, inputs
+    g = np.load(os.path.join(ROOT, "tests", "golden", "auralnet_golden.npz"))
+    torch.manual_seed(0)
+    m = mt.build_model_auralnet_active().to(DEV).eval()
+    assert m.bifb is None and m.last_Q is None
+    wl, wr, x3 = (torch.from_numpy(a).to(DEV) for a in inputs())
+    from torch.nn.attention import SDPBackend, sdpa_kernel
+    n0 = _lib.launch_count()
+    with sdpa_kernel(SDPBackend.MATH):               # plain fp32 matmuls in the library attention (no reduced-precision kernel)
+        sound, aoa, dist = m(wl, wr, x3)
+    assert _lib.launch_count() - n0 >= 3             # STFT + band GEMM per ear, the heads: the native path ran
+    for name, t in (("sound", sound), ("aoa", aoa), ("dist", dist)):
+        ref32, ref64 = g[f"a32.{name}"], g[f"a64.{name}"]
+        e = rel_err(t.detach().cpu().numpy(), ref32)
+        assert e <= max(RTOL, 3 * rel_err(ref32, ref64)), (name, e)
+    ws, wa, wd = (torch.from_numpy(a).to(DEV) for a in loss_weights(3))
+    with sdpa_kernel(SDPBackend.MATH):
+        ((ws * sound).sum() + (wa * aoa).sum() + (wd * dist).sum()).backward()
+    params = dict(m.named_parameters())
+    for k in A_KEYS:
+        ref32, ref64 = g[f"a32.grad.{k}"], g[f"a64.grad.{k}"]
+        e = rel_err(sub(params[k].grad.cpu().numpy()), ref32)
+        assert e <= max(RTOL, 3 * rel_err(ref32, ref64)), (k, e)
+    # the reference's constructor keywords (n_bands, not Nbands) and its errors
+    fb = mt.AuralNetGammatoneFB(fs=16000, n_bands=64, fmin=80.0, fmax=7000.0, timesteps=19, hop_ratio=1.0, n_fft=1024)
+    assert fb.n_bands == 64 and fb.fc.shape == (64,)
+    with pytest.raises(ValueError):
+        mt.AuralNetGammatoneFB(timesteps=0)
+    with pytest.raises(ValueError):
+        fb.to(DEV)(wl[0])
