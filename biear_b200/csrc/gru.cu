@@ -378,7 +378,7 @@ extern "C" int biear_gru_fwd(const BiearGruParams* p, void* stream) {
     if (int e = validate(p, "biear_gru_fwd", false)) return e;
     cudaStream_t st = as_stream(stream);
     BIEAR_REQUIRE(biear_gru_supported(p->H), "biear_gru_fwd: H=%d does not fit in shared memory", p->H);
-    gru_pack_kernel<<<dim3(kCS, 8), 256, 0, st>>>(*p, p->workspace);
+    gru_pack_kernel<<<dim3(kCS, 64), 256, 0, st>>>(*p, p->workspace);   // ~2 strided reads per thread: latency, not bandwidth
     BIEAR_LAUNCH_CHECK("gru_pack_kernel");
     return launch(gru_fwd_kernel, "gru_fwd_kernel", (p->B + kRowsT - 1) / kRowsT, sizeof(float) * (size_t)FwdSmemG(p->H).total(), st, *p,
                   (const float*)p->workspace);
