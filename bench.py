@@ -528,6 +528,11 @@ def run_ours(args):
         out["full_step"] = full_multi
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = bench_extra.reference_cpu(sample_batch=16, budget_s=20.0)
+        if isinstance(out.get("full_step"), dict) and "error" not in out["full_step"]:
+            try:      # config 1 (ii): the reference's own full training step on the host cores, next to `full_step`
+                out["full_step"]["cpu_reference"] = bench_extra.reference_cpu_full_step(sample_batch=16, budget_s=10.0)
+            except Exception as e:  # noqa: BLE001
+                out["full_step"]["cpu_reference"] = {"error": repr(e)[:300]}
     print(json.dumps(out), flush=True)
     if dist is not None:
         if not args.eager:          # graphs that recorded NCCL work must be gone before the communicator is

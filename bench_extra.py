@@ -132,6 +132,79 @@ def reference_cpu(sample_batch=16, steps=None, warmup=3, budget_s=25.0, min_step
             "ms_per_step": el / n * 1e3, "steps": n}
 
 
+def reference_cpu_full_step(sample_batch=16, warmup=2, budget_s=10.0, min_steps=5):
+    """one FULL training step of the unmodified reference (oracle/_ref:
+    model_torch.build_model_active with the conf/config.yaml settings, train mode) on the host cores -- CC in the worker
+    pool, model forward, the losses and Q regularisers of train_biear.py:417-431, 476-490, backward, the two global-norm
+    clips (:523-525) and Adam with the two parameter groups (:617-621).  The CPU counterpart of `full_step`."""
+    from oracle import stage_ref
+    if not stage_ref.available():
+        return {"unavailable": "oracle/_ref not staged on this machine"}
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:  # noqa: BLE001
+        pass
+    import bench
+    import torch.nn.functional as F
+    ref_model, _ = stage_ref.load_reference()
+    torch.manual_seed(0)
+    model = ref_model.build_model_active(use_cc=True, fb_alpha=0.0, **CONFIG_YAML)
+    with torch.no_grad():
+        for fb in (model.bifb.fb_L, model.bifb.fb_R):
+            torch.nn.init.normal_(fb.q_out[-1].weight, std=0.02)
+    model.train()
+    fb_params = list(model.bifb.parameters())
+    be_params = [p for n, p in model.named_parameters() if not n.startswith("bifb.")]
+    opt = torch.optim.Adam([{"params": fb_params, "lr": 5e-5}, {"params": be_params, "lr": 1e-4}], weight_decay=1e-5, eps=1e-7)
+    B = sample_batch
+    wl_np, wr_np = bench.synth_binaural(B, 1234)
+    wl, wr = torch.from_numpy(wl_np), torch.from_numpy(wr_np)
+    rs = np.random.RandomState(5)
+    pres = torch.from_numpy((rs.uniform(size=(B, 8)) < 0.25).astype(np.float32))
+    ang = torch.from_numpy(rs.uniform(size=(B, 8)).astype(np.float32))
+    dist_cls = torch.from_numpy(rs.randint(0, 5, size=(B, 8)))
+    log_q0 = torch.log(model.bifb.Q0 + 1e-8).view(1, 1, -1)
+    pos_w = torch.tensor(3.0)
+    pool = stage_ref.CcPool(min(max(1, len(os.sched_getaffinity(0))), B))
+
+    def step():
+        fut = pool.submit(wl_np, wr_np, FS, NBANDS, 3.0)
+        x3 = torch.from_numpy(fut())
+        opt.zero_grad(set_to_none=True)
+        sound, aoa, dl = model(wl, wr, x3)
+        l_sound = F.binary_cross_entropy_with_logits(sound, pres, pos_weight=pos_w)
+        l_aoa = (F.smooth_l1_loss(aoa, ang, beta=0.02, reduction="none") * pres).sum() / pres.sum().clamp_min(1.0)
+        l_dist = (F.cross_entropy(dl.reshape(-1, 5), dist_cls.reshape(-1), reduction="none") * pres.reshape(-1)).sum() \
+            / pres.sum().clamp_min(1.0)
+        lq = torch.log(model.last_Q + 1e-8)
+        reg = REG_Q_W * ((lq - log_q0) ** 2).mean() + REG_SMOOTH_W * ((lq[..., 1:] - lq[..., :-1]) ** 2).mean()
+        loss = 0.2 * l_sound + 0.45 * l_aoa + 0.35 * l_dist + reg
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(fb_params, 0.2)
+        torch.nn.utils.clip_grad_norm_(be_params, 3.0)
+        opt.step()
+        return float(loss.detach())
+
+    try:
+        for _ in range(warmup):
+            step()
+        t0 = time.perf_counter()
+        n = 0
+        while True:
+            loss = step()
+            n += 1
+            el = time.perf_counter() - t0
+            if n >= min_steps and (el >= budget_s or n >= 30):
+                break
+    finally:
+        pool.close()
+    return {"value": B * n / el, "unit": UNIT, "ms_per_step": el / n * 1e3, "steps": n, "batch": B, "loss": loss,
+            "cores": torch.get_num_threads(), "kind": "reference",
+            "what": f"{n} full training steps (after {warmup} warm-up) of batch {B} through the UNMODIFIED reference staged in "
+                    "oracle/_ref (build_model_active, conf/config.yaml settings, train mode; CC in a process pool; losses, Q "
+                    "regularisers, two global-norm clips, Adam with two groups) on the host cores, torch CPU fp32"}
+
+
 def gpu_eager_reference(batch=256, steps=5, warmup=2, device="cuda:0"):
     """The reference's own front-end code in PyTorch eager on this GPU: same batch, same loss, fwd+bwd, train mode.
     CC is left out (the reference computes it offline with numpy on the CPU; there is no GPU path for it there)."""
