@@ -112,3 +112,93 @@ def test_gradient_averaging_op_choice():
     from biear_b200 import dist as bdist
     src = inspect.getsource(bdist.FlatGradAllReducer.__call__)
     assert "ReduceOp.AVG" in src and 'get_backend(self.group) == "nccl"' in src and "mul_(1.0 / world)" in src
+
+
+def test_gru_backward_partial_sum_exchange_layout():
+    """Index arithmetic of gru_bwd_kernel (csrc/gru.cu) emulated thread by thread in numpy for one cluster: every CTA forms
+    the partial sums of W_hh^T dgh over ITS gate rows for all H units in 4 x 4 tiles and sends each unit's partial to the CTA
+    that owns the unit (slot = sender CTA x gate-row half, layout [slot][row group][unit][4 rows]); the owner adds its 8
+    slots.  Checks that every slot element is written exactly once per step (the mbarrier's expected byte count) and that
+    dL/dx, dW_hh equal torch.nn.GRU's autograd in float64 -- including H / 4 not a multiple of 4, where a tile's four
+    units belong to two CTAs."""
+    import numpy as np
+    import torch
+
+    def run(B, T, I, H):
+        torch.manual_seed(H)
+        cs, HU = 4, H // 4
+        O = 3 * HU
+        gru = torch.nn.GRU(I, H, batch_first=True).double()
+        x = torch.randn(B, T, I, dtype=torch.double, requires_grad=True)
+        up = torch.randn(B, T, H, dtype=torch.double)
+        (gru(x)[0] * up).sum().backward()
+        w_ih, w_hh, b_ih, b_hh = (p.detach().numpy() for p in (gru.weight_ih_l0, gru.weight_hh_l0, gru.bias_ih_l0, gru.bias_hh_l0))
+        sig = lambda v: 1 / (1 + np.exp(-v))
+        gi = (x.detach().numpy().reshape(B * T, I) @ w_ih.T + b_ih).reshape(B, T, 3 * H)
+        h = np.zeros((B, H))
+        gates, hprev = np.zeros((B, T, 4, H)), np.zeros((B, T, H))
+        for t in range(T):                      # what gru_fwd_kernel saves
+            gh = h @ w_hh.T + b_hh
+            r, z = sig(gi[:, t, :H] + gh[:, :H]), sig(gi[:, t, H:2 * H] + gh[:, H:2 * H])
+            n = np.tanh(gi[:, t, 2 * H:] + r * gh[:, 2 * H:])
+            hprev[:, t] = h
+            h = (1 - z) * n + z * h
+            gates[:, t] = np.stack([r, z, n, gh[:, 2 * H:]], 1)
+        part_buf = 8 * HU * 16
+        w_s = [np.concatenate([w_hh[g * H + c * HU:g * H + (c + 1) * HU] for g in range(3)], 0).reshape(-1) for c in range(cs)]
+        d_s = [np.zeros(O * 16) for _ in range(cs)]
+        part = [np.full(2 * part_buf, np.nan) for _ in range(cs)]
+        direct = np.zeros((cs, H, 4))
+        dgi, dgh = np.zeros((B, T, 3 * H)), np.zeros((B, T, 3 * H))
+        it = 0
+        for t in range(T - 1, -1, -1):
+            for c in range(cs):
+                for tid in range(H):            # owner role: (unit u, rows 4 rg ..)
+                    rg, u = divmod(tid, HU)
+                    unit = c * HU + u
+                    carry = np.zeros(4)
+                    if it > 0:
+                        pb = ((it - 1) & 1) * part_buf + (rg * HU + u) * 4
+                        for slot in range(8):
+                            carry += part[c][pb + slot * 16 * HU: pb + slot * 16 * HU + 4]
+                    d = np.zeros((3, 4))
+                    for i in range(4):
+                        row, dirn = rg * 4 + i, 0.0
+                        if row < B:
+                            dh = up[row, t, unit].item() + carry[i] + direct[c, tid, i]
+                            r, z, n, hn = gates[row, t, :, unit]
+                            dnp = dh * (1 - z) * (1 - n * n)
+                            dirn = dh * z
+                            d[:, i] = dnp * hn * r * (1 - r), dh * (hprev[row, t, unit] - n) * z * (1 - z), dnp * r
+                            dgi[row, t, [unit, H + unit, 2 * H + unit]] = d[0, i], d[1, i], dnp
+                            dgh[row, t, [unit, H + unit, 2 * H + unit]] = d[:, i]
+                        direct[c, tid, i] = dirn
+                    for g in range(3):
+                        d_s[c][(g * HU + u) * 16 + rg * 4:(g * HU + u) * 16 + rg * 4 + 4] = d[g]
+            if t == 0:
+                break
+            hits = [np.zeros(2 * part_buf, int) for _ in range(cs)]
+            for c in range(cs):
+                for tid in range(2 * H):        # product role: units 4 jg .. 4 jg + 3 of all H, gate-row half ks
+                    ks, tile = divmod(tid, H)
+                    rg, jg = divmod(tile, HU)
+                    acc = np.zeros((4, 4))
+                    for o in (range(0, O // 2) if ks == 0 else range(O // 2, O)):
+                        acc += np.outer(w_s[c][o * H + 4 * jg:o * H + 4 * jg + 4], d_s[c][o * 16 + rg * 4:o * 16 + rg * 4 + 4])
+                    base = (it & 1) * part_buf + ((c * 2 + ks) * 4 + rg) * HU * 4
+                    for i in range(4):
+                        dest, uu = divmod(4 * jg + i, HU)
+                        part[dest][base + uu * 4:base + uu * 4 + 4] = acc[i]
+                        hits[dest][base + uu * 4:base + uu * 4 + 4] += 1
+            for c in range(cs):                 # exactly the expected transaction bytes, every element once
+                buf = slice((it & 1) * part_buf, (it & 1) * part_buf + part_buf)
+                assert hits[c][buf].min() == 1 and hits[c][buf].max() == 1 and hits[c].sum() == part_buf
+            it += 1
+        dx = (dgi.reshape(B * T, 3 * H) @ w_ih).reshape(B, T, I)
+        assert np.abs(dx - x.grad.numpy()).max() <= 1e-12
+        assert np.abs(dgh.reshape(-1, 3 * H).T @ hprev.reshape(-1, H) - gru.weight_hh_l0.grad.numpy()).max() <= 1e-12
+        assert np.abs(dgi.sum((0, 1)) - gru.bias_ih_l0.grad.numpy()).max() <= 1e-12
+
+    run(5, 4, 6, 8)        # H / 4 = 2
+    run(16, 5, 6, 12)      # H / 4 = 3: tiles straddle CTAs
+    run(9, 3, 5, 20)       # H / 4 = 5
