@@ -934,7 +934,7 @@ class GruLayer(torch.autograd.Function):
             need = ctx.needs_input_grad
             # dL/dx continues the chain on this stream.  While a step is being captured, the four parameter gradients (two
             # GEMMs with a 4864-long contraction and few output tiles, two column sums) go to two side streams and become
-            # parallel branches of the graph, joined before the node returns (full step 2.51 -> 2.43 ms); issued eagerly
+            # parallel branches of the graph, joined before the node returns (full step 2.51 -> 2.41 ms); issued eagerly
             # the launches are host-bound and the extra event calls cost more than the overlap gives, so they stay in line.
             cur = torch.cuda.current_stream(dev)
             sides = _gru_side_streams(dev, cur) if torch.cuda.is_current_stream_capturing() else (cur, cur)
