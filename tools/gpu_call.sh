@@ -1,6 +1,3 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 200 python -m pytest tests -m gpu -q > gpurun_out/r2z7_pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2z7_pytest_gpu.log
-tail -3 gpurun_out/r2z7_pytest_gpu.log
-timeout 60 python tools/time_gru.py 256 2>&1 | grep -i "pack" > gpurun_out/r2z7_time_gru.log; cat gpurun_out/r2z7_time_gru.log
-timeout 100 python tools/train_step_bench.py 256 30 > gpurun_out/r2z7_full_native.log 2>&1; tail -1 gpurun_out/r2z7_full_native.log
+timeout 28 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/train_step_bench.py 256 10 > gpurun_out/r2z8_full_2gpu.log 2>&1; echo "rc=$?"; tail -1 gpurun_out/r2z8_full_2gpu.log
